@@ -1,0 +1,188 @@
+/*
+ * mppb.h — C ABI of libmpp_b200.so: the B200-native replacement of the hot path of
+ * MRPT/mrpt_path_planning (batched TP-space collision + cost evaluation of candidate
+ * motion-primitive edges). Plain C: pointers and sizes only, no C++/torch types.
+ *
+ * Reference interfaces replaced (paths relative to mrpt_path_planning/ in the reference):
+ *   mppb_set_obstacles*      <- the obstacle clouds handed to
+ *                               TPS_Astar::find_feasible_paths_to_neighbors
+ *                               (src/algos/TPS_Astar.cpp:124-137, 542) and consumed by
+ *                               transform_pc_square_clipping (include/mpp/algos/
+ *                               transform_pc_square_clipping.h:16-19)
+ *   mppb_set_ptg_grid        <- DiffDriveCollisionGridBased collision grid + robot shape
+ *                               (include/mpp/ptgs/DiffDriveCollisionGridBased.h:162-215)
+ *   mppb_eval_nodes*         <- cached_local_obstacles + tp_obstacles_single_path for every
+ *                               (node, PTG, k) (src/algos/TPS_Astar.cpp:561-562,744-745;
+ *                               include/mpp/algos/tp_obstacles_single_path.h:17-19)
+ * Later sections of this header (added as the path widens) cover the HolonomicBlend PTG,
+ * the cost evaluators and the costmap builder.
+ *
+ * Conventions
+ *   - every function returns 0 (MPPB_OK) or a negative error code; mppb_last_error(ctx)
+ *     returns the message of the last failure on that context.
+ *   - a context is bound to ONE CUDA device and ONE stream and is not thread-safe; use one
+ *     context per host thread (TPS_Astar::plan is single-threaded per planner object).
+ *   - "host" entry points take host pointers, copy in/out and return after the result is
+ *     in the caller's buffer; "_device" entry points take device pointers, only enqueue
+ *     work on the context's stream and return immediately (call mppb_sync()).
+ *   - there is NO CPU fallback: if no CUDA device is usable, mppb_ctx_create fails.
+ */
+#ifndef MPPB_H_
+#define MPPB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPB_OK 0
+#define MPPB_ERR_INVALID_ARG (-1)
+#define MPPB_ERR_CUDA (-2)
+#define MPPB_ERR_STATE (-3)
+#define MPPB_ERR_UNSUPPORTED (-4)
+
+#define MPPB_MAX_PTGS 8
+#define MPPB_MAX_SHAPE_VERTS 32
+
+typedef struct mppb_ctx mppb_ctx;
+
+/* ---- library / context --------------------------------------------------------------- */
+const char* mppb_version(void);
+/* message of the last failure that had no context (e.g. mppb_ctx_create) */
+const char* mppb_last_global_error(void);
+
+/* device: CUDA ordinal. cuda_stream: a cudaStream_t to run on (e.g. the caller's
+ * framework stream), or NULL to let the context create its own non-blocking stream. */
+int         mppb_ctx_create(int device, void* cuda_stream, mppb_ctx** out_ctx);
+void        mppb_ctx_destroy(mppb_ctx* ctx);
+const char* mppb_last_error(const mppb_ctx* ctx);
+int         mppb_sync(mppb_ctx* ctx);
+/* the cudaStream_t the context enqueues on */
+void*       mppb_stream(mppb_ctx* ctx);
+/* number of kernels this context has launched so far (for launch accounting) */
+uint64_t    mppb_launch_count(const mppb_ctx* ctx);
+
+/* pinned host memory for zero-staging transfers (cudaHostAlloc / cudaFreeHost) */
+int mppb_host_alloc(size_t bytes, void** out_ptr);
+int mppb_host_free(void* ptr);
+
+/* CUDA-event stopwatch on the context's stream: begin records, end records + waits and
+ * returns the elapsed device time in milliseconds. */
+int mppb_timer_begin(mppb_ctx* ctx);
+int mppb_timer_end(mppb_ctx* ctx, float* out_ms);
+
+/* Roofline denominators not in MEASURED_PEAKS.json: CUDA-core FMA throughput (2 FLOP per
+ * FMA) measured on this device, best of 4 runs after one warm-up. */
+int mppb_measure_fp32_tflops(mppb_ctx* ctx, double* out_tflops);
+int mppb_measure_fp64_tflops(mppb_ctx* ctx, double* out_tflops);
+
+/* ---- obstacle cloud -------------------------------------------------------------------
+ * Float SoA cloud in the global frame, exactly the layout of mrpt::maps::CPointsMap
+ * buffers read at transform_pc_square_clipping.cpp:14-16. The call copies the points to
+ * HBM and builds a uniform-bin index over them (bin_size metres; <=0 selects the default).
+ * Several clouds (obstacle sources) are concatenated by calling with append != 0.
+ * Non-finite points are dropped (they can never produce a TP-obstacle). */
+int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int append);
+int mppb_set_obstacles_device(mppb_ctx* ctx, const float* d_xs, const float* d_ys, size_t n, double bin_size,
+                              int append);
+/* number of finite points currently indexed */
+size_t mppb_num_obstacles(const mppb_ctx* ctx);
+
+/* ---- PTG tables: collision-grid family ------------------------------------------------
+ * One descriptor per PTG of the DiffDriveCollisionGridBased family. All arrays are host
+ * pointers and are copied. cell (cx,cy) owns entries [cell_offsets[cx+cy*nx],
+ * cell_offsets[cx+cy*nx+1]) of (entry_k, entry_d): the (k, min TP-distance) list of
+ * DiffDriveCollisionGridBased::TCollisionCell (.h:162). */
+typedef struct mppb_ptg_grid_desc
+{
+    int32_t         num_paths;    /* K */
+    double          ref_distance; /* PTG refDistance */
+    double          grid_x_min, grid_y_min, grid_res;
+    int32_t         grid_nx, grid_ny;
+    const uint32_t* cell_offsets; /* [nx*ny+1] */
+    const uint16_t* entry_k;      /* [cell_offsets[nx*ny]] */
+    const float*    entry_d;      /* [cell_offsets[nx*ny]] */
+    int32_t         shape_nverts; /* polygonal robot shape (<= MPPB_MAX_SHAPE_VERTS) */
+    const double*   shape_x;
+    const double*   shape_y;
+    double          max_radius;   /* getMaxRobotRadius() */
+} mppb_ptg_grid_desc;
+
+int mppb_clear_ptgs(mppb_ctx* ctx);
+/* ptg_index must be the next free index (0,1,2,...) */
+int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* desc);
+int mppb_num_ptgs(const mppb_ctx* ctx);
+/* sum over PTGs of num_paths = row length of the eval output */
+int mppb_total_paths(const mppb_ctx* ctx);
+
+/* ---- stage (a)+(b): free TP-distance per (node, PTG, k) --------------------------------
+ * For every node pose and every path k of every PTG: the minimum, over all obstacle
+ * points inside the node's +-clip_dist square (global axes), of the TP-space collision
+ * distance, as tp_obstacles_single_path() computes it BEFORE the initial value is
+ * applied:   out[node][ptg_offset + k] = min_p c(p,k)   or +INF if no point constrains k.
+ * The reference value is  freeDistance = min(init_k, (double)out)  with
+ * init_k = min(refDistance, pathDist(k, last)) [initTPObstacleSingle]; the caller holds
+ * init_k. out is row-major [n_nodes][mppb_total_paths]. */
+int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi /* host [n][3] */,
+                    double clip_dist, float* out /* host [n][total_paths] */);
+/* Device-resident variant: d_nodes is [n][4] doubles (x, y, cos(phi), sin(phi)) with the
+ * cos/sin evaluated by the caller's libm (glibc for bit parity with the reference). */
+int mppb_eval_nodes_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, double clip_dist,
+                           float* d_out);
+/* Fill [n][4] (x, y, cos, sin) from [n][3] (x, y, phi) on the host with the C library. */
+void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, double* out_xycs);
+
+
+/* ---- host-side PTG objects ---------------------------------------------------------------
+ * Mirror of the PTG "operator" the planner calls (mrpt::nav::CParameterizedTrajectoryGenerator
+ * virtuals at src/algos/TPS_Astar.cpp:120,279-292,578-795). A PTG object owns the host
+ * tables (trajectories, collision grid) and can upload itself into a context. */
+typedef struct mppb_ptg mppb_ptg;
+
+typedef struct mppb_diffdrive_c_params
+{
+    int32_t       num_paths;
+    double        ref_distance;
+    double        resolution;             /* collision grid cell size [m] */
+    double        v_max_mps;
+    double        w_max_rps;              /* rad/s (ini w_max_dps * pi / 180) */
+    double        K;                      /* +1 forward, -1 backward */
+    double        turning_radius_ref;     /* default 0.10 */
+    int32_t       shape_nverts;
+    const double* shape_x;
+    const double* shape_y;
+} mppb_diffdrive_c_params;
+
+/* mpp::ptg::DiffDrive_C (src/ptgs/DiffDrive_C.cpp): simulates the trajectories and builds
+ * the collision grid (DiffDriveCollisionGridBased.cpp:615-764). */
+int  mppb_ptg_create_diffdrive_c(const mppb_diffdrive_c_params* params, mppb_ptg** out_ptg);
+void mppb_ptg_destroy(mppb_ptg* ptg);
+/* message of the last failure on a PTG object or PTG constructor */
+const char* mppb_ptg_last_error(void);
+
+int    mppb_ptg_num_paths(const mppb_ptg* ptg);
+double mppb_ptg_ref_distance(const mppb_ptg* ptg);
+double mppb_ptg_step_duration(const mppb_ptg* ptg);
+double mppb_ptg_max_radius(const mppb_ptg* ptg);
+/* getPathStepCount; <0 on error */
+int64_t mppb_ptg_step_count(const mppb_ptg* ptg, int k);
+/* getPathPose + getPathDist: out4 = x, y, phi, dist */
+int mppb_ptg_path_pose(const mppb_ptg* ptg, int k, uint32_t step, double* out4);
+/* getPathStepForDist: returns 1 found / 0 not found / <0 error */
+int mppb_ptg_step_for_dist(const mppb_ptg* ptg, int k, double dist, uint32_t* out_step);
+/* inverseMap_WS2TP: returns 1 exact / 0 not / <0 error; out_d is normalised by refDistance */
+int mppb_ptg_inverse_map(const mppb_ptg* ptg, double x, double y, double tol, int* out_k, double* out_d);
+/* initTPObstacleSingle value for path k */
+double mppb_ptg_init_dist(const mppb_ptg* ptg, int k);
+/* collision-grid tables (pointers stay valid while the PTG object lives); error if the PTG
+ * is not of the collision-grid family */
+int mppb_ptg_grid_export(const mppb_ptg* ptg, mppb_ptg_grid_desc* out_desc);
+/* upload this PTG's tables as the next PTG of the context */
+int mppb_ctx_add_ptg(mppb_ctx* ctx, const mppb_ptg* ptg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPB_H_ */

@@ -1,0 +1,331 @@
+// C ABI of libmpp_b200 (see include/mppb.h). Host-side plumbing only: context, uploads,
+// staging and launches. There is deliberately no CPU fallback anywhere in this file.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "mppb_internal.cuh"
+
+namespace mppb
+{
+static std::mutex  g_errMtx;
+static std::string g_globalError;
+
+void set_global_error(const std::string& msg)
+{
+    std::lock_guard<std::mutex> lk(g_errMtx);
+    g_globalError = msg;
+}
+int fail(mppb_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx)
+        ctx->lastError = msg;
+    else
+        set_global_error(msg);
+    return code;
+}
+int cuda_fail(mppb_ctx* ctx, cudaError_t e, const char* what)
+{
+    return fail(ctx, MPPB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+}  // namespace mppb
+
+using namespace mppb;
+
+extern "C" {
+
+const char* mppb_version(void) { return "mpp-b200 0.1 (sm_100a)"; }
+
+const char* mppb_last_global_error(void)
+{
+    std::lock_guard<std::mutex> lk(g_errMtx);
+    static thread_local std::string copy;
+    copy = g_globalError;
+    return copy.c_str();
+}
+
+int mppb_ctx_create(int device, void* cuda_stream, mppb_ctx** out_ctx)
+{
+    if (!out_ctx) return fail(nullptr, MPPB_ERR_INVALID_ARG, "out_ctx is null");
+    *out_ctx  = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MPPB_ERR_CUDA,
+                    std::string("no usable CUDA device (libmpp_b200 has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(nullptr, MPPB_ERR_INVALID_ARG, "device ordinal out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    auto* ctx   = new mppb_ctx();
+    ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
+    if (cuda_stream)
+    {
+        ctx->stream    = static_cast<cudaStream_t>(cuda_stream);
+        ctx->ownStream = false;
+    }
+    else
+    {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess)
+        {
+            delete ctx;
+            return cuda_fail(nullptr, e, "cudaStreamCreateWithFlags");
+        }
+        ctx->ownStream = true;
+    }
+    cudaEventCreate(&ctx->evBegin);
+    cudaEventCreate(&ctx->evEnd);
+    *out_ctx = ctx;
+    return MPPB_OK;
+}
+
+void mppb_ctx_destroy(mppb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->rawX.release();
+    ctx->rawY.release();
+    ctx->sortedPts.release();
+    ctx->binStart.release();
+    ctx->binCursor.release();
+    ctx->bboxScratch.release();
+    for (auto& g : ctx->grids)
+    {
+        g.offsets.release();
+        g.entries.release();
+    }
+    ctx->gridDescs.release();
+    ctx->hNodes.release();
+    ctx->hOut.release();
+    ctx->dNodes.release();
+    ctx->dOut.release();
+    if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
+    if (ctx->evEnd) cudaEventDestroy(ctx->evEnd);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mppb_last_error(const mppb_ctx* ctx) { return ctx ? ctx->lastError.c_str() : mppb_last_global_error(); }
+
+int mppb_sync(mppb_ctx* ctx)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
+void*    mppb_stream(mppb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+uint64_t mppb_launch_count(const mppb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mppb_host_alloc(size_t bytes, void** out_ptr)
+{
+    if (!out_ptr) return MPPB_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+    return MPPB_OK;
+}
+int mppb_host_free(void* ptr)
+{
+    if (!ptr) return MPPB_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFreeHost");
+    return MPPB_OK;
+}
+
+int mppb_timer_begin(mppb_ctx* ctx)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    MPPB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
+    return MPPB_OK;
+}
+int mppb_timer_end(mppb_ctx* ctx, float* out_ms)
+{
+    if (!ctx || !out_ms) return MPPB_ERR_INVALID_ARG;
+    MPPB_CUDA(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
+    MPPB_CUDA(ctx, cudaEventSynchronize(ctx->evEnd));
+    MPPB_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->evBegin, ctx->evEnd));
+    return MPPB_OK;
+}
+
+// ---- obstacle cloud -------------------------------------------------------------------
+static int set_obstacles_impl(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int append,
+                              cudaMemcpyKind kind)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n > 0 && (!xs || !ys)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null cloud pointers");
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t keep  = append ? ctx->rawN : 0;
+    const size_t total = keep + n;
+    if (total * sizeof(float) > ctx->rawX.bytes)
+    {
+        // grow, preserving the already-uploaded sources
+        DevBuf nx, ny;
+        MPPB_CUDA(ctx, nx.reserve(std::max<size_t>(total, 1) * sizeof(float)));
+        MPPB_CUDA(ctx, ny.reserve(std::max<size_t>(total, 1) * sizeof(float)));
+        if (keep)
+        {
+            MPPB_CUDA(ctx, cudaMemcpyAsync(nx.p, ctx->rawX.p, keep * sizeof(float), cudaMemcpyDeviceToDevice,
+                                           ctx->stream));
+            MPPB_CUDA(ctx, cudaMemcpyAsync(ny.p, ctx->rawY.p, keep * sizeof(float), cudaMemcpyDeviceToDevice,
+                                           ctx->stream));
+            MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->rawX.release();
+        ctx->rawY.release();
+        ctx->rawX = nx;
+        ctx->rawY = ny;
+    }
+    if (n)
+    {
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->rawX.as<float>() + keep, xs, n * sizeof(float), kind, ctx->stream));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->rawY.as<float>() + keep, ys, n * sizeof(float), kind, ctx->stream));
+    }
+    ctx->rawN = total;
+    return build_cloud_bins(ctx, bin_size > 0 ? bin_size : (ctx->binSize > 0 && append ? ctx->binSize : 0.5));
+}
+
+int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int append)
+{
+    return set_obstacles_impl(ctx, xs, ys, n, bin_size, append, cudaMemcpyHostToDevice);
+}
+int mppb_set_obstacles_device(mppb_ctx* ctx, const float* d_xs, const float* d_ys, size_t n, double bin_size,
+                              int append)
+{
+    return set_obstacles_impl(ctx, d_xs, d_ys, n, bin_size, append, cudaMemcpyDeviceToDevice);
+}
+size_t mppb_num_obstacles(const mppb_ctx* ctx) { return ctx ? ctx->bins.n : 0; }
+
+// ---- PTG tables -------------------------------------------------------------------------
+int mppb_clear_ptgs(mppb_ctx* ctx)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& g : ctx->grids)
+    {
+        g.offsets.release();
+        g.entries.release();
+    }
+    ctx->grids.clear();
+    ctx->totalPaths = 0;
+    return MPPB_OK;
+}
+
+static int upload_descs(mppb_ctx* ctx)
+{
+    std::vector<PtgGridDev> h;
+    for (auto& g : ctx->grids) h.push_back(g.dev);
+    MPPB_CUDA(ctx, ctx->gridDescs.reserve(std::max<size_t>(h.size(), 1) * sizeof(PtgGridDev)));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->gridDescs.p, h.data(), h.size() * sizeof(PtgGridDev), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
+
+int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* d)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (!d) return fail(ctx, MPPB_ERR_INVALID_ARG, "null PTG descriptor");
+    if (ptg_index != static_cast<int>(ctx->grids.size()))
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "ptg_index must be the next free index");
+    if (ptg_index >= MPPB_MAX_PTGS) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many PTGs");
+    if (d->num_paths <= 0 || d->num_paths > 65535) return fail(ctx, MPPB_ERR_INVALID_ARG, "bad num_paths");
+    if (d->grid_nx <= 0 || d->grid_ny <= 0 || !(d->grid_res > 0) || !d->cell_offsets)
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "bad collision grid geometry");
+    if (d->shape_nverts < 3 || d->shape_nverts > MPPB_MAX_SHAPE_VERTS || !d->shape_x || !d->shape_y)
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "robot shape must have 3..32 vertices");
+    const size_t   ncells = static_cast<size_t>(d->grid_nx) * d->grid_ny;
+    const uint32_t nent   = d->cell_offsets[ncells];
+    if (nent && (!d->entry_k || !d->entry_d)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null entry arrays");
+    for (size_t c = 0; c < ncells; c++)
+        if (d->cell_offsets[c] > d->cell_offsets[c + 1]) return fail(ctx, MPPB_ERR_INVALID_ARG, "offsets not sorted");
+    std::vector<uint2> packed(nent);
+    for (uint32_t i = 0; i < nent; i++)
+    {
+        if (d->entry_k[i] >= d->num_paths) return fail(ctx, MPPB_ERR_INVALID_ARG, "entry_k out of range");
+        if (!(d->entry_d[i] >= 0.f)) return fail(ctx, MPPB_ERR_INVALID_ARG, "entry_d must be >= 0");
+        uint32_t bits;
+        std::memcpy(&bits, &d->entry_d[i], 4);
+        packed[i] = make_uint2(d->entry_k[i], bits);
+    }
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PtgGridHost g;
+    MPPB_CUDA(ctx, g.offsets.reserve((ncells + 1) * sizeof(uint32_t)));
+    MPPB_CUDA(ctx, g.entries.reserve(std::max<size_t>(nent, 1) * sizeof(uint2)));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(g.offsets.p, d->cell_offsets, (ncells + 1) * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    if (nent)
+        MPPB_CUDA(ctx, cudaMemcpyAsync(g.entries.p, packed.data(), nent * sizeof(uint2), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PtgGridDev& v = g.dev;
+    std::memset(&v, 0, sizeof(v));
+    v.xmin      = d->grid_x_min;
+    v.ymin      = d->grid_y_min;
+    v.res       = d->grid_res;
+    v.nx        = d->grid_nx;
+    v.ny        = d->grid_ny;
+    v.offsets   = g.offsets.as<uint32_t>();
+    v.entries   = g.entries.as<uint2>();
+    v.K         = d->num_paths;
+    v.outOffset = ctx->totalPaths;
+    v.nverts    = d->shape_nverts;
+    v.maxRadius = d->max_radius;
+    // float upper bound of R^2 with a relative guard band far above any rounding of fx*fx+fy*fy
+    v.insideGuardR2 = static_cast<float>(d->max_radius * d->max_radius * 1.0001 + 1e-12);
+    for (int i = 0; i < d->shape_nverts; i++)
+    {
+        v.shapeX[i] = d->shape_x[i];
+        v.shapeY[i] = d->shape_y[i];
+    }
+    ctx->grids.push_back(g);
+    ctx->totalPaths += d->num_paths;
+    return upload_descs(ctx);
+}
+int mppb_num_ptgs(const mppb_ctx* ctx) { return ctx ? static_cast<int>(ctx->grids.size()) : 0; }
+int mppb_total_paths(const mppb_ctx* ctx) { return ctx ? ctx->totalPaths : 0; }
+
+// ---- evaluation ---------------------------------------------------------------------------
+void mppb_nodes_xycs_from_poses(size_t n, const double* poses, double* out)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        out[4 * i + 0] = poses[3 * i + 0];
+        out[4 * i + 1] = poses[3 * i + 1];
+        out[4 * i + 2] = std::cos(poses[3 * i + 2]);
+        out[4 * i + 3] = std::sin(poses[3 * i + 2]);
+    }
+}
+
+int mppb_eval_nodes_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, double clip_dist, float* d_out)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n_nodes && (!d_nodes_xycs || !d_out)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null device pointers");
+    return launch_tpobs_grid(ctx, n_nodes, d_nodes_xycs, clip_dist, d_out);
+}
+
+int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, double clip_dist, float* out)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n_nodes == 0) return MPPB_OK;
+    if (!poses_xyphi || !out) return fail(ctx, MPPB_ERR_INVALID_ARG, "null host pointers");
+    if (ctx->grids.empty()) return fail(ctx, MPPB_ERR_STATE, "no PTG tables set (mppb_set_ptg_grid)");
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t inBytes  = n_nodes * 4 * sizeof(double);
+    const size_t outBytes = n_nodes * static_cast<size_t>(ctx->totalPaths) * sizeof(float);
+    MPPB_CUDA(ctx, ctx->hNodes.reserve(inBytes));
+    MPPB_CUDA(ctx, ctx->dNodes.reserve(inBytes));
+    MPPB_CUDA(ctx, ctx->dOut.reserve(outBytes));
+    mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodes.as<double>());
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, inBytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_tpobs_grid(ctx, n_nodes, ctx->dNodes.as<double>(), clip_dist, ctx->dOut.as<float>());
+    if (rc != MPPB_OK) return rc;
+    // D2H straight into the caller's buffer: a true async DMA if it is pinned
+    // (mppb_host_alloc), a staged copy inside the driver otherwise.
+    MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dOut.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Uniform-bin index over the global obstacle cloud (built once per cloud upload).
+//
+// The reference rescans the whole cloud for every expanded node
+// (transform_pc_square_clipping.cpp:26-36, "MRPT_TODO Impl actual cache" at
+// TPS_Astar.cpp:835). Here the cloud is counting-sorted by bin once, so a node only
+// touches the bin rows overlapping its clipping square. All kernels are HBM streaming
+// passes over the cloud (8 B/point read, 8 B/point written).
+#include <cfloat>
+#include <cmath>
+
+#include "mppb_internal.cuh"
+
+namespace mppb
+{
+namespace
+{
+__device__ __forceinline__ int ordered_int(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+inline float from_ordered_int(int i)
+{
+    const int   j = i >= 0 ? i : i ^ 0x7fffffff;
+    float       f;
+    memcpy(&f, &j, sizeof(f));
+    return f;
+}
+
+// scratch: [0]=minx [1]=miny [2]=maxx [3]=maxy (ordered ints)
+__global__ void bbox_kernel(const float* __restrict__ xs, const float* __restrict__ ys, size_t n, int* scratch)
+{
+    float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    {
+        const float x = xs[i], y = ys[i];
+        if (isfinite(x) && isfinite(y))
+        {
+            mnx = fminf(mnx, x);
+            mxx = fmaxf(mxx, x);
+            mny = fminf(mny, y);
+            mxy = fmaxf(mxy, y);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(&scratch[0], ordered_int(mnx));
+        atomicMin(&scratch[1], ordered_int(mny));
+        atomicMax(&scratch[2], ordered_int(mxx));
+        atomicMax(&scratch[3], ordered_int(mxy));
+    }
+}
+
+__global__ void bin_count_kernel(
+    const float* __restrict__ xs, const float* __restrict__ ys, size_t n, float minx, float miny, float invBin,
+    int nbx, int nby, uint32_t* counts)
+{
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    {
+        const float x = xs[i], y = ys[i];
+        if (isfinite(x) && isfinite(y))
+        {
+            const int b = bin_coord(y, miny, invBin, nby) * nbx + bin_coord(x, minx, invBin, nbx);
+            atomicAdd(&counts[b], 1u);
+        }
+    }
+}
+
+// Single-CTA exclusive scan (the bin table is small next to the cloud): counts[nb] ->
+// start[nb+1]; counts is zeroed afterwards so it can serve as the scatter cursor.
+__global__ void bin_scan_kernel(uint32_t* counts, uint32_t* start, int nb)
+{
+    __shared__ uint32_t partial[1024];
+    const int           t     = threadIdx.x;
+    const int           chunk = (nb + blockDim.x - 1) / blockDim.x;
+    const int           b0 = t * chunk, b1 = min(nb, b0 + chunk);
+    uint32_t            s = 0;
+    for (int b = b0; b < b1; b++) s += counts[b];
+    partial[t] = s;
+    __syncthreads();
+    // exclusive scan of partial[] by thread 0..: simple Hillis-Steele
+    for (int off = 1; off < blockDim.x; off <<= 1)
+    {
+        uint32_t v = t >= off ? partial[t - off] : 0;
+        __syncthreads();
+        partial[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[t] - s;
+    for (int b = b0; b < b1; b++)
+    {
+        const uint32_t c = counts[b];
+        start[b]         = run;
+        run += c;
+        counts[b] = 0;
+    }
+    if (t == blockDim.x - 1) start[nb] = partial[t];
+}
+
+__global__ void bin_scatter_kernel(
+    const float* __restrict__ xs, const float* __restrict__ ys, size_t n, float minx, float miny, float invBin,
+    int nbx, int nby, const uint32_t* __restrict__ start, uint32_t* cursor, float2* sorted)
+{
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    {
+        const float x = xs[i], y = ys[i];
+        if (isfinite(x) && isfinite(y))
+        {
+            const int      b   = bin_coord(y, miny, invBin, nby) * nbx + bin_coord(x, minx, invBin, nbx);
+            const uint32_t pos = start[b] + atomicAdd(&cursor[b], 1u);
+            sorted[pos]        = make_float2(x, y);
+        }
+    }
+}
+}  // namespace
+
+int build_cloud_bins(mppb_ctx* ctx, double binSize)
+{
+    cudaStream_t st = ctx->stream;
+    const size_t n  = ctx->rawN;
+    ctx->bins       = CloudBins();
+    if (n == 0) return MPPB_OK;
+    if (n > 0xfffffff0ull) return fail(ctx, MPPB_ERR_UNSUPPORTED, "obstacle cloud larger than 2^32 points");
+    if (!(binSize > 0)) binSize = 0.5;
+
+    const float* xs = ctx->rawX.as<float>();
+    const float* ys = ctx->rawY.as<float>();
+
+    // 1) bounding box of the finite points
+    MPPB_CUDA(ctx, ctx->bboxScratch.reserve(4 * sizeof(int)));
+    const int init[4] = {INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN};
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->bboxScratch.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int threads = 256;
+    const int blocks  = static_cast<int>(std::min<size_t>((n + threads - 1) / threads, ctx->numSMs * 8));
+    bbox_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, ctx->bboxScratch.as<int>());
+    ctx->launches++;
+    int h[4];
+    MPPB_CUDA(ctx, cudaMemcpyAsync(h, ctx->bboxScratch.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h[0] == INT32_MAX) return MPPB_OK;  // no finite point at all
+    const float minx = from_ordered_int(h[0]), miny = from_ordered_int(h[1]);
+    const float maxx = from_ordered_int(h[2]), maxy = from_ordered_int(h[3]);
+
+    // 2) bin grid: at most 2^24 bins
+    double s = binSize;
+    for (;;)
+    {
+        const double nbx = std::floor((static_cast<double>(maxx) - minx) / s) + 1;
+        const double nby = std::floor((static_cast<double>(maxy) - miny) / s) + 1;
+        if (nbx * nby <= 16777216.0 && nbx < 1e6 && nby < 1e6) break;
+        s *= 2;
+    }
+    CloudBins b;
+    b.minx        = minx;
+    b.miny        = miny;
+    b.invBin      = static_cast<float>(1.0 / s);
+    b.nbx         = static_cast<int>(std::floor((static_cast<double>(maxx) - minx) / s)) + 1;
+    b.nby         = static_cast<int>(std::floor((static_cast<double>(maxy) - miny) / s)) + 1;
+    const int nb  = b.nbx * b.nby;
+    ctx->binSize  = s;
+
+    // 3) histogram, scan, scatter
+    MPPB_CUDA(ctx, ctx->binStart.reserve((static_cast<size_t>(nb) + 1) * sizeof(uint32_t)));
+    MPPB_CUDA(ctx, ctx->binCursor.reserve(static_cast<size_t>(nb) * sizeof(uint32_t)));
+    MPPB_CUDA(ctx, ctx->sortedPts.reserve(n * sizeof(float2)));
+    MPPB_CUDA(ctx, cudaMemsetAsync(ctx->binCursor.p, 0, static_cast<size_t>(nb) * sizeof(uint32_t), st));
+    bin_count_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, b.minx, b.miny, b.invBin, b.nbx, b.nby,
+                                                ctx->binCursor.as<uint32_t>());
+    bin_scan_kernel<<<1, 1024, 0, st>>>(ctx->binCursor.as<uint32_t>(), ctx->binStart.as<uint32_t>(), nb);
+    bin_scatter_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, b.minx, b.miny, b.invBin, b.nbx, b.nby,
+                                                  ctx->binStart.as<uint32_t>(), ctx->binCursor.as<uint32_t>(),
+                                                  ctx->sortedPts.as<float2>());
+    ctx->launches += 3;
+    uint32_t total = 0;
+    MPPB_CUDA(ctx, cudaMemcpyAsync(&total, ctx->binStart.as<uint32_t>() + nb, sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, st));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(st));
+    MPPB_CUDA(ctx, cudaGetLastError());
+    b.n        = total;
+    b.pts      = ctx->sortedPts.as<float2>();
+    b.binStart = ctx->binStart.as<uint32_t>();
+    ctx->bins  = b;
+    return MPPB_OK;
+}
+
+}  // namespace mppb

@@ -1,0 +1,165 @@
+// Internal declarations of libmpp_b200 (context, device-side table layouts, launch helpers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/mppb.h"
+
+namespace mppb
+{
+// ---------------------------------------------------------------------------------------
+// Device-side layouts
+// ---------------------------------------------------------------------------------------
+
+// Uniform-bin index over the obstacle cloud (global frame). Points are stored sorted by bin
+// (row-major: y-row slowest) as interleaved float2, so the points of `ix0..ix1` of one bin
+// row are ONE contiguous run: [binStart[iy*nbx+ix0], binStart[iy*nbx+ix1+1]).
+struct CloudBins
+{
+    const float2*   pts      = nullptr;  // [n] sorted by bin
+    const uint32_t* binStart = nullptr;  // [nbx*nby+1]
+    float           minx = 0, miny = 0;  // bin grid origin
+    float           invBin = 0;          // 1 / bin size
+    int             nbx = 0, nby = 0;
+    uint32_t        n = 0;
+};
+
+// The bin coordinate of a float coordinate: monotone non-decreasing in v, which is all the
+// query needs for exactness (a point inside [lo,hi] has bin(lo) <= bin(v) <= bin(hi)).
+__host__ __device__ inline int bin_coord(float v, float origin, float invBin, int nb)
+{
+    const float q = (v - origin) * invBin;
+    int         i = q <= 0.f ? 0 : (q >= static_cast<float>(nb) ? nb - 1 : static_cast<int>(q));
+    return i < nb ? i : nb - 1;
+}
+
+// One collision-grid PTG (DiffDriveCollisionGridBased family) as the kernel sees it.
+struct PtgGridDev
+{
+    double          xmin, ymin, res;  // CDynamicGrid extents/resolution of the collision grid
+    int             nx, ny;
+    const uint32_t* offsets;  // CSR [nx*ny+1]
+    const uint2*    entries;  // (k, float bits of d)
+    int             K;
+    int             outOffset;  // column of k=0 in the output row
+    int             nverts;
+    double          maxRadius;
+    float           insideGuardR2;  // float upper bound of maxRadius^2 (quick reject of PNPOLY)
+    double          shapeX[MPPB_MAX_SHAPE_VERTS];
+    double          shapeY[MPPB_MAX_SHAPE_VERTS];
+};
+
+// ---------------------------------------------------------------------------------------
+// Host-side context
+// ---------------------------------------------------------------------------------------
+struct DevBuf
+{
+    void*  p     = nullptr;
+    size_t bytes = 0;
+    // grow-only device buffer
+    cudaError_t reserve(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p             = nullptr;
+        bytes         = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p     = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const
+    {
+        return static_cast<T*>(p);
+    }
+};
+
+struct PinnedBuf
+{
+    void*       p     = nullptr;
+    size_t      bytes = 0;
+    cudaError_t reserve(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p             = nullptr;
+        bytes         = 0;
+        cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p     = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const
+    {
+        return static_cast<T*>(p);
+    }
+};
+
+struct PtgGridHost
+{
+    PtgGridDev dev;
+    DevBuf     offsets, entries;
+};
+
+}  // namespace mppb
+
+struct mppb_ctx
+{
+    int          device    = 0;
+    cudaStream_t stream    = nullptr;
+    bool         ownStream = false;
+    int          numSMs    = 0;
+    std::string  lastError;
+    uint64_t     launches = 0;
+    cudaEvent_t  evBegin = nullptr, evEnd = nullptr;
+
+    // obstacle cloud: raw SoA (concatenated sources) + bin index
+    mppb::DevBuf    rawX, rawY;
+    size_t          rawN = 0;
+    mppb::DevBuf    sortedPts, binStart, binCursor, bboxScratch;
+    mppb::CloudBins bins;
+    double          binSize = 0;
+
+    // PTG tables
+    std::vector<mppb::PtgGridHost> grids;
+    mppb::DevBuf                   gridDescs;  // PtgGridDev[numPtgs] on the device
+    int                            totalPaths = 0;
+
+    // staging for the host entry points
+    mppb::PinnedBuf hNodes, hOut;
+    mppb::DevBuf    dNodes, dOut;
+};
+
+namespace mppb
+{
+int  fail(mppb_ctx* ctx, int code, const std::string& msg);
+int  cuda_fail(mppb_ctx* ctx, cudaError_t e, const char* what);
+void set_global_error(const std::string& msg);
+
+#define MPPB_CUDA(ctx, call)                                           \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return mppb::cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// kernels / launchers implemented in the .cu files
+int build_cloud_bins(mppb_ctx* ctx, double binSize);
+int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, float* dOut);
+
+}  // namespace mppb

@@ -1,0 +1,147 @@
+"""GPU parity of stage (a)+(b) for collision-grid PTGs: libmpp_b200 (through the C ABI) vs the
+CPU oracle on the same seeded inputs. Bar: bit-exact (the values are table floats, 0 or +inf)."""
+import numpy as np
+import pytest
+
+from conftest import free_dist
+from mrpt_path_planning_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(gpu_ctx, orc, oracle_ptgs, xs, ys, poses, clip=5.0, bin_size=0.0):
+    gpu_ctx.set_obstacles(xs, ys, bin_size=bin_size)
+    out = gpu_ctx.eval_nodes(poses, clip)
+    got = free_dist(out, oracle_ptgs)
+    ref, _ = orc.eval_nodes(oracle_ptgs, xs, ys, poses, clip, mode=1, nthreads=0)
+    assert got.shape == ref.shape
+    bad = np.argwhere(got != ref)
+    assert bad.size == 0, "first mismatches (node, col): %s got %s ref %s" % (
+        bad[:5].tolist(), got[tuple(bad[:5].T)], ref[tuple(bad[:5].T)])
+    return got
+
+
+@pytest.mark.parametrize("density,seed", [(0.05, 1), (0.5, 2), (3.0, 3), (26.0, 4)])
+def test_uniform_cloud_parity(gpu_ctx, orc, oracle_ackermann, density, seed):
+    extent = 60.0
+    n = int(density * extent * extent)
+    xs, ys = wl.uniform_cloud(n, extent, seed=seed)
+    poses = wl.node_poses(192, extent, margin=2.0, seed=seed + 100)
+    got = _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+    if density <= 0.5:
+        assert (got == 5.0).any() and (got < 5.0).any()  # both free and constrained paths exercised
+
+
+def test_walls_cloud_parity(gpu_ctx, orc, oracle_ackermann):
+    xs, ys = wl.walls_cloud(60000, 80.0, seed=11)
+    poses = wl.node_poses(256, 80.0, margin=1.0, seed=12)
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+
+
+def test_reference_call_pattern_equals_all_k(orc, oracle_ackermann):
+    """mode 0 (tp_obstacles_single_path per k) and mode 1 (all-k virtual) of the oracle agree."""
+    xs, ys = wl.uniform_cloud(5000, 40.0, seed=5)
+    poses = wl.node_poses(16, 40.0, seed=6)
+    a, _ = orc.eval_nodes(oracle_ackermann, xs, ys, poses, 5.0, mode=0)
+    b, _ = orc.eval_nodes(oracle_ackermann, xs, ys, poses, 5.0, mode=1)
+    assert np.array_equal(a, b)
+
+
+def test_empty_cloud(gpu_ctx, oracle_ackermann):
+    gpu_ctx.set_obstacles(np.zeros(0, np.float32), np.zeros(0, np.float32))
+    out = gpu_ctx.eval_nodes(wl.node_poses(7, 10.0, margin=1.0, seed=3), 5.0)
+    assert out.shape == (7, 242) and np.isinf(out).all()
+
+
+def test_zero_nodes(gpu_ctx):
+    xs, ys = wl.uniform_cloud(100, 10.0, seed=1)
+    gpu_ctx.set_obstacles(xs, ys)
+    out = gpu_ctx.eval_nodes(np.zeros((0, 3)), 5.0)
+    assert out.shape == (0, 242)
+
+
+def test_nodes_outside_cloud_bbox(gpu_ctx, orc, oracle_ackermann):
+    xs, ys = wl.uniform_cloud(3000, 20.0, seed=21)
+    poses = np.array([[-100.0, -100.0, 0.3], [-4.0, 10.0, 1.0], [24.9, 10.0, -2.0], [10.0, 25.1, 3.0],
+                      [1e6, 1e6, 0.0], [10.0, -4.99, 0.5], [10.0, 10.0, -3.14159]])
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+
+
+def test_nonfinite_points_are_ignored(gpu_ctx, orc, oracle_ackermann):
+    xs, ys = wl.uniform_cloud(4000, 30.0, seed=31)
+    xs[::97] = np.nan
+    ys[5::101] = np.inf
+    xs[7::89] = -np.inf
+    poses = wl.node_poses(64, 30.0, margin=1.0, seed=32)
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+
+
+def test_clip_boundary_points(gpu_ctx, orc, oracle_ackermann):
+    """Points exactly on, one ulp inside and one ulp outside the +-clip square (global axes)."""
+    x0, y0 = 12.3, 45.6
+    pts = []
+    for base, other in ((x0 + 5.0, y0 + 0.2), (x0 - 5.0, y0 - 0.3)):
+        f = np.float32(base)
+        for v in (f, np.nextafter(f, np.float32(1e9)), np.nextafter(f, np.float32(-1e9))):
+            pts.append((v, np.float32(other)))
+            pts.append((np.float32(other - y0 + x0), np.float32(v - x0 + y0)))
+    xs = np.array([p[0] for p in pts], np.float32)
+    ys = np.array([p[1] for p in pts], np.float32)
+    poses = np.array([[x0, y0, a] for a in np.linspace(-3.1, 3.1, 23)])
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+
+
+def test_points_near_robot(gpu_ctx, orc, oracle_ackermann):
+    """Obstacles inside / on the edge of the robot polygon: the BACK_AWAY post-process branch."""
+    rng = np.random.default_rng(41)
+    xs = rng.uniform(9.5, 10.5, 400).astype(np.float32)
+    ys = rng.uniform(9.5, 10.5, 400).astype(np.float32)
+    for i in range(0, 400, 25):  # one point at a time: each node sees a single near obstacle
+        poses = np.array([[10.0, 10.0, a] for a in np.linspace(-np.pi, np.pi, 9)])
+        _check(gpu_ctx, orc, oracle_ackermann, xs[i:i + 1], ys[i:i + 1], poses)
+    poses = np.stack([rng.uniform(9.0, 11.0, 64), rng.uniform(9.0, 11.0, 64), rng.uniform(-np.pi, np.pi, 64)], 1)
+    _check(gpu_ctx, orc, oracle_ackermann, xs[:40], ys[:40], poses)
+
+
+@pytest.mark.parametrize("bin_size", [0.1, 0.5, 3.0, 50.0])
+def test_bin_size_independence(gpu_ctx, orc, oracle_ackermann, bin_size):
+    xs, ys = wl.uniform_cloud(20000, 50.0, seed=51)
+    poses = wl.node_poses(96, 50.0, margin=0.0, seed=52)
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses, bin_size=bin_size)
+
+
+def test_other_clip_distance(gpu_ctx, orc, oracle_ackermann):
+    xs, ys = wl.uniform_cloud(20000, 50.0, seed=61)
+    poses = wl.node_poses(64, 50.0, margin=0.0, seed=62)
+    for clip in (0.0, 1.25, 3.0, 7.5):
+        _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses, clip=clip)
+
+
+def test_append_sources(gpu_ctx, orc, oracle_ackermann):
+    xs, ys = wl.uniform_cloud(9000, 40.0, seed=71)
+    poses = wl.node_poses(64, 40.0, margin=0.0, seed=72)
+    gpu_ctx.set_obstacles(xs[:4000], ys[:4000])
+    gpu_ctx.set_obstacles(xs[4000:], ys[4000:], append=True)
+    assert gpu_ctx.num_obstacles == 9000
+    got = free_dist(gpu_ctx.eval_nodes(poses, 5.0), oracle_ackermann)
+    ref, _ = orc.eval_nodes(oracle_ackermann, xs, ys, poses, 5.0, mode=1, nthreads=0)
+    assert np.array_equal(got, ref)
+
+
+def test_full_size_properties(gpu_ctx, oracle_ackermann):
+    """Config C3 at full size (1M points, 4096 nodes): size-independent properties.
+    (i) batch evaluation == evaluation of a sub-batch; (ii) min over a split cloud == whole cloud
+    (the cloud-sharding identity of config C5); (iii) value set is {0} U table floats U {inf}."""
+    xs, ys = wl.uniform_cloud(1 << 20, 200.0)
+    poses = wl.node_poses(4096, 200.0)
+    gpu_ctx.set_obstacles(xs, ys)
+    full = gpu_ctx.eval_nodes(poses, 5.0)
+    sub = gpu_ctx.eval_nodes(poses[1000:1100], 5.0)
+    assert np.array_equal(full[1000:1100], sub)
+    half = len(xs) // 2
+    gpu_ctx.set_obstacles(xs[:half], ys[:half])
+    a = gpu_ctx.eval_nodes(poses, 5.0)
+    gpu_ctx.set_obstacles(xs[half:], ys[half:])
+    b = gpu_ctx.eval_nodes(poses, 5.0)
+    assert np.array_equal(np.minimum(a, b), full)
+    assert (full >= 0).all() and not np.isnan(full).any()
