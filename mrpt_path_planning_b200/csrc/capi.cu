@@ -1,7 +1,9 @@
 // C ABI of libmpp_b200 (see include/mppb.h). Host-side plumbing only: context, uploads,
 // staging and launches. There is deliberately no CPU fallback anywhere in this file.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <mutex>
 
 #include "mppb_internal.cuh"
@@ -92,12 +94,8 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     ctx->binStart.release();
     ctx->binCursor.release();
     ctx->bboxScratch.release();
-    for (auto& g : ctx->grids)
-    {
-        g.offsets.release();
-        g.entries.release();
-    }
-    ctx->gridDescs.release();
+    for (auto& g : ctx->groups) g.release();
+    ctx->groupDescs.release();
     ctx->hNodes.release();
     ctx->hOut.release();
     ctx->dNodes.release();
@@ -198,27 +196,150 @@ int mppb_set_obstacles_device(mppb_ctx* ctx, const float* d_xs, const float* d_y
 size_t mppb_num_obstacles(const mppb_ctx* ctx) { return ctx ? ctx->bins.n : 0; }
 
 // ---- PTG tables -------------------------------------------------------------------------
+static void release_groups(mppb_ctx* ctx)
+{
+    for (auto& g : ctx->groups) g.release();
+    ctx->groups.clear();
+}
+
 int mppb_clear_ptgs(mppb_ctx* ctx)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (auto& g : ctx->grids)
-    {
-        g.offsets.release();
-        g.entries.release();
-    }
+    release_groups(ctx);
     ctx->grids.clear();
     ctx->totalPaths = 0;
     return MPPB_OK;
 }
 
-static int upload_descs(mppb_ctx* ctx)
+// Merge PTGs with identical grid geometry and robot shape into one CSR per group and upload.
+static int rebuild_groups(mppb_ctx* ctx)
 {
-    std::vector<PtgGridDev> h;
-    for (auto& g : ctx->grids) h.push_back(g.dev);
-    MPPB_CUDA(ctx, ctx->gridDescs.reserve(std::max<size_t>(h.size(), 1) * sizeof(PtgGridDev)));
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->gridDescs.p, h.data(), h.size() * sizeof(PtgGridDev), cudaMemcpyHostToDevice,
-                                   ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    release_groups(ctx);
+    std::vector<std::vector<size_t>> members;
+    for (size_t i = 0; i < ctx->grids.size(); i++)
+    {
+        bool placed = false;
+        for (auto& m : members)
+            if (ctx->grids[m[0]].sameGeometryAndShape(ctx->grids[i]))
+            {
+                m.push_back(i);
+                placed = true;
+                break;
+            }
+        if (!placed) members.push_back({i});
+    }
+    std::vector<GridGroupDev> descs;
+    for (const auto& m : members)
+    {
+        const PtgGridHost& g0     = ctx->grids[m[0]];
+        const size_t       ncells = static_cast<size_t>(g0.nx) * g0.ny;
+        std::vector<uint32_t> off(ncells + 1, 0);
+        for (size_t c = 0; c < ncells; c++)
+        {
+            uint32_t n = 0;
+            for (size_t i : m) n += ctx->grids[i].offsets[c + 1] - ctx->grids[i].offsets[c];
+            off[c + 1] = off[c] + n;
+        }
+        std::vector<uint2> ent(off[ncells]);
+        for (size_t c = 0; c < ncells; c++)
+        {
+            uint32_t pos = off[c];
+            for (size_t i : m)
+            {
+                const PtgGridHost& g = ctx->grids[i];
+                for (uint32_t e = g.offsets[c]; e < g.offsets[c + 1]; e++)
+                {
+                    uint32_t bits;
+                    std::memcpy(&bits, &g.entryD[e], 4);
+                    ent[pos++] = make_uint2(static_cast<uint32_t>(g.outOffset) + g.entryK[e], bits);
+                }
+            }
+        }
+        GridGroupHost G;
+        MPPB_CUDA(ctx, G.offsets.reserve((ncells + 1) * sizeof(uint32_t)));
+        MPPB_CUDA(ctx, G.entries.reserve(std::max<size_t>(ent.size(), 1) * sizeof(uint2)));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(G.offsets.p, off.data(), (ncells + 1) * sizeof(uint32_t),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        if (!ent.empty())
+            MPPB_CUDA(ctx, cudaMemcpyAsync(G.entries.p, ent.data(), ent.size() * sizeof(uint2),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        // by-column view: per output column the (cell, d) pairs sorted by ascending d
+        std::vector<uint32_t> colStart(1, 0), colCell;
+        std::vector<float>    colD;
+        std::vector<int>      colOut;
+        for (size_t i : m)
+        {
+            const PtgGridHost&                            g = ctx->grids[i];
+            std::vector<std::vector<std::pair<float, uint32_t>>> perK(g.K);
+            for (size_t c = 0; c < ncells; c++)
+                for (uint32_t e = g.offsets[c]; e < g.offsets[c + 1]; e++)
+                    perK[g.entryK[e]].emplace_back(g.entryD[e], static_cast<uint32_t>(c));
+            for (int k = 0; k < g.K; k++)
+            {
+                std::sort(perK[k].begin(), perK[k].end());
+                for (const auto& dc : perK[k])
+                {
+                    colD.push_back(dc.first);
+                    colCell.push_back(dc.second);
+                }
+                // pad to a multiple of 4 entries (16-byte vector loads) with a cell that is never occupied
+                while (colCell.size() % 4)
+                {
+                    colD.push_back(std::numeric_limits<float>::infinity());
+                    colCell.push_back(static_cast<uint32_t>(ncells));
+                }
+                colStart.push_back(static_cast<uint32_t>(colCell.size()));
+                colOut.push_back(g.outOffset + k);
+            }
+        }
+        MPPB_CUDA(ctx, G.colStart.reserve(colStart.size() * sizeof(uint32_t)));
+        MPPB_CUDA(ctx, G.colCell.reserve(std::max<size_t>(colCell.size(), 1) * sizeof(uint32_t)));
+        MPPB_CUDA(ctx, G.colD.reserve(std::max<size_t>(colD.size(), 1) * sizeof(float)));
+        MPPB_CUDA(ctx, G.colOut.reserve(colOut.size() * sizeof(int)));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(G.colStart.p, colStart.data(), colStart.size() * sizeof(uint32_t),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        if (!colCell.empty())
+        {
+            MPPB_CUDA(ctx, cudaMemcpyAsync(G.colCell.p, colCell.data(), colCell.size() * sizeof(uint32_t),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+            MPPB_CUDA(ctx, cudaMemcpyAsync(G.colD.p, colD.data(), colD.size() * sizeof(float),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        }
+        MPPB_CUDA(ctx, cudaMemcpyAsync(G.colOut.p, colOut.data(), colOut.size() * sizeof(int),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GridGroupDev& v = G.dev;
+        std::memset(&v, 0, sizeof(v));
+        v.nCols    = static_cast<int>(colOut.size());
+        v.colStart = G.colStart.as<uint32_t>();
+        v.colCell  = G.colCell.as<uint32_t>();
+        v.colD     = G.colD.as<float>();
+        v.colOut   = G.colOut.as<int>();
+        v.xmin      = g0.xmin;
+        v.ymin      = g0.ymin;
+        v.res       = g0.res;
+        v.invRes    = 1.0 / g0.res;
+        v.nx        = g0.nx;
+        v.ny        = g0.ny;
+        v.offsets   = G.offsets.as<uint32_t>();
+        v.entries   = G.entries.as<uint2>();
+        v.nverts    = static_cast<int>(g0.shapeX.size());
+        v.maxRadius = g0.maxRadius;
+        // float upper bound of R^2 with a relative guard band far above any rounding of fx*fx+fy*fy
+        v.insideGuardR2 = static_cast<float>(g0.maxRadius * g0.maxRadius * 1.0001 + 1e-12);
+        for (int i = 0; i < v.nverts; i++)
+        {
+            v.shapeX[i] = g0.shapeX[i];
+            v.shapeY[i] = g0.shapeY[i];
+        }
+        ctx->groups.push_back(G);
+        descs.push_back(v);
+    }
+    MPPB_CUDA(ctx, ctx->groupDescs.reserve(std::max<size_t>(descs.size(), 1) * sizeof(GridGroupDev)));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->groupDescs.p, descs.data(), descs.size() * sizeof(GridGroupDev),
+                                   cudaMemcpyHostToDevice, ctx->stream));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MPPB_OK;
 }
@@ -240,48 +361,29 @@ int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* d)
     if (nent && (!d->entry_k || !d->entry_d)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null entry arrays");
     for (size_t c = 0; c < ncells; c++)
         if (d->cell_offsets[c] > d->cell_offsets[c + 1]) return fail(ctx, MPPB_ERR_INVALID_ARG, "offsets not sorted");
-    std::vector<uint2> packed(nent);
     for (uint32_t i = 0; i < nent; i++)
     {
         if (d->entry_k[i] >= d->num_paths) return fail(ctx, MPPB_ERR_INVALID_ARG, "entry_k out of range");
         if (!(d->entry_d[i] >= 0.f)) return fail(ctx, MPPB_ERR_INVALID_ARG, "entry_d must be >= 0");
-        uint32_t bits;
-        std::memcpy(&bits, &d->entry_d[i], 4);
-        packed[i] = make_uint2(d->entry_k[i], bits);
     }
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
     PtgGridHost g;
-    MPPB_CUDA(ctx, g.offsets.reserve((ncells + 1) * sizeof(uint32_t)));
-    MPPB_CUDA(ctx, g.entries.reserve(std::max<size_t>(nent, 1) * sizeof(uint2)));
-    MPPB_CUDA(ctx, cudaMemcpyAsync(g.offsets.p, d->cell_offsets, (ncells + 1) * sizeof(uint32_t),
-                                   cudaMemcpyHostToDevice, ctx->stream));
-    if (nent)
-        MPPB_CUDA(ctx, cudaMemcpyAsync(g.entries.p, packed.data(), nent * sizeof(uint2), cudaMemcpyHostToDevice,
-                                       ctx->stream));
-    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    PtgGridDev& v = g.dev;
-    std::memset(&v, 0, sizeof(v));
-    v.xmin      = d->grid_x_min;
-    v.ymin      = d->grid_y_min;
-    v.res       = d->grid_res;
-    v.nx        = d->grid_nx;
-    v.ny        = d->grid_ny;
-    v.offsets   = g.offsets.as<uint32_t>();
-    v.entries   = g.entries.as<uint2>();
-    v.K         = d->num_paths;
-    v.outOffset = ctx->totalPaths;
-    v.nverts    = d->shape_nverts;
-    v.maxRadius = d->max_radius;
-    // float upper bound of R^2 with a relative guard band far above any rounding of fx*fx+fy*fy
-    v.insideGuardR2 = static_cast<float>(d->max_radius * d->max_radius * 1.0001 + 1e-12);
-    for (int i = 0; i < d->shape_nverts; i++)
-    {
-        v.shapeX[i] = d->shape_x[i];
-        v.shapeY[i] = d->shape_y[i];
-    }
-    ctx->grids.push_back(g);
+    g.K         = d->num_paths;
+    g.outOffset = ctx->totalPaths;
+    g.xmin      = d->grid_x_min;
+    g.ymin      = d->grid_y_min;
+    g.res       = d->grid_res;
+    g.nx        = d->grid_nx;
+    g.ny        = d->grid_ny;
+    g.maxRadius = d->max_radius;
+    g.offsets.assign(d->cell_offsets, d->cell_offsets + ncells + 1);
+    g.entryK.assign(d->entry_k, d->entry_k + nent);
+    g.entryD.assign(d->entry_d, d->entry_d + nent);
+    g.shapeX.assign(d->shape_x, d->shape_x + d->shape_nverts);
+    g.shapeY.assign(d->shape_y, d->shape_y + d->shape_nverts);
+    ctx->grids.push_back(std::move(g));
     ctx->totalPaths += d->num_paths;
-    return upload_descs(ctx);
+    return rebuild_groups(ctx);
 }
 int mppb_num_ptgs(const mppb_ctx* ctx) { return ctx ? static_cast<int>(ctx->grids.size()) : 0; }
 int mppb_total_paths(const mppb_ctx* ctx) { return ctx ? ctx->totalPaths : 0; }

@@ -37,15 +37,23 @@ __host__ __device__ inline int bin_coord(float v, float origin, float invBin, in
     return i < nb ? i : nb - 1;
 }
 
-// One collision-grid PTG (DiffDriveCollisionGridBased family) as the kernel sees it.
-struct PtgGridDev
+// A group of collision-grid PTGs (DiffDriveCollisionGridBased family) that share the grid
+// geometry and the robot shape, as the kernel sees it: ONE merged CSR whose entries carry the
+// output column (ptg offset + k) and the float bits of the TP-distance d. Points are mapped to
+// a cell once per group instead of once per PTG.
+struct GridGroupDev
 {
-    double          xmin, ymin, res;  // CDynamicGrid extents/resolution of the collision grid
+    double          xmin, ymin, res, invRes;  // CDynamicGrid extents/resolution of the collision grid
     int             nx, ny;
-    const uint32_t* offsets;  // CSR [nx*ny+1]
-    const uint2*    entries;  // (k, float bits of d)
-    int             K;
-    int             outOffset;  // column of k=0 in the output row
+    const uint32_t* offsets;  // by-cell CSR [nx*ny+1]
+    const uint2*    entries;  // by-cell entries (output column, float bits of d)
+    // by-column view of the same table: column j of the group owns [colStart[j], colStart[j+1])
+    // of (colCell, colD), sorted by ascending d, and writes output column colOut[j].
+    int             nCols;
+    const uint32_t* colStart;
+    const uint32_t* colCell;
+    const float*    colD;
+    const int*      colOut;
     int             nverts;
     double          maxRadius;
     float           insideGuardR2;  // float upper bound of maxRadius^2 (quick reject of PNPOLY)
@@ -111,10 +119,35 @@ struct PinnedBuf
     }
 };
 
+// host copy of one uploaded collision-grid PTG (kept to rebuild the merged groups)
 struct PtgGridHost
 {
-    PtgGridDev dev;
-    DevBuf     offsets, entries;
+    int                   K = 0, outOffset = 0;
+    double                xmin = 0, ymin = 0, res = 0, maxRadius = 0;
+    int                   nx = 0, ny = 0;
+    std::vector<uint32_t> offsets;
+    std::vector<uint16_t> entryK;
+    std::vector<float>    entryD;
+    std::vector<double>   shapeX, shapeY;
+    bool sameGeometryAndShape(const PtgGridHost& o) const
+    {
+        return xmin == o.xmin && ymin == o.ymin && res == o.res && nx == o.nx && ny == o.ny &&
+               maxRadius == o.maxRadius && shapeX == o.shapeX && shapeY == o.shapeY;
+    }
+};
+struct GridGroupHost
+{
+    GridGroupDev dev;
+    DevBuf       offsets, entries, colStart, colCell, colD, colOut;
+    void         release()
+    {
+        offsets.release();
+        entries.release();
+        colStart.release();
+        colCell.release();
+        colD.release();
+        colOut.release();
+    }
 };
 
 }  // namespace mppb
@@ -137,8 +170,9 @@ struct mppb_ctx
     double          binSize = 0;
 
     // PTG tables
-    std::vector<mppb::PtgGridHost> grids;
-    mppb::DevBuf                   gridDescs;  // PtgGridDev[numPtgs] on the device
+    std::vector<mppb::PtgGridHost>   grids;   // one per PTG, in PTG order
+    std::vector<mppb::GridGroupHost> groups;  // merged tables, rebuilt when a PTG is added
+    mppb::DevBuf                     groupDescs;  // GridGroupDev[numGroups] on the device
     int                            totalPaths = 0;
 
     // staging for the host entry points

@@ -11,13 +11,24 @@
 // Exactness (bit parity of the free/blocked decision): the local point is formed with the
 // reference's operation order in IEEE double without FMA contraction (__dmul_rn/__dadd_rn),
 // rounded to float as CPointsMap stores it, promoted again, and mapped to a collision-grid
-// cell with a true double division and truncation (CDynamicGrid::x2idx). cos/sin of the node
-// heading come from the host C library. The per-path result is an order-independent min,
-// so it is reduced with atomicMin on the (non-negative) float bit pattern in shared memory.
+// cell exactly as CDynamicGrid::x2idx does (double division + truncation; a reciprocal
+// multiply decides all cases that are not within 1e-7 of a cell boundary, the true division
+// decides the rest). cos/sin of the node heading come from the host C library. The per-path
+// result is an order-independent min, reduced with atomicMin on the (non-negative) float bit
+// pattern in shared memory.
 //
-// Work decomposition: one CTA per node. The node's clipping square selects a range of bin
-// rows of the cloud index; each row contributes one contiguous run of points. Threads walk
-// the concatenated runs with coalesced 8-byte loads.
+// Work decomposition: one CTA per node, two phases per PTG group.
+//  Phase 1 (points -> occupancy bitmap): the node's clipping square selects a range of bin
+//    rows of the cloud index; each row contributes one contiguous run of points. Warps take
+//    rows round-robin, lanes take consecutive points (coalesced 8-byte loads), transform them
+//    and set the bit of the collision-grid cell they fall in (shared-memory bitmap, one bit per
+//    cell). The rare points inside the robot polygon do not set a bit; their cell's (k,d) list
+//    is applied directly with the BACK_AWAY rule.
+//  Phase 2 (bitmap -> per-path minimum): every output column (PTG, k) owns its (cell, d) list
+//    sorted by ascending d; a warp scans it 32 entries at a time and stops at the first
+//    occupied cell, whose d IS the minimum. Blocked paths exit after a few entries, and no
+//    atomics or variable-length per-point lists remain on the common path.
+#include <algorithm>
 #include <cfloat>
 
 #include "mppb_internal.cuh"
@@ -26,14 +37,12 @@ namespace mppb
 {
 namespace
 {
-constexpr int kThreads     = 128;
-constexpr int kRowsPerPass = 64;
+constexpr int      kThreads = 128;
+constexpr int      kWarps   = kThreads / 32;
+constexpr int      kRowsPerPass = 64;   // bin rows whose runs are flattened together
+constexpr int      kMaxChunks   = 512;  // 32-point chunks indexed per pass
 constexpr unsigned kInfBits = 0x7f800000u;
-
-struct NodeWindow
-{
-    double x0, y0, c, s, ix, iy, D;
-};
+constexpr unsigned kFull    = 0xffffffffu;
 
 // reference predicate transform_pc_square_clipping.cpp:30-31 (true => point skipped)
 __device__ __forceinline__ bool clipped_out(double g, double center, double D)
@@ -41,8 +50,19 @@ __device__ __forceinline__ bool clipped_out(double g, double center, double D)
     return fabs(__dsub_rn(g, center)) > D;
 }
 
+// CDynamicGrid::x2idx: (int)((v - vmin) / res), exact. The reciprocal multiply is trusted
+// unless it lands within 1e-7 of a cell boundary; then the true division decides.
+__device__ __noinline__ int grid_index_exact(double a, double res) { return __double2int_rz(__ddiv_rn(a, res)); }
+__device__ __forceinline__ int grid_index(double v, double vmin, double res, double invRes)
+{
+    const double a = __dsub_rn(v, vmin);
+    const double q = __dmul_rn(a, invRes);
+    if (__builtin_expect(fabs(q - rint(q)) < 1e-7, 0)) return grid_index_exact(a, res);
+    return __double2int_rz(q);
+}
+
 // mrpt::math::TPolygon2D::contains (PNPOLY) in the reference's operation order.
-__device__ bool polygon_contains(const PtgGridDev& g, double px, double py)
+__device__ __noinline__ bool polygon_contains(const GridGroupDev& g, double px, double py)
 {
     bool      c = false;
     const int n = g.nverts;
@@ -59,17 +79,20 @@ __device__ bool polygon_contains(const PtgGridDev& g, double px, double py)
     return c;
 }
 
-__global__ void __launch_bounds__(kThreads)
-    tpobs_grid_kernel(CloudBins bins, const PtgGridDev* __restrict__ ptgs, int numPtgs, int totalPaths,
-                      const double* __restrict__ nodes /* [n][4] x,y,cos,sin */, double clip,
+__global__ void __launch_bounds__(kThreads, 8)
+    tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
+                      int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */, double clip,
                       float* __restrict__ out)
 {
-    extern __shared__ unsigned char smemRaw[];
-    unsigned*                       smin = reinterpret_cast<unsigned*>(smemRaw);  // [totalPaths]
-    __shared__ uint32_t             rowBeg[kRowsPerPass];
-    __shared__ uint32_t             rowPrefix[kRowsPerPass + 1];
+    extern __shared__ unsigned smem[];
+    unsigned*           smin   = smem;               // [totalPaths] float bits
+    unsigned*           bitmap = smem + totalPaths;  // [bitmapWords] one bit per grid cell (+1 never-set bit)
+    __shared__ uint32_t rowBeg[kRowsPerPass];
+    __shared__ uint32_t rowPrefix[kRowsPerPass + 1];
+    __shared__ uint8_t  chunkRow[kMaxChunks];
 
     const int    node = blockIdx.x;
+    const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double x0 = nodes[4 * node + 0], y0 = nodes[4 * node + 1];
     const double c = nodes[4 * node + 2], s = nodes[4 * node + 3];
 
@@ -80,8 +103,8 @@ __global__ void __launch_bounds__(kThreads)
     const double iy = __dsub_rn(__dmul_rn(x0, s), __dmul_rn(y0, c));
 
     // conservative float window for the bin range (the exact test is per point, in double)
-    int  bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
-    bool any = bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0;
+    int        bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+    const bool any = bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0;
     if (any)
     {
         const float lox = nextafterf(__double2float_rd(x0 - clip), -FLT_MAX);
@@ -93,82 +116,138 @@ __global__ void __launch_bounds__(kThreads)
         by0             = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
         by1             = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
     }
-    __syncthreads();
 
-    for (int rowBase = by0; any && rowBase <= by1; rowBase += kRowsPerPass)
+    for (int gi = 0; any && gi < numGroups; gi++)
     {
-        const int nRows = min(kRowsPerPass, by1 - rowBase + 1);
-        if (threadIdx.x < nRows)
+        const GridGroupDev& G = groups[gi];
+        // group constants into registers (the descriptor lives in global memory)
+        const double          gxmin = G.xmin, gymin = G.ymin, gres = G.res, ginv = G.invRes;
+        const int             gnx = G.nx, gny = G.ny, nCols = G.nCols;
+        const float           guardR2  = G.insideGuardR2;
+        const uint32_t* const colStart = G.colStart;
+        const uint4* const    colCell4 = reinterpret_cast<const uint4*>(G.colCell);
+        const float* const    colD     = G.colD;
+        const int* const      colOut   = G.colOut;
+
+        __syncthreads();  // previous group's phase 2 has finished reading the bitmap
+        const int words = ((gnx * gny) >> 5) + 1;
+        for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
+
+        // ---- phase 1: points -> occupancy bitmap ----
+        for (int rowBase = by0; rowBase <= by1; rowBase += kRowsPerPass)
         {
-            const size_t   r = static_cast<size_t>(rowBase + threadIdx.x) * bins.nbx;
-            const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
-            rowBeg[threadIdx.x]        = b;
-            rowPrefix[threadIdx.x + 1] = e - b;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            uint32_t run = 0;
-            rowPrefix[0] = 0;
-            for (int r = 0; r < nRows; r++)
+            const int nRows = min(kRowsPerPass, by1 - rowBase + 1);
+            __syncthreads();  // bitmap cleared / previous pass done with the row tables
+            if (threadIdx.x < nRows)
             {
-                run += rowPrefix[r + 1];
-                rowPrefix[r + 1] = run;
+                const size_t   r = static_cast<size_t>(rowBase + threadIdx.x) * bins.nbx;
+                const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
+                rowBeg[threadIdx.x]        = b;
+                rowPrefix[threadIdx.x + 1] = e - b;
             }
-        }
-        __syncthreads();
-        const uint32_t total = rowPrefix[nRows];
-
-        for (uint32_t f = threadIdx.x; f < total; f += kThreads)
-        {
-            // locate the row of flat index f (binary search over <= 64 prefix sums)
-            int lo = 0, hi = nRows;
-            while (hi - lo > 1)
+            __syncthreads();
+            if (warp == 0)
             {
-                const int mid = (lo + hi) >> 1;
-                if (rowPrefix[mid] <= f)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-            const float2 g  = bins.pts[rowBeg[lo] + (f - rowPrefix[lo])];
-            const double gx = g.x, gy = g.y;
-            if (clipped_out(gx, x0, clip) || clipped_out(gy, y0, clip)) continue;
-
-            // composePoint with the inverse pose, reference operation order, no FMA
-            const double ox = __dadd_rn(__dadd_rn(ix, __dmul_rn(gx, c)), __dmul_rn(gy, s));
-            const double oy = __dadd_rn(__dsub_rn(iy, __dmul_rn(gx, s)), __dmul_rn(gy, c));
-            const float  fx = __double2float_rn(ox), fy = __double2float_rn(oy);
-            const double lx = fx, ly = fy;
-
-            for (int p = 0; p < numPtgs; p++)
-            {
-                const PtgGridDev& G  = ptgs[p];
-                const int         cx = __double2int_rz(__ddiv_rn(__dsub_rn(lx, G.xmin), G.res));
-                const int         cy = __double2int_rz(__ddiv_rn(__dsub_rn(ly, G.ymin), G.res));
-                if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny) continue;
-                const uint32_t cell = cx + cy * G.nx;
-                const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
-                if (eb == ee) continue;
-                // isPointInsideRobotShape: only points within the shape's bounding radius can be inside
-                bool inside = false;
-                if (fx * fx + fy * fy <= G.insideGuardR2) inside = polygon_contains(G, lx, ly);
-                unsigned* sm = smin + G.outOffset;
-                for (uint32_t e = eb; e < ee; e++)
+                // inclusive scan of up to 64 run lengths, two per lane
+                static_assert(kRowsPerPass == 64, "scan below handles 64 rows");
+                uint32_t a0 = (2 * lane < nRows) ? rowPrefix[2 * lane + 1] : 0u;
+                uint32_t a1 = (2 * lane + 1 < nRows) ? rowPrefix[2 * lane + 2] : 0u;
+                uint32_t v  = a0 + a1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
                 {
-                    const uint2 kd = G.entries[e];
-                    unsigned    v  = kd.y;
-                    if (inside)
+                    const uint32_t t = __shfl_up_sync(kFull, v, o);
+                    if (lane >= o) v += t;
+                }
+                if (lane == 0) rowPrefix[0] = 0;
+                if (2 * lane < nRows) rowPrefix[2 * lane + 1] = v - a1;
+                if (2 * lane + 1 < nRows) rowPrefix[2 * lane + 2] = v;
+            }
+            __syncthreads();
+            const uint32_t total   = rowPrefix[nRows];
+            const uint32_t nChunks = (total + 31) >> 5;
+            for (uint32_t cBase = 0; cBase < nChunks; cBase += kMaxChunks)
+            {
+                const uint32_t nc = min(static_cast<uint32_t>(kMaxChunks), nChunks - cBase);
+                if (cBase) __syncthreads();
+                for (uint32_t ch = threadIdx.x; ch < nc; ch += kThreads)
+                {
+                    // row containing the first point of chunk (cBase + ch)
+                    const uint32_t f  = (cBase + ch) << 5;
+                    int            lo = 0, hi = nRows;
+                    while (hi - lo > 1)
                     {
-                        // COLL_BEH_BACK_AWAY: d < maxRobotRadius -> ignore, else block the path
-                        if (static_cast<double>(__uint_as_float(kd.y)) < G.maxRadius) continue;
-                        v = 0u;
+                        const int mid = (lo + hi) >> 1;
+                        if (rowPrefix[mid] <= f)
+                            lo = mid;
+                        else
+                            hi = mid;
                     }
-                    if (v < sm[kd.x]) atomicMin(&sm[kd.x], v);
+                    chunkRow[ch] = static_cast<uint8_t>(lo);
+                }
+                __syncthreads();
+                for (uint32_t ch = warp; ch < nc; ch += kWarps)
+                {
+                    const uint32_t f = ((cBase + ch) << 5) + lane;
+                    if (f >= total) continue;
+                    int row = chunkRow[ch];
+                    while (f >= rowPrefix[row + 1]) row++;  // f < total guarantees termination
+                    const float2 g  = bins.pts[rowBeg[row] + (f - rowPrefix[row])];
+                    const double gx = g.x, gy = g.y;
+                    if (clipped_out(gx, x0, clip) || clipped_out(gy, y0, clip)) continue;
+                    // composePoint with the inverse pose, reference operation order, no FMA
+                    const double ox = __dadd_rn(__dadd_rn(ix, __dmul_rn(gx, c)), __dmul_rn(gy, s));
+                    const double oy = __dadd_rn(__dsub_rn(iy, __dmul_rn(gx, s)), __dmul_rn(gy, c));
+                    const float  fx = __double2float_rn(ox), fy = __double2float_rn(oy);  // CPointsMap stores float
+                    const double lx = fx, ly = fy;
+                    const int    cx = grid_index(lx, gxmin, gres, ginv);
+                    const int    cy = grid_index(ly, gymin, gres, ginv);
+                    if (cx < 0 || cx >= gnx || cy < 0 || cy >= gny) continue;
+                    const uint32_t cell = cx + cy * gnx;
+                    // isPointInsideRobotShape: only points within the bounding radius can be inside
+                    if (__builtin_expect(fx * fx + fy * fy <= guardR2, 0))
+                    {
+                        if (polygon_contains(G, lx, ly))
+                        {
+                            // COLL_BEH_BACK_AWAY: d < maxRobotRadius -> ignore, else the path is blocked (0)
+                            const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
+                            for (uint32_t e = eb; e < ee; e++)
+                            {
+                                const uint2 kd = G.entries[e];
+                                if (!(static_cast<double>(__uint_as_float(kd.y)) < G.maxRadius))
+                                    atomicMin(&smin[kd.x], 0u);
+                            }
+                            continue;
+                        }
+                    }
+                    atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
                 }
             }
         }
         __syncthreads();
+
+        // ---- phase 2: per output column, first occupied cell in ascending-d order ----
+        for (int col = threadIdx.x; col < nCols; col += kThreads)
+        {
+            const int oc = colOut[col];
+            if (smin[oc] == 0u) continue;  // already blocked at distance 0 by a point inside the robot
+            const uint32_t beg = colStart[col] >> 2, end = colStart[col + 1] >> 2;  // lists are padded to x4
+            for (uint32_t i = beg; i < end; i++)
+            {
+                const uint4    q  = colCell4[i];
+                const unsigned h0 = (bitmap[q.x >> 5] >> (q.x & 31)) & 1u;
+                const unsigned h1 = (bitmap[q.y >> 5] >> (q.y & 31)) & 1u;
+                const unsigned h2 = (bitmap[q.z >> 5] >> (q.z & 31)) & 1u;
+                const unsigned h3 = (bitmap[q.w >> 5] >> (q.w & 31)) & 1u;
+                const unsigned m  = h0 | (h1 << 1) | (h2 << 2) | (h3 << 3);
+                if (m)
+                {
+                    const unsigned v = __float_as_uint(colD[4 * i + __ffs(m) - 1]);
+                    if (v < smin[oc]) smin[oc] = v;  // this thread is the only writer of column oc now
+                    break;
+                }
+            }
+        }
     }
     __syncthreads();
     float* o = out + static_cast<size_t>(node) * totalPaths;
@@ -181,14 +260,18 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double
     if (nNodes == 0) return MPPB_OK;
     if (ctx->grids.empty()) return fail(ctx, MPPB_ERR_STATE, "no PTG tables set (mppb_set_ptg_grid)");
     if (nNodes > 0x7fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many nodes in one batch");
-    const size_t smem = static_cast<size_t>(ctx->totalPaths) * sizeof(unsigned);
-    if (smem > 200 * 1024) return fail(ctx, MPPB_ERR_UNSUPPORTED, "sum of PTG path counts too large");
+    size_t words = 1;
+    for (const auto& g : ctx->groups)
+        words = std::max(words, (static_cast<size_t>(g.dev.nx) * g.dev.ny) / 32 + 1);
+    const size_t smem = (static_cast<size_t>(ctx->totalPaths) + words) * sizeof(unsigned);
+    if (smem > 200 * 1024)
+        return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
     if (smem > 48 * 1024)
         MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
     tpobs_grid_kernel<<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
-        ctx->bins, ctx->gridDescs.as<PtgGridDev>(), static_cast<int>(ctx->grids.size()), ctx->totalPaths, dNodes,
-        clip, dOut);
+        ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
+        static_cast<int>(words), dNodes, clip, dOut);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;

@@ -145,3 +145,22 @@ def test_full_size_properties(gpu_ctx, oracle_ackermann):
     b = gpu_ctx.eval_nodes(poses, 5.0)
     assert np.array_equal(np.minimum(a, b), full)
     assert (full >= 0).all() and not np.isnan(full).any()
+
+
+def test_mixed_geometry_ptg_groups(capi, orc):
+    """PTGs with different grid geometry / path counts form separate kernel groups."""
+    from oracle.orc import ACKERMANN_SHAPE_X as X, ACKERMANN_SHAPE_Y as Y
+
+    w = 60.0 * np.pi / 180.0
+    specs = [(121, 5.0, 0.05, 1.0, w, +1.0), (31, 3.0, 0.1, 0.8, 1.3 * w, -1.0), (61, 5.0, 0.05, 1.0, w, -1.0)]
+    optgs = [orc.diffdrive_c(n, rd, res, v, ww, K, X, Y) for (n, rd, res, v, ww, K) in specs]
+    pptgs = [capi.PTG.diffdrive_c(n, rd, res, v, ww, K, X, Y) for (n, rd, res, v, ww, K) in specs]
+    ctx = capi.Context(0)
+    for p in pptgs:
+        ctx.add_ptg(p)
+    assert ctx.total_paths == 121 + 31 + 61
+    for density, seed in ((0.3, 81), (8.0, 82)):
+        xs, ys = wl.uniform_cloud(int(density * 50 * 50), 50.0, seed=seed)
+        poses = wl.node_poses(128, 50.0, margin=0.0, seed=seed + 10)
+        _check(ctx, orc, optgs, xs, ys, poses, clip=5.0)
+    ctx.close()
