@@ -41,6 +41,7 @@ constexpr int      kThreads = 128;
 constexpr int      kWarps   = kThreads / 32;
 constexpr int      kRowsPerPass = 64;   // bin rows whose runs are flattened together
 constexpr int      kMaxChunks   = 512;  // 32-point chunks indexed per pass
+constexpr int      kMaxInside   = 128;  // queued points inside the robot shape per node and group
 constexpr unsigned kInfBits = 0x7f800000u;
 constexpr unsigned kFull    = 0xffffffffu;
 
@@ -79,6 +80,20 @@ __device__ __noinline__ bool polygon_contains(const GridGroupDev& g, double px, 
     return c;
 }
 
+// An obstacle inside the robot shape (internal_TPObsDistancePostprocess, COLL_BEH_BACK_AWAY):
+// for every (k,d) of its cell, d < maxRobotRadius -> ignored, else path k is blocked (distance 0).
+__device__ __forceinline__ void apply_inside_cell(const GridGroupDev& G, uint32_t cell, unsigned* smin, int first,
+                                                  int stride)
+{
+    const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
+    const double   R  = G.maxRadius;
+    for (uint32_t e = eb + first; e < ee; e += stride)
+    {
+        const uint2 kd = G.entries[e];
+        if (!(static_cast<double>(__uint_as_float(kd.y)) < R)) atomicMin(&smin[kd.x], 0u);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 8)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */, double clip,
@@ -90,6 +105,8 @@ __global__ void __launch_bounds__(kThreads, 8)
     __shared__ uint32_t rowBeg[kRowsPerPass];
     __shared__ uint32_t rowPrefix[kRowsPerPass + 1];
     __shared__ uint8_t  chunkRow[kMaxChunks];
+    __shared__ uint32_t insideCell[kMaxInside];
+    __shared__ unsigned nInside;
 
     const int    node = blockIdx.x;
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 8)
         const int* const      colOut   = G.colOut;
 
         __syncthreads();  // previous group's phase 2 has finished reading the bitmap
+        if (threadIdx.x == 0) nInside = 0;
         const int words = ((gnx * gny) >> 5) + 1;
         for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
 
@@ -209,14 +227,12 @@ __global__ void __launch_bounds__(kThreads, 8)
                     {
                         if (polygon_contains(G, lx, ly))
                         {
-                            // COLL_BEH_BACK_AWAY: d < maxRobotRadius -> ignore, else the path is blocked (0)
-                            const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
-                            for (uint32_t e = eb; e < ee; e++)
-                            {
-                                const uint2 kd = G.entries[e];
-                                if (!(static_cast<double>(__uint_as_float(kd.y)) < G.maxRadius))
-                                    atomicMin(&smin[kd.x], 0u);
-                            }
+                            // obstacle inside the robot shape: no bit; its cell is queued for phase 1b
+                            const unsigned slot = atomicAdd(&nInside, 1u);
+                            if (slot < kMaxInside)
+                                insideCell[slot] = cell;
+                            else
+                                apply_inside_cell(G, cell, smin, 0, 1);  // queue overflow: do it right here
                             continue;
                         }
                     }
@@ -225,6 +241,13 @@ __global__ void __launch_bounds__(kThreads, 8)
             }
         }
         __syncthreads();
+
+        // ---- phase 1b: points inside the robot polygon (COLL_BEH_BACK_AWAY), all threads per cell ----
+        {
+            const unsigned n = min(nInside, static_cast<unsigned>(kMaxInside));
+            for (unsigned q = 0; q < n; q++) apply_inside_cell(G, insideCell[q], smin, threadIdx.x, kThreads);
+            if (n) __syncthreads();
+        }
 
         // ---- phase 2: per output column, first occupied cell in ascending-d order ----
         for (int col = threadIdx.x; col < nCols; col += kThreads)
