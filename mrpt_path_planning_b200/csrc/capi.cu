@@ -100,6 +100,9 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     ctx->hOut.release();
     ctx->dNodes.release();
     ctx->dOut.release();
+    if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
     if (ctx->evEnd) cudaEventDestroy(ctx->evEnd);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -414,20 +417,54 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, do
     if (!poses_xyphi || !out) return fail(ctx, MPPB_ERR_INVALID_ARG, "null host pointers");
     if (ctx->grids.empty()) return fail(ctx, MPPB_ERR_STATE, "no PTG tables set (mppb_set_ptg_grid)");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t cols     = static_cast<size_t>(ctx->totalPaths);
     const size_t inBytes  = n_nodes * 4 * sizeof(double);
-    const size_t outBytes = n_nodes * static_cast<size_t>(ctx->totalPaths) * sizeof(float);
+    const size_t outBytes = n_nodes * cols * sizeof(float);
     MPPB_CUDA(ctx, ctx->hNodes.reserve(inBytes));
     MPPB_CUDA(ctx, ctx->dNodes.reserve(inBytes));
     MPPB_CUDA(ctx, ctx->dOut.reserve(outBytes));
-    mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodes.as<double>());
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, inBytes, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = launch_tpobs_grid(ctx, n_nodes, ctx->dNodes.as<double>(), clip_dist, ctx->dOut.as<float>());
-    if (rc != MPPB_OK) return rc;
-    // D2H straight into the caller's buffer: a true async DMA if it is pinned
+    if (!ctx->auxStream)
+    {
+        MPPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->auxStream, cudaStreamNonBlocking));
+        MPPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+        MPPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+    }
+    // Software pipeline over sub-batches on two streams: while the GPU evaluates sub-batch j
+    // the host prepares cos/sin of j+1 and the copy engine drains the result of j-1.
+    // D2H goes straight into the caller's buffer: a true async DMA if it is pinned
     // (mppb_host_alloc), a staged copy inside the driver otherwise.
-    MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dOut.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t sub      = std::max<size_t>(1024, (n_nodes + 3) / 4);  // <= 4 sub-batches: API calls cost ~5 us each
+    cudaStream_t streams[2] = {ctx->stream, ctx->auxStream};
+    MPPB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->evFork, 0));
+    cudaStream_t saved = ctx->stream;
+    int          rc    = MPPB_OK;
+    size_t       j     = 0;
+    for (size_t lo = 0; lo < n_nodes && rc == MPPB_OK; lo += sub, j++)
+    {
+        const size_t  n  = std::min(sub, n_nodes - lo);
+        cudaStream_t  st = streams[j & 1];
+        double*       hN = ctx->hNodes.as<double>() + 4 * lo;
+        double*       dN = ctx->dNodes.as<double>() + 4 * lo;
+        float*        dO = ctx->dOut.as<float>() + lo * cols;
+        mppb_nodes_xycs_from_poses(n, poses_xyphi + 3 * lo, hN);
+        cudaError_t e = cudaMemcpyAsync(dN, hN, n * 4 * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess)
+        {
+            rc = cuda_fail(ctx, e, "H2D node batch");
+            break;
+        }
+        ctx->stream = st;  // launch on the sub-batch's stream
+        rc          = launch_tpobs_grid(ctx, n, dN, clip_dist, dO);
+        ctx->stream = saved;
+        if (rc != MPPB_OK) break;
+        e = cudaMemcpyAsync(out + lo * cols, dO, n * cols * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "D2H result");
+    }
+    cudaEventRecord(ctx->evJoin, ctx->auxStream);
+    cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0);
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MPPB_OK;
+    return rc;
 }
 
 }  // extern "C"

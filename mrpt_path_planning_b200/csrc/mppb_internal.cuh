@@ -161,6 +161,9 @@ struct mppb_ctx
     std::string  lastError;
     uint64_t     launches = 0;
     cudaEvent_t  evBegin = nullptr, evEnd = nullptr;
+    // second stream + fork/join events: the host entry points pipeline sub-batches over two streams
+    cudaStream_t auxStream = nullptr;
+    cudaEvent_t  evFork = nullptr, evJoin = nullptr;
 
     // obstacle cloud: raw SoA (concatenated sources) + bin index
     mppb::DevBuf    rawX, rawY;
