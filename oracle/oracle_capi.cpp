@@ -10,7 +10,7 @@
 #include <mutex>
 #include <thread>
 
-#include "orc_algos.hpp"
+#include "orc_planner.hpp"
 
 using namespace orc;
 
@@ -257,6 +257,382 @@ double orc_eval_nodes(
     const auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
     ORC_CATCH(-1.0)
+}
+
+
+// ---- solve_poly* (second-opinion tests against numpy.roots) ----------------------------
+int orc_solve_poly4(double a, double b, double c, double d, double* x) { return poly::solve_poly4(x, a, b, c, d); }
+int orc_solve_poly3(double a, double b, double c, double* x) { return poly::solve_poly3(x, a, b, c); }
+int orc_solve_poly2(double a, double b, double c, double* r)
+{
+    return poly::solve_poly2(a, b, c, r[0], r[1]);
+}
+
+// ---- HolonomicBlend PTG ------------------------------------------------------------------
+void* orc_holo_new(
+    int numPaths, double refDist, double T_ramp_max, double vmax, double wmax_rad, double robotRadius,
+    const char* expr_V, const char* expr_W)
+{
+    ORC_TRY
+    auto* p        = new HolonomicBlend();
+    p->numPaths    = numPaths;
+    p->refDistance = refDist;
+    p->T_ramp_max  = T_ramp_max;
+    p->V_MAX       = vmax;
+    p->W_MAX       = wmax_rad;
+    p->robotRadius = robotRadius;
+    if (expr_V && *expr_V) p->expr_V = expr_V;
+    if (expr_W && *expr_W) p->expr_W = expr_W;
+    p->initialize();
+    return static_cast<PTG*>(p);
+    ORC_CATCH(nullptr)
+}
+// dyn = vxLocal, vyLocal, omega, relTargetX, relTargetY, relTargetPhi, targetRelSpeed
+int orc_ptg_update_dyn_state(void* h, const double* dyn, int force)
+{
+    ORC_TRY
+    NavDynState ds;
+    ds.curVelLocal.vx    = dyn[0];
+    ds.curVelLocal.vy    = dyn[1];
+    ds.curVelLocal.omega = dyn[2];
+    ds.relTarget         = TPose2D(dyn[3], dyn[4], dyn[5]);
+    ds.targetRelSpeed    = dyn[6];
+    static_cast<PTG*>(h)->updateNavDynamicState(ds, force != 0);
+    return 0;
+    ORC_CATCH(-1)
+}
+void orc_ptg_set_trim_speed(void* h, double s) { static_cast<PTG*>(h)->trimmableSpeed = s; }
+int  orc_ptg_path_twist(void* h, int k, unsigned step, double* out3)
+{
+    ORC_TRY
+    const TTwist2D t = static_cast<PTG*>(h)->getPathTwist(k, step);
+    out3[0]          = t.vx;
+    out3[1]          = t.vy;
+    out3[2]          = t.omega;
+    return 0;
+    ORC_CATCH(-1)
+}
+// one updateTPObstacleSingle call: returns the updated tp_obstacle_k
+double orc_ptg_update_tpobs_single(void* h, double ox, double oy, int k, double tp_obstacle_k)
+{
+    static_cast<PTG*>(h)->updateTPObstacleSingle(ox, oy, k, tp_obstacle_k);
+    return tp_obstacle_k;
+}
+
+// Stage (a)+(b) for explicit candidates (node, k, speed) of ONE trimmable PTG, as
+// find_feasible_paths_to_neighbors evaluates them (TPS_Astar.cpp:587-611, 721-745).
+// nodes: [B][6] = x, y, phi, vx, vy, omega (global velocity); relTargets: [B][3].
+// out_raw[m]  = min over in-window points of the collision distance (+inf if none)
+// out_free[m] = tp_obstacles_single_path() with the init value taken at the candidate's speed
+//               on a fresh step-count cache.
+double orc_eval_candidates(
+    void* h, const float* xs, const float* ys, size_t n, const double* nodes, const double* relTargets, size_t B,
+    const int* cand_node, const int* cand_k, const double* cand_speed, size_t M, double clip, double* out_raw,
+    double* out_free)
+{
+    ORC_TRY
+    PTG*       ptg = static_cast<PTG*>(h);
+    PointCloud cloud;
+    cloud.xs.assign(xs, xs + n);
+    cloud.ys.assign(ys, ys + n);
+    std::vector<const PointCloud*> clouds{&cloud};
+    std::vector<PointCloud>        locals(B);
+    const auto                     t0 = std::chrono::steady_clock::now();
+    for (size_t b = 0; b < B; b++)
+        locals[b] = cached_local_obstacles(TPose2D(nodes[6 * b], nodes[6 * b + 1], nodes[6 * b + 2]), clouds, clip);
+    for (size_t m = 0; m < M; m++)
+    {
+        const size_t b = cand_node[m];
+        NavDynState  ds;
+        ds.curVelLocal.vx    = nodes[6 * b + 3];
+        ds.curVelLocal.vy    = nodes[6 * b + 4];
+        ds.curVelLocal.omega = nodes[6 * b + 5];
+        ds.curVelLocal.rotate(-nodes[6 * b + 2]);
+        ds.relTarget      = TPose2D(relTargets[3 * b], relTargets[3 * b + 1], relTargets[3 * b + 2]);
+        ds.targetRelSpeed = 0;
+        ptg->trimmableSpeed = cand_speed[m];
+        ptg->updateNavDynamicState(ds, true /*fresh caches*/);
+        ptg->trimmableSpeed = cand_speed[m];
+        double raw = std::numeric_limits<double>::infinity();
+        const PointCloud& L = locals[b];
+        for (size_t i = 0; i < L.size(); i++) ptg->updateTPObstacleSingle(L.xs[i], L.ys[i], cand_k[m], raw);
+        out_raw[m] = raw;
+        if (out_free) out_free[m] = tp_obstacles_single_path(cand_k[m], L, *ptg);
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ORC_CATCH(-1.0)
+}
+
+// ---- cost evaluators ---------------------------------------------------------------------
+struct OrcCostmap
+{
+    std::shared_ptr<CostEvaluatorCostMap> cm;
+};
+void* orc_costmap_new(
+    const float* xs, const float* ys, size_t n, double resolution, double clearance, double maxCost, int useAverage,
+    double maxRadiusFromRobot, const double* robot_xyphi)
+{
+    ORC_TRY
+    PointCloud c;
+    c.xs.assign(xs, xs + n);
+    c.ys.assign(ys, ys + n);
+    CostEvaluatorCostMap::Parameters p;
+    p.resolution                 = resolution;
+    p.preferredClearanceDistance = clearance;
+    p.maxCost                    = maxCost;
+    p.useAverageOfPath           = useAverage != 0;
+    p.maxRadiusFromRobot         = maxRadiusFromRobot;
+    std::optional<TPose2D> pose;
+    if (robot_xyphi) pose = TPose2D(robot_xyphi[0], robot_xyphi[1], robot_xyphi[2]);
+    auto* h = new OrcCostmap();
+    h->cm   = CostEvaluatorCostMap::FromStaticPointObstacles(c, p, pose);
+    return h;
+    ORC_CATCH(nullptr)
+}
+void orc_costmap_free(void* h) { delete static_cast<OrcCostmap*>(h); }
+// info: xmin, ymin, res, nx, ny
+void orc_costmap_info(void* h, double* info)
+{
+    const auto& g = static_cast<OrcCostmap*>(h)->cm->costmap;
+    info[0]       = g.x_min;
+    info[1]       = g.y_min;
+    info[2]       = g.res;
+    info[3]       = g.size_x;
+    info[4]       = g.size_y;
+}
+void orc_costmap_cells(void* h, double* out)
+{
+    const auto& g = static_cast<OrcCostmap*>(h)->cm->costmap;
+    std::memcpy(out, g.cells.data(), g.cells.size() * sizeof(double));
+}
+double orc_costmap_eval_pose(void* h, double x, double y)
+{
+    return static_cast<OrcCostmap*>(h)->cm->eval_single_pose(TPose2D(x, y, 0));
+}
+
+struct OrcWaypoints
+{
+    std::shared_ptr<CostEvaluatorPreferredWaypoint> ev;
+};
+void* orc_waypoints_new(const double* xs, const double* ys, size_t n, double radius, double scale, int useAverage)
+{
+    ORC_TRY
+    auto* h                             = new OrcWaypoints();
+    h->ev                               = std::make_shared<CostEvaluatorPreferredWaypoint>();
+    h->ev->params.waypointInfluenceRadius = radius;
+    h->ev->params.costScale               = scale;
+    h->ev->params.useAverageOfPath        = useAverage != 0;
+    std::vector<TPoint2D> pts(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        pts[i].x = xs[i];
+        pts[i].y = ys[i];
+    }
+    h->ev->setPreferredWaypoints(pts);
+    return h;
+    ORC_CATCH(nullptr)
+}
+void   orc_waypoints_free(void* h) { delete static_cast<OrcWaypoints*>(h); }
+double orc_waypoints_eval_pose(void* h, double x, double y)
+{
+    return static_cast<OrcWaypoints*>(h)->ev->eval_single_pose(TPose2D(x, y, 0));
+}
+
+// Per-edge evaluator costs for explicit sample lists (stage c): edge e has samples
+// [sample_offsets[e], sample_offsets[e+1]) of relative poses (x,y) composed with from_xyphi[e].
+// kind 0 = costmap handle, 1 = waypoint handle. Mirrors reduce_over_path.
+int orc_eval_edge_costs(
+    void* evaluator, int kind, size_t nEdges, const double* from_xyphi, const uint32_t* sample_offsets,
+    const double* rel_xy, double* out_cost)
+{
+    ORC_TRY
+    for (size_t e = 0; e < nEdges; e++)
+    {
+        MoveEdge edge;
+        edge.stateFrom.pose = TPose2D(from_xyphi[3 * e], from_xyphi[3 * e + 1], from_xyphi[3 * e + 2]);
+        for (uint32_t s = sample_offsets[e]; s < sample_offsets[e + 1]; s++)
+            edge.interpolatedPath[static_cast<double>(s)] = TPose2D(rel_xy[2 * s], rel_xy[2 * s + 1], 0);
+        if (kind == 0)
+            out_cost[e] = (*static_cast<OrcCostmap*>(evaluator)->cm)(edge);
+        else
+            out_cost[e] = (*static_cast<OrcWaypoints*>(evaluator)->ev)(edge);
+    }
+    return 0;
+    ORC_CATCH(-1)
+}
+
+// ---- TPS_Astar ----------------------------------------------------------------------------
+struct OrcPlanner
+{
+    TPS_Astar     planner;
+    PlannerInput  in;
+    PlannerOutput out;
+    bool          planned = false;
+    std::list<MotionTree::Node> path;
+    std::list<MoveEdge*>        pathEdges;
+    std::string                 text;
+};
+void* orc_planner_new() { return new OrcPlanner(); }
+void  orc_planner_free(void* h) { delete static_cast<OrcPlanner*>(h); }
+// p: grid_xy, grid_yaw_rad, SE2_metricAngleWeight, heuristic_heading_weight, max_traj, max_speeds,
+//    pathInterpolatedSegments, maximumComputationTime (<=0: unlimited), maxExpansions (<=0: unlimited)
+void orc_planner_set_params(void* h, const double* p, const double* timestamps, int nTimestamps)
+{
+    auto& q                           = static_cast<OrcPlanner*>(h)->planner.params_;
+    q.grid_resolution_xy              = p[0];
+    q.grid_resolution_yaw             = p[1];
+    q.SE2_metricAngleWeight           = p[2];
+    q.heuristic_heading_weight        = p[3];
+    q.max_ptg_trajectories_to_explore = static_cast<uint32_t>(p[4]);
+    q.max_ptg_speeds_to_explore       = static_cast<uint32_t>(p[5]);
+    q.pathInterpolatedSegments        = static_cast<size_t>(p[6]);
+    q.maximumComputationTime          = p[7] > 0 ? p[7] : std::numeric_limits<double>::max();
+    q.maxExpansions = p[8] > 0 ? static_cast<size_t>(p[8]) : std::numeric_limits<size_t>::max();
+    q.ptg_sample_timestamps.assign(timestamps, timestamps + nTimestamps);
+}
+void orc_planner_add_ptg(void* h, void* ptg)
+{
+    static_cast<OrcPlanner*>(h)->in.ptgs.emplace_back(static_cast<PTG*>(ptg), [](PTG*) {});
+}
+void orc_planner_add_obstacles(void* h, const float* xs, const float* ys, size_t n)
+{
+    PointCloud c;
+    c.xs.assign(xs, xs + n);
+    c.ys.assign(ys, ys + n);
+    static_cast<OrcPlanner*>(h)->in.obstacles.push_back(std::move(c));
+}
+void orc_planner_add_costmap(void* h, void* costmap)
+{
+    static_cast<OrcPlanner*>(h)->planner.costEvaluators_.push_back(static_cast<OrcCostmap*>(costmap)->cm);
+}
+void orc_planner_add_waypoints(void* h, void* wps)
+{
+    static_cast<OrcPlanner*>(h)->planner.costEvaluators_.push_back(static_cast<OrcWaypoints*>(wps)->ev);
+}
+// start: x y phi vx vy w ; goal: x y phi vx vy w (+ goalIsPoint) ; bbox min/max: x y phi
+// result: success, pathCost, nTreeNodes, nTreeParents, nExpanded, nTpsPoints, nEdgesCosted, bestNodeId,
+//         goalNodeId, computationTime, bestNodeIdCostToGoal
+int orc_planner_plan(
+    void* h, const double* start, const double* goal, int goalIsPoint, const double* bboxMin, const double* bboxMax,
+    double* result)
+{
+    ORC_TRY
+    auto& P                 = *static_cast<OrcPlanner*>(h);
+    P.in.stateStart.pose    = TPose2D(start[0], start[1], start[2]);
+    P.in.stateStart.vel.vx  = start[3];
+    P.in.stateStart.vel.vy  = start[4];
+    P.in.stateStart.vel.omega = start[5];
+    P.in.stateGoal.isPoint  = goalIsPoint != 0;
+    P.in.stateGoal.pose     = TPose2D(goal[0], goal[1], goalIsPoint ? 0.0 : goal[2]);
+    P.in.stateGoal.vel.vx   = goal[3];
+    P.in.stateGoal.vel.vy   = goal[4];
+    P.in.stateGoal.vel.omega = goal[5];
+    P.in.worldBboxMin       = TPose2D(bboxMin[0], bboxMin[1], bboxMin[2]);
+    P.in.worldBboxMax       = TPose2D(bboxMax[0], bboxMax[1], bboxMax[2]);
+    P.out                   = P.planner.plan(P.in);
+    P.planned               = true;
+    P.path.clear();
+    P.pathEdges.clear();
+    if (P.out.bestNodeId) P.out.motionTree.backtrack_path(*P.out.bestNodeId, P.path, P.pathEdges);
+    result[0]  = P.out.success ? 1 : 0;
+    result[1]  = P.out.pathCost;
+    result[2]  = static_cast<double>(P.out.motionTree.nodes.size());
+    result[3]  = static_cast<double>(P.out.motionTree.edges_to_children.size());
+    result[4]  = static_cast<double>(P.out.nExpanded);
+    result[5]  = static_cast<double>(P.out.nTpsPointsEvaluated);
+    result[6]  = static_cast<double>(P.out.nEdgesCosted);
+    result[7]  = P.out.bestNodeId ? static_cast<double>(*P.out.bestNodeId) : -1;
+    result[8]  = P.out.goalNodeId ? static_cast<double>(*P.out.goalNodeId) : -1;
+    result[9]  = P.out.computationTime;
+    result[10] = P.out.bestNodeIdCostToGoal;
+    return 0;
+    ORC_CATCH(-1)
+}
+int orc_planner_refine(void* h)
+{
+    ORC_TRY
+    auto& P = *static_cast<OrcPlanner*>(h);
+    refine_trajectory(P.path, P.pathEdges, P.in.ptgs);
+    return 0;
+    ORC_CATCH(-1)
+}
+long orc_planner_path_len(void* h) { return static_cast<long>(static_cast<OrcPlanner*>(h)->path.size()); }
+// nodes: [n][8] = id, x, y, phi, vx, vy, omega, cost ; edges: [n-1][8] = ptgIndex, k, step, ptgDist, cost,
+// estimatedExecTime, trimSpeed, nInterpolated
+int orc_planner_path(void* h, double* nodes, double* edges)
+{
+    ORC_TRY
+    auto&  P = *static_cast<OrcPlanner*>(h);
+    size_t i = 0;
+    for (const auto& n : P.path)
+    {
+        double* o = nodes + 8 * i++;
+        o[0]      = static_cast<double>(n.nodeID);
+        o[1]      = n.pose.x;
+        o[2]      = n.pose.y;
+        o[3]      = n.pose.phi;
+        o[4]      = n.vel.vx;
+        o[5]      = n.vel.vy;
+        o[6]      = n.vel.omega;
+        o[7]      = n.cost;
+    }
+    i = 0;
+    for (const MoveEdge* e : P.pathEdges)
+    {
+        double* o = edges + 8 * i++;
+        o[0]      = e->ptgIndex;
+        o[1]      = e->ptgPathIndex;
+        o[2]      = e->ptgStep;
+        o[3]      = e->ptgDist;
+        o[4]      = e->cost;
+        o[5]      = e->estimatedExecTime;
+        o[6]      = e->ptgTrimmableSpeed;
+        o[7]      = static_cast<double>(e->interpolatedPath.size());
+    }
+    return 0;
+    ORC_CATCH(-1)
+}
+// whole motion tree: [n][7] = id, parent(-1 root), x, y, phi, cost, edgeCost(to parent)
+long orc_planner_tree(void* h, double* out, long cap)
+{
+    ORC_TRY
+    auto& P = *static_cast<OrcPlanner*>(h);
+    long  i = 0;
+    for (const auto& kv : P.out.motionTree.nodes)
+    {
+        if (out && i < cap)
+        {
+            double* o = out + 7 * i;
+            o[0]      = static_cast<double>(kv.first);
+            o[1]      = kv.second.parentID ? static_cast<double>(*kv.second.parentID) : -1;
+            o[2]      = kv.second.pose.x;
+            o[3]      = kv.second.pose.y;
+            o[4]      = kv.second.pose.phi;
+            o[5]      = kv.second.cost;
+            o[6]      = kv.second.parentID ? P.out.motionTree.edge_to_parent(kv.first).cost : 0;
+        }
+        i++;
+    }
+    return i;
+    ORC_CATCH(-1)
+}
+// plan_to_trajectory + save_to_txt text; returns needed length
+long orc_planner_trajectory_txt(void* h, double samplePeriod, char* buf, long cap)
+{
+    ORC_TRY
+    auto& P = *static_cast<OrcPlanner*>(h);
+    auto  traj = plan_to_trajectory(P.pathEdges, P.in.ptgs, samplePeriod);
+    // trajectories are relative to the start pose; the CLI re-bases them (path-planner-cli.cpp:396-399)
+    for (auto& kv : traj) kv.second.state.pose = P.in.stateStart.pose + kv.second.state.pose;
+    P.text = trajectory_to_txt(traj);
+    if (buf && cap > 0)
+    {
+        const long m = std::min<long>(cap - 1, static_cast<long>(P.text.size()));
+        std::memcpy(buf, P.text.data(), m);
+        buf[m] = 0;
+    }
+    return static_cast<long>(P.text.size());
+    ORC_CATCH(-1)
 }
 
 }  // extern "C"
