@@ -14,8 +14,22 @@
  *   mppb_eval_nodes*         <- cached_local_obstacles + tp_obstacles_single_path for every
  *                               (node, PTG, k) (src/algos/TPS_Astar.cpp:561-562,744-745;
  *                               include/mpp/algos/tp_obstacles_single_path.h:17-19)
- * Later sections of this header (added as the path widens) cover the HolonomicBlend PTG,
- * the cost evaluators and the costmap builder.
+ *   mppb_set_ptg_holo,
+ *   mppb_eval_holo_candidates <- HolonomicBlend::updateTPObstacleSingle folded over the local
+ *                               obstacles (src/ptgs/HolonomicBlend.cpp:719-840) for explicit
+ *                               (node, k, speed) candidates
+ *   mppb_set_costmap / mppb_set_waypoints / mppb_eval_edge_costs
+ *                            <- CostEvaluatorCostMap::operator() (src/algos/
+ *                               CostEvaluatorCostMap.cpp:122-162) and
+ *                               CostEvaluatorPreferredWaypoint::operator() (src/algos/
+ *                               CostEvaluatorPreferredWaypoint.cpp:59-120) over the interpolated
+ *                               samples of an edge (src/algos/edge_interpolated_path.cpp:51-72)
+ *   mppb_costmap_nearest_d2  <- the nearest-obstacle search of CostEvaluatorCostMap::
+ *                               FromStaticPointObstacles (CostEvaluatorCostMap.cpp:91-97)
+ *   mppb_set_obstacles_clipped <- ObstacleSource::apply_clipping_box (src/interfaces/
+ *                               ObstacleSource.cpp:19-42)
+ *   mppb_planner_*           <- mpp::TPS_Astar::plan (src/algos/TPS_Astar.cpp:86-475) behind the
+ *                               mpp::Planner interface (include/mpp/algos/Planner.h:23-62)
  *
  * Conventions
  *   - every function returns 0 (MPPB_OK) or a negative error code; mppb_last_error(ctx)
@@ -45,6 +59,7 @@ extern "C" {
 
 #define MPPB_MAX_PTGS 8
 #define MPPB_MAX_SHAPE_VERTS 32
+#define MPPB_MAX_EVALUATORS 4
 
 typedef struct mppb_ctx mppb_ctx;
 
@@ -87,7 +102,12 @@ int mppb_measure_fp64_tflops(mppb_ctx* ctx, double* out_tflops);
 int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int append);
 int mppb_set_obstacles_device(mppb_ctx* ctx, const float* d_xs, const float* d_ys, size_t n, double bin_size,
                               int append);
-/* number of finite points currently indexed */
+/* Same, keeping only the points inside box = {minx, miny, maxx, maxy} (float comparisons,
+ * inclusive bounds: ObstacleSource.cpp:29-40). The box applies to this and to appended sources
+ * until the cloud is replaced. box == NULL means no clipping. */
+int mppb_set_obstacles_clipped(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size,
+                               int append, const float* box);
+/* number of finite (and in-box) points currently indexed */
 size_t mppb_num_obstacles(const mppb_ctx* ctx);
 
 /* ---- PTG tables: collision-grid family ------------------------------------------------
@@ -111,11 +131,35 @@ typedef struct mppb_ptg_grid_desc
 } mppb_ptg_grid_desc;
 
 int mppb_clear_ptgs(mppb_ctx* ctx);
-/* ptg_index must be the next free index (0,1,2,...) */
+/* ptg_index must be the next free index (0,1,2,...) over PTGs of all kinds */
 int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* desc);
 int mppb_num_ptgs(const mppb_ctx* ctx);
-/* sum over PTGs of num_paths = row length of the eval output */
+/* sum over the collision-grid PTGs of num_paths = row length of the mppb_eval_nodes output */
 int mppb_total_paths(const mppb_ctx* ctx);
+/* first output column of collision-grid PTG ptg_index, or -1 if it is of another kind */
+int mppb_ptg_column_offset(const mppb_ctx* ctx, int ptg_index);
+
+/* ---- PTG constants: HolonomicBlend ------------------------------------------------------
+ * Closed-form PTG: nothing is tabulated. The device needs the circular robot radius and V_MAX;
+ * everything that depends on (k, speed, dynamic state) travels with each candidate. */
+typedef struct mppb_ptg_holo_desc
+{
+    int32_t num_paths;
+    double  ref_distance;
+    double  robot_radius;
+    double  v_max;
+} mppb_ptg_holo_desc;
+int mppb_set_ptg_holo(mppb_ctx* ctx, int ptg_index, const mppb_ptg_holo_desc* desc);
+
+/* One (node, trajectory, speed) candidate of a HolonomicBlend PTG: InternalParams of
+ * HolonomicBlend::internal_params_from_dir_and_dynstate (HolonomicBlend.cpp:942-973), computed by
+ * the caller (mppb_ptg_holo_params does it for a host PTG object). */
+typedef struct mppb_holo_cand
+{
+    int32_t node;      /* index into the node batch */
+    int32_t ptg_index; /* a PTG set with mppb_set_ptg_holo */
+    double  T_ramp, vxi, vyi, vxf, vyf, vf;
+} mppb_holo_cand;
 
 /* ---- stage (a)+(b): free TP-distance per (node, PTG, k) --------------------------------
  * For every node pose and every path k of every PTG: the minimum, over all obstacle
@@ -133,6 +177,48 @@ int mppb_eval_nodes_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_
                            float* d_out);
 /* Fill [n][4] (x, y, cos, sin) from [n][3] (x, y, phi) on the host with the C library. */
 void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, double* out_xycs);
+
+/* HolonomicBlend: out[c] = min over the in-window points of node cands[c].node of the
+ * TP-space collision distance of candidate c (+INF if unconstrained), in double.
+ * freeDistance = min(init, out[c]) with init from mppb_ptg_init_dist (the caller holds it). */
+int mppb_eval_holo_candidates(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi /* host [n][3] */,
+                              size_t n_cands, const mppb_holo_cand* cands /* host */, double clip_dist,
+                              double* out /* host [n_cands] */);
+int mppb_eval_holo_candidates_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
+                                     const double* d_nodes_xycs, double clip_dist, double* d_out);
+
+/* ---- stage (c): cost evaluators ---------------------------------------------------------
+ * Evaluator slots are evaluated in slot order, like Planner::costEvaluators_ (Planner.cpp:22-26). */
+typedef struct mppb_costmap_desc
+{
+    double        x_min, y_min, res; /* CDynamicGrid<double> geometry */
+    int32_t       nx, ny;
+    const double* cells;       /* host, row-major [ny][nx] */
+    int32_t       use_average; /* CostEvaluatorCostMap::Parameters::useAverageOfPath */
+} mppb_costmap_desc;
+int mppb_clear_evaluators(mppb_ctx* ctx);
+int mppb_set_costmap(mppb_ctx* ctx, int slot, const mppb_costmap_desc* desc);
+/* waypoints are stored as float (CSimplePointsMap::insertPoint) */
+int mppb_set_waypoints(mppb_ctx* ctx, int slot, const double* xs, const double* ys, size_t n, double influence_radius,
+                       double cost_scale, int use_average);
+int mppb_num_evaluators(const mppb_ctx* ctx);
+/* Edge e starts at from_xyphi[e] and has the interpolated samples
+ * [sample_offsets[e], sample_offsets[e+1]) of rel_xy (poses relative to the start, in time
+ * order: MoveEdgeSE2_TPS::interpolatedPath). out[e][slot] = evaluator(edge), row length
+ * mppb_num_evaluators(). The edge cost of Planner::cost_path_segment is
+ * estimatedExecTime + out[e][0] + out[e][1] + ... */
+int mppb_eval_edge_costs(mppb_ctx* ctx, size_t n_edges, const double* from_xyphi /* host [n][3] */,
+                         const uint32_t* sample_offsets /* host [n+1] */, const double* rel_xy /* host [m][2] */,
+                         double* out /* host [n][evaluators] */);
+int mppb_eval_edge_costs_device(mppb_ctx* ctx, size_t n_edges, const double* d_from_xycs /* [n][4] */,
+                                const uint32_t* d_sample_offsets, const double* d_rel_xy, double* d_out);
+
+/* Nearest-obstacle search of the costmap builder: for every cell centre of the grid
+ * (x = (float)(x_min + (cx+0.5) res), likewise y) the minimum float squared distance to the
+ * cloud (xs, ys), exact whenever sqrt(d2) < clearance and +INF or any value >= clearance^2
+ * otherwise (such cells have zero cost). out_d2 is host, row-major [ny][nx]. */
+int mppb_costmap_nearest_d2(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double x_min, double y_min,
+                            double res, int nx, int ny, float clearance, float* out_d2);
 
 
 /* ---- host-side PTG objects ---------------------------------------------------------------
@@ -181,6 +267,28 @@ double mppb_ptg_init_dist(const mppb_ptg* ptg, int k);
 int mppb_ptg_grid_export(const mppb_ptg* ptg, mppb_ptg_grid_desc* out_desc);
 /* upload this PTG's tables as the next PTG of the context */
 int mppb_ctx_add_ptg(mppb_ctx* ctx, const mppb_ptg* ptg);
+
+typedef struct mppb_holo_params
+{
+    int32_t     num_paths;
+    double      ref_distance;
+    double      T_ramp_max;
+    double      v_max_mps;
+    double      w_max_rps;
+    double      robot_radius;
+    const char* expr_V; /* NULL or "" = "V_MAX" */
+    const char* expr_W; /* NULL or "" = "W_MAX" */
+} mppb_holo_params;
+/* mpp::ptg::HolonomicBlend (src/ptgs/HolonomicBlend.cpp) */
+int mppb_ptg_create_holo(const mppb_holo_params* params, mppb_ptg** out_ptg);
+/* updateNavDynamicState: dyn = vxLocal, vyLocal, omega, relTargetX, relTargetY, relTargetPhi, targetRelSpeed */
+int mppb_ptg_update_dyn_state(mppb_ptg* ptg, const double* dyn7, int force);
+/* SpeedTrimmablePTG::trimmableSpeed_ */
+int mppb_ptg_set_trim_speed(mppb_ptg* ptg, double speed);
+/* getPathTwist: out3 = vx, vy, omega */
+int mppb_ptg_path_twist(const mppb_ptg* ptg, int k, uint32_t step, double* out3);
+/* HolonomicBlend: candidate parameters of path k at the current dynamic state and trimmed speed */
+int mppb_ptg_holo_params(const mppb_ptg* ptg, int k, mppb_holo_cand* out_cand);
 
 #ifdef __cplusplus
 }

@@ -17,10 +17,17 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-Wall",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-ffp-contract=off",
     "-ccbin", "/usr/bin/g++",
-    "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
+              "-gencode", "arch=compute_100a,code=sm_100a"]
+# Kernels whose arithmetic must round exactly like the reference's x86-64 build (no FMA contraction).
+PER_FILE_FLAGS = {
+    "tpobs_holo.cu": ["-fmad=false"],
+    "edge_cost.cu": ["-fmad=false"],
+}
+OBJ_DIR = os.path.join(HERE, "lib", "obj")
 
 
 def sources():
@@ -43,18 +50,41 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in _deps() if os.path.exists(f))
 
 
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [NVCC] + NVCC_FLAGS + PER_FILE_FLAGS.get(os.path.basename(src), []) + (["-Xptxas", "-v"] if verbose else [])
+    cmd += ["-c", "-o", obj, src]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return src, r.returncode, r.stdout
+
+
 def build_library(force=False, verbose=False):
-    """Compile every CUDA/C++ source of the package into lib/libmpp_b200.so."""
+    """Compile every CUDA/C++ source of the package (one object per source, in parallel) and link
+    lib/libmpp_b200.so."""
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(f) for f in _deps() if os.path.exists(f) and not f.endswith((".cu", ".cpp")))
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, obj, verbose))
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for src, rc, out in ex.map(_compile_one, jobs):
+            if rc != 0:
+                sys.stderr.write(out)
+                raise RuntimeError("nvcc failed compiling %s" % src)
+            if verbose:
+                print(out)
+    r = subprocess.run([NVCC] + LINK_FLAGS + ["-o", LIB_PATH] + objs, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed building libmpp_b200.so")
-    if verbose:
-        print(r.stdout)
+        raise RuntimeError("nvcc failed linking libmpp_b200.so")
     return LIB_PATH
 
 

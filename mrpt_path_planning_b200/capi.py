@@ -52,6 +52,33 @@ class DiffDriveCParams(C.Structure):
     ]
 
 
+class HoloDesc(C.Structure):
+    _fields_ = [("num_paths", C.c_int32), ("ref_distance", C.c_double), ("robot_radius", C.c_double),
+                ("v_max", C.c_double)]
+
+
+class HoloCand(C.Structure):
+    _fields_ = [("node", C.c_int32), ("ptg_index", C.c_int32), ("T_ramp", C.c_double), ("vxi", C.c_double),
+                ("vyi", C.c_double), ("vxf", C.c_double), ("vyf", C.c_double), ("vf", C.c_double)]
+
+
+HOLO_CAND_DTYPE = np.dtype([("node", np.int32), ("ptg_index", np.int32), ("T_ramp", np.float64),
+                            ("vxi", np.float64), ("vyi", np.float64), ("vxf", np.float64), ("vyf", np.float64),
+                            ("vf", np.float64)])
+assert HOLO_CAND_DTYPE.itemsize == C.sizeof(HoloCand) == 56
+
+
+class HoloParams(C.Structure):
+    _fields_ = [("num_paths", C.c_int32), ("ref_distance", C.c_double), ("T_ramp_max", C.c_double),
+                ("v_max_mps", C.c_double), ("w_max_rps", C.c_double), ("robot_radius", C.c_double),
+                ("expr_V", C.c_char_p), ("expr_W", C.c_char_p)]
+
+
+class CostmapDesc(C.Structure):
+    _fields_ = [("x_min", C.c_double), ("y_min", C.c_double), ("res", C.c_double), ("nx", C.c_int32),
+                ("ny", C.c_int32), ("cells", c_double_p), ("use_average", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/mppb.h declares must be listed here
 _SIGS = {
     "mppb_version": (C.c_char_p, []),
@@ -93,6 +120,29 @@ _SIGS = {
     "mppb_ptg_init_dist": (C.c_double, [C.c_void_p, C.c_int]),
     "mppb_ptg_grid_export": (C.c_int, [C.c_void_p, C.POINTER(GridDesc)]),
     "mppb_ctx_add_ptg": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mppb_set_obstacles_clipped": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int,
+                                             C.c_void_p]),
+    "mppb_ptg_column_offset": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppb_set_ptg_holo": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(HoloDesc)]),
+    "mppb_eval_holo_candidates": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double,
+                                            C.c_void_p]),
+    "mppb_eval_holo_candidates_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
+                                                   C.c_void_p]),
+    "mppb_clear_evaluators": (C.c_int, [C.c_void_p]),
+    "mppb_set_costmap": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(CostmapDesc)]),
+    "mppb_set_waypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
+                                     C.c_double, C.c_int]),
+    "mppb_num_evaluators": (C.c_int, [C.c_void_p]),
+    "mppb_eval_edge_costs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mppb_eval_edge_costs_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
+    "mppb_costmap_nearest_d2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double,
+                                          C.c_double, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "mppb_ptg_create_holo": (C.c_int, [C.POINTER(HoloParams), C.POINTER(C.c_void_p)]),
+    "mppb_ptg_update_dyn_state": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
+    "mppb_ptg_set_trim_speed": (C.c_int, [C.c_void_p, C.c_double]),
+    "mppb_ptg_path_twist": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, c_double_p]),
+    "mppb_ptg_holo_params": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(HoloCand)]),
 }
 
 
@@ -149,6 +199,37 @@ class PTG:
         if lib().mppb_ptg_create_diffdrive_c(C.byref(p), C.byref(h)) != 0:
             raise MppbError(lib().mppb_ptg_last_error().decode())
         return PTG(h.value)
+
+    @staticmethod
+    def holonomic_blend(num_paths, ref_distance, T_ramp_max, v_max_mps, w_max_rps, robot_radius, expr_V="",
+                        expr_W=""):
+        p = HoloParams(num_paths, ref_distance, T_ramp_max, v_max_mps, w_max_rps, robot_radius, expr_V.encode(),
+                       expr_W.encode())
+        h = C.c_void_p()
+        if lib().mppb_ptg_create_holo(C.byref(p), C.byref(h)) != 0:
+            raise MppbError(lib().mppb_ptg_last_error().decode())
+        return PTG(h.value)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MppbError(lib().mppb_ptg_last_error().decode())
+
+    def update_dyn_state(self, vel_local=(0, 0, 0), rel_target=(20.0, 0, 0), target_rel_speed=0.0, force=False):
+        d = np.array(list(vel_local) + list(rel_target) + [target_rel_speed], dtype=np.float64)
+        self._ck(lib().mppb_ptg_update_dyn_state(self.h, d.ctypes.data_as(c_double_p), int(force)))
+
+    def set_trim_speed(self, s):
+        self._ck(lib().mppb_ptg_set_trim_speed(self.h, s))
+
+    def path_twist(self, k, step):
+        out = np.zeros(3)
+        self._ck(lib().mppb_ptg_path_twist(self.h, k, step, out.ctypes.data_as(c_double_p)))
+        return out
+
+    def holo_params(self, k):
+        c = HoloCand()
+        self._ck(lib().mppb_ptg_holo_params(self.h, k, C.byref(c)))
+        return c
 
     def __del__(self):
         try:
@@ -284,6 +365,13 @@ class Context:
     def set_obstacles_device(self, d_xs, d_ys, n, bin_size=0.0, append=False):
         self._ck(lib().mppb_set_obstacles_device(self.h, _ptr(d_xs), _ptr(d_ys), n, bin_size, int(append)))
 
+    def set_obstacles_clipped(self, xs, ys, box, bin_size=0.0, append=False):
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        b = np.ascontiguousarray(box, dtype=np.float32) if box is not None else None
+        self._ck(lib().mppb_set_obstacles_clipped(self.h, _ptr(xs), _ptr(ys), xs.size, bin_size, int(append),
+                                                  _ptr(b)))
+
     @property
     def num_obstacles(self):
         return lib().mppb_num_obstacles(self.h)
@@ -324,6 +412,57 @@ class Context:
         if out is None:
             out = np.empty((n, self.total_paths), dtype=np.float32)
         self._ck(lib().mppb_eval_nodes(self.h, n, _ptr(poses), clip_dist, _ptr(out)))
+        return out
+
+    def column_offset(self, ptg_index):
+        return lib().mppb_ptg_column_offset(self.h, ptg_index)
+
+    def eval_holo_candidates(self, poses, cands, clip_dist):
+        """poses [n][3]; cands: numpy structured array (HOLO_CAND_DTYPE) -> float64 [len(cands)]."""
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        cands = np.ascontiguousarray(cands, dtype=HOLO_CAND_DTYPE)
+        out = np.empty(len(cands), dtype=np.float64)
+        self._ck(lib().mppb_eval_holo_candidates(self.h, poses.shape[0], _ptr(poses), len(cands), _ptr(cands),
+                                                 clip_dist, _ptr(out)))
+        return out
+
+    def eval_holo_candidates_device(self, n_cands, d_cands, d_nodes_xycs, clip_dist, d_out):
+        self._ck(lib().mppb_eval_holo_candidates_device(self.h, n_cands, _ptr(d_cands), _ptr(d_nodes_xycs),
+                                                        clip_dist, _ptr(d_out)))
+
+    # -- stage (c) --
+    def clear_evaluators(self):
+        self._ck(lib().mppb_clear_evaluators(self.h))
+
+    def set_costmap(self, slot, cells, x_min, y_min, res, use_average):
+        cells = np.ascontiguousarray(cells, dtype=np.float64)
+        ny, nx = cells.shape
+        d = CostmapDesc(x_min, y_min, res, nx, ny, cells.ctypes.data_as(c_double_p), int(use_average))
+        self._ck(lib().mppb_set_costmap(self.h, slot, C.byref(d)))
+
+    def set_waypoints(self, slot, xs, ys, radius, scale, use_average):
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        ys = np.ascontiguousarray(ys, dtype=np.float64)
+        self._ck(lib().mppb_set_waypoints(self.h, slot, _ptr(xs), _ptr(ys), xs.size, radius, scale, int(use_average)))
+
+    @property
+    def num_evaluators(self):
+        return lib().mppb_num_evaluators(self.h)
+
+    def eval_edge_costs(self, from_xyphi, sample_offsets, rel_xy):
+        f = np.ascontiguousarray(from_xyphi, dtype=np.float64).reshape(-1, 3)
+        off = np.ascontiguousarray(sample_offsets, dtype=np.uint32)
+        rel = np.ascontiguousarray(rel_xy, dtype=np.float64).reshape(-1, 2)
+        out = np.empty((len(f), self.num_evaluators), dtype=np.float64)
+        self._ck(lib().mppb_eval_edge_costs(self.h, len(f), _ptr(f), _ptr(off), _ptr(rel), _ptr(out)))
+        return out
+
+    def costmap_nearest_d2(self, xs, ys, x_min, y_min, res, nx, ny, clearance):
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        out = np.empty((ny, nx), dtype=np.float32)
+        self._ck(lib().mppb_costmap_nearest_d2(self.h, _ptr(xs), _ptr(ys), xs.size, x_min, y_min, res, nx, ny,
+                                               clearance, _ptr(out)))
         return out
 
     def eval_nodes_device(self, n, d_nodes_xycs, clip_dist, d_out):
@@ -368,3 +507,12 @@ def ackermann_ptgs(num_paths=121, ref_distance=5.0, resolution=0.05):
     w = 60.0 * np.pi / 180.0
     return [PTG.diffdrive_c(num_paths, ref_distance, resolution, 1.0, w, K, ACKERMANN_SHAPE_X, ACKERMANN_SHAPE_Y)
             for K in (+1.0, -1.0)]
+
+
+HOLO_EXPR_V = "V_MAX * trimmable_speed"
+HOLO_EXPR_W = "W_MAX * trimmable_speed * min(1.0, 0.1+abs(dir)/(10*PI/180))"
+
+
+def holonomic_ptgs():
+    """PTG set of share/ptgs_holonomic_robot.ini (values typed here as data)."""
+    return [PTG.holonomic_blend(191, 5.0, 1.0, 1.0, 60.0 * np.pi / 180.0, 0.15, HOLO_EXPR_V, HOLO_EXPR_W)]

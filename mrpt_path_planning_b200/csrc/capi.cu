@@ -88,18 +88,26 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->rawX.release();
-    ctx->rawY.release();
-    ctx->sortedPts.release();
-    ctx->binStart.release();
-    ctx->binCursor.release();
+    ctx->cloud.release();
+    ctx->auxCloud.release();
     ctx->bboxScratch.release();
     for (auto& g : ctx->groups) g.release();
     ctx->groupDescs.release();
+    ctx->holoDescs.release();
+    for (int i = 0; i < MPPB_MAX_EVALUATORS; i++)
+    {
+        ctx->evalCells[i].release();
+        ctx->evalWps[i].release();
+    }
+    ctx->evalDescs.release();
     ctx->hNodes.release();
     ctx->hOut.release();
+    ctx->hStage.release();
     ctx->dNodes.release();
     ctx->dOut.release();
+    ctx->dStage.release();
+    ctx->dStage2.release();
+    ctx->dStage3.release();
     if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
@@ -151,15 +159,24 @@ int mppb_timer_end(mppb_ctx* ctx, float* out_ms)
 }
 
 // ---- obstacle cloud -------------------------------------------------------------------
-static int set_obstacles_impl(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int append,
-                              cudaMemcpyKind kind)
+static int set_cloud(mppb_ctx* ctx, CloudStore& cs, const float* xs, const float* ys, size_t n, double bin_size,
+                     int append, const float* box, cudaMemcpyKind kind)
 {
-    if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n > 0 && (!xs || !ys)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null cloud pointers");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t keep  = append ? ctx->rawN : 0;
+    const size_t keep  = append ? cs.rawN : 0;
     const size_t total = keep + n;
-    if (total * sizeof(float) > ctx->rawX.bytes)
+    if (!append)
+    {
+        cs.hasBox = box != nullptr;
+        if (box) std::memcpy(cs.box, box, 4 * sizeof(float));
+    }
+    else if (box)
+    {
+        if (!cs.hasBox || std::memcmp(cs.box, box, 4 * sizeof(float)) != 0)
+            return fail(ctx, MPPB_ERR_INVALID_ARG, "appended obstacle sources must use the same clipping box");
+    }
+    if (total * sizeof(float) > cs.rawX.bytes)
     {
         // grow, preserving the already-uploaded sources
         DevBuf nx, ny;
@@ -167,34 +184,42 @@ static int set_obstacles_impl(mppb_ctx* ctx, const float* xs, const float* ys, s
         MPPB_CUDA(ctx, ny.reserve(std::max<size_t>(total, 1) * sizeof(float)));
         if (keep)
         {
-            MPPB_CUDA(ctx, cudaMemcpyAsync(nx.p, ctx->rawX.p, keep * sizeof(float), cudaMemcpyDeviceToDevice,
+            MPPB_CUDA(ctx, cudaMemcpyAsync(nx.p, cs.rawX.p, keep * sizeof(float), cudaMemcpyDeviceToDevice,
                                            ctx->stream));
-            MPPB_CUDA(ctx, cudaMemcpyAsync(ny.p, ctx->rawY.p, keep * sizeof(float), cudaMemcpyDeviceToDevice,
+            MPPB_CUDA(ctx, cudaMemcpyAsync(ny.p, cs.rawY.p, keep * sizeof(float), cudaMemcpyDeviceToDevice,
                                            ctx->stream));
             MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
-        ctx->rawX.release();
-        ctx->rawY.release();
-        ctx->rawX = nx;
-        ctx->rawY = ny;
+        cs.rawX.release();
+        cs.rawY.release();
+        cs.rawX = nx;
+        cs.rawY = ny;
     }
     if (n)
     {
-        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->rawX.as<float>() + keep, xs, n * sizeof(float), kind, ctx->stream));
-        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->rawY.as<float>() + keep, ys, n * sizeof(float), kind, ctx->stream));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(cs.rawX.as<float>() + keep, xs, n * sizeof(float), kind, ctx->stream));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(cs.rawY.as<float>() + keep, ys, n * sizeof(float), kind, ctx->stream));
     }
-    ctx->rawN = total;
-    return build_cloud_bins(ctx, bin_size > 0 ? bin_size : (ctx->binSize > 0 && append ? ctx->binSize : 0.5));
+    cs.rawN = total;
+    return build_cloud_bins(ctx, cs, bin_size > 0 ? bin_size : (cs.binSize > 0 && append ? cs.binSize : 0.5));
 }
 
 int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int append)
 {
-    return set_obstacles_impl(ctx, xs, ys, n, bin_size, append, cudaMemcpyHostToDevice);
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    return set_cloud(ctx, ctx->cloud, xs, ys, n, bin_size, append, nullptr, cudaMemcpyHostToDevice);
 }
 int mppb_set_obstacles_device(mppb_ctx* ctx, const float* d_xs, const float* d_ys, size_t n, double bin_size,
                               int append)
 {
-    return set_obstacles_impl(ctx, d_xs, d_ys, n, bin_size, append, cudaMemcpyDeviceToDevice);
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    return set_cloud(ctx, ctx->cloud, d_xs, d_ys, n, bin_size, append, nullptr, cudaMemcpyDeviceToDevice);
+}
+int mppb_set_obstacles_clipped(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size,
+                               int append, const float* box)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    return set_cloud(ctx, ctx->cloud, xs, ys, n, bin_size, append, box, cudaMemcpyHostToDevice);
 }
 size_t mppb_num_obstacles(const mppb_ctx* ctx) { return ctx ? ctx->bins.n : 0; }
 
@@ -211,6 +236,8 @@ int mppb_clear_ptgs(mppb_ctx* ctx)
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     release_groups(ctx);
     ctx->grids.clear();
+    ctx->holos.clear();
+    ctx->ptgKinds.clear();
     ctx->totalPaths = 0;
     return MPPB_OK;
 }
@@ -351,7 +378,7 @@ int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* d)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (!d) return fail(ctx, MPPB_ERR_INVALID_ARG, "null PTG descriptor");
-    if (ptg_index != static_cast<int>(ctx->grids.size()))
+    if (ptg_index != static_cast<int>(ctx->ptgKinds.size()))
         return fail(ctx, MPPB_ERR_INVALID_ARG, "ptg_index must be the next free index");
     if (ptg_index >= MPPB_MAX_PTGS) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many PTGs");
     if (d->num_paths <= 0 || d->num_paths > 65535) return fail(ctx, MPPB_ERR_INVALID_ARG, "bad num_paths");
@@ -385,11 +412,41 @@ int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* d)
     g.shapeX.assign(d->shape_x, d->shape_x + d->shape_nverts);
     g.shapeY.assign(d->shape_y, d->shape_y + d->shape_nverts);
     ctx->grids.push_back(std::move(g));
+    ctx->ptgKinds.push_back(0);
+    ctx->holos.push_back(HoloPtgDev{0, 0});
     ctx->totalPaths += d->num_paths;
     return rebuild_groups(ctx);
 }
-int mppb_num_ptgs(const mppb_ctx* ctx) { return ctx ? static_cast<int>(ctx->grids.size()) : 0; }
+int mppb_num_ptgs(const mppb_ctx* ctx) { return ctx ? static_cast<int>(ctx->ptgKinds.size()) : 0; }
 int mppb_total_paths(const mppb_ctx* ctx) { return ctx ? ctx->totalPaths : 0; }
+int mppb_ptg_column_offset(const mppb_ctx* ctx, int ptg_index)
+{
+    if (!ctx || ptg_index < 0 || ptg_index >= static_cast<int>(ctx->ptgKinds.size())) return -1;
+    if (ctx->ptgKinds[ptg_index] != 0) return -1;
+    int g = 0;
+    for (int i = 0; i < ptg_index; i++) g += ctx->ptgKinds[i] == 0;
+    return ctx->grids[g].outOffset;
+}
+
+int mppb_set_ptg_holo(mppb_ctx* ctx, int ptg_index, const mppb_ptg_holo_desc* d)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (!d) return fail(ctx, MPPB_ERR_INVALID_ARG, "null PTG descriptor");
+    if (ptg_index != static_cast<int>(ctx->ptgKinds.size()))
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "ptg_index must be the next free index");
+    if (ptg_index >= MPPB_MAX_PTGS) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many PTGs");
+    if (!(d->robot_radius > 0) || !(d->v_max > 0) || d->num_paths <= 0)
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "bad HolonomicBlend constants");
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->ptgKinds.push_back(1);
+    ctx->holos.push_back(HoloPtgDev{d->robot_radius, d->v_max});
+    HoloPtgDev table[MPPB_MAX_PTGS] = {};
+    for (size_t i = 0; i < ctx->holos.size(); i++) table[i] = ctx->holos[i];
+    MPPB_CUDA(ctx, ctx->holoDescs.reserve(sizeof(table)));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->holoDescs.p, table, sizeof(table), cudaMemcpyHostToDevice, ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
 
 // ---- evaluation ---------------------------------------------------------------------------
 void mppb_nodes_xycs_from_poses(size_t n, const double* poses, double* out)
@@ -465,6 +522,186 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, do
     cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0);
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+
+// ---- HolonomicBlend candidates --------------------------------------------------------------
+int mppb_eval_holo_candidates_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
+                                     const double* d_nodes_xycs, double clip_dist, double* d_out)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n_cands && (!d_cands || !d_nodes_xycs || !d_out)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null device pointers");
+    return launch_tpobs_holo(ctx, n_cands, d_cands, d_nodes_xycs, clip_dist, d_out);
+}
+
+int mppb_eval_holo_candidates(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, size_t n_cands,
+                              const mppb_holo_cand* cands, double clip_dist, double* out)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n_cands == 0) return MPPB_OK;
+    if (!poses_xyphi || !cands || !out || n_nodes == 0) return fail(ctx, MPPB_ERR_INVALID_ARG, "null host pointers");
+    for (size_t i = 0; i < n_cands; i++)
+    {
+        const mppb_holo_cand& c = cands[i];
+        if (c.node < 0 || static_cast<size_t>(c.node) >= n_nodes)
+            return fail(ctx, MPPB_ERR_INVALID_ARG, "candidate node index out of range");
+        if (c.ptg_index < 0 || c.ptg_index >= static_cast<int>(ctx->ptgKinds.size()) || ctx->ptgKinds[c.ptg_index] != 1)
+            return fail(ctx, MPPB_ERR_INVALID_ARG, "candidate ptg_index is not a HolonomicBlend PTG");
+        if (!(c.T_ramp > 0)) return fail(ctx, MPPB_ERR_INVALID_ARG, "candidate T_ramp must be > 0");
+    }
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nodeBytes = n_nodes * 4 * sizeof(double), candBytes = n_cands * sizeof(mppb_holo_cand);
+    const size_t outBytes  = n_cands * sizeof(double);
+    MPPB_CUDA(ctx, ctx->hNodes.reserve(nodeBytes));
+    MPPB_CUDA(ctx, ctx->dNodes.reserve(nodeBytes));
+    MPPB_CUDA(ctx, ctx->dStage.reserve(candBytes));
+    MPPB_CUDA(ctx, ctx->dStage2.reserve(outBytes));
+    mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodes.as<double>());
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, nodeBytes, cudaMemcpyHostToDevice, ctx->stream));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, cands, candBytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = launch_tpobs_holo(ctx, n_cands, ctx->dStage.as<mppb_holo_cand>(), ctx->dNodes.as<double>(),
+                                     clip_dist, ctx->dStage2.as<double>());
+    if (rc != MPPB_OK) return rc;
+    MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dStage2.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
+
+// ---- cost evaluators ----------------------------------------------------------------------------
+static int upload_evaluators(mppb_ctx* ctx)
+{
+    int n = 0;
+    for (int i = 0; i < MPPB_MAX_EVALUATORS; i++)
+        if (ctx->evals[i].kind != 0) n = i + 1;
+    for (int i = 0; i < n; i++)
+        if (ctx->evals[i].kind == 0) return fail(ctx, MPPB_ERR_STATE, "cost evaluator slots must be filled in order");
+    ctx->numEvals = n;
+    MPPB_CUDA(ctx, ctx->evalDescs.reserve(sizeof(ctx->evals)));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->evalDescs.p, ctx->evals, sizeof(ctx->evals), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
+
+int mppb_clear_evaluators(mppb_ctx* ctx)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < MPPB_MAX_EVALUATORS; i++) ctx->evals[i] = EvaluatorDev{};
+    ctx->numEvals = 0;
+    return MPPB_OK;
+}
+int mppb_num_evaluators(const mppb_ctx* ctx) { return ctx ? ctx->numEvals : 0; }
+
+int mppb_set_costmap(mppb_ctx* ctx, int slot, const mppb_costmap_desc* d)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= MPPB_MAX_EVALUATORS) return fail(ctx, MPPB_ERR_INVALID_ARG, "evaluator slot out of range");
+    if (!d || !d->cells || d->nx <= 0 || d->ny <= 0 || !(d->res > 0))
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "bad costmap descriptor");
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t bytes = static_cast<size_t>(d->nx) * d->ny * sizeof(double);
+    MPPB_CUDA(ctx, ctx->evalCells[slot].reserve(bytes));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->evalCells[slot].p, d->cells, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    EvaluatorDev E{};
+    E.kind       = 1;
+    E.useAverage = d->use_average != 0;
+    E.xmin       = d->x_min;
+    E.ymin       = d->y_min;
+    E.res        = d->res;
+    E.nx         = d->nx;
+    E.ny         = d->ny;
+    E.cells      = ctx->evalCells[slot].as<double>();
+    ctx->evals[slot] = E;
+    return upload_evaluators(ctx);
+}
+
+int mppb_set_waypoints(mppb_ctx* ctx, int slot, const double* xs, const double* ys, size_t n, double influence_radius,
+                       double cost_scale, int use_average)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= MPPB_MAX_EVALUATORS) return fail(ctx, MPPB_ERR_INVALID_ARG, "evaluator slot out of range");
+    if (n && (!xs || !ys)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null waypoint arrays");
+    if (!(influence_radius > 0)) return fail(ctx, MPPB_ERR_INVALID_ARG, "influence radius must be > 0");
+    if (n > 0x7fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many waypoints");
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<float2> w(n);
+    for (size_t i = 0; i < n; i++) w[i] = make_float2(static_cast<float>(xs[i]), static_cast<float>(ys[i]));
+    MPPB_CUDA(ctx, ctx->evalWps[slot].reserve(std::max<size_t>(n, 1) * sizeof(float2)));
+    if (n)
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->evalWps[slot].p, w.data(), n * sizeof(float2), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EvaluatorDev E{};
+    E.kind       = 2;
+    E.useAverage = use_average != 0;
+    E.wps        = ctx->evalWps[slot].as<float2>();
+    E.nWps       = static_cast<int>(n);
+    E.radius     = influence_radius;
+    E.scale      = cost_scale;
+    E.radiusSqrF = static_cast<float>(influence_radius * influence_radius);
+    ctx->evals[slot] = E;
+    return upload_evaluators(ctx);
+}
+
+int mppb_eval_edge_costs_device(mppb_ctx* ctx, size_t n_edges, const double* d_from_xycs,
+                                const uint32_t* d_sample_offsets, const double* d_rel_xy, double* d_out)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n_edges && ctx->numEvals && (!d_from_xycs || !d_sample_offsets || !d_rel_xy || !d_out))
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "null device pointers");
+    return launch_edge_costs(ctx, n_edges, d_from_xycs, d_sample_offsets, d_rel_xy, d_out);
+}
+
+int mppb_eval_edge_costs(mppb_ctx* ctx, size_t n_edges, const double* from_xyphi, const uint32_t* sample_offsets,
+                         const double* rel_xy, double* out)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (n_edges == 0 || ctx->numEvals == 0) return MPPB_OK;
+    if (!from_xyphi || !sample_offsets || !rel_xy || !out) return fail(ctx, MPPB_ERR_INVALID_ARG, "null host pointers");
+    for (size_t e = 0; e < n_edges; e++)
+        if (sample_offsets[e] > sample_offsets[e + 1]) return fail(ctx, MPPB_ERR_INVALID_ARG, "sample_offsets not sorted");
+    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t m         = sample_offsets[n_edges];
+    const size_t fromBytes = n_edges * 4 * sizeof(double), offBytes = (n_edges + 1) * sizeof(uint32_t);
+    const size_t relBytes  = std::max<size_t>(m, 1) * 2 * sizeof(double);
+    const size_t outBytes  = n_edges * ctx->numEvals * sizeof(double);
+    MPPB_CUDA(ctx, ctx->hNodes.reserve(fromBytes));
+    MPPB_CUDA(ctx, ctx->dNodes.reserve(fromBytes));
+    MPPB_CUDA(ctx, ctx->dStage.reserve(offBytes));
+    MPPB_CUDA(ctx, ctx->dStage2.reserve(relBytes));
+    MPPB_CUDA(ctx, ctx->dStage3.reserve(outBytes));
+    mppb_nodes_xycs_from_poses(n_edges, from_xyphi, ctx->hNodes.as<double>());
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, fromBytes, cudaMemcpyHostToDevice, ctx->stream));
+    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, sample_offsets, offBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (m) MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage2.p, rel_xy, m * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = launch_edge_costs(ctx, n_edges, ctx->dNodes.as<double>(), ctx->dStage.as<uint32_t>(),
+                                     ctx->dStage2.as<double>(), ctx->dStage3.as<double>());
+    if (rc != MPPB_OK) return rc;
+    MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dStage3.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
+}
+
+int mppb_costmap_nearest_d2(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double x_min, double y_min,
+                            double res, int nx, int ny, float clearance, float* out_d2)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    if (nx <= 0 || ny <= 0 || !(res > 0) || !(clearance > 0) || !out_d2)
+        return fail(ctx, MPPB_ERR_INVALID_ARG, "bad costmap geometry");
+    // bins of about the clearance distance keep the per-cell search window at a few bins
+    const double bin = std::max(0.05, static_cast<double>(clearance));
+    int          rc  = set_cloud(ctx, ctx->auxCloud, xs, ys, n, bin, 0, nullptr, cudaMemcpyHostToDevice);
+    if (rc != MPPB_OK) return rc;
+    const size_t bytes = static_cast<size_t>(nx) * ny * sizeof(float);
+    MPPB_CUDA(ctx, ctx->dStage3.reserve(bytes));
+    rc = launch_costmap_d2(ctx, ctx->auxCloud, x_min, y_min, res, nx, ny, clearance, ctx->dStage3.as<float>());
+    if (rc != MPPB_OK) return rc;
+    MPPB_CUDA(ctx, cudaMemcpyAsync(out_d2, ctx->dStage3.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPPB_OK;
 }
 
 }  // extern "C"

@@ -28,14 +28,29 @@ inline float from_ordered_int(int i)
 }
 
 // scratch: [0]=minx [1]=miny [2]=maxx [3]=maxy (ordered ints)
-__global__ void bbox_kernel(const float* __restrict__ xs, const float* __restrict__ ys, size_t n, int* scratch)
+// a point takes part in the index if it is finite and inside the optional clipping box
+// (ObstacleSource.cpp:29-40: float comparisons, inclusive bounds)
+struct KeepTest
+{
+    bool  hasBox;
+    float minx, miny, maxx, maxy;
+    __device__ __forceinline__ bool operator()(float x, float y) const
+    {
+        if (!(isfinite(x) && isfinite(y))) return false;
+        if (hasBox && (x < minx || x > maxx || y < miny || y > maxy)) return false;
+        return true;
+    }
+};
+
+__global__ void bbox_kernel(const float* __restrict__ xs, const float* __restrict__ ys, size_t n, KeepTest keep,
+                            int* scratch)
 {
     float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
     {
         const float x = xs[i], y = ys[i];
-        if (isfinite(x) && isfinite(y))
+        if (keep(x, y))
         {
             mnx = fminf(mnx, x);
             mxx = fmaxf(mxx, x);
@@ -60,14 +75,14 @@ __global__ void bbox_kernel(const float* __restrict__ xs, const float* __restric
 }
 
 __global__ void bin_count_kernel(
-    const float* __restrict__ xs, const float* __restrict__ ys, size_t n, float minx, float miny, float invBin,
-    int nbx, int nby, uint32_t* counts)
+    const float* __restrict__ xs, const float* __restrict__ ys, size_t n, KeepTest keep, float minx, float miny,
+    float invBin, int nbx, int nby, uint32_t* counts)
 {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
     {
         const float x = xs[i], y = ys[i];
-        if (isfinite(x) && isfinite(y))
+        if (keep(x, y))
         {
             const int b = bin_coord(y, miny, invBin, nby) * nbx + bin_coord(x, minx, invBin, nbx);
             atomicAdd(&counts[b], 1u);
@@ -107,14 +122,14 @@ __global__ void bin_scan_kernel(uint32_t* counts, uint32_t* start, int nb)
 }
 
 __global__ void bin_scatter_kernel(
-    const float* __restrict__ xs, const float* __restrict__ ys, size_t n, float minx, float miny, float invBin,
-    int nbx, int nby, const uint32_t* __restrict__ start, uint32_t* cursor, float2* sorted)
+    const float* __restrict__ xs, const float* __restrict__ ys, size_t n, KeepTest keep, float minx, float miny,
+    float invBin, int nbx, int nby, const uint32_t* __restrict__ start, uint32_t* cursor, float2* sorted)
 {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
     {
         const float x = xs[i], y = ys[i];
-        if (isfinite(x) && isfinite(y))
+        if (keep(x, y))
         {
             const int      b   = bin_coord(y, miny, invBin, nby) * nbx + bin_coord(x, minx, invBin, nbx);
             const uint32_t pos = start[b] + atomicAdd(&cursor[b], 1u);
@@ -124,17 +139,18 @@ __global__ void bin_scatter_kernel(
 }
 }  // namespace
 
-int build_cloud_bins(mppb_ctx* ctx, double binSize)
+int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize)
 {
     cudaStream_t st = ctx->stream;
-    const size_t n  = ctx->rawN;
-    ctx->bins       = CloudBins();
+    const size_t n  = cs.rawN;
+    cs.bins         = CloudBins();
+    const KeepTest keep{cs.hasBox, cs.box[0], cs.box[1], cs.box[2], cs.box[3]};
     if (n == 0) return MPPB_OK;
     if (n > 0xfffffff0ull) return fail(ctx, MPPB_ERR_UNSUPPORTED, "obstacle cloud larger than 2^32 points");
     if (!(binSize > 0)) binSize = 0.5;
 
-    const float* xs = ctx->rawX.as<float>();
-    const float* ys = ctx->rawY.as<float>();
+    const float* xs = cs.rawX.as<float>();
+    const float* ys = cs.rawY.as<float>();
 
     // 1) bounding box of the finite points
     MPPB_CUDA(ctx, ctx->bboxScratch.reserve(4 * sizeof(int)));
@@ -142,7 +158,7 @@ int build_cloud_bins(mppb_ctx* ctx, double binSize)
     MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->bboxScratch.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const int threads = 256;
     const int blocks  = static_cast<int>(std::min<size_t>((n + threads - 1) / threads, ctx->numSMs * 8));
-    bbox_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, ctx->bboxScratch.as<int>());
+    bbox_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, keep, ctx->bboxScratch.as<int>());
     ctx->launches++;
     int h[4];
     MPPB_CUDA(ctx, cudaMemcpyAsync(h, ctx->bboxScratch.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -167,29 +183,29 @@ int build_cloud_bins(mppb_ctx* ctx, double binSize)
     b.nbx         = static_cast<int>(std::floor((static_cast<double>(maxx) - minx) / s)) + 1;
     b.nby         = static_cast<int>(std::floor((static_cast<double>(maxy) - miny) / s)) + 1;
     const int nb  = b.nbx * b.nby;
-    ctx->binSize  = s;
+    cs.binSize    = s;
 
     // 3) histogram, scan, scatter
-    MPPB_CUDA(ctx, ctx->binStart.reserve((static_cast<size_t>(nb) + 1) * sizeof(uint32_t)));
-    MPPB_CUDA(ctx, ctx->binCursor.reserve(static_cast<size_t>(nb) * sizeof(uint32_t)));
-    MPPB_CUDA(ctx, ctx->sortedPts.reserve(n * sizeof(float2)));
-    MPPB_CUDA(ctx, cudaMemsetAsync(ctx->binCursor.p, 0, static_cast<size_t>(nb) * sizeof(uint32_t), st));
-    bin_count_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, b.minx, b.miny, b.invBin, b.nbx, b.nby,
-                                                ctx->binCursor.as<uint32_t>());
-    bin_scan_kernel<<<1, 1024, 0, st>>>(ctx->binCursor.as<uint32_t>(), ctx->binStart.as<uint32_t>(), nb);
-    bin_scatter_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, b.minx, b.miny, b.invBin, b.nbx, b.nby,
-                                                  ctx->binStart.as<uint32_t>(), ctx->binCursor.as<uint32_t>(),
-                                                  ctx->sortedPts.as<float2>());
+    MPPB_CUDA(ctx, cs.binStart.reserve((static_cast<size_t>(nb) + 1) * sizeof(uint32_t)));
+    MPPB_CUDA(ctx, cs.binCursor.reserve(static_cast<size_t>(nb) * sizeof(uint32_t)));
+    MPPB_CUDA(ctx, cs.sortedPts.reserve(n * sizeof(float2)));
+    MPPB_CUDA(ctx, cudaMemsetAsync(cs.binCursor.p, 0, static_cast<size_t>(nb) * sizeof(uint32_t), st));
+    bin_count_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, keep, b.minx, b.miny, b.invBin, b.nbx, b.nby,
+                                                cs.binCursor.as<uint32_t>());
+    bin_scan_kernel<<<1, 1024, 0, st>>>(cs.binCursor.as<uint32_t>(), cs.binStart.as<uint32_t>(), nb);
+    bin_scatter_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, keep, b.minx, b.miny, b.invBin, b.nbx, b.nby,
+                                                  cs.binStart.as<uint32_t>(), cs.binCursor.as<uint32_t>(),
+                                                  cs.sortedPts.as<float2>());
     ctx->launches += 3;
     uint32_t total = 0;
-    MPPB_CUDA(ctx, cudaMemcpyAsync(&total, ctx->binStart.as<uint32_t>() + nb, sizeof(uint32_t),
+    MPPB_CUDA(ctx, cudaMemcpyAsync(&total, cs.binStart.as<uint32_t>() + nb, sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, st));
     MPPB_CUDA(ctx, cudaStreamSynchronize(st));
     MPPB_CUDA(ctx, cudaGetLastError());
     b.n        = total;
-    b.pts      = ctx->sortedPts.as<float2>();
-    b.binStart = ctx->binStart.as<uint32_t>();
-    ctx->bins  = b;
+    b.pts      = cs.sortedPts.as<float2>();
+    b.binStart = cs.binStart.as<uint32_t>();
+    cs.bins    = b;
     return MPPB_OK;
 }
 

@@ -120,10 +120,83 @@ int mppb_ptg_grid_export(const mppb_ptg* p, mppb_ptg_grid_desc* out)
 int mppb_ctx_add_ptg(mppb_ctx* ctx, const mppb_ptg* p)
 {
     if (!ctx || !p) return MPPB_ERR_INVALID_ARG;
+    if (auto* holo = dynamic_cast<const mpp::HolonomicBlend*>(p->obj.get()))
+    {
+        const mppb_ptg_holo_desc d = holo->holoDesc();
+        return mppb_set_ptg_holo(ctx, mppb_num_ptgs(ctx), &d);
+    }
     mppb_ptg_grid_desc d;
     int                rc = mppb_ptg_grid_export(p, &d);
     if (rc != MPPB_OK) return rc;
     return mppb_set_ptg_grid(ctx, mppb_num_ptgs(ctx), &d);
+}
+
+int mppb_ptg_create_holo(const mppb_holo_params* p, mppb_ptg** out)
+{
+    HOST_TRY
+    if (!p || !out) throw std::runtime_error("null argument");
+    *out = nullptr;
+    mpp::HolonomicBlendParams q;
+    q.num_paths    = p->num_paths;
+    q.refDistance  = p->ref_distance;
+    q.T_ramp_max   = p->T_ramp_max;
+    q.v_max_mps    = p->v_max_mps;
+    q.w_max_rps    = p->w_max_rps;
+    q.robot_radius = p->robot_radius;
+    if (p->expr_V && *p->expr_V) q.expr_V = p->expr_V;
+    if (p->expr_W && *p->expr_W) q.expr_W = p->expr_W;
+    auto* h = new mppb_ptg();
+    try
+    {
+        h->obj = std::make_unique<mpp::HolonomicBlend>(q);
+    }
+    catch (...)
+    {
+        delete h;
+        throw;
+    }
+    *out = h;
+    return MPPB_OK;
+    HOST_CATCH(MPPB_ERR_INVALID_ARG)
+}
+int mppb_ptg_update_dyn_state(mppb_ptg* p, const double* dyn, int force)
+{
+    HOST_TRY
+    if (!p || !dyn) throw std::runtime_error("bad argument");
+    mpp::TNavDynamicState ds;
+    ds.curVelLocal    = mpp::TTwist2D(dyn[0], dyn[1], dyn[2]);
+    ds.relTarget      = mpp::TPose2D(dyn[3], dyn[4], dyn[5]);
+    ds.targetRelSpeed = dyn[6];
+    p->obj->updateNavDynamicState(ds, force != 0);
+    return MPPB_OK;
+    HOST_CATCH(MPPB_ERR_INVALID_ARG)
+}
+int mppb_ptg_set_trim_speed(mppb_ptg* p, double speed)
+{
+    if (!p) return MPPB_ERR_INVALID_ARG;
+    p->obj->trimmableSpeed_ = speed;
+    return MPPB_OK;
+}
+int mppb_ptg_path_twist(const mppb_ptg* p, int k, uint32_t step, double* out3)
+{
+    HOST_TRY
+    if (!p || !out3 || k < 0 || k >= p->obj->getPathCount()) throw std::runtime_error("bad argument");
+    const mpp::TTwist2D t = p->obj->getPathTwist(static_cast<uint16_t>(k), step);
+    out3[0]               = t.vx;
+    out3[1]               = t.vy;
+    out3[2]               = t.omega;
+    return MPPB_OK;
+    HOST_CATCH(MPPB_ERR_INVALID_ARG)
+}
+int mppb_ptg_holo_params(const mppb_ptg* p, int k, mppb_holo_cand* out)
+{
+    HOST_TRY
+    if (!p || !out || k < 0 || k >= p->obj->getPathCount()) throw std::runtime_error("bad argument");
+    auto* holo = dynamic_cast<const mpp::HolonomicBlend*>(p->obj.get());
+    if (!holo) throw std::runtime_error("PTG is not a HolonomicBlend");
+    holo->holoParams(static_cast<uint16_t>(k), *out);
+    return MPPB_OK;
+    HOST_CATCH(MPPB_ERR_UNSUPPORTED)
 }
 
 }  // extern "C"

@@ -326,6 +326,45 @@ void DiffDrive_C::buildCollisionGrid()
         }
 }
 
+namespace
+{
+// A DiffDrive_C with its own mutable state (dynamic state, trimmed speed) over the tables of a
+// shared, immutable one. None of the table look-ups depends on that state.
+class DiffDriveView final : public ptg_t
+{
+   public:
+    explicit DiffDriveView(const DiffDrive_C* base) : base_(base)
+    {
+        numPaths_    = base->getPathCount();
+        refDistance_ = base->getRefDistance();
+        initialized_ = true;
+    }
+    PtgKind  kind() const override { return PtgKind::CollisionGrid; }
+    size_t   getPathStepCount(uint16_t k) const override { return base_->getPathStepCount(k); }
+    TPose2D  getPathPose(uint16_t k, uint32_t step) const override { return base_->getPathPose(k, step); }
+    double   getPathDist(uint16_t k, uint32_t step) const override { return base_->getPathDist(k, step); }
+    bool     getPathStepForDist(uint16_t k, double d, uint32_t& s) const override
+    {
+        return base_->getPathStepForDist(k, d, s);
+    }
+    double   getPathStepDuration() const override { return base_->getPathStepDuration(); }
+    TTwist2D getPathTwist(uint16_t k, uint32_t step) const override { return base_->getPathTwist(k, step); }
+    bool     inverseMap_WS2TP(double x, double y, int& k, double& d, double tol) const override
+    {
+        return base_->inverseMap_WS2TP(x, y, k, d, tol);
+    }
+    bool   isSpeedTrimmable() const override { return true; }
+    bool   isPointInsideRobotShape(double x, double y) const override { return base_->isPointInsideRobotShape(x, y); }
+    double getMaxRobotRadius() const override { return base_->getMaxRobotRadius(); }
+    std::unique_ptr<ptg_t> cloneForQuery() const override { return std::make_unique<DiffDriveView>(base_); }
+
+   private:
+    const DiffDrive_C* base_;
+};
+}  // namespace
+
+std::unique_ptr<ptg_t> DiffDrive_C::cloneForQuery() const { return std::make_unique<DiffDriveView>(this); }
+
 mppb_ptg_grid_desc DiffDrive_C::gridDesc() const
 {
     mppb_ptg_grid_desc d;

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../../include/mppb.h"
+#include "expr.h"
 #include "mpp_math.h"
 
 namespace mpp
@@ -77,6 +78,11 @@ class ptg_t
     /** speed modulation in (0,1] of SpeedTrimmablePTG (only meaningful if isSpeedTrimmable()) */
     double trimmableSpeed_ = 1.0;
 
+    /** A PTG object with its own mutable state (dynamic state, trimmed speed, caches) that shares
+     *  the immutable tables of this one. Independent planning queries each use their own clone
+     *  so that they can run interleaved / concurrently; `this` must outlive the clone. */
+    virtual std::unique_ptr<ptg_t> cloneForQuery() const = 0;
+
    protected:
     virtual void     onNewNavDynamicState() {}
     unsigned         numPaths_    = 0;
@@ -120,6 +126,7 @@ class DiffDrive_C : public ptg_t
 
     /** descriptor of the collision grid for mppb_set_ptg_grid (pointers owned by this object) */
     mppb_ptg_grid_desc gridDesc() const;
+    std::unique_ptr<ptg_t> cloneForQuery() const override;
 
     const DiffDriveCParams& params() const { return p_; }
 
@@ -140,6 +147,74 @@ class DiffDrive_C : public ptg_t
     std::vector<uint32_t> cellOffsets_;
     std::vector<uint16_t> entryK_;
     std::vector<float>    entryD_;
+};
+
+/** Parameters of mpp::ptg::HolonomicBlend (ini keys of share/ptgs_holonomic_robot.ini). */
+struct HolonomicBlendParams
+{
+    unsigned    num_paths    = 191;
+    double      refDistance  = 5.0;
+    double      T_ramp_max   = 1.0;
+    double      v_max_mps    = 1.0;
+    double      w_max_rps    = 1.0;
+    double      robot_radius = 0.15;
+    std::string expr_V = "V_MAX", expr_W = "W_MAX";
+};
+
+/** Closed-form holonomic PTG with a velocity ramp (src/ptgs/HolonomicBlend.cpp). The host side
+ *  provides the path geometry the planner asks for; the per-obstacle collision arithmetic
+ *  (updateTPObstacleSingle) runs on the GPU from the per-candidate parameters of holoParams(). */
+class HolonomicBlend : public ptg_t
+{
+   public:
+    explicit HolonomicBlend(const HolonomicBlendParams& p);
+    HolonomicBlend(const HolonomicBlend&)            = delete;
+    HolonomicBlend& operator=(const HolonomicBlend&) = delete;
+
+    PtgKind kind() const override { return PtgKind::HolonomicBlend; }
+
+    static constexpr double PATH_TIME_STEP = 10e-3;
+    static constexpr double eps            = 1e-4;
+
+    size_t   getPathStepCount(uint16_t k) const override;
+    TPose2D  getPathPose(uint16_t k, uint32_t step) const override;
+    double   getPathDist(uint16_t k, uint32_t step) const override;
+    bool     getPathStepForDist(uint16_t k, double dist, uint32_t& step) const override;
+    double   getPathStepDuration() const override { return PATH_TIME_STEP; }
+    bool     inverseMap_WS2TP(double x, double y, int& k, double& d, double tol = 0.10) const override;
+    bool     supportSpeedAtTarget() const override { return true; }
+    bool     isSpeedTrimmable() const override { return true; }
+    bool     isPointInsideRobotShape(double x, double y) const override { return ::hypot(x, y) < p_.robot_radius; }
+    double   getMaxRobotRadius() const override { return p_.robot_radius; }
+    std::unique_ptr<ptg_t> cloneForQuery() const override { return std::make_unique<HolonomicBlend>(p_); }
+
+    /** (vxi, vyi, vxf, vyf, vf, T_ramp) of path k at the current dynamic state and trimmed speed */
+    void holoParams(uint16_t k, mppb_holo_cand& out) const;
+    mppb_ptg_holo_desc holoDesc() const
+    {
+        return {static_cast<int32_t>(numPaths_), refDistance_, p_.robot_radius, p_.v_max_mps};
+    }
+    const HolonomicBlendParams& params() const { return p_; }
+
+   protected:
+    void onNewNavDynamicState() override;
+
+   private:
+    struct Internal
+    {
+        double vxi, vyi, vxf, vyf, vf, wf, T_ramp;
+    };
+    Internal      paramsForDir(double dir) const;
+    double        pathDistAt(uint32_t step, double T_ramp, double vxf, double vyf) const;
+    static double rampDistance(double k2, double k4, double vxi, double vyi, double t);
+    static double rampIntegral(double T, double a, double b, double c);
+
+    HolonomicBlendParams     p_;
+    RuntimeExpr              exprV_, exprW_;
+    mutable double           exprDir_    = 0;
+    double                   targetDir_  = 0;
+    double                   targetDist_ = 0;
+    mutable std::vector<int> stepCountCache_;
 };
 
 }  // namespace mpp

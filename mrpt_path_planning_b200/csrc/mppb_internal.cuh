@@ -61,6 +61,29 @@ struct GridGroupDev
     double          shapeY[MPPB_MAX_SHAPE_VERTS];
 };
 
+// HolonomicBlend PTG constants as the kernel sees them (indexed by the context's PTG index)
+struct HoloPtgDev
+{
+    double robotRadius;  // CPTG_RobotShape_Circular radius
+    double vMax;         // V_MAX (cruise-phase distance uses the untrimmed V_MAX, HolonomicBlend.cpp:835)
+};
+
+// One cost evaluator slot as the edge-cost kernel sees it
+struct EvaluatorDev
+{
+    int           kind;  // 0 = empty, 1 = CostEvaluatorCostMap, 2 = CostEvaluatorPreferredWaypoint
+    int           useAverage;
+    // costmap (CDynamicGrid<double> geometry)
+    double        xmin, ymin, res;
+    int           nx, ny;
+    const double* cells;
+    // preferred waypoints (stored as float, like CSimplePointsMap)
+    const float2* wps;
+    int           nWps;
+    double        radius, scale;
+    float         radiusSqrF;
+};
+
 // ---------------------------------------------------------------------------------------
 // Host-side context
 // ---------------------------------------------------------------------------------------
@@ -119,6 +142,28 @@ struct PinnedBuf
     }
 };
 
+// One obstacle cloud on the device: raw SoA (concatenated sources) + its bin index
+struct CloudStore
+{
+    DevBuf    rawX, rawY;
+    size_t    rawN = 0;
+    DevBuf    sortedPts, binStart, binCursor;
+    CloudBins bins;
+    double    binSize = 0;
+    bool      hasBox  = false;
+    float     box[4]  = {0, 0, 0, 0};  // minx, miny, maxx, maxy (inclusive, float compare)
+    void      release()
+    {
+        rawX.release();
+        rawY.release();
+        sortedPts.release();
+        binStart.release();
+        binCursor.release();
+        rawN = 0;
+        bins = CloudBins();
+    }
+};
+
 // host copy of one uploaded collision-grid PTG (kept to rebuild the merged groups)
 struct PtgGridHost
 {
@@ -166,21 +211,30 @@ struct mppb_ctx
     cudaEvent_t  evFork = nullptr, evJoin = nullptr;
 
     // obstacle cloud: raw SoA (concatenated sources) + bin index
-    mppb::DevBuf    rawX, rawY;
-    size_t          rawN = 0;
-    mppb::DevBuf    sortedPts, binStart, binCursor, bboxScratch;
-    mppb::CloudBins bins;
-    double          binSize = 0;
+    mppb::CloudStore cloud;
+    // second cloud used only by the costmap builder (it may differ from the planner's cloud)
+    mppb::CloudStore auxCloud;
+    mppb::DevBuf     bboxScratch;
+    mppb::CloudBins& bins = cloud.bins;
 
-    // PTG tables
-    std::vector<mppb::PtgGridHost>   grids;   // one per PTG, in PTG order
+    // PTGs in planner order: kind per index (0 = collision grid, 1 = HolonomicBlend)
+    std::vector<int>                 ptgKinds;
+    std::vector<mppb::PtgGridHost>   grids;   // one per collision-grid PTG, in PTG order
     std::vector<mppb::GridGroupHost> groups;  // merged tables, rebuilt when a PTG is added
     mppb::DevBuf                     groupDescs;  // GridGroupDev[numGroups] on the device
-    int                            totalPaths = 0;
+    int                              totalPaths = 0;
+    std::vector<mppb::HoloPtgDev>    holos;      // indexed by PTG index (zero for other kinds)
+    mppb::DevBuf                     holoDescs;  // HoloPtgDev[MPPB_MAX_PTGS]
+
+    // cost evaluators
+    mppb::EvaluatorDev evals[MPPB_MAX_EVALUATORS] = {};
+    mppb::DevBuf       evalCells[MPPB_MAX_EVALUATORS], evalWps[MPPB_MAX_EVALUATORS];
+    mppb::DevBuf       evalDescs;  // EvaluatorDev[MPPB_MAX_EVALUATORS]
+    int                numEvals = 0;
 
     // staging for the host entry points
-    mppb::PinnedBuf hNodes, hOut;
-    mppb::DevBuf    dNodes, dOut;
+    mppb::PinnedBuf hNodes, hOut, hStage;
+    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3;
 };
 
 namespace mppb
@@ -196,7 +250,13 @@ void set_global_error(const std::string& msg);
     } while (0)
 
 // kernels / launchers implemented in the .cu files
-int build_cloud_bins(mppb_ctx* ctx, double binSize);
+int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize);
 int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, float* dOut);
+int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes, double clip,
+                      double* dOut);
+int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const uint32_t* dOffsets, const double* dRel,
+                      double* dOut);
+int launch_costmap_d2(mppb_ctx* ctx, const CloudStore& cs, double xmin, double ymin, double res, int nx, int ny,
+                      float clearance, float* dOut);
 
 }  // namespace mppb

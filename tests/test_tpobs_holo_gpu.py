@@ -1,0 +1,155 @@
+"""GPU parity of stage (a)+(b) for the HolonomicBlend PTG: libmpp_b200 (through the C ABI) vs the CPU
+oracle on the same seeded candidates (node pose + velocity, trajectory k, trimmed speed).
+
+Bar: the arithmetic is FP64 with the reference's operation order; only acos/cos inside the cubic
+solver come from a different libm, so distances must agree to 1e-9 relative (north_star allows 1e-4)
+and the set of unconstrained candidates (+inf) and of blocked-at-zero candidates must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from mrpt_path_planning_b200 import capi as _capi, workloads as wl
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def holo_ctx(capi):
+    ptg = capi.holonomic_ptgs()[0]
+    ctx = capi.Context(0)
+    ctx.add_ptg(ptg)
+    yield ctx, ptg
+    ctx.close()
+
+
+def make_candidates(ptg, nodes, rel_targets, ks, speeds):
+    """Candidate list in find_feasible order (speed-major), parameters from the product's host PTG."""
+    cn, ck, cs, rows = [], [], [], []
+    for b, nd in enumerate(nodes):
+        c, s = np.cos(-nd[2]), np.sin(-nd[2])
+        vloc = [nd[3] * c - nd[4] * s, nd[3] * s + nd[4] * c, nd[5]]
+        for sp in speeds:
+            ptg.set_trim_speed(sp)
+            ptg.update_dyn_state(vloc, rel_targets[b], 0.0, force=True)
+            for k in ks[b]:
+                p = ptg.holo_params(int(k))
+                rows.append((b, 0, p.T_ramp, p.vxi, p.vyi, p.vxf, p.vyf, p.vf))
+                cn.append(b)
+                ck.append(int(k))
+                cs.append(sp)
+    return np.array(rows, dtype=_capi.HOLO_CAND_DTYPE), cn, ck, cs
+
+
+def check(holo_ctx, orc, xs, ys, nodes, rel_targets, ks, speeds=(1 / 3, 2 / 3, 1.0), clip=5.0):
+    ctx, ptg = holo_ctx
+    optg = orc.holonomic_ptgs()[0]
+    cands, cn, ck, cs = make_candidates(ptg, nodes, rel_targets, ks, speeds)
+    ctx.set_obstacles(xs, ys)
+    got = ctx.eval_holo_candidates(nodes[:, :3], cands, clip)
+    ref, _, _ = orc.eval_candidates(optg, xs, ys, nodes, rel_targets, cn, ck, cs, clip, want_free=False)
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    assert np.array_equal(got == 0.0, ref == 0.0)
+    fin = np.isfinite(ref)
+    err = np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-12)
+    assert err.size == 0 or err.max() <= RTOL, "max rel err %g" % err.max()
+    return got, ref
+
+
+def random_nodes(rng, b, extent, moving=True):
+    nodes = np.zeros((b, 6))
+    nodes[:, 0] = rng.uniform(1, extent - 1, b)
+    nodes[:, 1] = rng.uniform(1, extent - 1, b)
+    nodes[:, 2] = rng.uniform(-np.pi, np.pi, b)
+    if moving:
+        sp = rng.uniform(0, 1.0, b) * (rng.uniform(size=b) < 0.7)
+        th = rng.uniform(-np.pi, np.pi, b)
+        nodes[:, 3], nodes[:, 4] = sp * np.cos(th), sp * np.sin(th)
+    rel = np.stack([rng.uniform(-8, 8, b), rng.uniform(-8, 8, b), rng.uniform(-3, 3, b)], axis=1)
+    return nodes, rel
+
+
+def test_c1_cloud_parity(holo_ctx, orc):
+    """the reference's own demo cloud (share/obstacles_01.txt, 155 points), planner k-subset"""
+    obs = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "obstacles_01.txt")).astype(np.float32)
+    rng = np.random.default_rng(5)
+    nodes, rel = random_nodes(rng, 48, 3.0)
+    nodes[:, 0] = rng.uniform(-1.0, 5.5, 48)
+    nodes[:, 1] = rng.uniform(-1.5, 4.0, 48)
+    k13 = [0, 15, 31, 47, 63, 79, 95, 110, 126, 142, 158, 174, 190]
+    got, ref = check(holo_ctx, orc, obs[:, 0].copy(), obs[:, 1].copy(), nodes, rel, [k13] * 48)
+    assert np.isfinite(ref).any() and np.isinf(ref).any()
+
+
+@pytest.mark.parametrize("density,seed", [(0.2, 1), (2.0, 2), (26.0, 3)])
+def test_uniform_cloud_all_paths(holo_ctx, orc, density, seed):
+    extent = 30.0
+    xs, ys = wl.uniform_cloud(int(density * extent * extent), extent, seed=seed)
+    rng = np.random.default_rng(seed + 50)
+    nodes, rel = random_nodes(rng, 6, extent)
+    check(holo_ctx, orc, xs, ys, nodes, rel, [list(range(0, 191, 3))] * 6)
+
+
+def test_zero_velocity_straight_known_answer(holo_ctx):
+    """single obstacle dead ahead of a node at rest: free distance = ox - R in ramp and cruise phase"""
+    ctx, ptg = holo_ctx
+    nodes = np.array([[10.0, 10.0, 0.0, 0, 0, 0]])
+    for ox in (0.3, 0.45, 2.0, 4.5):
+        ctx.set_obstacles(np.float32([10.0 + ox]), np.float32([10.0]))
+        cands, *_ = make_candidates(ptg, nodes, [[20.0, 0, 0]], [[95]], [1.0])
+        got = ctx.eval_holo_candidates(nodes[:, :3], cands, 5.0)
+        assert abs(got[0] - (ox - 0.15)) < 1e-6  # the float narrowing of the local point costs ~1e-7
+
+
+def test_empty_cloud_and_empty_batch(holo_ctx):
+    ctx, ptg = holo_ctx
+    ctx.set_obstacles(np.zeros(0, np.float32), np.zeros(0, np.float32))
+    nodes = np.array([[1.0, 2.0, 0.3, 0, 0, 0]])
+    cands, *_ = make_candidates(ptg, nodes, [[3.0, 1.0, 0]], [[0, 95, 190]], [1.0])
+    assert np.isinf(ctx.eval_holo_candidates(nodes[:, :3], cands, 5.0)).all()
+    assert ctx.eval_holo_candidates(nodes[:, :3], cands[:0], 5.0).shape == (0,)
+
+
+def test_bad_candidate_is_rejected(holo_ctx, capi):
+    ctx, ptg = holo_ctx
+    nodes = np.array([[1.0, 2.0, 0.3, 0, 0, 0]])
+    cands, *_ = make_candidates(ptg, nodes, [[3.0, 1.0, 0]], [[5]], [1.0])
+    bad = cands.copy()
+    bad["node"] = 7
+    with pytest.raises(capi.MppbError):
+        ctx.eval_holo_candidates(nodes[:, :3], bad, 5.0)
+    bad = cands.copy()
+    bad["ptg_index"] = 3
+    with pytest.raises(capi.MppbError):
+        ctx.eval_holo_candidates(nodes[:, :3], bad, 5.0)
+
+
+def test_blocked_decisions_match(holo_ctx, orc):
+    """the free/blocked decision of TPS_Astar.cpp:749 for the planner's sample timestamps"""
+    ctx, ptg = holo_ctx
+    optg = orc.holonomic_ptgs()[0]
+    extent = 20.0
+    xs, ys = wl.uniform_cloud(400, extent, seed=9)
+    rng = np.random.default_rng(77)
+    nodes, rel = random_nodes(rng, 24, extent)
+    ks = [[0, 15, 31, 47, 63, 79, 95, 110, 126, 142, 158, 174, 190]] * 24
+    got, ref = check(holo_ctx, orc, xs, ys, nodes, rel, ks)
+    cands, cn, ck, cs = make_candidates(ptg, nodes, rel, ks, (1 / 3, 2 / 3, 1.0))
+    n_dec = 0
+    for i in range(len(cn)):
+        b = cn[i]
+        c, s = np.cos(-nodes[b, 2]), np.sin(-nodes[b, 2])
+        vloc = [nodes[b, 3] * c - nodes[b, 4] * s, nodes[b, 3] * s + nodes[b, 4] * c, nodes[b, 5]]
+        for P in (ptg, optg):
+            P.set_trim_speed(cs[i])
+            P.update_dyn_state(vloc, rel[b], 0.0, force=True)
+        init_g, init_r = ptg.init_dist(ck[i]), optg.init_dist(ck[i])
+        assert init_g == init_r
+        for step in (50, 150, 400):
+            if step >= ptg.step_count(ck[i]):
+                continue
+            d = ptg.path_pose(ck[i], step)[3]
+            assert (d >= min(init_g, got[i])) == (d >= min(init_r, ref[i]))
+            n_dec += 1
+    assert n_dec > 1000
