@@ -175,6 +175,14 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi /* 
  * cos/sin evaluated by the caller's libm (glibc for bit parity with the reference). */
 int mppb_eval_nodes_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, double clip_dist,
                            float* d_out);
+/* Same with a world box per node: node_boxes is NULL or [n][4] floats {minx, miny, maxx, maxy};
+ * obstacle points outside node i's box are ignored for node i (float comparisons, inclusive
+ * bounds). This is ObstacleSource::apply_clipping_box (ObstacleSource.cpp:29-40) applied per
+ * query, so that independent queries with different world boxes share one resident cloud. */
+int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                          double clip_dist, float* out);
+int mppb_eval_nodes_boxed_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, const float* d_node_boxes,
+                                 double clip_dist, float* d_out);
 /* Fill [n][4] (x, y, cos, sin) from [n][3] (x, y, phi) on the host with the C library. */
 void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, double* out_xycs);
 
@@ -186,6 +194,12 @@ int mppb_eval_holo_candidates(mppb_ctx* ctx, size_t n_nodes, const double* poses
                               double* out /* host [n_cands] */);
 int mppb_eval_holo_candidates_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
                                      const double* d_nodes_xycs, double clip_dist, double* d_out);
+/* per-node world boxes as in mppb_eval_nodes_boxed */
+int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                    size_t n_cands, const mppb_holo_cand* cands, double clip_dist, double* out);
+int mppb_eval_holo_candidates_boxed_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
+                                           const double* d_nodes_xycs, const float* d_node_boxes, double clip_dist,
+                                           double* d_out);
 
 /* ---- stage (c): cost evaluators ---------------------------------------------------------
  * Evaluator slots are evaluated in slot order, like Planner::costEvaluators_ (Planner.cpp:22-26). */
@@ -289,6 +303,81 @@ int mppb_ptg_set_trim_speed(mppb_ptg* ptg, double speed);
 int mppb_ptg_path_twist(const mppb_ptg* ptg, int k, uint32_t step, double* out3);
 /* HolonomicBlend: candidate parameters of path k at the current dynamic state and trimmed speed */
 int mppb_ptg_holo_params(const mppb_ptg* ptg, int k, mppb_holo_cand* out_cand);
+
+/* ---- planner ----------------------------------------------------------------------------------
+ * mpp::TPS_Astar behind a C surface (reference: mpp::Planner::plan, include/mpp/algos/Planner.h:36;
+ * TPS_Astar_Parameters, include/mpp/algos/TPS_Astar.h:24-57; the set-up sequence of
+ * apps/path-planner-cli/path-planner-cli.cpp:200-341). The A* search runs on the host; every
+ * expanded node's collision rows and every tentative edge's evaluator costs are computed on the
+ * GPU of `ctx`. */
+typedef struct mppb_planner mppb_planner;
+
+typedef struct mppb_astar_params
+{
+    double        grid_resolution_xy;
+    double        grid_resolution_yaw; /* radians */
+    double        SE2_metricAngleWeight;
+    double        heuristic_heading_weight;
+    uint32_t      max_ptg_trajectories_to_explore;
+    uint32_t      max_ptg_speeds_to_explore;
+    uint32_t      path_interpolated_segments;
+    double        maximum_computation_time; /* seconds; <= 0: unlimited */
+    uint64_t      max_expansions;           /* extension for deterministic runs; 0: unlimited */
+    const double* ptg_sample_timestamps;
+    uint32_t      num_timestamps;
+} mppb_astar_params;
+
+typedef struct mppb_plan_query
+{
+    double  start[6]; /* x y phi vx vy omega (global frame) */
+    double  goal[6];  /* x y phi vx vy omega; phi ignored if goal_is_point */
+    int32_t goal_is_point;
+    double  bbox_min[3], bbox_max[3]; /* world box: x y phi */
+} mppb_plan_query;
+
+typedef struct mppb_plan_result
+{
+    int32_t  success;
+    double   path_cost;
+    uint64_t tree_nodes, tree_parents, nodes_expanded, tps_points, edges_costed;
+    int64_t  best_node, goal_node;
+    double   computation_time, best_cost_to_goal;
+    uint32_t path_len; /* nodes on the path root -> best node */
+} mppb_plan_result;
+
+int         mppb_planner_create(mppb_ctx* ctx, mppb_planner** out_planner);
+void        mppb_planner_destroy(mppb_planner* p);
+const char* mppb_planner_last_error(const mppb_planner* p);
+int         mppb_planner_set_params(mppb_planner* p, const mppb_astar_params* params);
+/* the PTG object is borrowed and must outlive the planner; PTGs are used in the order added */
+int mppb_planner_add_ptg(mppb_planner* p, mppb_ptg* ptg);
+/* one static obstacle source (ObstacleSource::FromStaticPointcloud); the points are copied */
+int mppb_planner_add_obstacles(mppb_planner* p, const float* xs, const float* ys, size_t n);
+/* CostEvaluatorCostMap::FromStaticPointObstacles + push_back into costEvaluators_ */
+int mppb_planner_add_costmap(mppb_planner* p, const float* xs, const float* ys, size_t n, double resolution,
+                             double preferred_clearance, double max_cost, int use_average, double max_radius_from_robot,
+                             const double* robot_pose_xyphi /* NULL if max_radius_from_robot <= 0 */);
+/* geometry (x_min, y_min, res, nx, ny) and cells [ny][nx] of costmap evaluator #evaluator; either may be NULL */
+int mppb_planner_costmap_cells(mppb_planner* p, int evaluator, double* info5, double* cells);
+/* CostEvaluatorPreferredWaypoint + setPreferredWaypoints + push_back into costEvaluators_ */
+int mppb_planner_add_waypoints(mppb_planner* p, const double* xs, const double* ys, size_t n, double influence_radius,
+                               double cost_scale, int use_average);
+/* n_queries == 1: TPS_Astar::plan. n_queries > 1: independent queries over the same obstacles,
+ * advanced in lock-step with one GPU batch per A* iteration (n_threads host threads, 0 = all);
+ * each result equals what plan() returns for that query alone. */
+int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* queries, int n_threads,
+                      mppb_plan_result* results);
+/* refine_trajectory on the backtracked path of a query (src/algos/refine_trajectory.cpp:14-89) */
+int mppb_planner_refine(mppb_planner* p, size_t query);
+/* nodes [path_len][8] = id x y phi vx vy omega cost; edges [path_len-1][8] = ptgIndex k step ptgDist cost
+ * estimatedExecTime trimSpeed nInterpolated; either may be NULL */
+int mppb_planner_path(mppb_planner* p, size_t query, double* nodes, double* edges);
+/* whole motion tree, rows [id parent(-1 for the root) x y phi cost edgeCost]; returns the node count */
+int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t cap);
+/* plan_to_trajectory + save_to_txt text (src/algos/trajectories.cpp:15-106); returns the text length */
+int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample_period, char* buf, int64_t cap);
+/* GPU work of the last plan: collision batches, cost batches, nodes, holo candidates, edges, seconds in GPU calls */
+int mppb_planner_gpu_stats(const mppb_planner* p, double* out6);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,26 @@ class CostmapDesc(C.Structure):
                 ("ny", C.c_int32), ("cells", c_double_p), ("use_average", C.c_int32)]
 
 
+class AstarParams(C.Structure):
+    _fields_ = [("grid_resolution_xy", C.c_double), ("grid_resolution_yaw", C.c_double),
+                ("SE2_metricAngleWeight", C.c_double), ("heuristic_heading_weight", C.c_double),
+                ("max_ptg_trajectories_to_explore", C.c_uint32), ("max_ptg_speeds_to_explore", C.c_uint32),
+                ("path_interpolated_segments", C.c_uint32), ("maximum_computation_time", C.c_double),
+                ("max_expansions", C.c_uint64), ("ptg_sample_timestamps", c_double_p), ("num_timestamps", C.c_uint32)]
+
+
+class PlanQuery(C.Structure):
+    _fields_ = [("start", C.c_double * 6), ("goal", C.c_double * 6), ("goal_is_point", C.c_int32),
+                ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3)]
+
+
+class PlanResult(C.Structure):
+    _fields_ = [("success", C.c_int32), ("path_cost", C.c_double), ("tree_nodes", C.c_uint64),
+                ("tree_parents", C.c_uint64), ("nodes_expanded", C.c_uint64), ("tps_points", C.c_uint64),
+                ("edges_costed", C.c_uint64), ("best_node", C.c_int64), ("goal_node", C.c_int64),
+                ("computation_time", C.c_double), ("best_cost_to_goal", C.c_double), ("path_len", C.c_uint32)]
+
+
 # name -> (restype, argtypes); every symbol include/mppb.h declares must be listed here
 _SIGS = {
     "mppb_version": (C.c_char_p, []),
@@ -143,6 +163,30 @@ _SIGS = {
     "mppb_ptg_set_trim_speed": (C.c_int, [C.c_void_p, C.c_double]),
     "mppb_ptg_path_twist": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, c_double_p]),
     "mppb_ptg_holo_params": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(HoloCand)]),
+    "mppb_eval_nodes_boxed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "mppb_eval_nodes_boxed_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
+                                               C.c_void_p]),
+    "mppb_eval_holo_candidates_boxed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                  C.c_void_p, C.c_double, C.c_void_p]),
+    "mppb_eval_holo_candidates_boxed_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.c_double, C.c_void_p]),
+    "mppb_planner_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mppb_planner_destroy": (None, [C.c_void_p]),
+    "mppb_planner_last_error": (C.c_char_p, [C.c_void_p]),
+    "mppb_planner_set_params": (C.c_int, [C.c_void_p, C.POINTER(AstarParams)]),
+    "mppb_planner_add_ptg": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mppb_planner_add_obstacles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mppb_planner_add_costmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double,
+                                           C.c_double, C.c_int, C.c_double, C.c_void_p]),
+    "mppb_planner_costmap_cells": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mppb_planner_add_waypoints": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double,
+                                             C.c_int]),
+    "mppb_planner_plan": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(PlanQuery), C.c_int, C.POINTER(PlanResult)]),
+    "mppb_planner_refine": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mppb_planner_path": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "mppb_planner_tree": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64]),
+    "mppb_planner_trajectory_txt": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int64]),
+    "mppb_planner_gpu_stats": (C.c_int, [C.c_void_p, c_double_p]),
 }
 
 
@@ -465,6 +509,22 @@ class Context:
                                                clearance, _ptr(out)))
         return out
 
+    def eval_nodes_boxed(self, poses, boxes, clip_dist):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+        out = np.empty((poses.shape[0], self.total_paths), dtype=np.float32)
+        self._ck(lib().mppb_eval_nodes_boxed(self.h, poses.shape[0], _ptr(poses), _ptr(boxes), clip_dist, _ptr(out)))
+        return out
+
+    def eval_holo_candidates_boxed(self, poses, boxes, cands, clip_dist):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+        cands = np.ascontiguousarray(cands, dtype=HOLO_CAND_DTYPE)
+        out = np.empty(len(cands), dtype=np.float64)
+        self._ck(lib().mppb_eval_holo_candidates_boxed(self.h, poses.shape[0], _ptr(poses), _ptr(boxes), len(cands),
+                                                       _ptr(cands), clip_dist, _ptr(out)))
+        return out
+
     def eval_nodes_device(self, n, d_nodes_xycs, clip_dist, d_out):
         self._ck(lib().mppb_eval_nodes_device(self.h, n, _ptr(d_nodes_xycs), clip_dist, _ptr(d_out)))
 
@@ -516,3 +576,124 @@ HOLO_EXPR_W = "W_MAX * trimmable_speed * min(1.0, 0.1+abs(dir)/(10*PI/180))"
 def holonomic_ptgs():
     """PTG set of share/ptgs_holonomic_robot.ini (values typed here as data)."""
     return [PTG.holonomic_blend(191, 5.0, 1.0, 1.0, 60.0 * np.pi / 180.0, 0.15, HOLO_EXPR_V, HOLO_EXPR_W)]
+
+
+RESULT_KEYS = ["success", "path_cost", "tree_nodes", "tree_parents", "expanded", "tps_points", "edges_costed",
+               "best_node", "goal_node", "time_s", "best_cost_to_goal", "path_len"]
+
+
+class Planner:
+    """mpp::TPS_Astar over a libmpp_b200 context (C ABI section "planner")."""
+
+    def __init__(self, ctx, ptgs, params, timestamps):
+        """params: [grid_xy, grid_yaw_rad, SE2_metricAngleWeight, heuristic_heading_weight, max_trajs, max_speeds,
+        path_interpolated_segments, max_time_s (<=0 unlimited), max_expansions (0 unlimited)]"""
+        self.ctx = ctx
+        self._keep = list(ptgs)
+        h = C.c_void_p()
+        if lib().mppb_planner_create(ctx.h, C.byref(h)) != 0:
+            raise MppbError(lib().mppb_planner_last_error(None).decode())
+        self.h = h
+        ts = np.ascontiguousarray(timestamps, dtype=np.float64)
+        a = AstarParams(params[0], params[1], params[2], params[3], int(params[4]), int(params[5]), int(params[6]),
+                        params[7], int(params[8]), ts.ctypes.data_as(c_double_p), len(ts))
+        self._ck(lib().mppb_planner_set_params(self.h, C.byref(a)))
+        for p in ptgs:
+            self._ck(lib().mppb_planner_add_ptg(self.h, p.h))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MppbError(lib().mppb_planner_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().mppb_planner_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_obstacles(self, xs, ys):
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        self._ck(lib().mppb_planner_add_obstacles(self.h, _ptr(xs), _ptr(ys), xs.size))
+
+    def add_costmap(self, xs, ys, resolution, clearance, max_cost, use_average, max_radius_from_robot, robot_pose):
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        rp = np.ascontiguousarray(robot_pose, dtype=np.float64) if robot_pose is not None else None
+        self._ck(lib().mppb_planner_add_costmap(self.h, _ptr(xs), _ptr(ys), xs.size, resolution, clearance, max_cost,
+                                                int(use_average), max_radius_from_robot, _ptr(rp)))
+
+    def costmap_cells(self, evaluator=0):
+        info = np.zeros(5)
+        self._ck(lib().mppb_planner_costmap_cells(self.h, evaluator, _ptr(info), None))
+        cells = np.zeros((int(info[4]), int(info[3])))
+        self._ck(lib().mppb_planner_costmap_cells(self.h, evaluator, None, _ptr(cells)))
+        return dict(xmin=info[0], ymin=info[1], res=info[2], nx=int(info[3]), ny=int(info[4])), cells
+
+    def add_waypoints(self, xs, ys, radius, scale, use_average):
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        ys = np.ascontiguousarray(ys, dtype=np.float64)
+        self._ck(lib().mppb_planner_add_waypoints(self.h, _ptr(xs), _ptr(ys), xs.size, radius, scale,
+                                                  int(use_average)))
+
+    def plan_many(self, queries, n_threads=0):
+        """queries: list of (start6, goal6, bbox_min3, bbox_max3, goal_is_point). Returns a list of dicts."""
+        n = len(queries)
+        qs = (PlanQuery * n)()
+        for i, (start, goal, lo, hi, is_pt) in enumerate(queries):
+            qs[i].start[:] = list(start)
+            qs[i].goal[:] = list(goal)
+            qs[i].goal_is_point = int(is_pt)
+            qs[i].bbox_min[:] = list(lo)
+            qs[i].bbox_max[:] = list(hi)
+        rs = (PlanResult * n)()
+        self._ck(lib().mppb_planner_plan(self.h, n, qs, n_threads, rs))
+        out = []
+        for r in rs:
+            out.append(dict(success=float(r.success), path_cost=r.path_cost, tree_nodes=float(r.tree_nodes),
+                            tree_parents=float(r.tree_parents), expanded=float(r.nodes_expanded),
+                            tps_points=float(r.tps_points), edges_costed=float(r.edges_costed),
+                            best_node=float(r.best_node), goal_node=float(r.goal_node), time_s=r.computation_time,
+                            best_cost_to_goal=r.best_cost_to_goal, path_len=int(r.path_len)))
+        self._path_len = [d["path_len"] for d in out]
+        return out
+
+    def plan(self, start, goal, bbox_min, bbox_max, goal_is_point=False):
+        return self.plan_many([(start, goal, bbox_min, bbox_max, goal_is_point)])[0]
+
+    def refine(self, query=0):
+        self._ck(lib().mppb_planner_refine(self.h, query))
+
+    def path(self, query=0):
+        n = self._path_len[query]
+        nodes = np.zeros((n, 8))
+        edges = np.zeros((max(n - 1, 0), 8))
+        self._ck(lib().mppb_planner_path(self.h, query, _ptr(nodes), _ptr(edges)))
+        return nodes, edges
+
+    def tree(self, query=0):
+        n = lib().mppb_planner_tree(self.h, query, None, 0)
+        if n < 0:
+            raise MppbError(lib().mppb_planner_last_error(self.h).decode())
+        out = np.zeros((n, 7))
+        lib().mppb_planner_tree(self.h, query, _ptr(out), n)
+        return out
+
+    def trajectory_txt(self, query=0, period=0.05):
+        n = lib().mppb_planner_trajectory_txt(self.h, query, period, None, 0)
+        if n < 0:
+            raise MppbError(lib().mppb_planner_last_error(self.h).decode())
+        buf = C.create_string_buffer(n + 1)
+        lib().mppb_planner_trajectory_txt(self.h, query, period, buf, n + 1)
+        return buf.value.decode()
+
+    def gpu_stats(self):
+        v = np.zeros(6)
+        self._ck(lib().mppb_planner_gpu_stats(self.h, v.ctypes.data_as(c_double_p)))
+        return dict(collision_batches=int(v[0]), cost_batches=int(v[1]), nodes=int(v[2]), holo_candidates=int(v[3]),
+                    edges=int(v[4]), gpu_seconds=v[5])

@@ -108,6 +108,7 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     ctx->dStage.release();
     ctx->dStage2.release();
     ctx->dStage3.release();
+    ctx->dBoxes.release();
     if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
@@ -462,12 +463,23 @@ void mppb_nodes_xycs_from_poses(size_t n, const double* poses, double* out)
 
 int mppb_eval_nodes_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, double clip_dist, float* d_out)
 {
+    return mppb_eval_nodes_boxed_device(ctx, n_nodes, d_nodes_xycs, nullptr, clip_dist, d_out);
+}
+int mppb_eval_nodes_boxed_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, const float* d_node_boxes,
+                                 double clip_dist, float* d_out)
+{
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n_nodes && (!d_nodes_xycs || !d_out)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null device pointers");
-    return launch_tpobs_grid(ctx, n_nodes, d_nodes_xycs, clip_dist, d_out);
+    return launch_tpobs_grid(ctx, n_nodes, d_nodes_xycs, d_node_boxes, clip_dist, d_out);
 }
 
 int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, double clip_dist, float* out)
+{
+    return mppb_eval_nodes_boxed(ctx, n_nodes, poses_xyphi, nullptr, clip_dist, out);
+}
+
+int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                          double clip_dist, float* out)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n_nodes == 0) return MPPB_OK;
@@ -480,6 +492,12 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, do
     MPPB_CUDA(ctx, ctx->hNodes.reserve(inBytes));
     MPPB_CUDA(ctx, ctx->dNodes.reserve(inBytes));
     MPPB_CUDA(ctx, ctx->dOut.reserve(outBytes));
+    if (node_boxes)
+    {
+        MPPB_CUDA(ctx, ctx->dBoxes.reserve(n_nodes * 4 * sizeof(float)));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxes.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    }
     if (!ctx->auxStream)
     {
         MPPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->auxStream, cudaStreamNonBlocking));
@@ -512,7 +530,7 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, do
             break;
         }
         ctx->stream = st;  // launch on the sub-batch's stream
-        rc          = launch_tpobs_grid(ctx, n, dN, clip_dist, dO);
+        rc          = launch_tpobs_grid(ctx, n, dN, node_boxes ? ctx->dBoxes.as<float>() + 4 * lo : nullptr, clip_dist, dO);
         ctx->stream = saved;
         if (rc != MPPB_OK) break;
         e = cudaMemcpyAsync(out + lo * cols, dO, n * cols * sizeof(float), cudaMemcpyDeviceToHost, st);
@@ -529,13 +547,25 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, do
 int mppb_eval_holo_candidates_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
                                      const double* d_nodes_xycs, double clip_dist, double* d_out)
 {
+    return mppb_eval_holo_candidates_boxed_device(ctx, n_cands, d_cands, d_nodes_xycs, nullptr, clip_dist, d_out);
+}
+int mppb_eval_holo_candidates_boxed_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
+                                           const double* d_nodes_xycs, const float* d_node_boxes, double clip_dist,
+                                           double* d_out)
+{
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n_cands && (!d_cands || !d_nodes_xycs || !d_out)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null device pointers");
-    return launch_tpobs_holo(ctx, n_cands, d_cands, d_nodes_xycs, clip_dist, d_out);
+    return launch_tpobs_holo(ctx, n_cands, d_cands, d_nodes_xycs, d_node_boxes, clip_dist, d_out);
 }
 
 int mppb_eval_holo_candidates(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, size_t n_cands,
                               const mppb_holo_cand* cands, double clip_dist, double* out)
+{
+    return mppb_eval_holo_candidates_boxed(ctx, n_nodes, poses_xyphi, nullptr, n_cands, cands, clip_dist, out);
+}
+
+int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                    size_t n_cands, const mppb_holo_cand* cands, double clip_dist, double* out)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n_cands == 0) return MPPB_OK;
@@ -559,8 +589,15 @@ int mppb_eval_holo_candidates(mppb_ctx* ctx, size_t n_nodes, const double* poses
     mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodes.as<double>());
     MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, nodeBytes, cudaMemcpyHostToDevice, ctx->stream));
     MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, cands, candBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (node_boxes)
+    {
+        MPPB_CUDA(ctx, ctx->dBoxes.reserve(n_nodes * 4 * sizeof(float)));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxes.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    }
     const int rc = launch_tpobs_holo(ctx, n_cands, ctx->dStage.as<mppb_holo_cand>(), ctx->dNodes.as<double>(),
-                                     clip_dist, ctx->dStage2.as<double>());
+                                     node_boxes ? ctx->dBoxes.as<float>() : nullptr, clip_dist,
+                                     ctx->dStage2.as<double>());
     if (rc != MPPB_OK) return rc;
     MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dStage2.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

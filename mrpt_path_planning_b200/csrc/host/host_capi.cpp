@@ -4,12 +4,7 @@
 #include <string>
 
 #include "../../../include/mppb.h"
-#include "ptg.h"
-
-struct mppb_ptg
-{
-    std::unique_ptr<mpp::ptg_t> obj;
-};
+#include "host_internal.h"
 
 namespace
 {

@@ -1,0 +1,1024 @@
+// mpp::TPS_Astar (product code): A* over the SE(2) lattice with the per-node collision rows and the
+// per-edge evaluator costs computed by the GPU library in batches.
+//
+// Reference: src/algos/TPS_Astar.cpp (plan :86-475, find_feasible_paths_to_neighbors :538-826,
+// heuristics :477-537) and include/mpp/algos/TPS_Astar.h. The reference interleaves, per expanded
+// node, candidate enumeration, collision checks, neighbour selection, edge construction, cost
+// evaluation and relaxation. Here the same work is cut into phases so that the two data-parallel
+// parts leave the host:
+//   A  (host)  enumerate the candidate TPS points of the node, reconstruct their end poses
+//   B  (GPU)   free TP-distance of every (node, PTG, k[, speed])      -> mppb_eval_nodes / _holo_
+//   C  (host)  blocked test, goal-cell rule, best candidate per reached lattice cell
+//   D  (host)  neighbour nodes, tentative edges and their interpolated samples
+//   E  (GPU)   evaluator costs of all tentative edges                  -> mppb_eval_edge_costs
+//   F  (host)  relaxation: gScore/fScore, open set, motion tree
+// Every container whose iteration order decides results (the unordered_map of best paths, the
+// multimap open set with its stale keys, node-id assignment order) is kept as in the reference,
+// and every PTG object sees the same sequence of state changes, so a query produces the same tree
+// whether it runs alone (plan) or interleaved with thousands of others (plan_batch).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "mpp.h"
+
+namespace mpp
+{
+namespace
+{
+using Clock = std::chrono::steady_clock;
+double seconds_since(const Clock::time_point& t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+void ck(mppb_ctx* ctx, int rc)
+{
+    if (rc != MPPB_OK) throw std::runtime_error(std::string("libmpp_b200: ") + mppb_last_error(ctx));
+}
+
+// ---- lattice ---------------------------------------------------------------------------------------
+struct NodeCoords
+{
+    int32_t                idxX = 0, idxY = 0;
+    std::optional<int32_t> idxYaw;
+    NodeCoords() = default;
+    NodeCoords(int32_t ix, int32_t iy) : idxX(ix), idxY(iy) {}
+    NodeCoords(int32_t ix, int32_t iy, int32_t iphi) : idxX(ix), idxY(iy), idxYaw(iphi) {}
+    bool operator==(const NodeCoords& o) const { return idxX == o.idxX && idxY == o.idxY && idxYaw == o.idxYaw; }
+    /** same (x,y) cell and, when both carry a heading index, the same heading */
+    bool sameLocation(const NodeCoords& o) const
+    {
+        if (idxX != o.idxX || idxY != o.idxY) return false;
+        return !(idxYaw.has_value() && o.idxYaw.has_value()) || *idxYaw == *o.idxYaw;
+    }
+};
+struct NodeCoordsHash
+{
+    size_t operator()(const NodeCoords& x) const
+    {
+        size_t res = 17;
+        res        = res * 31 + std::hash<int32_t>()(x.idxX);
+        res        = res * 31 + std::hash<int32_t>()(x.idxY);
+        if (x.idxYaw) res = res * 31 + std::hash<int32_t>()(x.idxYaw.value());
+        return res;
+    }
+};
+struct Node
+{
+    std::optional<TNodeID> id;
+    SE2_KinState           state;
+    cost_t                 gScore = std::numeric_limits<cost_t>::max();
+    cost_t                 fScore = std::numeric_limits<cost_t>::max();
+    const Node*            cameFrom         = nullptr;
+    bool                   pendingInOpenSet = false;
+    bool                   visited          = false;
+};
+struct PathToNeighbor
+{
+    std::optional<size_t>    ptgIndex;
+    trajectory_index_t       ptgTrajIndex = -1;
+    ptg_step_t               relTrgStep   = 0;
+    TNavDynamicState         ptgDynState;
+    normalized_speed_t       ptgTrimmableSpeed = 1.0;  // never assigned by the reference: stays 1.0
+    distance_t               ptgDist           = std::numeric_limits<distance_t>::max();
+    TPose2D                  relReconstrPose;
+};
+// one candidate TPS point whose end pose passed the world-box test (phase A output)
+struct Candidate
+{
+    size_t             ptgIdx;
+    trajectory_index_t k;
+    ptg_step_t         step;
+    distance_t         relTrgDist;
+    TPose2D            relPose;
+    NodeCoords         nc;
+    distance_t         initDist;   // initTPObstacleSingle(k) at the moment the reference would take it
+    bool               isTarget;   // direct-to-goal TPS point
+    bool               onGrid;     // result lives in the collision-grid row (else in the holo list)
+    uint32_t           evalIndex;  // column of the row / index into the query's holo candidates
+};
+struct PendingEdge
+{
+    Node*           neighbor;
+    SE2_KinState    x_i;
+    MoveEdgeSE2_TPS edge;
+};
+
+// ---- persistent host thread pool for the per-query phases --------------------------------------------
+class Workers
+{
+   public:
+    explicit Workers(int n) : n_(std::max(1, n))
+    {
+        for (int i = 1; i < n_; i++) threads_.emplace_back([this]() { loop(); });
+    }
+    ~Workers()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    // fn(i) for i in [0,count); exceptions are collected and the first one rethrown
+    void run(size_t count, const std::function<void(size_t)>& fn)
+    {
+        if (count == 0) return;
+        if (n_ == 1 || count == 1)
+        {
+            for (size_t i = 0; i < count; i++) fn(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_      = &fn;
+            count_   = count;
+            next_    = 0;
+            pending_ = n_ - 1;
+            err_.clear();
+            gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this]() { return pending_ == 0; });
+        fn_ = nullptr;
+        if (!err_.empty()) throw std::runtime_error(err_);
+    }
+
+   private:
+    void work()
+    {
+        for (;;)
+        {
+            const size_t i = next_.fetch_add(1);
+            if (i >= count_) break;
+            try
+            {
+                (*fn_)(i);
+            }
+            catch (const std::exception& e)
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (err_.empty()) err_ = e.what();
+            }
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&]() { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                pending_--;
+            }
+            done_.notify_one();
+        }
+    }
+    int                                n_;
+    std::vector<std::thread>           threads_;
+    std::mutex                         m_;
+    std::condition_variable            cv_, done_;
+    bool                               stop_ = false;
+    uint64_t                           gen_  = 0;
+    const std::function<void(size_t)>* fn_   = nullptr;
+    size_t                             count_ = 0;
+    std::atomic<size_t>                next_{0};
+    int                                pending_ = 0;
+    std::string                        err_;
+};
+
+// pinned host buffer (grow-only)
+template <class T>
+struct Pinned
+{
+    T*     p   = nullptr;
+    size_t cap = 0;
+    ~Pinned() { mppb_host_free(p); }
+    T* reserve(size_t n)
+    {
+        if (n > cap)
+        {
+            mppb_host_free(p);
+            p   = nullptr;
+            cap = 0;
+            void* q = nullptr;
+            if (mppb_host_alloc(std::max<size_t>(n, 64) * sizeof(T) * 2, &q) != MPPB_OK)
+                throw std::runtime_error("libmpp_b200: pinned host allocation failed");
+            p   = static_cast<T*>(q);
+            cap = std::max<size_t>(n, 64) * 2;
+        }
+        return p;
+    }
+};
+}  // namespace
+
+// ======================================================================================================
+struct TPS_Astar::Impl
+{
+    TPS_Astar* self   = nullptr;
+    mppb_ctx*  ctx    = nullptr;
+    bool       ownCtx = false;
+
+    // what is resident in the context
+    std::vector<const ptg_t*> uploadedPtgs;
+    std::vector<int>          columnOffset;  // per PTG: first column of its collision-grid row, or -1
+    struct CloudKey
+    {
+        std::vector<const void*> data;
+        std::vector<size_t>      sizes;
+        bool                     hasBox = false;
+        float                    box[4] = {0, 0, 0, 0};
+        bool                     operator==(const CloudKey& o) const
+        {
+            return data == o.data && sizes == o.sizes && hasBox == o.hasBox && std::memcmp(box, o.box, sizeof(box)) == 0;
+        }
+    } uploadedCloud;
+    bool cloudValid = false;
+
+    // evaluator slots of the current plan
+    std::vector<int> evalSlot;  // per costEvaluators_ entry: GPU slot or -1 (host plugin)
+    int              numGpuEvals = 0;
+
+    Pinned<double>         hPoses, hHoloOut, hFrom, hRel, hCost;
+    Pinned<float>          hRows, hBoxes;
+    Pinned<mppb_holo_cand> hCands;
+    Pinned<uint32_t>       hOffsets;
+
+    struct Query;
+    void                       ensureContext();
+    void                       uploadPtgs(const TrajectoriesAndRobotShape& trs);
+    void                       uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, const float* box);
+    void                       uploadEvaluators();
+    std::vector<PlannerOutput> run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads);
+};
+
+// ---- one planning query: all the A* state of the reference's plan() ----------------------------------
+struct TPS_Astar::Impl::Query
+{
+    TPS_Astar*                   planner = nullptr;
+    const TPS_Astar_Parameters*  P       = nullptr;
+    const PlannerInput*          in      = nullptr;
+    PlannerOutput                po;
+    TrajectoriesAndRobotShape    trs;  // the PTG objects this query mutates
+    const std::vector<int>*      columnOffset = nullptr;
+    Clock::time_point            t0;
+    double                       tLastCallback = 0;
+
+    std::unordered_map<NodeCoords, Node, NodeCoordsHash>   grid;
+    std::multimap<distance_t, Node*>                       openSet;
+    TNodeID                                                nextFreeId = 0;
+    Node*                                                  nodeGoal   = nullptr;
+    NodeCoords                                             goalCellIndices;
+    std::unordered_map<NodeCoords, normalized_speed_t, NodeCoordsHash> nodesWithDesiredSpeed;
+    double                                                 MAX_XY_DIST = 0;
+    Node*                                                  current     = nullptr;
+    bool                                                   done        = false;
+    float                                                  box[4]      = {0, 0, 0, 0};
+
+    // phase scratch
+    std::vector<Candidate>        cands;
+    std::vector<TNavDynamicState> dynOfPtg;
+    std::vector<mppb_holo_cand>   holoCands;
+    std::vector<PendingEdge>      pending;
+
+    // TPS_Astar.h:224-230: the lattice index takes its argument as float ([MRPT] wrapToPi<float>)
+    int32_t x2idx(float x) const { return static_cast<int32_t>(x / P->grid_resolution_xy); }
+    int32_t phi2idx(float yaw) const
+    {
+        const float pi = static_cast<float>(M_PI), twoPi = static_cast<float>(2.0 * M_PI);
+        float       a   = yaw + pi;
+        const bool  neg = a < 0;
+        a               = std::fmod(a, twoPi);
+        if (neg) a += twoPi;
+        return static_cast<int32_t>((a - pi) / P->grid_resolution_yaw);
+    }
+    NodeCoords nodeGridCoords(const TPose2D& p) const { return NodeCoords(x2idx(p.x), x2idx(p.y), phi2idx(p.phi)); }
+    NodeCoords nodeGridCoords(const TPoint2D& p) const { return NodeCoords(x2idx(p.x), x2idx(p.y)); }
+
+    Node& getOrCreateNodeByPose(const SE2_KinState& p)
+    {
+        Node& n = grid[nodeGridCoords(p.pose)];
+        if (!n.id.has_value())
+        {
+            n.id    = nextFreeId++;
+            n.state = p;
+        }
+        return n;
+    }
+
+    void start()
+    {
+        t0 = Clock::now();
+        MPP_ASSERT(in->ptgs.initialized());
+        MPP_ASSERT(in->worldBboxMin != in->worldBboxMax);
+        MPP_ASSERT(within_bbox(in->stateStart.pose, in->worldBboxMax, in->worldBboxMin));
+        MPP_ASSERT(!in->stateGoal.state.isEmpty());
+        if (in->stateGoal.state.isPoint())
+            MPP_ASSERT(within_bbox(in->stateGoal.state.point(), in->worldBboxMax, in->worldBboxMin));
+        else
+            MPP_ASSERT(within_bbox(in->stateGoal.state.pose(), in->worldBboxMax, in->worldBboxMin));
+        po.originalInput = *in;
+        for (const auto& ptg : trs.ptgs) MAX_XY_DIST = std::max(MAX_XY_DIST, ptg->getRefDistance());
+        MPP_ASSERT(MAX_XY_DIST > 0);
+        // world box as apply_clipping_box sees it: double -> float (ObstacleSource.cpp:29-30)
+        box[0] = static_cast<float>(in->worldBboxMin.x);
+        box[1] = static_cast<float>(in->worldBboxMin.y);
+        box[2] = static_cast<float>(in->worldBboxMax.x);
+        box[3] = static_cast<float>(in->worldBboxMax.y);
+
+        auto& tree = po.motionTree;
+        {
+            Node& n   = getOrCreateNodeByPose(in->stateStart);
+            n.state   = in->stateStart;
+            tree.root = n.id.value();
+            tree.insert_root_node(tree.root, n.state);
+            n.gScore           = 0;
+            n.fScore           = planner->heuristic(n.state, in->stateGoal);
+            n.pendingInOpenSet = true;
+            openSet.insert({n.fScore, &n});
+        }
+        nodeGoal      = &getOrCreateNodeByPose(in->stateGoal.asSE2KinState());
+        po.goalNodeId = nodeGoal->id.value();
+        goalCellIndices = in->stateGoal.state.isPoint() ? nodeGridCoords(in->stateGoal.state.point())
+                                                        : nodeGridCoords(in->stateGoal.state.pose());
+        nodesWithDesiredSpeed[goalCellIndices] = 0;  // goal speed = 0
+    }
+
+    // head of the A* iteration (TPS_Astar.cpp:193-255): pick the open node with the lowest fScore,
+    // finish if it lies in the goal cell. Returns false when the query has ended.
+    bool popNext()
+    {
+        if (done) return false;
+        if (openSet.empty())
+        {
+            finish();
+            return false;
+        }
+        Node& cur = *openSet.begin()->second;
+        if (nodeGridCoords(cur.state.pose).sameLocation(goalCellIndices))
+        {
+            // snap the node onto the exact goal; refine_trajectory() fixes the last edge later
+            if (in->stateGoal.state.isPoint())
+            {
+                const TPoint2D g        = in->stateGoal.state.point();
+                cur.state.pose.x        = g.x;
+                cur.state.pose.y        = g.y;
+                nodeGoal                = &cur;
+                po.goalNodeId           = cur.id.value();
+                po.bestNodeId           = po.goalNodeId;
+                po.bestNodeIdCostToGoal = 0;
+            }
+            else
+            {
+                cur.state.pose          = in->stateGoal.state.pose();
+                po.bestNodeIdCostToGoal = 0;
+            }
+            po.motionTree.node_state(*cur.id).pose = cur.state.pose;
+            finish();
+            return false;
+        }
+        cur.pendingInOpenSet = false;
+        cur.visited          = true;
+        openSet.erase(openSet.begin());
+        current = &cur;
+        po.nodesExpanded++;
+        return true;
+    }
+
+    void finish()
+    {
+        done       = true;
+        current    = nullptr;
+        po.success = po.goalNodeId == po.bestNodeId;
+        if (po.bestNodeId) po.pathCost = po.motionTree.nodes().at(*po.bestNodeId).cost_;
+        po.computationTime = seconds_since(t0);
+    }
+
+    // ---- phase A: candidate TPS points of `current` (TPS_Astar.cpp:549-736) ----
+    void phaseA(int slot)
+    {
+        cands.clear();
+        holoCands.clear();
+        dynOfPtg.assign(trs.ptgs.size(), TNavDynamicState());
+        const Node&      from        = *current;
+        const NodeCoords iGoalCoords = goalCellIndices;
+        const TPose2D    relGoal     = in->stateGoal.asSE2KinState().pose - from.state.pose;
+        const double     halfCell    = P->grid_resolution_xy * 0.5;
+        const TPose2D&   lo = in->worldBboxMin, &hi = in->worldBboxMax;
+
+        struct TpsPoint
+        {
+            trajectory_index_t k;
+            ptg_step_t         step;
+            normalized_speed_t speed;
+        };
+        std::vector<TpsPoint>                                         tps;
+        std::map<std::pair<trajectory_index_t, double>, uint32_t>     holoIndex;
+
+        for (size_t ptgIdx = 0; ptgIdx < trs.ptgs.size(); ptgIdx++)
+        {
+            ptg_t& ptg = *trs.ptgs[ptgIdx];
+            MPP_ASSERT(ptg.isInitialized());
+            const bool               trimmable = ptg.isSpeedTrimmable();
+            const duration_seconds_t ptg_dt    = ptg.getPathStepDuration();
+            {
+                TNavDynamicState ds;
+                (ds.curVelLocal = from.state.vel).rotate(-from.state.pose.phi);
+                ds.relTarget        = relGoal;
+                const auto it       = nodesWithDesiredSpeed.find(iGoalCoords);
+                ds.targetRelSpeed   = it != nodesWithDesiredSpeed.end() ? it->second : 0;
+                ptg.updateNavDynamicState(ds);
+            }
+            dynOfPtg[ptgIdx] = ptg.getCurrentNavDynamicState();
+
+            std::set<trajectory_index_t> trajIdxs;
+            std::set<size_t>             targetIdx;
+            tps.clear();
+            MPP_ASSERT(P->max_ptg_trajectories_to_explore >= 2);
+            for (size_t i = 0; i < P->max_ptg_trajectories_to_explore; i++)
+            {
+                // integer division first, then round (TPS_Astar.cpp:619-623)
+                const size_t q = i * (ptg.getPathCount() - 1) / (P->max_ptg_trajectories_to_explore - 1);
+                trajIdxs.insert(round_i(static_cast<double>(q)));
+            }
+            std::vector<normalized_speed_t> speeds;
+            if (trimmable)
+            {
+                MPP_ASSERT(P->max_ptg_speeds_to_explore >= 1);
+                const normalized_speed_t inc = 1.0 / P->max_ptg_speeds_to_explore;
+                for (normalized_speed_t s = inc; s < 1.001; s += inc) speeds.push_back(s);
+            }
+            else
+                speeds.push_back(1.0);
+            {
+                // the trajectory straight to the goal, when the PTG can reach it
+                int    goalK = 0;
+                double goalD = 0;
+                if (ptg.inverseMap_WS2TP(relGoal.x, relGoal.y, goalK, goalD, P->grid_resolution_xy))
+                {
+                    ptg_step_t goalStep = 0;
+                    // the reference passes the normalised distance here (TPS_Astar.cpp:658)
+                    if (ptg.getPathStepForDist(static_cast<uint16_t>(goalK), goalD, goalStep))
+                        for (const auto s : speeds)
+                        {
+                            tps.push_back({goalK, goalStep, s});
+                            targetIdx.insert(tps.size() - 1);
+                        }
+                    trajIdxs.insert(goalK);
+                }
+            }
+            for (const auto s : speeds)
+                for (const auto k : trajIdxs)
+                    for (const duration_seconds_t t : P->ptg_sample_timestamps)
+                    {
+                        const ptg_step_t step     = static_cast<ptg_step_t>(round_i(t / ptg_dt));
+                        const size_t     maxSteps = ptg.getPathStepCount(static_cast<uint16_t>(k));
+                        MPP_ASSERT(maxSteps >= 1);
+                        if (step >= maxSteps) continue;
+                        tps.push_back({k, step, s});
+                    }
+
+            const bool onGrid = ptg.kind() == PtgKind::CollisionGrid;
+            holoIndex.clear();
+            for (size_t i = 0; i < tps.size(); i++)
+            {
+                const TpsPoint& tp = tps[i];
+                if (tp.step == 0) continue;  // no motion
+                if (trimmable && tp.speed != ptg.trimmableSpeed_) ptg.trimmableSpeed_ = tp.speed;
+                const uint16_t   k16        = static_cast<uint16_t>(tp.k);
+                const distance_t relTrgDist = ptg.getPathDist(k16, tp.step);
+                const TPose2D    relPose    = ptg.getPathPose(k16, tp.step);
+                const TPose2D    absPose    = from.state.pose + relPose;
+                if (absPose.x < lo.x || absPose.y < lo.y || absPose.phi < lo.phi) continue;
+                if (absPose.x > hi.x - halfCell || absPose.y > hi.y - halfCell || absPose.phi > hi.phi) continue;
+                Candidate c;
+                c.ptgIdx     = ptgIdx;
+                c.k          = tp.k;
+                c.step       = tp.step;
+                c.relTrgDist = relTrgDist;
+                c.relPose    = relPose;
+                c.nc         = nodeGridCoords(absPose);
+                c.initDist   = ptg.initTPObstacleSingle(k16);
+                c.isTarget   = targetIdx.count(i) != 0;
+                c.onGrid     = onGrid;
+                if (onGrid)
+                    c.evalIndex = static_cast<uint32_t>((*columnOffset)[ptgIdx] + tp.k);
+                else
+                {
+                    const auto key = std::make_pair(tp.k, tp.speed);
+                    auto       it  = holoIndex.find(key);
+                    if (it == holoIndex.end())
+                    {
+                        mppb_holo_cand hc;
+                        static_cast<const HolonomicBlend&>(ptg).holoParams(k16, hc);
+                        hc.node      = slot;
+                        hc.ptg_index = static_cast<int32_t>(ptgIdx);
+                        holoCands.push_back(hc);
+                        it = holoIndex.emplace(key, static_cast<uint32_t>(holoCands.size() - 1)).first;
+                    }
+                    c.evalIndex = it->second;
+                }
+                cands.push_back(c);
+            }
+        }
+    }
+
+    // ---- phases C + D: neighbour selection and tentative edges (TPS_Astar.cpp:738-814, 269-341) ----
+    void phaseCD(const float* gridRow, const double* holoOut)
+    {
+        std::unordered_map<NodeCoords, PathToNeighbor, NodeCoordsHash> bestPaths;
+        std::unordered_set<NodeCoords, NodeCoordsHash>                 goalNodeCoords;
+        size_t                                                         lastPtg = static_cast<size_t>(-1);
+        for (const Candidate& c : cands)
+        {
+            if (c.ptgIdx != lastPtg)
+            {
+                goalNodeCoords.clear();  // the reference declares this set inside the per-PTG loop
+                lastPtg = c.ptgIdx;
+            }
+            po.tpsPointsEvaluated++;
+            const double     raw          = c.onGrid ? static_cast<double>(gridRow[c.evalIndex]) : holoOut[c.evalIndex];
+            const distance_t freeDistance = std::min(c.initDist, raw);
+            if (c.relTrgDist >= freeDistance) continue;  // blocked
+            if (c.isTarget)
+                goalNodeCoords.insert(c.nc);
+            else if (goalNodeCoords.count(c.nc) != 0)
+                continue;  // a direct-to-goal path already owns this cell
+            PathToNeighbor& path = bestPaths[c.nc];
+            if (c.relTrgDist < path.ptgDist)
+            {
+                path.ptgDist         = c.relTrgDist;
+                path.ptgIndex        = c.ptgIdx;
+                path.ptgTrajIndex    = c.k;
+                path.relReconstrPose = c.relPose;
+                path.relTrgStep      = c.step;
+                path.ptgDynState     = dynOfPtg[c.ptgIdx];
+            }
+        }
+
+        pending.clear();
+        const TPose2D& lo = in->worldBboxMin, &hi = in->worldBboxMax;
+        for (const auto& kv : bestPaths)  // unordered_map order, as in the reference
+        {
+            const PathToNeighbor& nb = kv.second;
+            if (!nb.ptgIndex.has_value()) continue;
+            ptg_t& ptg = *trs.ptgs.at(*nb.ptgIndex);
+            ptg.updateNavDynamicState(nb.ptgDynState);
+            if (ptg.isSpeedTrimmable()) ptg.trimmableSpeed_ = nb.ptgTrimmableSpeed;
+            const TPose2D  q_i      = current->state.pose + nb.relReconstrPose;
+            const TTwist2D relTwist = ptg.getPathTwist(static_cast<uint16_t>(nb.ptgTrajIndex), nb.relTrgStep);
+            SE2_KinState   x_i;
+            x_i.pose = q_i;
+            (x_i.vel = relTwist).rotate(current->state.pose.phi);
+            if (q_i.x < lo.x || q_i.y < lo.y || q_i.phi < lo.phi) continue;
+            if (q_i.x > hi.x || q_i.y > hi.y || q_i.phi > hi.phi) continue;
+            Node& neighborNode = getOrCreateNodeByPose(x_i);
+            if (neighborNode.visited) continue;
+
+            PendingEdge pe;
+            pe.neighbor = &neighborNode;
+            pe.x_i      = x_i;
+            MoveEdgeSE2_TPS& e     = pe.edge;
+            e.parentId             = current->id.value();
+            e.ptgDist              = nb.ptgDist;
+            e.ptgIndex             = static_cast<int8_t>(*nb.ptgIndex);
+            e.ptgPathIndex         = static_cast<int16_t>(nb.ptgTrajIndex);
+            e.ptgTrimmableSpeed    = nb.ptgTrimmableSpeed;
+            e.ptgFinalGoalRelSpeed = 0;
+            e.ptgFinalRelativeGoal = in->stateGoal.asSE2KinState().pose - current->state.pose;
+            e.stateFrom            = current->state;
+            e.stateTo              = x_i;
+            e.ptgStep              = nb.relTrgStep;
+            edge_interpolated_path(e, trs, nb.relReconstrPose, nb.relTrgStep, P->pathInterpolatedSegments);
+            pending.push_back(std::move(pe));
+        }
+    }
+
+    // ---- phase F: relaxation (TPS_Astar.cpp:343-451) ----
+    // gpuCosts: [pending.size()][numGpuEvals] evaluator values of this query's tentative edges
+    void phaseF(const double* gpuCosts, int numGpuEvals, const std::vector<int>& evalSlot)
+    {
+        auto& tree = po.motionTree;
+        for (size_t i = 0; i < pending.size(); i++)
+        {
+            PendingEdge&     pe      = pending[i];
+            MoveEdgeSE2_TPS& newEdge = pe.edge;
+            Node&            nbNode  = *pe.neighbor;
+            // Planner::cost_path_segment: execution time + evaluators in their registered order
+            cost_t c = newEdge.estimatedExecTime;
+            for (size_t e = 0; e < planner->costEvaluators_.size(); e++)
+            {
+                if (evalSlot[e] >= 0)
+                    c += gpuCosts[i * numGpuEvals + evalSlot[e]];
+                else
+                    c += (*planner->costEvaluators_[e])(newEdge);  // user plugin on the host
+            }
+            newEdge.cost = c;
+            po.edgesCosted++;
+            MPP_ASSERT(newEdge.cost > .0);
+
+            const cost_t tentative_gScore = current->gScore + newEdge.cost;
+            if (tentative_gScore >= nbNode.gScore) continue;
+            const bool hasToRewire = nbNode.cameFrom != nullptr;
+            nbNode.cameFrom        = current;
+            nbNode.gScore          = tentative_gScore;
+            // NOTE: the heuristic is taken at the node's previous state, before it is overwritten
+            const cost_t costToGoal = planner->heuristic(nbNode.state, in->stateGoal);
+            nbNode.fScore           = tentative_gScore + costToGoal;
+            if (!nbNode.pendingInOpenSet)
+            {
+                nbNode.pendingInOpenSet = true;
+                openSet.insert({nbNode.fScore, &nbNode});
+            }
+            nbNode.state = pe.x_i;
+            if (hasToRewire)
+                tree.rewire_node_parent(nbNode.id.value(), newEdge);
+            else
+                tree.insert_node_and_edge(newEdge.parentId, nbNode.id.value(), nbNode.state, newEdge);
+            if (costToGoal < po.bestNodeIdCostToGoal)
+            {
+                po.bestNodeIdCostToGoal = costToGoal;
+                po.bestNodeId           = nbNode.id.value();
+            }
+        }
+        pending.clear();
+
+        const double tNow = seconds_since(t0);
+        if (tNow > P->maximumComputationTime || po.nodesExpanded >= P->maxExpansions)
+        {
+            finish();  // timeout: the best node so far is the result
+            return;
+        }
+        if (planner->progressCallback_ && (tNow - tLastCallback) > planner->progressCallbackCallPeriod_ && po.bestNodeId)
+        {
+            tLastCallback = tNow;
+            auto [foundPath, pathEdges] = tree.backtrack_path(*po.bestNodeId);
+            ProgressCallbackData pcd;
+            pcd.bestCostFromStart = tree.nodes().at(*po.bestNodeId).cost_;
+            pcd.bestCostToGoal    = po.bestNodeIdCostToGoal;
+            pcd.bestFinalNode     = po.bestNodeId;
+            pcd.bestPath          = std::move(pathEdges);
+            pcd.costEvaluators    = &planner->costEvaluators_;
+            pcd.originalPlanInput = in;
+            pcd.tree              = &tree;
+            planner->progressCallback_(pcd);
+        }
+    }
+};
+
+// ======================================================================================================
+TPS_Astar::TPS_Astar(mppb_ctx* ctx) : impl_(new Impl())
+{
+    impl_->self = this;
+    impl_->ctx  = ctx;
+    heuristic   = [this](const SE2_KinState& from, const SE2orR2_KinState& goal) { return default_heuristic(from, goal); };
+}
+TPS_Astar::~TPS_Astar()
+{
+    if (impl_->ownCtx && impl_->ctx) mppb_ctx_destroy(impl_->ctx);
+}
+mppb_ctx* TPS_Astar::context()
+{
+    impl_->ensureContext();
+    return impl_->ctx;
+}
+
+void TPS_Astar::Impl::ensureContext()
+{
+    if (ctx) return;
+    if (mppb_ctx_create(0, nullptr, &ctx) != MPPB_OK)
+        throw std::runtime_error(std::string("TPS_Astar needs a CUDA device: ") + mppb_last_global_error());
+    ownCtx = true;
+}
+
+void TPS_Astar::Impl::uploadPtgs(const TrajectoriesAndRobotShape& trs)
+{
+    std::vector<const ptg_t*> want;
+    for (const auto& p : trs.ptgs) want.push_back(p.get());
+    if (want == uploadedPtgs && static_cast<int>(want.size()) == mppb_num_ptgs(ctx)) return;
+    ck(ctx, mppb_clear_ptgs(ctx));
+    uploadedPtgs.clear();
+    columnOffset.clear();
+    for (size_t i = 0; i < trs.ptgs.size(); i++)
+    {
+        const ptg_t* p = trs.ptgs[i].get();
+        if (auto* dd = dynamic_cast<const DiffDrive_C*>(p))
+        {
+            const mppb_ptg_grid_desc d = dd->gridDesc();
+            ck(ctx, mppb_set_ptg_grid(ctx, static_cast<int>(i), &d));
+        }
+        else if (auto* hb = dynamic_cast<const HolonomicBlend*>(p))
+        {
+            const mppb_ptg_holo_desc d = hb->holoDesc();
+            ck(ctx, mppb_set_ptg_holo(ctx, static_cast<int>(i), &d));
+        }
+        else
+            throw std::runtime_error("TPS_Astar: PTG #" + std::to_string(i) + " is of a kind the GPU library does not know");
+        columnOffset.push_back(mppb_ptg_column_offset(ctx, static_cast<int>(i)));
+    }
+    uploadedPtgs = want;
+}
+
+void TPS_Astar::Impl::uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, const float* box)
+{
+    CloudKey                     key;
+    std::vector<PointCloud::Ptr> clouds;
+    bool                         dynamic = false;
+    for (const auto& os : srcs)
+    {
+        if (!os) continue;
+        clouds.push_back(os->obstacles());
+        dynamic = dynamic || os->dynamic();
+        key.data.push_back(clouds.back() ? clouds.back()->xs.data() : nullptr);
+        key.sizes.push_back(clouds.back() ? clouds.back()->size() : 0);
+    }
+    key.hasBox = box != nullptr;
+    if (box) std::memcpy(key.box, box, sizeof(key.box));
+    if (cloudValid && !dynamic && key == uploadedCloud) return;  // still resident from the previous plan
+    bool first = true;
+    for (const auto& c : clouds)
+    {
+        static const float none = 0;
+        const float*       xs   = c && c->size() ? c->xs.data() : &none;
+        const float*       ys   = c && c->size() ? c->ys.data() : &none;
+        ck(ctx, mppb_set_obstacles_clipped(ctx, xs, ys, c ? c->size() : 0, 0.0, first ? 0 : 1, box));
+        first = false;
+    }
+    if (first) ck(ctx, mppb_set_obstacles_clipped(ctx, nullptr, nullptr, 0, 0.0, 0, box));
+    uploadedCloud = key;
+    cloudValid    = true;
+}
+
+void TPS_Astar::Impl::uploadEvaluators()
+{
+    ck(ctx, mppb_clear_evaluators(ctx));
+    evalSlot.assign(self->costEvaluators_.size(), -1);
+    numGpuEvals = 0;
+    for (size_t e = 0; e < self->costEvaluators_.size(); e++)
+    {
+        const CostEvaluator* ce = self->costEvaluators_[e].get();
+        MPP_ASSERT(ce);
+        if (numGpuEvals >= MPPB_MAX_EVALUATORS) continue;  // the rest runs as host plugins
+        if (auto* cm = dynamic_cast<const CostEvaluatorCostMap*>(ce))
+        {
+            mppb_costmap_desc d{cm->x_min, cm->y_min, cm->params_.resolution, cm->size_x, cm->size_y, cm->cells.data(),
+                                cm->params_.useAverageOfPath ? 1 : 0};
+            ck(ctx, mppb_set_costmap(ctx, numGpuEvals, &d));
+            evalSlot[e] = numGpuEvals++;
+        }
+        else if (auto* wp = dynamic_cast<const CostEvaluatorPreferredWaypoint*>(ce))
+        {
+            std::vector<double> xs, ys;
+            for (const auto& w : wp->waypoints_)
+            {
+                xs.push_back(w.x);
+                ys.push_back(w.y);
+            }
+            ck(ctx, mppb_set_waypoints(ctx, numGpuEvals, xs.data(), ys.data(), xs.size(), wp->params_.waypointInfluenceRadius,
+                                       wp->params_.costScale, wp->params_.useAverageOfPath ? 1 : 0));
+            evalSlot[e] = numGpuEvals++;
+        }
+    }
+}
+
+std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads)
+{
+    ensureContext();
+    self->lastGpuStats = GpuStats();
+    const size_t Q     = ins.size();
+    std::vector<PlannerOutput> outs(Q);
+    if (Q == 0) return outs;
+    for (const PlannerInput* in : ins)
+    {
+        MPP_ASSERT(in->ptgs.initialized());
+        if (in->ptgs.ptgs.size() != ins[0]->ptgs.ptgs.size()) throw std::runtime_error("plan_batch: all queries must use the same PTG set");
+        for (size_t i = 0; i < in->ptgs.ptgs.size(); i++)
+            if (in->ptgs.ptgs[i].get() != ins[0]->ptgs.ptgs[i].get())
+                throw std::runtime_error("plan_batch: all queries must share the same PTG objects");
+        if (sharedCloud && in->obstacles != ins[0]->obstacles)
+            throw std::runtime_error("plan_batch: all queries must share the same obstacle sources");
+    }
+    uploadPtgs(ins[0]->ptgs);
+    uploadEvaluators();
+
+    std::vector<std::unique_ptr<Query>> qs(Q);
+    for (size_t i = 0; i < Q; i++)
+    {
+        qs[i]               = std::make_unique<Query>();
+        Query& q            = *qs[i];
+        q.planner           = self;
+        q.P                 = &self->params_;
+        q.in                = ins[i];
+        q.columnOffset      = &columnOffset;
+        q.trs               = ins[i]->ptgs;
+        if (Q > 1)  // interleaved queries must not share mutable PTG state
+            for (auto& p : q.trs.ptgs) p = std::shared_ptr<ptg_t>(p->cloneForQuery());
+        q.start();
+    }
+    // obstacles: one query -> clipped to its world box at upload (ObstacleSource::apply_clipping_box);
+    // many queries -> the shared cloud stays whole and each node carries its query's box
+    if (sharedCloud)
+        uploadCloud(ins[0]->obstacles, nullptr);
+    else
+        uploadCloud(ins[0]->obstacles, qs[0]->box);
+
+    const int       hw = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+    Workers         pool(Q == 1 ? 1 : (nThreads > 0 ? nThreads : hw));
+    const int       cols = mppb_total_paths(ctx);
+    std::vector<size_t> active, holoBase, edgeBase;
+    active.reserve(Q);
+    GpuStats& st = self->lastGpuStats;
+
+    for (;;)
+    {
+        // ---- pop: which queries expand a node this round ----
+        active.clear();
+        for (size_t i = 0; i < Q; i++)
+            if (qs[i]->popNext()) active.push_back(i);
+        if (active.empty()) break;
+        const size_t A = active.size();
+
+        // ---- phase A ----
+        pool.run(A, [&](size_t a) { qs[active[a]]->phaseA(static_cast<int>(a)); });
+
+        // ---- phase B: one collision batch for all current nodes ----
+        double* poses = hPoses.reserve(3 * A);
+        float*  boxes = sharedCloud ? hBoxes.reserve(4 * A) : nullptr;
+        holoBase.assign(A + 1, 0);
+        for (size_t a = 0; a < A; a++)
+        {
+            const Query& q   = *qs[active[a]];
+            poses[3 * a + 0] = q.current->state.pose.x;
+            poses[3 * a + 1] = q.current->state.pose.y;
+            poses[3 * a + 2] = q.current->state.pose.phi;
+            if (boxes) std::memcpy(boxes + 4 * a, q.box, sizeof(q.box));
+            holoBase[a + 1] = holoBase[a] + q.holoCands.size();
+        }
+        const auto tB   = Clock::now();
+        float*     rows = nullptr;
+        if (cols > 0)
+        {
+            rows = hRows.reserve(static_cast<size_t>(cols) * A);
+            ck(ctx, mppb_eval_nodes_boxed(ctx, A, poses, boxes, qs[active[0]]->MAX_XY_DIST, rows));
+        }
+        double* holoOut = nullptr;
+        if (holoBase[A] > 0)
+        {
+            mppb_holo_cand* hc = hCands.reserve(holoBase[A]);
+            for (size_t a = 0; a < A; a++)
+            {
+                const auto& v = qs[active[a]]->holoCands;
+                if (!v.empty()) std::memcpy(hc + holoBase[a], v.data(), v.size() * sizeof(mppb_holo_cand));
+            }
+            holoOut = hHoloOut.reserve(holoBase[A]);
+            ck(ctx, mppb_eval_holo_candidates_boxed(ctx, A, poses, boxes, holoBase[A], hc, qs[active[0]]->MAX_XY_DIST, holoOut));
+        }
+        st.gpuSeconds += seconds_since(tB);
+        st.collisionBatches++;
+        st.nodesEvaluated += A;
+        st.holoCandidates += holoBase[A];
+
+        // ---- phases C + D ----
+        pool.run(A, [&](size_t a) {
+            qs[active[a]]->phaseCD(rows ? rows + static_cast<size_t>(cols) * a : nullptr, holoOut ? holoOut + holoBase[a] : nullptr);
+        });
+
+        // ---- phase E: one cost batch for all tentative edges ----
+        edgeBase.assign(A + 1, 0);
+        for (size_t a = 0; a < A; a++) edgeBase[a + 1] = edgeBase[a] + qs[active[a]]->pending.size();
+        const size_t E     = edgeBase[A];
+        double*      costs = nullptr;
+        if (E > 0 && numGpuEvals > 0)
+        {
+            size_t nSamples = 0;
+            for (size_t a = 0; a < A; a++)
+                for (const auto& pe : qs[active[a]]->pending) nSamples += pe.edge.interpolatedPath.size();
+            double*   from = hFrom.reserve(3 * E);
+            uint32_t* off  = hOffsets.reserve(E + 1);
+            double*   rel  = hRel.reserve(2 * nSamples);
+            costs          = hCost.reserve(E * numGpuEvals);
+            size_t e = 0, s = 0;
+            off[0] = 0;
+            for (size_t a = 0; a < A; a++)
+                for (const auto& pe : qs[active[a]]->pending)
+                {
+                    from[3 * e + 0] = pe.edge.stateFrom.pose.x;
+                    from[3 * e + 1] = pe.edge.stateFrom.pose.y;
+                    from[3 * e + 2] = pe.edge.stateFrom.pose.phi;
+                    for (const auto& kv : pe.edge.interpolatedPath)
+                    {
+                        rel[2 * s + 0] = kv.second.x;
+                        rel[2 * s + 1] = kv.second.y;
+                        s++;
+                    }
+                    off[++e] = static_cast<uint32_t>(s);
+                }
+            const auto tE = Clock::now();
+            ck(ctx, mppb_eval_edge_costs(ctx, E, from, off, rel, costs));
+            st.gpuSeconds += seconds_since(tE);
+            st.costBatches++;
+            st.edgesCosted += E;
+        }
+
+        // ---- phase F ----
+        pool.run(A, [&](size_t a) {
+            qs[active[a]]->phaseF(costs ? costs + edgeBase[a] * numGpuEvals : nullptr, numGpuEvals, evalSlot);
+        });
+    }
+    for (size_t i = 0; i < Q; i++) outs[i] = std::move(qs[i]->po);
+    return outs;
+}
+
+PlannerOutput TPS_Astar::plan(const PlannerInput& in)
+{
+    std::vector<const PlannerInput*> v{&in};
+    return std::move(impl_->run(v, false, 1)[0]);
+}
+
+std::vector<PlannerOutput> TPS_Astar::plan_batch(const std::vector<PlannerInput>& ins, int nThreads)
+{
+    std::vector<const PlannerInput*> v;
+    for (const auto& i : ins) v.push_back(&i);
+    return impl_->run(v, true, nThreads);
+}
+
+// ---- heuristics (TPS_Astar.cpp:477-537) --------------------------------------------------------------
+cost_t TPS_Astar::default_heuristic_SE2(const SE2_KinState& from, const TPose2D& goal) const
+{
+    const TPose2D relPose     = goal - from.pose;
+    const double  distSE2     = relPose.norm() + params_.SE2_metricAngleWeight * std::abs(relPose.phi);
+    const double  distHeading = (relPose.norm() < 0.1) ? 0.0 : std::abs(ang_distance(std::atan2(relPose.y, relPose.x), from.pose.phi));
+    return distSE2 + params_.heuristic_heading_weight * distHeading;
+}
+cost_t TPS_Astar::default_heuristic_R2(const SE2_KinState& from, const TPoint2D& goal) const
+{
+    // `goal - from.pose` with a point goal: plain vector difference (MRPT ambiguity)
+    const double dx = from.pose.x - goal.x, dy = from.pose.y - goal.y;
+    const double distR2 = std::sqrt(dx * dx + dy * dy);
+    const double rx = goal.x - from.pose.x, ry = goal.y - from.pose.y;
+    const double distHeading = (std::sqrt(rx * rx + ry * ry) < 0.1) ? 0.0 : std::abs(ang_distance(std::atan2(ry, rx), from.pose.phi));
+    return distR2 + params_.heuristic_heading_weight * distHeading;
+}
+cost_t TPS_Astar::default_heuristic(const SE2_KinState& from, const SE2orR2_KinState& goal) const
+{
+    if (goal.state.isPoint()) return default_heuristic_R2(from, goal.state.point());
+    if (goal.state.isPose()) return default_heuristic_SE2(from, goal.state.pose());
+    throw std::runtime_error("Goal of unknown type?");
+}
+
+// ---- parameters (TPS_Astar.cpp:26-79) ------------------------------------------------------------------
+void TPS_Astar_Parameters::load_from_yaml(const Yaml& c)
+{
+    MPP_ASSERT(c.isMap());
+    grid_resolution_xy              = c.getDouble("grid_resolution_xy");
+    grid_resolution_yaw             = c.getDouble("grid_resolution_yaw") * M_PI / 180.0;
+    SE2_metricAngleWeight           = c.getDouble("SE2_metricAngleWeight");
+    max_ptg_trajectories_to_explore = static_cast<uint32_t>(c.getDouble("max_ptg_trajectories_to_explore"));
+    max_ptg_speeds_to_explore       = static_cast<uint32_t>(c.getDouble("max_ptg_speeds_to_explore"));
+    ptg_sample_timestamps           = c.getDoubleVector("ptg_sample_timestamps");
+    pathInterpolatedSegments        = c.getOrDefault<size_t>("pathInterpolatedSegments", pathInterpolatedSegments);
+    heuristic_heading_weight        = c.getOrDefault<double>("heuristic_heading_weight", heuristic_heading_weight);
+    maximumComputationTime          = c.getOrDefault<double>("maximumComputationTime", maximumComputationTime);
+    if (c.has("maxExpansions")) maxExpansions = static_cast<size_t>(c.getDouble("maxExpansions"));
+}
+TPS_Astar_Parameters TPS_Astar_Parameters::FromYAML(const Yaml& c)
+{
+    TPS_Astar_Parameters p;
+    p.load_from_yaml(c);
+    return p;
+}
+std::string TPS_Astar_Parameters::as_yaml_text() const
+{
+    std::stringstream s;
+    s << "SE2_metricAngleWeight: " << SE2_metricAngleWeight << "\n"
+      << "pathInterpolatedSegments: " << pathInterpolatedSegments << "\n"
+      << "grid_resolution_xy: " << grid_resolution_xy << "\n"
+      << "heuristic_heading_weight: " << heuristic_heading_weight << "\n"
+      << "max_ptg_trajectories_to_explore: " << max_ptg_trajectories_to_explore << "\n"
+      << "max_ptg_speeds_to_explore: " << max_ptg_speeds_to_explore << "\n"
+      << "grid_resolution_yaw: " << grid_resolution_yaw * 180.0 / M_PI << "\n"
+      << "maximumComputationTime: " << maximumComputationTime << "\n"
+      << "ptg_sample_timestamps: [";
+    for (size_t i = 0; i < ptg_sample_timestamps.size(); i++) s << (i ? ", " : "") << ptg_sample_timestamps[i];
+    s << "]\n";
+    return s.str();
+}
+
+}  // namespace mpp

@@ -1,0 +1,315 @@
+// C ABI over the mpp::TPS_Astar mirror (see include/mppb.h, section "planner").
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../../include/mppb.h"
+#include "host_internal.h"
+
+struct mppb_planner
+{
+    mppb_ctx*                                    ctx = nullptr;
+    std::unique_ptr<mpp::TPS_Astar>              planner;
+    mpp::TrajectoriesAndRobotShape               trs;
+    std::vector<mpp::ObstacleSource::Ptr>        obstacles;
+    std::vector<mpp::PlannerInput>               inputs;
+    std::vector<mpp::PlannerOutput>              outputs;
+    std::vector<mpp::MotionPrimitivesTreeSE2::path_t>          paths;
+    std::vector<mpp::MotionPrimitivesTreeSE2::edge_sequence_t> pathEdges;
+    std::string                                  lastError, text;
+};
+
+namespace
+{
+thread_local std::string g_plannerErr;
+template <class F>
+int guarded(mppb_planner* p, F&& fn)
+{
+    try
+    {
+        fn();
+        return MPPB_OK;
+    }
+    catch (const std::exception& e)
+    {
+        if (p)
+            p->lastError = e.what();
+        else
+            g_plannerErr = e.what();
+        return MPPB_ERR_STATE;
+    }
+}
+void require(bool cond, const char* msg)
+{
+    if (!cond) throw std::runtime_error(msg);
+}
+}  // namespace
+
+extern "C" {
+
+int mppb_planner_create(mppb_ctx* ctx, mppb_planner** out)
+{
+    if (!ctx || !out) return MPPB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(nullptr, [&]() {
+        auto* p    = new mppb_planner();
+        p->ctx     = ctx;
+        p->planner = std::make_unique<mpp::TPS_Astar>(ctx);
+        *out       = p;
+    });
+}
+void        mppb_planner_destroy(mppb_planner* p) { delete p; }
+const char* mppb_planner_last_error(const mppb_planner* p) { return p ? p->lastError.c_str() : g_plannerErr.c_str(); }
+
+int mppb_planner_set_params(mppb_planner* p, const mppb_astar_params* a)
+{
+    if (!p || !a) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        require(a->num_timestamps > 0 && a->ptg_sample_timestamps, "ptg_sample_timestamps is required");
+        auto& q                           = p->planner->params_;
+        q.grid_resolution_xy              = a->grid_resolution_xy;
+        q.grid_resolution_yaw             = a->grid_resolution_yaw;
+        q.SE2_metricAngleWeight           = a->SE2_metricAngleWeight;
+        q.heuristic_heading_weight        = a->heuristic_heading_weight;
+        q.max_ptg_trajectories_to_explore = a->max_ptg_trajectories_to_explore;
+        q.max_ptg_speeds_to_explore       = a->max_ptg_speeds_to_explore;
+        q.pathInterpolatedSegments        = a->path_interpolated_segments;
+        q.maximumComputationTime =
+            a->maximum_computation_time > 0 ? a->maximum_computation_time : std::numeric_limits<double>::max();
+        q.maxExpansions = a->max_expansions ? a->max_expansions : std::numeric_limits<size_t>::max();
+        q.ptg_sample_timestamps.assign(a->ptg_sample_timestamps, a->ptg_sample_timestamps + a->num_timestamps);
+    });
+}
+
+int mppb_planner_add_ptg(mppb_planner* p, mppb_ptg* ptg)
+{
+    if (!p || !ptg) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        auto list = p->trs.ptgs;
+        list.emplace_back(ptg->obj.get(), [](mpp::ptg_t*) {});  // borrowed: the PTG object outlives the planner
+        p->trs.initFromPtgs(std::move(list));
+    });
+}
+
+int mppb_planner_add_obstacles(mppb_planner* p, const float* xs, const float* ys, size_t n)
+{
+    if (!p || (n && (!xs || !ys))) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        auto pc = std::make_shared<mpp::PointCloud>();
+        pc->xs.assign(xs, xs + n);
+        pc->ys.assign(ys, ys + n);
+        p->obstacles.push_back(mpp::ObstacleSource::FromStaticPointcloud(pc));
+    });
+}
+
+int mppb_planner_add_costmap(mppb_planner* p, const float* xs, const float* ys, size_t n, double resolution,
+                             double preferred_clearance, double max_cost, int use_average, double max_radius_from_robot,
+                             const double* robot_pose_xyphi)
+{
+    if (!p || !xs || !ys) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        mpp::PointCloud pc;
+        pc.xs.assign(xs, xs + n);
+        pc.ys.assign(ys, ys + n);
+        mpp::CostEvaluatorCostMap::Parameters q;
+        q.resolution                 = resolution;
+        q.preferredClearanceDistance = preferred_clearance;
+        q.maxCost                    = max_cost;
+        q.useAverageOfPath           = use_average != 0;
+        q.maxRadiusFromRobot         = max_radius_from_robot;
+        std::optional<mpp::TPose2D> pose;
+        if (robot_pose_xyphi) pose = mpp::TPose2D(robot_pose_xyphi[0], robot_pose_xyphi[1], robot_pose_xyphi[2]);
+        p->planner->costEvaluators_.push_back(mpp::CostEvaluatorCostMap::FromStaticPointObstacles(p->ctx, pc, q, pose));
+    });
+}
+
+int mppb_planner_costmap_cells(mppb_planner* p, int evaluator, double* info5, double* cells)
+{
+    if (!p) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        require(evaluator >= 0 && evaluator < static_cast<int>(p->planner->costEvaluators_.size()), "bad evaluator index");
+        auto* cm = dynamic_cast<mpp::CostEvaluatorCostMap*>(p->planner->costEvaluators_[evaluator].get());
+        require(cm != nullptr, "evaluator is not a costmap");
+        if (info5)
+        {
+            info5[0] = cm->x_min;
+            info5[1] = cm->y_min;
+            info5[2] = cm->params_.resolution;
+            info5[3] = cm->size_x;
+            info5[4] = cm->size_y;
+        }
+        if (cells) std::memcpy(cells, cm->cells.data(), cm->cells.size() * sizeof(double));
+    });
+}
+
+int mppb_planner_add_waypoints(mppb_planner* p, const double* xs, const double* ys, size_t n, double influence_radius,
+                               double cost_scale, int use_average)
+{
+    if (!p || (n && (!xs || !ys))) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        auto ev                             = std::make_shared<mpp::CostEvaluatorPreferredWaypoint>(p->ctx);
+        ev->params_.waypointInfluenceRadius = influence_radius;
+        ev->params_.costScale               = cost_scale;
+        ev->params_.useAverageOfPath        = use_average != 0;
+        std::vector<mpp::TPoint2D> pts(n);
+        for (size_t i = 0; i < n; i++) pts[i] = {xs[i], ys[i]};
+        ev->setPreferredWaypoints(pts);
+        p->planner->costEvaluators_.push_back(ev);
+    });
+}
+
+int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* qs, int n_threads, mppb_plan_result* res)
+{
+    if (!p || !qs || !res || n_queries == 0) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        p->inputs.assign(n_queries, mpp::PlannerInput());
+        for (size_t i = 0; i < n_queries; i++)
+        {
+            const mppb_plan_query& q  = qs[i];
+            mpp::PlannerInput&     in = p->inputs[i];
+            in.stateStart.pose        = mpp::TPose2D(q.start[0], q.start[1], q.start[2]);
+            in.stateStart.vel         = mpp::TTwist2D(q.start[3], q.start[4], q.start[5]);
+            if (q.goal_is_point)
+                in.stateGoal.state = mpp::PoseOrPoint(mpp::TPoint2D{q.goal[0], q.goal[1]});
+            else
+                in.stateGoal.state = mpp::PoseOrPoint(mpp::TPose2D(q.goal[0], q.goal[1], q.goal[2]));
+            in.stateGoal.vel = mpp::TTwist2D(q.goal[3], q.goal[4], q.goal[5]);
+            in.worldBboxMin  = mpp::TPose2D(q.bbox_min[0], q.bbox_min[1], q.bbox_min[2]);
+            in.worldBboxMax  = mpp::TPose2D(q.bbox_max[0], q.bbox_max[1], q.bbox_max[2]);
+            in.obstacles     = p->obstacles;
+            in.ptgs          = p->trs;
+        }
+        if (n_queries == 1)
+        {
+            p->outputs.clear();
+            p->outputs.push_back(p->planner->plan(p->inputs[0]));
+        }
+        else
+            p->outputs = p->planner->plan_batch(p->inputs, n_threads);
+        p->paths.assign(n_queries, {});
+        p->pathEdges.assign(n_queries, {});
+        for (size_t i = 0; i < n_queries; i++)
+        {
+            const mpp::PlannerOutput& o = p->outputs[i];
+            if (o.bestNodeId) std::tie(p->paths[i], p->pathEdges[i]) = o.motionTree.backtrack_path(*o.bestNodeId);
+            mppb_plan_result& r = res[i];
+            r.success           = o.success ? 1 : 0;
+            r.path_cost         = o.pathCost;
+            r.tree_nodes        = o.motionTree.nodes().size();
+            r.tree_parents      = o.motionTree.edges_to_children.size();
+            r.nodes_expanded    = o.nodesExpanded;
+            r.tps_points        = o.tpsPointsEvaluated;
+            r.edges_costed      = o.edgesCosted;
+            r.best_node         = o.bestNodeId ? static_cast<int64_t>(*o.bestNodeId) : -1;
+            r.goal_node         = o.goalNodeId ? static_cast<int64_t>(*o.goalNodeId) : -1;
+            r.computation_time  = o.computationTime;
+            r.best_cost_to_goal = o.bestNodeIdCostToGoal;
+            r.path_len          = static_cast<uint32_t>(p->paths[i].size());
+        }
+    });
+}
+
+int mppb_planner_refine(mppb_planner* p, size_t query)
+{
+    if (!p) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        require(query < p->outputs.size(), "query index out of range");
+        mpp::refine_trajectory(p->paths[query], p->pathEdges[query], p->inputs[query].ptgs);
+    });
+}
+
+int mppb_planner_path(mppb_planner* p, size_t query, double* nodes, double* edges)
+{
+    if (!p) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        require(query < p->outputs.size(), "query index out of range");
+        size_t i = 0;
+        if (nodes)
+            for (const auto& n : p->paths[query])
+            {
+                double* o = nodes + 8 * i++;
+                o[0]      = static_cast<double>(n.nodeID_);
+                o[1]      = n.pose.x;
+                o[2]      = n.pose.y;
+                o[3]      = n.pose.phi;
+                o[4]      = n.vel.vx;
+                o[5]      = n.vel.vy;
+                o[6]      = n.vel.omega;
+                o[7]      = n.cost_;
+            }
+        i = 0;
+        if (edges)
+            for (const mpp::MoveEdgeSE2_TPS* e : p->pathEdges[query])
+            {
+                double* o = edges + 8 * i++;
+                o[0]      = e->ptgIndex;
+                o[1]      = e->ptgPathIndex;
+                o[2]      = e->ptgStep;
+                o[3]      = e->ptgDist;
+                o[4]      = e->cost;
+                o[5]      = e->estimatedExecTime;
+                o[6]      = e->ptgTrimmableSpeed;
+                o[7]      = static_cast<double>(e->interpolatedPath.size());
+            }
+    });
+}
+
+int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t cap)
+{
+    if (!p || query >= p->outputs.size()) return -1;
+    int64_t n  = 0;
+    const int rc = guarded(p, [&]() {
+        const auto& tree = p->outputs[query].motionTree;
+        for (const auto& kv : tree.nodes())
+        {
+            if (out && n < cap)
+            {
+                double* o = out + 7 * n;
+                o[0]      = static_cast<double>(kv.first);
+                o[1]      = kv.second.parentID_ ? static_cast<double>(*kv.second.parentID_) : -1;
+                o[2]      = kv.second.pose.x;
+                o[3]      = kv.second.pose.y;
+                o[4]      = kv.second.pose.phi;
+                o[5]      = kv.second.cost_;
+                o[6]      = kv.second.parentID_ ? tree.edge_to_parent(kv.first).cost : 0;
+            }
+            n++;
+        }
+    });
+    return rc == MPPB_OK ? n : -1;
+}
+
+int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample_period, char* buf, int64_t cap)
+{
+    if (!p || query >= p->outputs.size()) return -1;
+    const int rc = guarded(p, [&]() {
+        auto traj = mpp::plan_to_trajectory(p->pathEdges[query], p->inputs[query].ptgs, sample_period);
+        // the trajectory is relative to the start pose; path-planner-cli re-bases it (path-planner-cli.cpp:396-399)
+        const mpp::TPose2D start = p->outputs[query].originalInput.stateStart.pose;
+        for (auto& kv : traj) kv.second.state.pose = start + kv.second.state.pose;
+        p->text = mpp::trajectory_as_text(traj);
+    });
+    if (rc != MPPB_OK) return -1;
+    if (buf && cap > 0)
+    {
+        const int64_t m = std::min<int64_t>(cap - 1, static_cast<int64_t>(p->text.size()));
+        std::memcpy(buf, p->text.data(), m);
+        buf[m] = 0;
+    }
+    return static_cast<int64_t>(p->text.size());
+}
+
+int mppb_planner_gpu_stats(const mppb_planner* p, double* out6)
+{
+    if (!p || !out6) return MPPB_ERR_INVALID_ARG;
+    const auto& s = p->planner->lastGpuStats;
+    out6[0]       = static_cast<double>(s.collisionBatches);
+    out6[1]       = static_cast<double>(s.costBatches);
+    out6[2]       = static_cast<double>(s.nodesEvaluated);
+    out6[3]       = static_cast<double>(s.holoCandidates);
+    out6[4]       = static_cast<double>(s.edgesCosted);
+    out6[5]       = s.gpuSeconds;
+    return MPPB_OK;
+}
+
+}  // extern "C"

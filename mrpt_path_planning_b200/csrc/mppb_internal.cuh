@@ -234,7 +234,7 @@ struct mppb_ctx
 
     // staging for the host entry points
     mppb::PinnedBuf hNodes, hOut, hStage;
-    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3;
+    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes;
 };
 
 namespace mppb
@@ -251,9 +251,10 @@ void set_global_error(const std::string& msg);
 
 // kernels / launchers implemented in the .cu files
 int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize);
-int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, float* dOut);
-int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes, double clip,
-                      double* dOut);
+int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
+                      float* dOut);
+int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
+                      const float* dBoxes, double clip, double* dOut);
 int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const uint32_t* dOffsets, const double* dRel,
                       double* dOut);
 int launch_costmap_d2(mppb_ctx* ctx, const CloudStore& cs, double xmin, double ymin, double res, int nx, int ny,

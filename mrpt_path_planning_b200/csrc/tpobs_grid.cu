@@ -94,9 +94,14 @@ __device__ __forceinline__ void apply_inside_cell(const GridGroupDev& G, uint32_
     }
 }
 
+// HAS_BOX: obstacle points outside the node's own world box (float compare, inclusive bounds:
+// ObstacleSource.cpp:29-40) are ignored — the per-query clipping of independent planning queries
+// that share one resident cloud.
+template <bool HAS_BOX>
 __global__ void __launch_bounds__(kThreads, 8)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
-                      int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */, double clip,
+                      int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
+                      const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
                       float* __restrict__ out)
 {
     extern __shared__ unsigned smem[];
@@ -112,6 +117,9 @@ __global__ void __launch_bounds__(kThreads, 8)
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double x0 = nodes[4 * node + 0], y0 = nodes[4 * node + 1];
     const double c = nodes[4 * node + 2], s = nodes[4 * node + 3];
+
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HAS_BOX) box = boxes[node];
 
     for (int i = threadIdx.x; i < totalPaths; i += kThreads) smin[i] = kInfBits;
 
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(kThreads, 8)
                     int row = chunkRow[ch];
                     while (f >= rowPrefix[row + 1]) row++;  // f < total guarantees termination
                     const float2 g  = bins.pts[rowBeg[row] + (f - rowPrefix[row])];
+                    if (HAS_BOX && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) continue;
                     const double gx = g.x, gy = g.y;
                     if (clipped_out(gx, x0, clip) || clipped_out(gy, y0, clip)) continue;
                     // composePoint with the inverse pose, reference operation order, no FMA
@@ -278,7 +287,8 @@ __global__ void __launch_bounds__(kThreads, 8)
 }
 }  // namespace
 
-int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, float* dOut)
+int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
+                      float* dOut)
 {
     if (nNodes == 0) return MPPB_OK;
     if (ctx->grids.empty()) return fail(ctx, MPPB_ERR_STATE, "no PTG tables set (mppb_set_ptg_grid)");
@@ -290,11 +300,20 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double
     if (smem > 200 * 1024)
         return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
     if (smem > 48 * 1024)
-        MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    {
+        MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-    tpobs_grid_kernel<<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
-        ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
-        static_cast<int>(words), dNodes, clip, dOut);
+        MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+    }
+    if (dBoxes)
+        tpobs_grid_kernel<true><<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
+            ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
+            static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut);
+    else
+        tpobs_grid_kernel<false><<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
+            ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
+            static_cast<int>(words), dNodes, nullptr, clip, dOut);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;

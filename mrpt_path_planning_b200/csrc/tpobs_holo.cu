@@ -146,7 +146,8 @@ __device__ __forceinline__ double update_tp_obstacle(const CandConsts& q, double
 
 __global__ void __launch_bounds__(kThreads)
     tpobs_holo_kernel(CloudBins bins, const HoloPtgDev* __restrict__ ptgs, const mppb_holo_cand* __restrict__ cands,
-                      int nCands, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */, double clip,
+                      int nCands, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
+                      const float4* __restrict__ boxes /* NULL or [n] minx,miny,maxx,maxy */, double clip,
                       double* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
@@ -179,6 +180,10 @@ __global__ void __launch_bounds__(kThreads)
     const double ix = -x0 * c - y0 * s;  // CPose2D unary minus
     const double iy = x0 * s - y0 * c;
 
+    // optional per-node world box (ObstacleSource.cpp:29-40: float compare, inclusive bounds)
+    const bool   hasBox = boxes != nullptr;
+    const float4 box    = hasBox ? boxes[cd.node] : make_float4(0.f, 0.f, 0.f, 0.f);
+
     double best = CUDART_INF;
     if (bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0)
     {
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(kThreads)
             for (uint32_t p = beg + lane; p < end; p += 32)
             {
                 const float2 g  = bins.pts[p];
+                if (hasBox && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) continue;
                 const double gx = g.x, gy = g.y;
                 // transform_pc_square_clipping.cpp:30-31
                 if (fabs(gx - x0) > clip || fabs(gy - y0) > clip) continue;
@@ -214,15 +220,16 @@ __global__ void __launch_bounds__(kThreads)
 }
 }  // namespace
 
-int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes, double clip,
-                      double* dOut)
+int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
+                      const float* dBoxes, double clip, double* dOut)
 {
     if (nCands == 0) return MPPB_OK;
     if (ctx->holos.empty()) return fail(ctx, MPPB_ERR_STATE, "no HolonomicBlend PTG set (mppb_set_ptg_holo)");
     if (nCands > 0x3fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many candidates in one batch");
     const unsigned blocks = static_cast<unsigned>((nCands + kWarps - 1) / kWarps);
     tpobs_holo_kernel<<<blocks, kThreads, 0, ctx->stream>>>(ctx->bins, ctx->holoDescs.as<HoloPtgDev>(), dCands,
-                                                            static_cast<int>(nCands), dNodes, clip, dOut);
+                                                            static_cast<int>(nCands), dNodes,
+                                                            reinterpret_cast<const float4*>(dBoxes), clip, dOut);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;
