@@ -28,6 +28,9 @@ PER_FILE_FLAGS = {
     "edge_cost.cu": ["-fmad=false"],
 }
 OBJ_DIR = os.path.join(HERE, "lib", "obj")
+BIN_DIR = os.path.join(HERE, "bin")
+CLI_PATH = os.path.join(BIN_DIR, "path-planner-cli")
+CLI_SRC = os.path.join(CSRC, "apps", "path_planner_cli.cpp")
 
 
 def sources():
@@ -40,11 +43,12 @@ def _deps():
     d = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "host", "*.h"))
     d.append(os.path.join(HERE, "..", "include", "mppb.h"))
     d.append(os.path.abspath(__file__))
+    d.append(CLI_SRC)
     return d
 
 
 def needs_build():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(CLI_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
     return any(os.path.getmtime(f) > t for f in _deps() if os.path.exists(f))
@@ -85,6 +89,14 @@ def build_library(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("nvcc failed linking libmpp_b200.so")
+    # the headless path-planner-cli front end, linked against the library next to it
+    os.makedirs(BIN_DIR, exist_ok=True)
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-o", CLI_PATH, CLI_SRC,
+                        "-L" + LIB_DIR, "-lmpp_b200", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building path-planner-cli")
     return LIB_PATH
 
 
