@@ -162,6 +162,111 @@ def run_reference(args, rank, world):
     }))
 
 
+C4_MAX_EXPANSIONS = 400
+WAYPOINTS01 = ([3.0, 5.0, 9.0, 20.0, 26.0], [2.0, 5.0, 8.0, 7.0, 3.0])  # share/mvsim-demo-waypoints01.yaml targets
+
+
+def demo_inputs():
+    """Configs C1/C2: the reference's README command line (obstacles_01.txt, start [0.5 0 0], goal [4 2.5 45])."""
+    obs = np.loadtxt(os.path.join(ROOT, "tests", "golden", "obstacles_01.txt")).astype(np.float32)
+    xs, ys = obs[:, 0].copy(), obs[:, 1].copy()
+    start, goal = [0.5, 0, 0, 0, 0, 0], [4, 2.5, np.deg2rad(45.0), 0, 0, 0]
+    lo = np.minimum(np.minimum(obs.min(0), np.float32([0.5 - 2, 0 - 2])), np.float32([4 - 2, 2.5 - 2]))
+    hi = np.maximum(np.maximum(obs.max(0), np.float32([0.5 + 2, 0 + 2])), np.float32([4 + 2, 2.5 + 2]))
+    return xs, ys, start, goal, [float(lo[0]), float(lo[1]), -np.pi], [float(hi[0]), float(hi[1]), np.pi]
+
+
+def planner_bench(ctx_factory, rank, world, args, with_cpu):
+    """Planner-level numbers of BASELINE.json's metric: TPS_Astar plan ms on C1/C2 (single query, latency) and
+    plans/s on a C4-shaped batch (independent queries in lock-step, sharded by query id across ranks)."""
+    from mrpt_path_planning_b200 import capi
+
+    out = {}
+    xs, ys, start, goal, lo, hi = demo_inputs()
+    ctx = ctx_factory()
+    if with_cpu:
+        from oracle import orc
+    for name, mk_ptgs, wps in (("c1_holonomic", capi.holonomic_ptgs, False), ("c2_ackermann", capi.ackermann_ptgs, True)):
+        ptgs = mk_ptgs()
+        pl = capi.Planner(ctx, ptgs, wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
+        pl.add_obstacles(xs, ys)
+        t0 = time.perf_counter()
+        pl.add_costmap(xs, ys, 0.04, 0.5, 4.0, False, 15.0, start[:3])
+        t_cm = time.perf_counter() - t0
+        if wps:
+            pl.add_waypoints(WAYPOINTS01[0], WAYPOINTS01[1], 1.5, 0.5, True)
+        pl.plan(start, goal, lo, hi)  # warm-up: staging buffers, table upload
+        ts = []
+        for _ in range(5):
+            r = pl.plan(start, goal, lo, hi)
+            ts.append(r["time_s"])
+        st = pl.gpu_stats()
+        d = {"plan_ms": 1e3 * min(ts), "success": bool(r["success"]), "nodes_expanded": int(r["expanded"]),
+             "tps_points": int(r["tps_points"]), "edges_costed": int(r["edges_costed"]),
+             "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_ms": 1e3 * st["gpu_seconds"],
+             "costmap_build_ms": 1e3 * t_cm}
+        if with_cpu:
+            optgs = orc.holonomic_ptgs() if name.startswith("c1") else orc.ackermann_ptgs()
+            opl = orc.Planner(optgs, wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
+            opl.add_obstacles(xs, ys)
+            t0 = time.perf_counter()
+            ocm = orc.CostMap(xs, ys, 0.04, 0.5, 4.0, False, 15.0, start[:3])
+            d["cpu_costmap_build_ms"] = 1e3 * (time.perf_counter() - t0)
+            opl.add_costmap(ocm)
+            if wps:
+                opl.add_waypoints(orc.Waypoints(WAYPOINTS01[0], WAYPOINTS01[1], 1.5, 0.5, True))
+            ro = opl.plan(start, goal, lo, hi)
+            d["cpu_plan_ms"] = 1e3 * ro["time_s"]
+            d["identical_tree"] = bool(np.array_equal(pl.tree(), opl.tree()))
+        pl.close()
+        out[name] = d
+
+    # C4: independent queries on a 200x200 m wall map (2^20 points on ~8 km of wall segments)
+    nq = args.queries
+    mx, my = wl.walls_cloud(args.points, EXTENT, wall_fraction=1.0, spacing=0.008, seed=wl.C3_WALLS_SEED)
+    allq = wl.planning_queries(nq * world)
+    mine = [allq[i] for i in range(rank, nq * world, world)]
+    params = list(wl.DEMO_ASTAR_PARAMS)
+    params[8] = C4_MAX_EXPANSIONS
+    ptgs = capi.ackermann_ptgs()
+    pl = capi.Planner(ctx, ptgs, params, wl.DEMO_ASTAR_TIMESTAMPS)
+    pl.add_obstacles(mx, my)
+    pl.plan_many(mine[:8])  # warm-up
+    t0 = time.perf_counter()
+    res = pl.plan_many(mine)
+    t_batch = time.perf_counter() - t0
+    st = pl.gpu_stats()
+    d = {"queries_per_gpu": nq, "max_expansions": C4_MAX_EXPANSIONS, "batch_s": t_batch,
+         "expansions": int(sum(r["expanded"] for r in res)), "successes": int(sum(r["success"] for r in res)),
+         "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_s": st["gpu_seconds"],
+         "host_threads": os.cpu_count()}
+    if with_cpu:
+        # bounded CPU sample: a few of the same queries through the oracle planner, one per host thread
+        from concurrent.futures import ThreadPoolExecutor
+
+        optgs_pool = [orc.ackermann_ptgs() for _ in range(min(4, os.cpu_count() or 1))]
+
+        def one(i):
+            opl = orc.Planner(optgs_pool[i % len(optgs_pool)], params, wl.DEMO_ASTAR_TIMESTAMPS)
+            opl.add_obstacles(mx, my)
+            return opl.plan(*mine[i][:4]), opl.tree()
+
+        n_cpu = len(optgs_pool)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=n_cpu) as ex:
+            cpu_res = list(ex.map(one, range(n_cpu)))
+        t_cpu = time.perf_counter() - t0
+        d["cpu_sample_queries"] = n_cpu
+        d["cpu_sample_threads"] = n_cpu
+        d["cpu_plans_per_s"] = n_cpu / t_cpu
+        d["cpu_expansions_per_s"] = sum(r["expanded"] for r, _ in cpu_res) / t_cpu
+        d["identical_trees_on_sample"] = bool(all(np.array_equal(pl.tree(i), t) for i, (_, t) in enumerate(cpu_res)))
+    pl.close()
+    ctx.close()
+    out["c4_batch"] = d
+    return out
+
+
 def config_dict(args, **extra):
     c = {"workload": "C3: synthetic 1M-point cloud U[0,200)^2, 4096-node batch x 2 Ackermann PTGs x 121 k, clip 5 m",
          "points": args.points, "nodes_per_gpu": args.nodes, "ptgs": N_PTGS, "paths_per_ptg": K_PATHS,
@@ -169,6 +274,51 @@ def config_dict(args, **extra):
          "l2": "flushed between timed steps (256 MiB write)", "parallelism": "nodes sharded per GPU, cloud replicated"}
     c.update(extra)
     return c
+
+
+def cloud_sharded_bench(ctx, dev, stream, rank, world, args, d_nodes, d_out, flush):
+    """Config C5 in weak-scaling form: a cloud of world x 2^23 points, sharded by point index; every rank evaluates
+    the SAME 4096-node batch against its shard and the per-edge minima are merged with NCCL all_reduce(MIN)."""
+    import torch
+    import torch.distributed as dist
+
+    from mrpt_path_planning_b200 import capi, sharding
+
+    n_total = args.c5_points_per_gpu * world
+    xs, ys = wl.uniform_cloud(n_total, EXTENT, seed=wl.C5_CLOUD_SEED)
+    sx, sy = sharding.cloud_shard(xs, ys, rank, world)
+    ctx.set_obstacles(sx, sy)
+    poses = wl.node_poses(args.nodes, EXTENT, seed=wl.C3_NODES_SEED)  # same nodes on every rank
+    with torch.cuda.stream(stream):
+        d_nodes.copy_(torch.from_numpy(capi.nodes_xycs_from_poses(poses)).to(dev))
+
+    def steps(n):
+        evs = []
+        with torch.cuda.stream(stream):
+            for _ in range(n):
+                flush.zero_()
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record(stream)
+                ctx.eval_nodes_device(args.nodes, d_nodes, CLIP, d_out)
+                b.record(stream)
+                sharding.allreduce_min_(d_out)
+                c.record(stream)
+                evs.append((a, b, c))
+        torch.cuda.synchronize(dev)
+        return [(a.elapsed_time(b), b.elapsed_time(c)) for a, b, c in evs]
+
+    steps(3)
+    dist.barrier()
+    ts = steps(max(5, args.steps // 2))
+    k_ms = sum(t[0] for t in ts) / len(ts)
+    ar_ms = sum(t[1] for t in ts) / len(ts)
+    t = torch.tensor([k_ms + ar_ms, k_ms, ar_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot, k_ms, ar_ms = t.tolist()
+    edges = args.nodes * N_PTGS * K_PATHS
+    return {"points_total": n_total, "points_per_gpu": len(sx), "nodes": args.nodes, "ms_per_step": tot,
+            "kernel_ms": k_ms, "allreduce_min_ms": ar_ms, "allreduce_bytes": int(d_out.numel() * 4),
+            "edges_per_s": edges / (tot * 1e-3), "scaling": "weak in cloud size (edges fixed)"}
 
 
 def run_ours(args, rank, local_rank, world):
@@ -258,10 +408,24 @@ def run_ours(args, rank, local_rank, world):
 
     dev_ms = sum(step_ms) / len(step_ms)
     e2e_ms = 1e3 * sum(e2e_s) / len(e2e_s)
+
+    # ---- secondary measurements (not the headline): planner level and, for N > 1, the cloud-sharded path ----
+    planner = None
+    if not args.no_planner:
+        planner = planner_bench(lambda: capi.Context(local_rank), rank, world, args,
+                                with_cpu=(world == 1 and not args.no_cpu_baseline))
+    c5 = None
+    if world > 1 and not args.no_c5:
+        c5 = cloud_sharded_bench(ctx, dev, stream, rank, world, args, d_nodes, d_out, flush)
+    c4_s = planner["c4_batch"]["batch_s"] if planner else 0.0
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_ms, c4_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = t.tolist()
+        dev_ms, e2e_ms, c4_s = t.tolist()
+    if planner:
+        c4 = planner["c4_batch"]
+        c4["plans_per_s"] = world * c4["queries_per_gpu"] / c4_s
+        c4["batch_s_max_over_ranks"] = c4_s
     edges_total = world * B * cols
     value = edges_total / (dev_ms * 1e-3)
     e2e_value = edges_total / (e2e_ms * 1e-3)
@@ -300,6 +464,10 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches), "roofline": roofline,
         "setup": {"ptg_tables_s": t_tables, "cloud_upload_and_binning_s": t_cloud},
     }
+    if planner:
+        out["planner"] = planner
+    if c5:
+        out["c5_cloud_sharded"] = c5
     if world == 1 and not args.no_cpu_baseline:
         rate, done, secs, threads, ref_out = cpu_reference_rate(xs, ys, poses, args.cpu_budget)
         init = np.concatenate([p.init_dists() for p in ptgs])
@@ -325,6 +493,10 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 20)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-planner", action="store_true", help="skip the planner-level (C1/C2/C4) measurements")
+    ap.add_argument("--no-c5", action="store_true", help="skip the cloud-sharded (C5) measurement at N > 1")
+    ap.add_argument("--queries", type=int, default=512, help="C4: planning queries per GPU")
+    ap.add_argument("--c5-points-per-gpu", type=int, default=1 << 23)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

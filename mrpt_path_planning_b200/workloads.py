@@ -45,3 +45,30 @@ def walls_cloud(n, extent=200.0, wall_fraction=0.7, spacing=0.05, seed=C3_WALLS_
     np.clip(xs, 0, extent, out=xs)
     np.clip(ys, 0, extent, out=ys)
     return xs.astype(np.float32), ys.astype(np.float32)
+
+
+C4_QUERIES_SEED = 20240604
+
+# share/mvsim-demo-astar-planner-params.yaml (values typed here as data): grid 0.40 m / 25 deg, metric weights 0.1,
+# 13 trajectories, 3 speeds, 5 interpolated segments; [7] = time limit (0 = none), [8] = expansion cap (0 = none)
+DEMO_ASTAR_PARAMS = [0.40, 25.0 * np.pi / 180.0, 0.1, 0.1, 13, 3, 5, 0, 0]
+DEMO_ASTAR_TIMESTAMPS = [0.5, 1.5, 4.0]
+
+
+def planning_queries(n, extent=200.0, dmin=10.0, dmax=40.0, margin=4.0, seed=C4_QUERIES_SEED):
+    """Config C4: n independent queries, start/goal ~ U[10, extent-10)^2 with distance in [dmin, dmax], random
+    headings, per-query world box = start/goal +- margin. Returns tuples (start6, goal6, bbox_min3, bbox_max3, False)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    while len(out) < n:
+        s = rng.uniform(10.0, extent - 10.0, 2)
+        g = rng.uniform(10.0, extent - 10.0, 2)
+        d = float(np.hypot(*(g - s)))
+        hs, hg = rng.uniform(-np.pi, np.pi, 2)
+        if not (dmin <= d <= dmax):
+            continue
+        lo = np.minimum(s, g) - margin
+        hi = np.maximum(s, g) + margin
+        out.append(([s[0], s[1], hs, 0.0, 0.0, 0.0], [g[0], g[1], hg, 0.0, 0.0, 0.0],
+                    [lo[0], lo[1], -np.pi], [hi[0], hi[1], np.pi], False))
+    return out
