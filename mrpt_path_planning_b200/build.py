@@ -57,6 +57,7 @@ def needs_build():
 def _compile_one(args):
     src, obj, verbose = args
     cmd = [NVCC] + NVCC_FLAGS + PER_FILE_FLAGS.get(os.path.basename(src), []) + (["-Xptxas", "-v"] if verbose else [])
+    cmd += os.environ.get("MPPB_EXTRA_NVCC", "").split()  # experiments only (e.g. -DMPPB_GRID_MIN_BLOCKS=6)
     cmd += ["-c", "-o", obj, src]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     return src, r.returncode, r.stdout

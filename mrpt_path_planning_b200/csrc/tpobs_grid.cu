@@ -17,6 +17,13 @@
 // result is an order-independent min, reduced with atomicMin on the (non-negative) float bit
 // pattern in shared memory.
 //
+// Filtered fast path: the chain above is only needed to pick the right collision-grid CELL. Each
+// point is first transformed in FP32 (translation with a hi/lo split of the node position, so the
+// error of the local coordinates is bounded by E = 3e-6 * max(clip,1) m); if the FP32 result is
+// farther than that bound from every decision boundary (clip square, cell edges, grid border,
+// robot bounding circle) the cell it yields is provably the reference's cell and the FP64 chain
+// is skipped. The ~0.5 % of points near a boundary take the exact FP64 chain.
+//
 // Work decomposition: one CTA per node, two phases per PTG group.
 //  Phase 1 (points -> occupancy bitmap): the node's clipping square selects a range of bin
 //    rows of the cloud index; each row contributes one contiguous run of points. Warps take
@@ -97,8 +104,11 @@ __device__ __forceinline__ void apply_inside_cell(const GridGroupDev& G, uint32_
 // HAS_BOX: obstacle points outside the node's own world box (float compare, inclusive bounds:
 // ObstacleSource.cpp:29-40) are ignored — the per-query clipping of independent planning queries
 // that share one resident cloud.
+#ifndef MPPB_GRID_MIN_BLOCKS
+#define MPPB_GRID_MIN_BLOCKS 8
+#endif
 template <bool HAS_BOX>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
@@ -109,7 +119,9 @@ __global__ void __launch_bounds__(kThreads, 8)
     unsigned*           bitmap = smem + totalPaths;  // [bitmapWords] one bit per grid cell (+1 never-set bit)
     __shared__ uint32_t rowBeg[kRowsPerPass];
     __shared__ uint32_t rowPrefix[kRowsPerPass + 1];
-    __shared__ uint8_t  chunkRow[kMaxChunks];
+    __shared__ uint32_t rowLen[kRowsPerPass];
+    __shared__ uint32_t chunkStart[kMaxChunks];
+    __shared__ uint8_t  chunkCnt[kMaxChunks];
     __shared__ uint32_t insideCell[kMaxInside];
     __shared__ unsigned nInside;
 
@@ -126,6 +138,14 @@ __global__ void __launch_bounds__(kThreads, 8)
     // inverse pose (CPose2D unary minus): ix = -x*c - y*s ; iy = x*s - y*c
     const double ix = __dsub_rn(__dmul_rn(-x0, c), __dmul_rn(y0, s));
     const double iy = __dsub_rn(__dmul_rn(x0, s), __dmul_rn(y0, c));
+
+    // FP32 fast path constants: hi/lo split of the node position, float cos/sin, error bound E
+    const float x0h = __double2float_rn(x0), x0l = __double2float_rn(x0 - static_cast<double>(x0h));
+    const float y0h = __double2float_rn(y0), y0l = __double2float_rn(y0 - static_cast<double>(y0h));
+    const float cf = __double2float_rn(c), sf = __double2float_rn(s);
+    const float clipF  = __double2float_rn(clip);
+    const float errLoc = 3e-6f * fmaxf(clipF, 1.f);  // bound on |fast local coordinate - reference's|
+    const float clipHi = clipF + errLoc + 1e-6f * clipF, clipLo = clipF - errLoc - 1e-6f * clipF;
 
     // conservative float window for the bin range (the exact test is per point, in double)
     int        bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
@@ -149,6 +169,18 @@ __global__ void __launch_bounds__(kThreads, 8)
         const double          gxmin = G.xmin, gymin = G.ymin, gres = G.res, ginv = G.invRes;
         const int             gnx = G.nx, gny = G.ny, nCols = G.nCols;
         const float           guardR2  = G.insideGuardR2;
+        const float           gxminf = __double2float_rn(gxmin), gyminf = __double2float_rn(gymin);
+        const float           ginvf  = __double2float_rn(ginv);
+        // margin (in cells) inside which the FP32 cell index is not trusted
+        const float mq = 1.25f * ((errLoc + fabsf(__double2float_rn(gxmin - static_cast<double>(gxminf))) +
+                                   fabsf(__double2float_rn(gymin - static_cast<double>(gyminf)))) * ginvf +
+                                  3e-7f * static_cast<float>(max(gnx, gny))) + 1e-5f;
+        const bool  fastOk   = mq < 0.25f && isfinite(clipF) && clipLo > 0.f;
+        const float guardHi  = guardR2 + 4.f * errLoc * (sqrtf(guardR2) + errLoc) + 1e-6f;
+        // q = (c*dx + s*dy - gxmin) * inv  and  (c*dy - s*dx - gymin) * inv with pre-scaled constants
+        // (their rounding adds < 2e-7 * q to the error, inside the 3e-7 * n term of mq)
+        const float cq = cf * ginvf, sq = sf * ginvf, offx = -gxminf * ginvf, offy = -gyminf * ginvf;
+        const float halfMinusMq = 0.5f - mq;
         const uint32_t* const colStart = G.colStart;
         const uint4* const    colCell4 = reinterpret_cast<const uint4*>(G.colCell);
         const float* const    colD     = G.colD;
@@ -169,12 +201,13 @@ __global__ void __launch_bounds__(kThreads, 8)
                 const size_t   r = static_cast<size_t>(rowBase + threadIdx.x) * bins.nbx;
                 const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
                 rowBeg[threadIdx.x]        = b;
-                rowPrefix[threadIdx.x + 1] = e - b;
+                rowLen[threadIdx.x]        = e - b;
+                rowPrefix[threadIdx.x + 1] = (e - b + 31) >> 5;  // 32-point chunks of this row's run
             }
             __syncthreads();
             if (warp == 0)
             {
-                // inclusive scan of up to 64 run lengths, two per lane
+                // inclusive scan of up to 64 chunk counts, two per lane
                 static_assert(kRowsPerPass == 64, "scan below handles 64 rows");
                 uint32_t a0 = (2 * lane < nRows) ? rowPrefix[2 * lane + 1] : 0u;
                 uint32_t a1 = (2 * lane + 1 < nRows) ? rowPrefix[2 * lane + 2] : 0u;
@@ -190,39 +223,76 @@ __global__ void __launch_bounds__(kThreads, 8)
                 if (2 * lane + 1 < nRows) rowPrefix[2 * lane + 2] = v;
             }
             __syncthreads();
-            const uint32_t total   = rowPrefix[nRows];
-            const uint32_t nChunks = (total + 31) >> 5;
+            const uint32_t nChunks = rowPrefix[nRows];
             for (uint32_t cBase = 0; cBase < nChunks; cBase += kMaxChunks)
             {
                 const uint32_t nc = min(static_cast<uint32_t>(kMaxChunks), nChunks - cBase);
                 if (cBase) __syncthreads();
+                // chunk table: chunks never straddle two rows, so a chunk is (first point, count <= 32)
                 for (uint32_t ch = threadIdx.x; ch < nc; ch += kThreads)
                 {
-                    // row containing the first point of chunk (cBase + ch)
-                    const uint32_t f  = (cBase + ch) << 5;
+                    const uint32_t gch = cBase + ch;
                     int            lo = 0, hi = nRows;
                     while (hi - lo > 1)
                     {
                         const int mid = (lo + hi) >> 1;
-                        if (rowPrefix[mid] <= f)
+                        if (rowPrefix[mid] <= gch)
                             lo = mid;
                         else
                             hi = mid;
                     }
-                    chunkRow[ch] = static_cast<uint8_t>(lo);
+                    const uint32_t j = (gch - rowPrefix[lo]) << 5;
+                    chunkStart[ch]   = rowBeg[lo] + j;
+                    chunkCnt[ch]     = static_cast<uint8_t>(min(32u, rowLen[lo] - j));
                 }
                 __syncthreads();
+                // software pipeline: the point of the warp's next chunk is loaded before the current one is used
+                float2 gNext     = make_float2(0.f, 0.f);
+                bool   validNext = false;
+                if (warp < nc && lane < chunkCnt[warp])
+                {
+                    gNext     = bins.pts[chunkStart[warp] + lane];
+                    validNext = true;
+                }
                 for (uint32_t ch = warp; ch < nc; ch += kWarps)
                 {
-                    const uint32_t f = ((cBase + ch) << 5) + lane;
-                    if (f >= total) continue;
-                    int row = chunkRow[ch];
-                    while (f >= rowPrefix[row + 1]) row++;  // f < total guarantees termination
-                    const float2 g  = bins.pts[rowBeg[row] + (f - rowPrefix[row])];
+                    const float2 g     = gNext;
+                    const bool   valid = validNext;
+                    validNext          = false;
+                    if (ch + kWarps < nc && lane < chunkCnt[ch + kWarps])
+                    {
+                        gNext     = bins.pts[chunkStart[ch + kWarps] + lane];
+                        validNext = true;
+                    }
+                    if (!valid) continue;
                     if (HAS_BOX && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) continue;
+                    if (fastOk)
+                    {
+                        // ---- FP32 filtered path ----
+                        const float dx = (g.x - x0h) - x0l, dy = (g.y - y0h) - y0l;
+                        const float am = fmaxf(fabsf(dx), fabsf(dy));
+                        if (am > clipHi) continue;  // certainly outside the clipping square
+                        // cell coordinates q = (R^T d - gmin) / res, folded into two FMAs per axis
+                        const float qx = fmaf(dx, cq, fmaf(dy, sq, offx));
+                        const float qy = fmaf(dy, cq, fmaf(-dx, sq, offy));
+                        const float rx = qx - floorf(qx), ry = qy - floorf(qy);
+                        const float edge = fmaxf(fabsf(rx - 0.5f), fabsf(ry - 0.5f));  // > 0.5-mq: near a cell edge
+                        const bool  unsure = am >= clipLo || edge > halfMinusMq || fmaf(dx, dx, dy * dy) <= guardHi;
+                        if (!unsure)
+                        {
+                            // x2idx truncates toward zero: q in (-1,0) still maps to cell 0
+                            const unsigned cx = static_cast<unsigned>(__float2int_rz(qx));
+                            const unsigned cy = static_cast<unsigned>(__float2int_rz(qy));
+                            if (cx >= static_cast<unsigned>(gnx) || cy >= static_cast<unsigned>(gny)) continue;
+                            const uint32_t cell = cx + cy * gnx;
+                            atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
+                            continue;
+                        }
+                    }
+                    // ---- exact FP64 chain (reference operation order, no FMA) ----
                     const double gx = g.x, gy = g.y;
                     if (clipped_out(gx, x0, clip) || clipped_out(gy, y0, clip)) continue;
-                    // composePoint with the inverse pose, reference operation order, no FMA
+                    // composePoint with the inverse pose
                     const double ox = __dadd_rn(__dadd_rn(ix, __dmul_rn(gx, c)), __dmul_rn(gy, s));
                     const double oy = __dadd_rn(__dsub_rn(iy, __dmul_rn(gx, s)), __dmul_rn(gy, c));
                     const float  fx = __double2float_rn(ox), fy = __double2float_rn(oy);  // CPointsMap stores float
@@ -249,6 +319,29 @@ __global__ void __launch_bounds__(kThreads, 8)
                 }
             }
         }
+        // Phase 2 works on two columns per thread at a time (two independent load chains). Their first
+        // four cells do not depend on the bitmap: request them before the barrier that ends phase 1,
+        // so that the L2 latency overlaps the barrier wait and phase 1b.
+        struct ColScan
+        {
+            uint32_t i, end;
+            uint4    q;
+            int      oc;  // output column, -1 = nothing to scan
+        };
+        auto openColumn = [&](int col, ColScan& cs) {
+            cs.oc = -1;
+            cs.i = cs.end = 0;
+            cs.q          = make_uint4(0, 0, 0, 0);
+            if (col >= nCols) return;
+            cs.i   = colStart[col] >> 2;  // lists are padded to x4
+            cs.end = colStart[col + 1] >> 2;
+            if (cs.i >= cs.end) return;
+            cs.oc = colOut[col];
+            cs.q  = colCell4[cs.i];
+        };
+        ColScan A, B;
+        openColumn(threadIdx.x, A);
+        openColumn(threadIdx.x + kThreads, B);
         __syncthreads();
 
         // ---- phase 1b: points inside the robot polygon (COLL_BEH_BACK_AWAY), all threads per cell ----
@@ -259,26 +352,40 @@ __global__ void __launch_bounds__(kThreads, 8)
         }
 
         // ---- phase 2: per output column, first occupied cell in ascending-d order ----
-        for (int col = threadIdx.x; col < nCols; col += kThreads)
-        {
-            const int oc = colOut[col];
-            if (smin[oc] == 0u) continue;  // already blocked at distance 0 by a point inside the robot
-            const uint32_t beg = colStart[col] >> 2, end = colStart[col + 1] >> 2;  // lists are padded to x4
-            for (uint32_t i = beg; i < end; i++)
+        // one step of a column scan: test the 4 cells in hand, else move on to the prefetched 4
+        auto step = [&](ColScan& cs, const uint4& next) -> bool {
+            const uint4    q  = cs.q;
+            const unsigned h0 = (bitmap[q.x >> 5] >> (q.x & 31)) & 1u;
+            const unsigned h1 = (bitmap[q.y >> 5] >> (q.y & 31)) & 1u;
+            const unsigned h2 = (bitmap[q.z >> 5] >> (q.z & 31)) & 1u;
+            const unsigned h3 = (bitmap[q.w >> 5] >> (q.w & 31)) & 1u;
+            const unsigned m  = h0 | (h1 << 1) | (h2 << 2) | (h3 << 3);
+            if (m)
             {
-                const uint4    q  = colCell4[i];
-                const unsigned h0 = (bitmap[q.x >> 5] >> (q.x & 31)) & 1u;
-                const unsigned h1 = (bitmap[q.y >> 5] >> (q.y & 31)) & 1u;
-                const unsigned h2 = (bitmap[q.z >> 5] >> (q.z & 31)) & 1u;
-                const unsigned h3 = (bitmap[q.w >> 5] >> (q.w & 31)) & 1u;
-                const unsigned m  = h0 | (h1 << 1) | (h2 << 2) | (h3 << 3);
-                if (m)
-                {
-                    const unsigned v = __float_as_uint(colD[4 * i + __ffs(m) - 1]);
-                    if (v < smin[oc]) smin[oc] = v;  // this thread is the only writer of column oc now
-                    break;
-                }
+                const unsigned v = __float_as_uint(colD[4 * cs.i + __ffs(m) - 1]);
+                if (v < smin[cs.oc]) smin[cs.oc] = v;  // this thread is the only writer of the column now
+                return false;
             }
+            cs.q = next;
+            return ++cs.i < cs.end;
+        };
+        for (int base = 0;;)
+        {
+            // a column already blocked at distance 0 by a point inside the robot needs no scan
+            bool actA = A.oc >= 0 && smin[A.oc] != 0u;
+            bool actB = B.oc >= 0 && smin[B.oc] != 0u;
+            while (actA || actB)
+            {
+                uint4 nA = A.q, nB = B.q;
+                if (actA) nA = colCell4[min(A.i + 1, A.end - 1)];
+                if (actB) nB = colCell4[min(B.i + 1, B.end - 1)];
+                if (actA) actA = step(A, nA);
+                if (actB) actB = step(B, nB);
+            }
+            base += 2 * kThreads;
+            if (base >= nCols) break;
+            openColumn(base + threadIdx.x, A);
+            openColumn(base + threadIdx.x + kThreads, B);
         }
     }
     __syncthreads();

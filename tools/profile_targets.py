@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Small driver that launches each product kernel a few times on bench-shaped inputs (for ncu captures).
+
+  python tools/profile_targets.py [grid|holo|cost|all]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mrpt_path_planning_b200 import capi, workloads as wl  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+xs, ys = wl.uniform_cloud(1 << 20, 200.0)
+poses = wl.node_poses(4096, 200.0)
+
+if what in ("grid", "all"):
+    ctx = capi.Context(0)
+    for p in capi.ackermann_ptgs():
+        ctx.add_ptg(p)
+    ctx.set_obstacles(xs, ys)
+    for _ in range(4):
+        t = time.perf_counter()
+        ctx.eval_nodes(poses, 5.0)
+        print("grid: eval_nodes 4096 nodes %.3f ms" % (1e3 * (time.perf_counter() - t)))
+    ctx.close()
+
+if what in ("holo", "all"):
+    ptg = capi.holonomic_ptgs()[0]
+    ctx = capi.Context(0)
+    ctx.add_ptg(ptg)
+    ctx.set_obstacles(xs, ys)
+    nb = 512
+    ks = [0, 15, 31, 47, 63, 79, 95, 110, 126, 142, 158, 174, 190, 101]
+    rows = []
+    rng = np.random.default_rng(1)
+    for b in range(nb):
+        v = rng.uniform(-0.7, 0.7, 2) * (b % 3 != 0)
+        for sp in (1 / 3, 2 / 3, 1.0):
+            ptg.set_trim_speed(sp)
+            ptg.update_dyn_state([v[0], v[1], 0.0], [5.0, 1.0, 0.0], 0.0, force=True)
+            for k in ks:
+                p = ptg.holo_params(k)
+                rows.append((b, 0, p.T_ramp, p.vxi, p.vyi, p.vxf, p.vyf, p.vf))
+    cands = np.array(rows, dtype=capi.HOLO_CAND_DTYPE)
+    for _ in range(3):
+        t = time.perf_counter()
+        out = ctx.eval_holo_candidates(poses[:nb], cands, 5.0)
+        dt = time.perf_counter() - t
+        print("holo: %d candidates (%d nodes) %.3f ms -> %.3g candidates/s, finite %.2f" % (
+            len(cands), nb, 1e3 * dt, len(cands) / dt, np.isfinite(out).mean()))
+    ctx.close()
+
+if what in ("cost", "all"):
+    ctx = capi.Context(0)
+    rng = np.random.default_rng(2)
+    cells = rng.uniform(0, 4, (775, 775)) * (rng.uniform(size=(775, 775)) < 0.1)
+    ctx.set_costmap(0, cells, 0.0, 0.0, 0.04, False)
+    ctx.set_waypoints(1, rng.uniform(0, 31, 5), rng.uniform(0, 31, 5), 1.5, 0.5, True)
+    n = 200000
+    frm = np.stack([rng.uniform(0, 31, n), rng.uniform(0, 31, n), rng.uniform(-3, 3, n)], 1)
+    off = (np.arange(n + 1) * 7).astype(np.uint32)
+    rel = rng.uniform(-2, 2, (7 * n, 2))
+    for _ in range(3):
+        t = time.perf_counter()
+        ctx.eval_edge_costs(frm, off, rel)
+        dt = time.perf_counter() - t
+        print("cost: %d edges x 2 evaluators %.3f ms -> %.3g edges/s" % (n, 1e3 * dt, n / dt))
+    ctx.close()
