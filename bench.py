@@ -204,7 +204,7 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
         d = {"plan_ms": 1e3 * min(ts), "success": bool(r["success"]), "nodes_expanded": int(r["expanded"]),
              "tps_points": int(r["tps_points"]), "edges_costed": int(r["edges_costed"]),
              "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_ms": 1e3 * st["gpu_seconds"],
-             "costmap_build_ms": 1e3 * t_cm}
+             "phase_ms": {k: 1e3 * v for k, v in st["phase_seconds"].items()}, "costmap_build_ms": 1e3 * t_cm}
         if with_cpu:
             optgs = orc.holonomic_ptgs() if name.startswith("c1") else orc.ackermann_ptgs()
             opl = orc.Planner(optgs, wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
@@ -231,15 +231,16 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
     ptgs = capi.ackermann_ptgs()
     pl = capi.Planner(ctx, ptgs, params, wl.DEMO_ASTAR_TIMESTAMPS)
     pl.add_obstacles(mx, my)
-    pl.plan_many(mine[:8])  # warm-up
+    n_threads = max(1, (os.cpu_count() or 1) // world)
+    pl.plan_many(mine[:8], n_threads=n_threads)  # warm-up
     t0 = time.perf_counter()
-    res = pl.plan_many(mine)
+    res = pl.plan_many(mine, n_threads=n_threads)
     t_batch = time.perf_counter() - t0
     st = pl.gpu_stats()
     d = {"queries_per_gpu": nq, "max_expansions": C4_MAX_EXPANSIONS, "batch_s": t_batch,
          "expansions": int(sum(r["expanded"] for r in res)), "successes": int(sum(r["success"] for r in res)),
          "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_s": st["gpu_seconds"],
-         "host_threads": os.cpu_count()}
+         "phase_seconds": st["phase_seconds"], "host_threads": n_threads}
     if with_cpu:
         # bounded CPU sample: a few of the same queries through the oracle planner, one per host thread
         from concurrent.futures import ThreadPoolExecutor

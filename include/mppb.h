@@ -376,8 +376,10 @@ int mppb_planner_path(mppb_planner* p, size_t query, double* nodes, double* edge
 int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t cap);
 /* plan_to_trajectory + save_to_txt text (src/algos/trajectories.cpp:15-106); returns the text length */
 int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample_period, char* buf, int64_t cap);
-/* GPU work of the last plan: collision batches, cost batches, nodes, holo candidates, edges, seconds in GPU calls */
-int mppb_planner_gpu_stats(const mppb_planner* p, double* out6);
+/* Work of the last plan, out13 = collision batches, cost batches, nodes, holo candidates, edges, seconds in GPU
+ * calls, then wall seconds per phase: pop, A enumerate, B collision (GPU), C+D select/build, E assemble,
+ * E cost (GPU), F relax */
+int mppb_planner_gpu_stats(const mppb_planner* p, double* out13);
 
 #ifdef __cplusplus
 }

@@ -693,7 +693,9 @@ class Planner:
         return buf.value.decode()
 
     def gpu_stats(self):
-        v = np.zeros(6)
+        v = np.zeros(13)
         self._ck(lib().mppb_planner_gpu_stats(self.h, v.ctypes.data_as(c_double_p)))
+        names = ["setup_uploads", "F_relax+pop+A_enumerate", "B_collision_gpu", "CD_select_build", "E_assemble",
+                 "E_cost_gpu", "teardown"]
         return dict(collision_batches=int(v[0]), cost_batches=int(v[1]), nodes=int(v[2]), holo_candidates=int(v[3]),
-                    edges=int(v[4]), gpu_seconds=v[5])
+                    edges=int(v[4]), gpu_seconds=v[5], phase_seconds={n: float(x) for n, x in zip(names, v[6:]) if not n.startswith("_")})

@@ -13,7 +13,9 @@
 // What differs by design: TPS_Astar evaluates collisions and evaluator costs through libmpp_b200
 // (mppb_* C ABI) in batches, and offers plan_batch() for many independent queries in lock-step.
 #pragma once
+#include <algorithm>
 #include <functional>
+#include <iterator>
 #include <limits>
 #include <list>
 #include <map>
@@ -114,6 +116,87 @@ struct SE2orR2_KinState
     std::string  asString() const;
 };
 
+/** Time-keyed pose samples of an edge: a sorted flat map with inline storage and the subset of the
+ *  std::map interface the reference uses on MoveEdgeSE2_TPS::interpolatedPath (ordered iteration over
+ *  (time, pose) pairs, operator[] insert-or-assign, size/empty/clear, find). An edge holds at most
+ *  nSeg + 2 samples (9 after refine_trajectory), so no heap allocation is needed: motion trees with
+ *  millions of edges are built without touching the allocator for their samples. */
+class TimedPoseMap
+{
+   public:
+    using key_type       = duration_seconds_t;
+    using mapped_type    = TPose2D;
+    using value_type     = std::pair<duration_seconds_t, TPose2D>;
+    using iterator       = value_type*;
+    using const_iterator = const value_type*;
+    static constexpr size_t kInline = 10;
+
+    TimedPoseMap() = default;
+    TimedPoseMap(const TimedPoseMap& o) { *this = o; }
+    TimedPoseMap& operator=(const TimedPoseMap& o)
+    {
+        if (this == &o) return *this;
+        n_ = o.n_;
+        if (o.heap_.empty())
+        {
+            heap_.clear();
+            std::copy(o.inl_, o.inl_ + n_, inl_);
+        }
+        else
+            heap_ = o.heap_;
+        return *this;
+    }
+    iterator       begin() { return data(); }
+    iterator       end() { return data() + n_; }
+    const_iterator begin() const { return data(); }
+    const_iterator end() const { return data() + n_; }
+    std::reverse_iterator<const_iterator> rbegin() const { return std::reverse_iterator<const_iterator>(end()); }
+    std::reverse_iterator<const_iterator> rend() const { return std::reverse_iterator<const_iterator>(begin()); }
+    size_t size() const { return n_; }
+    bool   empty() const { return n_ == 0; }
+    void   clear()
+    {
+        n_ = 0;
+        heap_.clear();
+    }
+    const_iterator find(key_type k) const
+    {
+        const_iterator it = std::lower_bound(begin(), end(), k, [](const value_type& v, key_type x) { return v.first < x; });
+        return (it != end() && it->first == k) ? it : end();
+    }
+    size_t count(key_type k) const { return find(k) != end() ? 1 : 0; }
+    const mapped_type& at(key_type k) const
+    {
+        const_iterator it = find(k);
+        if (it == end()) throw std::out_of_range("TimedPoseMap::at");
+        return it->second;
+    }
+    mapped_type& operator[](key_type k)
+    {
+        value_type* d  = data();
+        size_t      lo = std::lower_bound(d, d + n_, k, [](const value_type& v, key_type x) { return v.first < x; }) - d;
+        if (lo < n_ && d[lo].first == k) return d[lo].second;
+        if (heap_.empty() && n_ == kInline) heap_.assign(inl_, inl_ + n_);  // rare: spill to the heap
+        if (!heap_.empty())
+        {
+            heap_.insert(heap_.begin() + lo, value_type(k, TPose2D()));
+            n_++;
+            return heap_[lo].second;
+        }
+        for (size_t i = n_; i > lo; i--) inl_[i] = inl_[i - 1];
+        inl_[lo] = value_type(k, TPose2D());
+        n_++;
+        return inl_[lo].second;
+    }
+
+   private:
+    value_type*       data() { return heap_.empty() ? inl_ : heap_.data(); }
+    const value_type* data() const { return heap_.empty() ? inl_ : heap_.data(); }
+    value_type              inl_[kInline];
+    std::vector<value_type> heap_;
+    size_t                  n_ = 0;
+};
+
 struct MoveEdgeSE2_TPS
 {
     TNodeID            parentId = static_cast<TNodeID>(-1);
@@ -126,7 +209,8 @@ struct MoveEdgeSE2_TPS
     TPose2D            ptgFinalRelativeGoal;
     normalized_speed_t ptgFinalGoalRelSpeed = .0;
     duration_seconds_t estimatedExecTime    = .0;
-    std::map<duration_seconds_t, TPose2D> interpolatedPath;
+    /** std::map<duration_seconds_t, TPose2D> in the reference; same ordered-map semantics, flat storage */
+    TimedPoseMap interpolatedPath;
     /** extension: the PTG step the edge ends at (relTrgStep of the accepted neighbour) */
     ptg_step_t ptgStep = 0;
 
@@ -378,6 +462,9 @@ class TPS_Astar : public Planner
     {
         size_t collisionBatches = 0, costBatches = 0, nodesEvaluated = 0, holoCandidates = 0, edgesCosted = 0;
         double gpuSeconds = 0;
+        /** wall seconds per phase: [0] set-up and uploads, [1] F relax + pop + A enumerate (fused per query), [2] B collision (GPU),
+         *  [3] C+D select/build, [4] E assemble, [5] E cost (GPU), [6] result hand-over and teardown */
+        double phaseSeconds[7] = {0, 0, 0, 0, 0, 0, 0};
     } lastGpuStats;
 
    private:

@@ -20,6 +20,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <memory_resource>
 #include <cstring>
 #include <mutex>
 #include <set>
@@ -281,8 +282,11 @@ struct TPS_Astar::Impl::Query
     Clock::time_point            t0;
     double                       tLastCallback = 0;
 
-    std::unordered_map<NodeCoords, Node, NodeCoordsHash>   grid;
-    std::multimap<distance_t, Node*>                       openSet;
+    // lattice and open set live in a per-query arena: node addresses stay stable (node-based containers),
+    // allocation is a pointer bump and the whole search state is dropped at once when the query ends
+    std::pmr::monotonic_buffer_resource                         searchArena{1 << 16};
+    std::pmr::unordered_map<NodeCoords, Node, NodeCoordsHash>   grid{&searchArena};
+    std::pmr::multimap<distance_t, Node*>                       openSet{&searchArena};
     TNodeID                                                nextFreeId = 0;
     Node*                                                  nodeGoal   = nullptr;
     NodeCoords                                             goalCellIndices;
@@ -290,9 +294,13 @@ struct TPS_Astar::Impl::Query
     double                                                 MAX_XY_DIST = 0;
     Node*                                                  current     = nullptr;
     bool                                                   done        = false;
+    bool                                                   active      = false;  // expands a node this round
+    bool                                                   needF       = false;  // tentative edges wait for relaxation
+    size_t                                                 costBase    = 0;      // first row of this query in the cost batch
     float                                                  box[4]      = {0, 0, 0, 0};
 
     // phase scratch
+    std::pmr::monotonic_buffer_resource arena{16384};
     std::vector<Candidate>        cands;
     std::vector<TNavDynamicState> dynOfPtg;
     std::vector<mppb_holo_cand>   holoCands;
@@ -412,7 +420,7 @@ struct TPS_Astar::Impl::Query
     }
 
     // ---- phase A: candidate TPS points of `current` (TPS_Astar.cpp:549-736) ----
-    void phaseA(int slot)
+    void phaseA()
     {
         cands.clear();
         holoCands.clear();
@@ -429,8 +437,9 @@ struct TPS_Astar::Impl::Query
             ptg_step_t         step;
             normalized_speed_t speed;
         };
-        std::vector<TpsPoint>                                         tps;
-        std::map<std::pair<trajectory_index_t, double>, uint32_t>     holoIndex;
+        arena.release();  // phase scratch of the previous expansion
+        std::pmr::vector<TpsPoint>                                         tps(&arena);
+        std::pmr::map<std::pair<trajectory_index_t, double>, uint32_t>     holoIndex(&arena);
 
         for (size_t ptgIdx = 0; ptgIdx < trs.ptgs.size(); ptgIdx++)
         {
@@ -448,8 +457,8 @@ struct TPS_Astar::Impl::Query
             }
             dynOfPtg[ptgIdx] = ptg.getCurrentNavDynamicState();
 
-            std::set<trajectory_index_t> trajIdxs;
-            std::set<size_t>             targetIdx;
+            std::pmr::set<trajectory_index_t> trajIdxs(&arena);
+            std::pmr::set<size_t>             targetIdx(&arena);
             tps.clear();
             MPP_ASSERT(P->max_ptg_trajectories_to_explore >= 2);
             for (size_t i = 0; i < P->max_ptg_trajectories_to_explore; i++)
@@ -458,7 +467,7 @@ struct TPS_Astar::Impl::Query
                 const size_t q = i * (ptg.getPathCount() - 1) / (P->max_ptg_trajectories_to_explore - 1);
                 trajIdxs.insert(round_i(static_cast<double>(q)));
             }
-            std::vector<normalized_speed_t> speeds;
+            std::pmr::vector<normalized_speed_t> speeds(&arena);
             if (trimmable)
             {
                 MPP_ASSERT(P->max_ptg_speeds_to_explore >= 1);
@@ -528,7 +537,7 @@ struct TPS_Astar::Impl::Query
                     {
                         mppb_holo_cand hc;
                         static_cast<const HolonomicBlend&>(ptg).holoParams(k16, hc);
-                        hc.node      = slot;
+                        hc.node      = 0;  // position in the round's node batch: filled in when the batch is assembled
                         hc.ptg_index = static_cast<int32_t>(ptgIdx);
                         holoCands.push_back(hc);
                         it = holoIndex.emplace(key, static_cast<uint32_t>(holoCands.size() - 1)).first;
@@ -543,8 +552,11 @@ struct TPS_Astar::Impl::Query
     // ---- phases C + D: neighbour selection and tentative edges (TPS_Astar.cpp:738-814, 269-341) ----
     void phaseCD(const float* gridRow, const double* holoOut)
     {
-        std::unordered_map<NodeCoords, PathToNeighbor, NodeCoordsHash> bestPaths;
-        std::unordered_set<NodeCoords, NodeCoordsHash>                 goalNodeCoords;
+        // same containers and hash as the reference (their iteration order decides node ids), fed from a
+        // per-expansion arena: the allocator does not influence bucket layout or iteration order
+        arena.release();
+        std::pmr::unordered_map<NodeCoords, PathToNeighbor, NodeCoordsHash> bestPaths(&arena);
+        std::pmr::unordered_set<NodeCoords, NodeCoordsHash>                 goalNodeCoords(&arena);
         size_t                                                         lastPtg = static_cast<size_t>(-1);
         for (const Candidate& c : cands)
         {
@@ -815,6 +827,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         if (sharedCloud && in->obstacles != ins[0]->obstacles)
             throw std::runtime_error("plan_batch: all queries must share the same obstacle sources");
     }
+    auto tSetup = Clock::now();
     uploadPtgs(ins[0]->ptgs);
     uploadEvaluators();
 
@@ -846,17 +859,35 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     active.reserve(Q);
     GpuStats& st = self->lastGpuStats;
 
+    auto lap = [&st](Clock::time_point& t, int phase) {
+        const auto now = Clock::now();
+        st.phaseSeconds[phase] += std::chrono::duration<double>(now - t).count();
+        t = now;
+    };
+    lap(tSetup, 0);
+    double* costs = nullptr;  // evaluator values of the previous round's tentative edges (pinned buffer)
     for (;;)
     {
-        // ---- pop: which queries expand a node this round ----
+        auto tl = Clock::now();
+        // ---- per query, no barrier in between: F of the previous round, pop, A of this round ----
+        pool.run(Q, [&](size_t i) {
+            Query& q = *qs[i];
+            q.active = false;
+            if (q.done) return;
+            if (q.needF)
+            {
+                q.phaseF(costs ? costs + q.costBase * numGpuEvals : nullptr, numGpuEvals, evalSlot);
+                q.needF = false;
+            }
+            q.active = q.popNext();
+            if (q.active) q.phaseA();
+        });
         active.clear();
         for (size_t i = 0; i < Q; i++)
-            if (qs[i]->popNext()) active.push_back(i);
+            if (qs[i]->active) active.push_back(i);
         if (active.empty()) break;
         const size_t A = active.size();
-
-        // ---- phase A ----
-        pool.run(A, [&](size_t a) { qs[active[a]]->phaseA(static_cast<int>(a)); });
+        lap(tl, 1);
 
         // ---- phase B: one collision batch for all current nodes ----
         double* poses = hPoses.reserve(3 * A);
@@ -885,7 +916,9 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
             for (size_t a = 0; a < A; a++)
             {
                 const auto& v = qs[active[a]]->holoCands;
-                if (!v.empty()) std::memcpy(hc + holoBase[a], v.data(), v.size() * sizeof(mppb_holo_cand));
+                if (v.empty()) continue;
+                std::memcpy(hc + holoBase[a], v.data(), v.size() * sizeof(mppb_holo_cand));
+                for (size_t j = 0; j < v.size(); j++) hc[holoBase[a] + j].node = static_cast<int32_t>(a);
             }
             holoOut = hHoloOut.reserve(holoBase[A]);
             ck(ctx, mppb_eval_holo_candidates_boxed(ctx, A, poses, boxes, holoBase[A], hc, qs[active[0]]->MAX_XY_DIST, holoOut));
@@ -894,17 +927,25 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         st.collisionBatches++;
         st.nodesEvaluated += A;
         st.holoCandidates += holoBase[A];
+        lap(tl, 2);
 
         // ---- phases C + D ----
         pool.run(A, [&](size_t a) {
-            qs[active[a]]->phaseCD(rows ? rows + static_cast<size_t>(cols) * a : nullptr, holoOut ? holoOut + holoBase[a] : nullptr);
+            Query& q = *qs[active[a]];
+            q.phaseCD(rows ? rows + static_cast<size_t>(cols) * a : nullptr, holoOut ? holoOut + holoBase[a] : nullptr);
+            q.needF = true;
         });
+        lap(tl, 3);
 
         // ---- phase E: one cost batch for all tentative edges ----
         edgeBase.assign(A + 1, 0);
-        for (size_t a = 0; a < A; a++) edgeBase[a + 1] = edgeBase[a] + qs[active[a]]->pending.size();
-        const size_t E     = edgeBase[A];
-        double*      costs = nullptr;
+        for (size_t a = 0; a < A; a++)
+        {
+            qs[active[a]]->costBase = edgeBase[a];
+            edgeBase[a + 1]         = edgeBase[a] + qs[active[a]]->pending.size();
+        }
+        const size_t E = edgeBase[A];
+        costs          = nullptr;
         if (E > 0 && numGpuEvals > 0)
         {
             size_t nSamples = 0;
@@ -930,19 +971,23 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
                     }
                     off[++e] = static_cast<uint32_t>(s);
                 }
+            lap(tl, 4);
             const auto tE = Clock::now();
             ck(ctx, mppb_eval_edge_costs(ctx, E, from, off, rel, costs));
             st.gpuSeconds += seconds_since(tE);
             st.costBatches++;
             st.edgesCosted += E;
+            lap(tl, 5);
         }
-
-        // ---- phase F ----
-        pool.run(A, [&](size_t a) {
-            qs[active[a]]->phaseF(costs ? costs + edgeBase[a] * numGpuEvals : nullptr, numGpuEvals, evalSlot);
-        });
+        // phase F (relaxation) of these edges runs at the head of the next round, fused with pop and A
     }
-    for (size_t i = 0; i < Q; i++) outs[i] = std::move(qs[i]->po);
+    // hand the results over and tear the per-query search state down in parallel (millions of small nodes)
+    auto tEnd = Clock::now();
+    pool.run(Q, [&](size_t i) {
+        outs[i] = std::move(qs[i]->po);
+        qs[i].reset();
+    });
+    lap(tEnd, 6);
     return outs;
 }
 

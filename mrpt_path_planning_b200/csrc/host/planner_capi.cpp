@@ -302,6 +302,7 @@ int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample
 int mppb_planner_gpu_stats(const mppb_planner* p, double* out6)
 {
     if (!p || !out6) return MPPB_ERR_INVALID_ARG;
+    for (int i = 0; i < 7; i++) out6[6 + i] = p->planner->lastGpuStats.phaseSeconds[i];
     const auto& s = p->planner->lastGpuStats;
     out6[0]       = static_cast<double>(s.collisionBatches);
     out6[1]       = static_cast<double>(s.costBatches);
