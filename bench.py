@@ -7,7 +7,7 @@ Ackermann PTGs x all 121 trajectories = 991 232 candidate edges per step and per
 A step = one pass of stage (a)+(b) over one node batch against the resident cloud.
 
   python bench.py --gpus N --steps K --warmup W            (ours; under torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port on host cores)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the reference's own code, oracle/_ref, on host cores)
 
 Prints ONE JSON line (rank 0). `value` = device-timed throughput with inputs resident in HBM;
 `e2e` = the same metric through the host C-ABI call (pinned host buffers, H2D + kernel + D2H and
@@ -106,11 +106,21 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def cpu_checker():
+    """(module, kind): the reference's own translation units (oracle/_ref/libmpp_ref.so, "reference") when the
+    prebuilt library is present, else the restatement (oracle/orc_*.hpp, "port"). Same interface either way."""
+    from oracle import orc, ref
+
+    if ref.available():
+        return ref.module(), "reference"
+    return orc, "port"
+
+
 def cpu_reference_rate(xs, ys, poses, budget_s, nthreads=0):
-    """Times the oracle's restatement of the reference call pattern (transform_pc_square_clipping +
+    """Times the reference call pattern (TPS_Astar::cached_local_obstacles -> transform_pc_square_clipping, then
     tp_obstacles_single_path per (PTG,k)) on a bounded sample of the node batch. Returns
-    (edges_per_s, nodes_done, seconds, threads, outputs)."""
-    from oracle import orc
+    (edges_per_s, nodes_done, seconds, threads, outputs, kind)."""
+    orc, kind = cpu_checker()
 
     optgs = orc.ackermann_ptgs()
     threads = orc.lib().orc_num_threads() if nthreads <= 0 else nthreads
@@ -124,7 +134,7 @@ def cpu_reference_rate(xs, ys, poses, budget_s, nthreads=0):
         outs.append(out)
         done += len(sl)
         secs += t
-    return done * N_PTGS * K_PATHS / secs, done, secs, threads, np.concatenate(outs, 0)
+    return done * N_PTGS * K_PATHS / secs, done, secs, threads, np.concatenate(outs, 0), kind
 
 
 def run_reference(args, rank, world):
@@ -132,7 +142,7 @@ def run_reference(args, rank, world):
         return
     xs, ys = wl.uniform_cloud(args.points, EXTENT)
     poses = wl.node_poses(args.nodes, EXTENT)
-    from oracle import orc
+    orc, kind = cpu_checker()
 
     optgs = orc.ackermann_ptgs()
     threads = orc.lib().orc_num_threads()
@@ -156,7 +166,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, sample_nodes=sample),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -185,7 +195,8 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
     xs, ys, start, goal, lo, hi = demo_inputs()
     ctx = ctx_factory()
     if with_cpu:
-        from oracle import orc
+        orc, cpu_kind = cpu_checker()
+        out["cpu_kind"] = cpu_kind
     for name, mk_ptgs, wps in (("c1_holonomic", capi.holonomic_ptgs, False), ("c2_ackermann", capi.ackermann_ptgs, True)):
         ptgs = mk_ptgs()
         pl = capi.Planner(ctx, ptgs, wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
@@ -478,12 +489,12 @@ def run_ours(args, rank, local_rank, world):
     if c5:
         out["c5_cloud_sharded"] = c5
     if world == 1 and not args.no_cpu_baseline:
-        rate, done, secs, threads, ref_out = cpu_reference_rate(xs, ys, poses, args.cpu_budget)
+        rate, done, secs, threads, ref_out, kind = cpu_reference_rate(xs, ys, poses, args.cpu_budget)
         init = np.concatenate([p.init_dists() for p in ptgs])
         ctx.eval_nodes(h_poses, CLIP, out=h_out)
         got = np.minimum(init[None, :], h_out[:done].astype(np.float64))
         out["cpu_baseline"] = {
-            "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "value": rate, "unit": UNIT, "cores": threads, "kind": kind,
             "sample": "first %d of %d nodes vs the full %d-point cloud (%.1f s on %d host threads)" % (
                 done, B, args.points, secs, threads),
             "parity_on_sample": bool(np.array_equal(got, ref_out))}

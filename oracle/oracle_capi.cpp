@@ -2,7 +2,8 @@
 //
 // extern "C" surface of the CPU oracle so that tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs can call it through ctypes.
-// Parity UNPINNED (no reference golden vectors exist).
+// Pinned against oracle/_ref (the reference's own sources behind the same interface, oracle/ref/ref_capi.cpp);
+// the MRPT layer is assumed.
 #include <chrono>
 #include <cstring>
 

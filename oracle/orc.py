@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module. The product (mrpt_path_planning_b200) never does.
-Parity UNPINNED: the reference ships no golden vectors (DESIGN.md, section Oracle).
+Pinned against the reference build oracle/_ref (tests/test_oracle_vs_reference.py); MRPT-layer arithmetic assumed.
 """
 import ctypes as C
 import os

@@ -1,8 +1,9 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the shipped product.
 //
 // CPU restatement of the free functions of the hot path (stage a/b drivers), following
-// /root/reference/mrpt_path_planning/src/algos/*.cpp line by line. Parity UNPINNED (the
-// reference has no tests or golden vectors).
+// /root/reference/mrpt_path_planning/src/algos/*.cpp line by line. Pinned against
+// the reference's own sources compiled as oracle/_ref (tests/test_oracle_vs_reference.py); the MRPT
+// layer underneath is assumed.
 #pragma once
 #include "orc_ptg.hpp"
 

@@ -4,7 +4,8 @@
 // (/root/reference/mrpt_path_planning/src/ptgs/HolonomicBlend.cpp; each method cites the lines
 // it follows). MRPT pieces it leans on (solve_poly*, the expression compiler, the circular
 // robot shape) are restated in orc_poly.hpp / orc_expr.hpp / below and marked [MRPT].
-// Parity UNPINNED: the reference ships no tests or golden vectors for this class.
+// Pinned against HolonomicBlend.cpp itself, compiled as oracle/_ref (tests/test_oracle_vs_reference.py);
+// the MRPT layer underneath is assumed.
 #pragma once
 #include "orc_expr.hpp"
 #include "orc_poly.hpp"

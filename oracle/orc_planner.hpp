@@ -5,7 +5,8 @@
 // evaluators (src/algos/CostEvaluator*.cpp), edge_interpolated_path, Planner::cost_path_segment,
 // TPS_Astar (whole file), refine_trajectory, plan_to_trajectory / save_to_txt and
 // ObstacleSource clipping. Each function cites the reference lines it follows; MRPT behaviour
-// that is not under /root/reference is marked [MRPT]. Parity UNPINNED (no reference tests).
+// that is not under /root/reference is marked [MRPT]. Pinned against
+// the reference's own sources compiled as oracle/_ref (tests/test_oracle_vs_reference.py).
 #pragma once
 #include <chrono>
 #include <deque>

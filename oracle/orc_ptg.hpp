@@ -4,7 +4,8 @@
 // hot path. Each function cites the reference lines it follows (paths relative to
 // /root/reference/mrpt_path_planning/). Behaviour of the un-vendored MRPT base class
 // (mrpt::nav::CParameterizedTrajectoryGenerator) is restated from SURVEY.md §8c and is
-// marked [MRPT]. Parity is UNPINNED: the reference ships no tests or golden vectors.
+// marked [MRPT]. The mpp:: parts are pinned against the reference's own sources
+// compiled as oracle/_ref (tests/test_oracle_vs_reference.py); the [MRPT] parts stay assumed.
 #pragma once
 #include "orc_math.hpp"
 

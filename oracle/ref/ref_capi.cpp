@@ -156,6 +156,10 @@ void* orc_holo_new(
 int orc_ptgs_from_ini(const char* iniPath, const char* section, void** out, int cap)
 {
     ORC_TRY
+    // share/ptgs_ackermann_vehicle.ini:22,30 names MRPT's upstream class `CPTG_DiffDrive_C`, whose
+    // source is not available; it is aliased to the in-repo fork mpp::ptg::DiffDrive_C (SURVEY.md §7
+    // hard part 7).
+    mrpt::rtti::registerClassCustomName("CPTG_DiffDrive_C", CLASS_ID(mpp::ptg::DiffDrive_C));
     mrpt::config::CConfigFile      cfg(iniPath);
     mpp::TrajectoriesAndRobotShape trs;
     // initFromConfigFile writes its collision-grid cache to "./ptg_grid_NNN.dat.gz": the stream

@@ -13,13 +13,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
 
-@pytest.fixture(scope="session")
-def orc():
-    """The CPU oracle (test infrastructure; never used by the product)."""
-    from oracle import orc as _orc
+@pytest.fixture(scope="session", params=["port", "reference"])
+def orc(request):
+    """The CPU checker (test infrastructure; never used by the product), in its two forms:
+    "port"      = oracle/orc_*.hpp, the line-by-line restatement (liboracle.so);
+    "reference" = the reference's own translation units compiled from /root/reference against the
+                  MRPT stand-in (oracle/_ref/libmpp_ref.so, built here, shipped prebuilt to the GPU box).
+    Every test that takes this fixture runs against both, through the same orc_* interface."""
+    if request.param == "port":
+        from oracle import orc as _orc
 
-    _orc.lib()
-    return _orc
+        _orc.lib()
+        return _orc
+    from oracle import ref as _ref
+
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libmpp_ref.so not built and /root/reference absent")
+    return _ref.module()
 
 
 @pytest.fixture(scope="session")
