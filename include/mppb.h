@@ -11,6 +11,8 @@
  *                               transform_pc_square_clipping.h:16-19)
  *   mppb_set_ptg_grid        <- DiffDriveCollisionGridBased collision grid + robot shape
  *                               (include/mpp/ptgs/DiffDriveCollisionGridBased.h:162-215)
+ *   mppb_build_collision_grid <- DiffDriveCollisionGridBased::internal_initialize, the table
+ *                               construction (src/ptgs/DiffDriveCollisionGridBased.cpp:673-754)
  *   mppb_eval_nodes*         <- cached_local_obstacles + tp_obstacles_single_path for every
  *                               (node, PTG, k) (src/algos/TPS_Astar.cpp:561-562,744-745;
  *                               include/mpp/algos/tp_obstacles_single_path.h:17-19)
@@ -129,6 +131,42 @@ typedef struct mppb_ptg_grid_desc
     const double*   shape_y;
     double          max_radius;   /* getMaxRobotRadius() */
 } mppb_ptg_grid_desc;
+
+/* Construction of that table on the device: the recompute branch of
+ * DiffDriveCollisionGridBased::internal_initialize (src/ptgs/DiffDriveCollisionGridBased.cpp:673-754)
+ * with CCollisionGrid::updateCellInfo's min rule (:233-258). Inputs are the simulated paths
+ * (simulateTrajectories, :103-176): path k owns steps [path_begin[k], path_begin[k+1]) of the float
+ * arrays x, y, phi, dist (TCPoint::x,y,phi,dist). The grid is CDynamicGrid::setSize(-ref_distance,
+ * ref_distance, -ref_distance, ref_distance, resolution). cos/sin of the headings are taken with
+ * the host C library inside this call; the device does the polygon-in-cell tests in IEEE double in
+ * the reference's operation order, so the result is bit-identical to the reference's table, with
+ * each cell's entries in ascending k (the order the reference produces). The arrays of `out` are
+ * owned by the context and stay valid until the next call or mppb_ctx_destroy. */
+typedef struct mppb_colgrid_build_desc
+{
+    int32_t         num_paths;
+    const uint32_t* path_begin; /* [num_paths+1] */
+    const float*    x;
+    const float*    y;
+    const float*    phi;
+    const float*    dist;
+    double          ref_distance, resolution;
+    int32_t         shape_nverts;
+    const double*   shape_x;
+    const double*   shape_y;
+} mppb_colgrid_build_desc;
+typedef struct mppb_colgrid
+{
+    double          x_min, y_min, res;
+    int32_t         nx, ny;
+    uint64_t        n_entries;
+    const uint32_t* cell_offsets; /* [nx*ny+1] */
+    const uint16_t* entry_k;      /* [n_entries] */
+    const float*    entry_d;      /* [n_entries] */
+} mppb_colgrid;
+int mppb_build_collision_grid(mppb_ctx* ctx, const mppb_colgrid_build_desc* desc, mppb_colgrid* out);
+/* timings of the last build: out4 = host cos/sin s, uploads+kernels+result s, kernels s (device clock), steps */
+int mppb_colgrid_build_stats(const mppb_ctx* ctx, double* out4);
 
 int mppb_clear_ptgs(mppb_ctx* ctx);
 /* ptg_index must be the next free index (0,1,2,...) over PTGs of all kinds */
@@ -258,6 +296,9 @@ typedef struct mppb_diffdrive_c_params
 /* mpp::ptg::DiffDrive_C (src/ptgs/DiffDrive_C.cpp): simulates the trajectories and builds
  * the collision grid (DiffDriveCollisionGridBased.cpp:615-764). */
 int  mppb_ptg_create_diffdrive_c(const mppb_diffdrive_c_params* params, mppb_ptg** out_ptg);
+/* Same PTG with the collision grid built on the GPU of `ctx` (mppb_build_collision_grid) instead of
+ * the multi-threaded host builder; identical tables. */
+int  mppb_ptg_create_diffdrive_c_on(mppb_ctx* ctx, const mppb_diffdrive_c_params* params, mppb_ptg** out_ptg);
 void mppb_ptg_destroy(mppb_ptg* ptg);
 /* message of the last failure on a PTG object or PTG constructor */
 const char* mppb_ptg_last_error(void);

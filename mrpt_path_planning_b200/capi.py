@@ -126,6 +126,10 @@ _SIGS = {
     "mppb_eval_nodes_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p]),
     "mppb_nodes_xycs_from_poses": (None, [C.c_size_t, C.c_void_p, C.c_void_p]),
     "mppb_ptg_create_diffdrive_c": (C.c_int, [C.POINTER(DiffDriveCParams), C.POINTER(C.c_void_p)]),
+    # (desc and result are passed as raw pointers: the host PTG object is the caller, see host/ptg.cpp)
+    "mppb_build_collision_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mppb_colgrid_build_stats": (C.c_int, [C.c_void_p, c_double_p]),
+    "mppb_ptg_create_diffdrive_c_on": (C.c_int, [C.c_void_p, C.POINTER(DiffDriveCParams), C.POINTER(C.c_void_p)]),
     "mppb_ptg_destroy": (None, [C.c_void_p]),
     "mppb_ptg_last_error": (C.c_char_p, []),
     "mppb_ptg_num_paths": (C.c_int, [C.c_void_p]),
@@ -234,13 +238,14 @@ class PTG:
 
     @staticmethod
     def diffdrive_c(num_paths, ref_distance, resolution, v_max_mps, w_max_rps, K, shape_x, shape_y,
-                    turning_radius_ref=0.10):
+                    turning_radius_ref=0.10, ctx=None):
+        """ctx=None: collision grid from the host builder; ctx=Context: built on that GPU (same table)."""
         sx = np.ascontiguousarray(shape_x, dtype=np.float64)
         sy = np.ascontiguousarray(shape_y, dtype=np.float64)
         p = DiffDriveCParams(num_paths, ref_distance, resolution, v_max_mps, w_max_rps, K, turning_radius_ref,
                              len(sx), sx.ctypes.data_as(c_double_p), sy.ctypes.data_as(c_double_p))
         h = C.c_void_p()
-        if lib().mppb_ptg_create_diffdrive_c(C.byref(p), C.byref(h)) != 0:
+        if lib().mppb_ptg_create_diffdrive_c_on(ctx.h if ctx is not None else None, C.byref(p), C.byref(h)) != 0:
             raise MppbError(lib().mppb_ptg_last_error().decode())
         return PTG(h.value)
 
@@ -380,6 +385,12 @@ class Context:
     @property
     def launch_count(self):
         return lib().mppb_launch_count(self.h)
+
+    def colgrid_build_stats(self):
+        """Timings of the last mppb_build_collision_grid on this context."""
+        v = np.zeros(4)
+        self._ck(lib().mppb_colgrid_build_stats(self.h, v.ctypes.data_as(c_double_p)))
+        return {"host_sincos_s": v[0], "gpu_total_s": v[1], "kernels_s": v[2], "steps": int(v[3])}
 
     def timer_begin(self):
         self._ck(lib().mppb_timer_begin(self.h))
@@ -563,9 +574,10 @@ ACKERMANN_SHAPE_X = np.array([-0.10, 0.00, 0.3, 0.3, 0.0, -0.10], dtype=np.float
 ACKERMANN_SHAPE_Y = np.array([0.15, 0.15, 0.1, -0.1, -0.15, -0.15], dtype=np.float32).astype(np.float64)
 
 
-def ackermann_ptgs(num_paths=121, ref_distance=5.0, resolution=0.05):
+def ackermann_ptgs(num_paths=121, ref_distance=5.0, resolution=0.05, ctx=None):
     w = 60.0 * np.pi / 180.0
-    return [PTG.diffdrive_c(num_paths, ref_distance, resolution, 1.0, w, K, ACKERMANN_SHAPE_X, ACKERMANN_SHAPE_Y)
+    return [PTG.diffdrive_c(num_paths, ref_distance, resolution, 1.0, w, K, ACKERMANN_SHAPE_X, ACKERMANN_SHAPE_Y,
+                            ctx=ctx)
             for K in (+1.0, -1.0)]
 
 

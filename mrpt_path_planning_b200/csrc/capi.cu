@@ -100,6 +100,7 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
         ctx->evalWps[i].release();
     }
     ctx->evalDescs.release();
+    ctx->colgrid.release();
     ctx->hNodes.release();
     ctx->hOut.release();
     ctx->hStage.release();

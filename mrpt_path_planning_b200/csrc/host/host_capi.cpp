@@ -26,6 +26,11 @@ const char* mppb_ptg_last_error(void) { return g_ptgErr.c_str(); }
 
 int mppb_ptg_create_diffdrive_c(const mppb_diffdrive_c_params* p, mppb_ptg** out)
 {
+    return mppb_ptg_create_diffdrive_c_on(nullptr, p, out);
+}
+
+int mppb_ptg_create_diffdrive_c_on(mppb_ctx* ctx, const mppb_diffdrive_c_params* p, mppb_ptg** out)
+{
     HOST_TRY
     if (!p || !out) throw std::runtime_error("null argument");
     *out = nullptr;
@@ -43,7 +48,7 @@ int mppb_ptg_create_diffdrive_c(const mppb_diffdrive_c_params* p, mppb_ptg** out
     auto* h = new mppb_ptg();
     try
     {
-        h->obj = std::make_unique<mpp::DiffDrive_C>(q);
+        h->obj = std::make_unique<mpp::DiffDrive_C>(q, ctx);
     }
     catch (...)
     {

@@ -80,7 +80,7 @@ struct GridGeom
 };
 }  // namespace
 
-DiffDrive_C::DiffDrive_C(const DiffDriveCParams& p) : p_(p)
+DiffDrive_C::DiffDrive_C(const DiffDriveCParams& p, mppb_ctx* buildCtx) : p_(p)
 {
     MPP_ASSERT(p_.shape_x.size() == p_.shape_y.size() && p_.shape_x.size() >= 3);
     MPP_ASSERT(p_.shape_x.size() <= MPPB_MAX_SHAPE_VERTS);
@@ -91,8 +91,41 @@ DiffDrive_C::DiffDrive_C(const DiffDriveCParams& p) : p_(p)
     for (size_t i = 0; i < p_.shape_x.size(); i++)
         maxRadius_ = std::max(maxRadius_, std::sqrt(p_.shape_x[i] * p_.shape_x[i] + p_.shape_y[i] * p_.shape_y[i]));
     simulate();
-    buildCollisionGrid();
+    if (buildCtx)
+        buildCollisionGridOn(buildCtx);
+    else
+        buildCollisionGrid();
     initialized_ = true;
+}
+
+// Collision grid on the GPU: the paths go up, the CSR comes back (csrc/colgrid_build.cu).
+void DiffDrive_C::buildCollisionGridOn(mppb_ctx* ctx)
+{
+    std::vector<uint32_t> begin(pathBegin_.size());
+    for (size_t i = 0; i < pathBegin_.size(); i++) begin[i] = static_cast<uint32_t>(pathBegin_[i]);
+    mppb_colgrid_build_desc d{};
+    d.num_paths    = static_cast<int32_t>(numPaths_);
+    d.path_begin   = begin.data();
+    d.x            = tx_.data();
+    d.y            = ty_.data();
+    d.phi          = tphi_.data();
+    d.dist         = tdist_.data();
+    d.ref_distance = refDistance_;
+    d.resolution   = p_.resolution;
+    d.shape_nverts = static_cast<int32_t>(p_.shape_x.size());
+    d.shape_x      = p_.shape_x.data();
+    d.shape_y      = p_.shape_y.data();
+    mppb_colgrid g{};
+    if (mppb_build_collision_grid(ctx, &d, &g) != MPPB_OK)
+        throw std::runtime_error(std::string("mppb_build_collision_grid: ") + mppb_last_error(ctx));
+    gxmin_ = g.x_min;
+    gymin_ = g.y_min;
+    gres_  = g.res;
+    gnx_   = g.nx;
+    gny_   = g.ny;
+    cellOffsets_.assign(g.cell_offsets, g.cell_offsets + static_cast<size_t>(g.nx) * g.ny + 1);
+    entryK_.assign(g.entry_k, g.entry_k + g.n_entries);
+    entryD_.assign(g.entry_d, g.entry_d + g.n_entries);
 }
 
 // Euler integration with float state, dt = 1e-3 s, until dist >= refDistance, t >= 100 s or
@@ -103,43 +136,75 @@ void DiffDrive_C::simulate()
 {
     const float max_time = 100.0f, max_dist = static_cast<float>(refDistance_), dt = 1.0e-3f;
     stepDuration_ = dt;
-    pathBegin_.assign(1, 0);
     const int sgn = sign_of(p_.K);
-    for (unsigned k = 0; k < numPaths_; k++)
+    // paths are independent: each one is integrated into its own buffer by a pool of host threads,
+    // then the buffers are concatenated in k order
+    struct Path
     {
-        const float alpha = static_cast<float>(index2alpha(k));
-        const float v     = static_cast<float>(p_.v_max_mps * sgn);
-        const float w     = static_cast<float>((alpha / M_PI) * p_.w_max_rps * sgn);
-        float       t = 0, dist = 0, turned = 0, x = 0, y = 0, phi = 0;
-        auto        push = [&](float pv, float pw) {
-            tx_.push_back(x);
-            ty_.push_back(y);
-            tphi_.push_back(phi);
-            tdist_.push_back(dist);
-            tv_.push_back(pv);
-            tw_.push_back(pw);
-        };
-        push(0.f, 0.f);
-        bool moved = false;
-        while (t < max_time && dist < max_dist && std::fabs(static_cast<double>(turned)) < 1.95 * M_PI)
+        std::vector<float> x, y, phi, dist, v, w;
+    };
+    std::vector<Path>     paths(numPaths_);
+    std::atomic<unsigned> next{0};
+    auto                  worker = [&]() {
+        for (;;)
         {
-            x += std::cos(static_cast<double>(phi)) * v * dt;
-            y += std::sin(static_cast<double>(phi)) * v * dt;
-            phi += w * dt;
-            turned += w * dt;
-            const double wr   = w * p_.turningRadiusReference;
-            const float  vtps = static_cast<float>(std::sqrt((v * v) + wr * wr));
-            dist += vtps * dt;
-            t += dt;
-            tv_.back() = v;  // the command that leaves the previous record
-            tw_.back() = w;
-            push(v, w);
-            moved = true;
+            const unsigned k = next.fetch_add(1);
+            if (k >= numPaths_) break;
+            Path&       P     = paths[k];
+            const float alpha = static_cast<float>(index2alpha(k));
+            const float v     = static_cast<float>(p_.v_max_mps * sgn);
+            const float w     = static_cast<float>((alpha / M_PI) * p_.w_max_rps * sgn);
+            float       t = 0, dist = 0, turned = 0, x = 0, y = 0, phi = 0;
+            auto        push = [&](float pv, float pw) {
+                P.x.push_back(x);
+                P.y.push_back(y);
+                P.phi.push_back(phi);
+                P.dist.push_back(dist);
+                P.v.push_back(pv);
+                P.w.push_back(pw);
+            };
+            push(0.f, 0.f);
+            bool moved = false;
+            while (t < max_time && dist < max_dist && std::fabs(static_cast<double>(turned)) < 1.95 * M_PI)
+            {
+                x += std::cos(static_cast<double>(phi)) * v * dt;
+                y += std::sin(static_cast<double>(phi)) * v * dt;
+                phi += w * dt;
+                turned += w * dt;
+                const double wr   = w * p_.turningRadiusReference;
+                const float  vtps = static_cast<float>(std::sqrt((v * v) + wr * wr));
+                dist += vtps * dt;
+                t += dt;
+                P.v.back() = v;  // the command that leaves the previous record
+                P.w.back() = w;
+                push(v, w);
+                moved = true;
+            }
+            // the reference appends the final state once more
+            P.v.back() = moved ? v : 0.f;
+            P.w.back() = moved ? w : 0.f;
+            push(moved ? v : 0.f, moved ? w : 0.f);
         }
-        // the reference appends the final state once more
-        tv_.back() = moved ? v : 0.f;
-        tw_.back() = moved ? w : 0.f;
-        push(moved ? v : 0.f, moved ? w : 0.f);
+    };
+    unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    nth          = std::min(nth, numPaths_);
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < nth; i++) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+
+    pathBegin_.assign(1, 0);
+    size_t total = 0;
+    for (const auto& P : paths) total += P.x.size();
+    for (auto* v : {&tx_, &ty_, &tphi_, &tdist_, &tv_, &tw_}) v->reserve(total);
+    for (const auto& P : paths)
+    {
+        tx_.insert(tx_.end(), P.x.begin(), P.x.end());
+        ty_.insert(ty_.end(), P.y.begin(), P.y.end());
+        tphi_.insert(tphi_.end(), P.phi.begin(), P.phi.end());
+        tdist_.insert(tdist_.end(), P.dist.begin(), P.dist.end());
+        tv_.insert(tv_.end(), P.v.begin(), P.v.end());
+        tw_.insert(tw_.end(), P.w.begin(), P.w.end());
         pathBegin_.push_back(tx_.size());
     }
 }

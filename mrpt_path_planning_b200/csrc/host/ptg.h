@@ -110,7 +110,9 @@ struct DiffDriveCParams
 class DiffDrive_C : public ptg_t
 {
    public:
-    explicit DiffDrive_C(const DiffDriveCParams& p);
+    /** buildCtx == nullptr: collision grid from the multi-threaded host builder; otherwise it is built on that
+     *  context's GPU (mppb_build_collision_grid). Both give the same table. */
+    explicit DiffDrive_C(const DiffDriveCParams& p, mppb_ctx* buildCtx = nullptr);
     PtgKind kind() const override { return PtgKind::CollisionGrid; }
 
     size_t   getPathStepCount(uint16_t k) const override { return pathBegin_.at(k + 1) - pathBegin_.at(k); }
@@ -133,6 +135,7 @@ class DiffDrive_C : public ptg_t
    private:
     void simulate();
     void buildCollisionGrid();
+    void buildCollisionGridOn(mppb_ctx* ctx);
     size_t at(uint16_t k, uint32_t step) const;
 
     DiffDriveCParams p_;

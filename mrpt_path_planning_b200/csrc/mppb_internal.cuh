@@ -164,6 +164,19 @@ struct CloudStore
     }
 };
 
+// scratch of mppb_build_collision_grid (colgrid_build.cu); the result's host arrays live here until the next build
+struct ColgridBuildBufs
+{
+    DevBuf    dBegin, dX, dY, dDist, dCs, dDense, dCounts, dOffsets, dEntryK, dEntryD;
+    PinnedBuf hCs, hOffsets, hEntryK, hEntryD;
+    double    stats[4] = {0, 0, 0, 0};
+    void      release()
+    {
+        for (DevBuf* b : {&dBegin, &dX, &dY, &dDist, &dCs, &dDense, &dCounts, &dOffsets, &dEntryK, &dEntryD}) b->release();
+        for (PinnedBuf* b : {&hCs, &hOffsets, &hEntryK, &hEntryD}) b->release();
+    }
+};
+
 // host copy of one uploaded collision-grid PTG (kept to rebuild the merged groups)
 struct PtgGridHost
 {
@@ -231,6 +244,8 @@ struct mppb_ctx
     mppb::DevBuf       evalCells[MPPB_MAX_EVALUATORS], evalWps[MPPB_MAX_EVALUATORS];
     mppb::DevBuf       evalDescs;  // EvaluatorDev[MPPB_MAX_EVALUATORS]
     int                numEvals = 0;
+
+    mppb::ColgridBuildBufs colgrid;
 
     // staging for the host entry points
     mppb::PinnedBuf hNodes, hOut, hStage;
