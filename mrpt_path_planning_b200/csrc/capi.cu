@@ -2,6 +2,7 @@
 // staging and launches. There is deliberately no CPU fallback anywhere in this file.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -33,6 +34,23 @@ int cuda_fail(mppb_ctx* ctx, cudaError_t e, const char* what)
 }  // namespace mppb
 
 using namespace mppb;
+
+// Device-visible alias of a PINNED host buffer (mppb_host_alloc / cudaHostRegister): under UVA a kernel can read and
+// write it directly over PCIe. Small latency-bound batches (one A* expansion) use this instead of staging copies:
+// it removes two to four cudaMemcpyAsync calls and their DMA set-up per batch. Returns nullptr for pageable memory.
+static const bool g_noZeroCopy = std::getenv("MPPB_NO_ZEROCOPY") != nullptr;  // A/B measurements only
+template <class T>
+static T* mapped_alias(const T* hostPtr)
+{
+    if (g_noZeroCopy || !hostPtr) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, hostPtr) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        return static_cast<T*>(attr.devicePointer);
+    cudaGetLastError();  // pageable memory may be reported as an error by older drivers: not ours
+    return nullptr;
+}
+// inputs of at most this many bytes are read in place by the kernels; larger ones are staged into HBM by DMA
+static constexpr size_t kZeroCopyInputBytes = 256 * 1024;
 
 extern "C" {
 
@@ -492,12 +510,18 @@ int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyp
     const size_t outBytes = n_nodes * cols * sizeof(float);
     MPPB_CUDA(ctx, ctx->hNodes.reserve(inBytes));
     MPPB_CUDA(ctx, ctx->dNodes.reserve(inBytes));
-    MPPB_CUDA(ctx, ctx->dOut.reserve(outBytes));
+    const bool   nodesInPlace = inBytes <= kZeroCopyInputBytes && n_nodes <= 1024 && mapped_alias(ctx->hNodes.as<double>());
+    const float* dBoxes       = nullptr;
     if (node_boxes)
     {
-        MPPB_CUDA(ctx, ctx->dBoxes.reserve(n_nodes * 4 * sizeof(float)));
-        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxes.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
-                                       ctx->stream));
+        if (nodesInPlace) dBoxes = mapped_alias(node_boxes);
+        if (!dBoxes)
+        {
+            MPPB_CUDA(ctx, ctx->dBoxes.reserve(n_nodes * 4 * sizeof(float)));
+            MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxes.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
+                                           ctx->stream));
+            dBoxes = ctx->dBoxes.as<float>();
+        }
     }
     if (!ctx->auxStream)
     {
@@ -509,10 +533,19 @@ int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyp
     // the host prepares cos/sin of j+1 and the copy engine drains the result of j-1.
     // D2H goes straight into the caller's buffer: a true async DMA if it is pinned
     // (mppb_host_alloc), a staged copy inside the driver otherwise.
+    // If the caller's buffer is pinned (mppb_host_alloc / cudaHostRegister) it is device-accessible under UVA: the
+    // kernel then stores its rows straight into it over PCIe (posted writes, 968 contiguous bytes per node), which
+    // overlaps the result transfer with the computation CTA by CTA and removes the D2H copies altogether.
+    float* const outDev = mapped_alias(out);
+    if (!outDev) MPPB_CUDA(ctx, ctx->dOut.reserve(outBytes));
     const size_t sub      = std::max<size_t>(1024, (n_nodes + 3) / 4);  // <= 4 sub-batches: API calls cost ~5 us each
     cudaStream_t streams[2] = {ctx->stream, ctx->auxStream};
-    MPPB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
-    MPPB_CUDA(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->evFork, 0));
+    const bool   single     = n_nodes <= sub;  // one sub-batch: no second stream, no fork/join events
+    if (!single)
+    {
+        MPPB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+        MPPB_CUDA(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->evFork, 0));
+    }
     cudaStream_t saved = ctx->stream;
     int          rc    = MPPB_OK;
     size_t       j     = 0;
@@ -522,23 +555,31 @@ int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyp
         cudaStream_t  st = streams[j & 1];
         double*       hN = ctx->hNodes.as<double>() + 4 * lo;
         double*       dN = ctx->dNodes.as<double>() + 4 * lo;
-        float*        dO = ctx->dOut.as<float>() + lo * cols;
+        float*        dO = outDev ? outDev + lo * cols : ctx->dOut.as<float>() + lo * cols;
         mppb_nodes_xycs_from_poses(n, poses_xyphi + 3 * lo, hN);
-        cudaError_t e = cudaMemcpyAsync(dN, hN, n * 4 * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaError_t e = cudaSuccess;
+        if (nodesInPlace)
+            dN = mapped_alias(hN);  // one small batch: the kernel reads the 32 B per node from the pinned staging
+        else
+            e = cudaMemcpyAsync(dN, hN, n * 4 * sizeof(double), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess)
         {
             rc = cuda_fail(ctx, e, "H2D node batch");
             break;
         }
         ctx->stream = st;  // launch on the sub-batch's stream
-        rc          = launch_tpobs_grid(ctx, n, dN, node_boxes ? ctx->dBoxes.as<float>() + 4 * lo : nullptr, clip_dist, dO);
+        rc          = launch_tpobs_grid(ctx, n, dN, dBoxes ? dBoxes + 4 * lo : nullptr, clip_dist, dO);
         ctx->stream = saved;
         if (rc != MPPB_OK) break;
+        if (outDev) continue;  // rows already land in the caller's pinned buffer
         e = cudaMemcpyAsync(out + lo * cols, dO, n * cols * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "D2H result");
     }
-    cudaEventRecord(ctx->evJoin, ctx->auxStream);
-    cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0);
+    if (!single)
+    {
+        cudaEventRecord(ctx->evJoin, ctx->auxStream);
+        cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0);
+    }
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
 }
@@ -584,23 +625,41 @@ int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double*
     const size_t nodeBytes = n_nodes * 4 * sizeof(double), candBytes = n_cands * sizeof(mppb_holo_cand);
     const size_t outBytes  = n_cands * sizeof(double);
     MPPB_CUDA(ctx, ctx->hNodes.reserve(nodeBytes));
-    MPPB_CUDA(ctx, ctx->dNodes.reserve(nodeBytes));
-    MPPB_CUDA(ctx, ctx->dStage.reserve(candBytes));
-    MPPB_CUDA(ctx, ctx->dStage2.reserve(outBytes));
     mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodes.as<double>());
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, nodeBytes, cudaMemcpyHostToDevice, ctx->stream));
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, cands, candBytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (node_boxes)
+    // small batch with pinned caller buffers: the kernel works on them in place (no staging copies)
+    const bool            small  = nodeBytes + candBytes <= kZeroCopyInputBytes;
+    const double*         dNodes = small ? mapped_alias(ctx->hNodes.as<double>()) : nullptr;
+    const mppb_holo_cand* dCands = small ? mapped_alias(cands) : nullptr;
+    const float*          dBoxes = (small && node_boxes) ? mapped_alias(node_boxes) : nullptr;
+    double*               dOut   = mapped_alias(out);
+    if (!dNodes)
+    {
+        MPPB_CUDA(ctx, ctx->dNodes.reserve(nodeBytes));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, nodeBytes, cudaMemcpyHostToDevice, ctx->stream));
+        dNodes = ctx->dNodes.as<double>();
+    }
+    if (!dCands)
+    {
+        MPPB_CUDA(ctx, ctx->dStage.reserve(candBytes));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, cands, candBytes, cudaMemcpyHostToDevice, ctx->stream));
+        dCands = ctx->dStage.as<mppb_holo_cand>();
+    }
+    if (node_boxes && !dBoxes)
     {
         MPPB_CUDA(ctx, ctx->dBoxes.reserve(n_nodes * 4 * sizeof(float)));
         MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxes.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
                                        ctx->stream));
+        dBoxes = ctx->dBoxes.as<float>();
     }
-    const int rc = launch_tpobs_holo(ctx, n_cands, ctx->dStage.as<mppb_holo_cand>(), ctx->dNodes.as<double>(),
-                                     node_boxes ? ctx->dBoxes.as<float>() : nullptr, clip_dist,
-                                     ctx->dStage2.as<double>());
+    const bool outInPlace = dOut != nullptr;
+    if (!outInPlace)
+    {
+        MPPB_CUDA(ctx, ctx->dStage2.reserve(outBytes));
+        dOut = ctx->dStage2.as<double>();
+    }
+    const int rc = launch_tpobs_holo(ctx, n_cands, dCands, dNodes, dBoxes, clip_dist, dOut);
     if (rc != MPPB_OK) return rc;
-    MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dStage2.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!outInPlace) MPPB_CUDA(ctx, cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MPPB_OK;
 }
@@ -707,18 +766,40 @@ int mppb_eval_edge_costs(mppb_ctx* ctx, size_t n_edges, const double* from_xyphi
     const size_t relBytes  = std::max<size_t>(m, 1) * 2 * sizeof(double);
     const size_t outBytes  = n_edges * ctx->numEvals * sizeof(double);
     MPPB_CUDA(ctx, ctx->hNodes.reserve(fromBytes));
-    MPPB_CUDA(ctx, ctx->dNodes.reserve(fromBytes));
-    MPPB_CUDA(ctx, ctx->dStage.reserve(offBytes));
-    MPPB_CUDA(ctx, ctx->dStage2.reserve(relBytes));
-    MPPB_CUDA(ctx, ctx->dStage3.reserve(outBytes));
     mppb_nodes_xycs_from_poses(n_edges, from_xyphi, ctx->hNodes.as<double>());
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, fromBytes, cudaMemcpyHostToDevice, ctx->stream));
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, sample_offsets, offBytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (m) MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage2.p, rel_xy, m * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = launch_edge_costs(ctx, n_edges, ctx->dNodes.as<double>(), ctx->dStage.as<uint32_t>(),
-                                     ctx->dStage2.as<double>(), ctx->dStage3.as<double>());
+    // small batch with pinned caller buffers: the kernel works on them in place (no staging copies)
+    const bool      small = fromBytes + offBytes + relBytes <= kZeroCopyInputBytes;
+    const double*   dFrom = small ? mapped_alias(ctx->hNodes.as<double>()) : nullptr;
+    const uint32_t* dOff  = small ? mapped_alias(sample_offsets) : nullptr;
+    const double*   dRel  = small ? mapped_alias(rel_xy) : nullptr;
+    double*         dOut  = mapped_alias(out);
+    if (!dFrom)
+    {
+        MPPB_CUDA(ctx, ctx->dNodes.reserve(fromBytes));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, fromBytes, cudaMemcpyHostToDevice, ctx->stream));
+        dFrom = ctx->dNodes.as<double>();
+    }
+    if (!dOff)
+    {
+        MPPB_CUDA(ctx, ctx->dStage.reserve(offBytes));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage.p, sample_offsets, offBytes, cudaMemcpyHostToDevice, ctx->stream));
+        dOff = ctx->dStage.as<uint32_t>();
+    }
+    if (!dRel)
+    {
+        MPPB_CUDA(ctx, ctx->dStage2.reserve(relBytes));
+        if (m) MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dStage2.p, rel_xy, m * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dRel = ctx->dStage2.as<double>();
+    }
+    const bool outInPlace = dOut != nullptr;
+    if (!outInPlace)
+    {
+        MPPB_CUDA(ctx, ctx->dStage3.reserve(outBytes));
+        dOut = ctx->dStage3.as<double>();
+    }
+    const int rc = launch_edge_costs(ctx, n_edges, dFrom, dOff, dRel, dOut);
     if (rc != MPPB_OK) return rc;
-    MPPB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dStage3.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!outInPlace) MPPB_CUDA(ctx, cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MPPB_OK;
 }

@@ -44,11 +44,20 @@ namespace mppb
 {
 namespace
 {
-constexpr int      kThreads = 128;
+#ifndef MPPB_GRID_THREADS
+#define MPPB_GRID_THREADS 128
+#endif
+constexpr int      kThreads = MPPB_GRID_THREADS;
 constexpr int      kWarps   = kThreads / 32;
 constexpr int      kRowsPerPass = 64;   // bin rows whose runs are flattened together
 constexpr int      kMaxChunks   = 512;  // 32-point chunks indexed per pass
 constexpr int      kMaxInside   = 128;  // queued points inside the robot shape per node and group
+#ifndef MPPB_GRID_SCATTER_MAX
+#define MPPB_GRID_SCATTER_MAX 640
+#endif
+constexpr int      kLongList    = 32;   // by-cell lists longer than this are folded by the whole block
+constexpr int      kMaxLong     = 128;  // queue of such cells per node and group
+constexpr int      kScatterMax  = MPPB_GRID_SCATTER_MAX;  // <= this many points in the bin window: sparse phase 2
 constexpr unsigned kInfBits = 0x7f800000u;
 constexpr unsigned kFull    = 0xffffffffu;
 
@@ -101,6 +110,71 @@ __device__ __forceinline__ void apply_inside_cell(const GridGroupDev& G, uint32_
     }
 }
 
+// Phase 2 for sparse clouds: scatter the (column, d) lists of the few occupied cells.
+// A column scan walks a whole ascending-d list (hundreds of dependent steps) when nothing blocks the path; with few
+// occupied cells it is far cheaper to visit those cells' by-cell lists instead: every thread walks its share of the
+// bitmap words and folds the list of each set bit into smin (order-independent atomicMin). Kept out of line so that
+// its registers do not weigh on the dense path of the kernel.
+__device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned* bitmap, int words, unsigned* smin,
+                                           uint32_t* longCell, unsigned* nLongPtr)
+{
+    // a thread folds the short lists of its cells itself; long lists (cells near the origin carry one entry per
+    // path) are queued and folded by the whole block afterwards
+    auto foldCell = [&](uint32_t cell, uint32_t eb, uint32_t ee) {
+        if (ee - eb > static_cast<uint32_t>(kLongList))
+        {
+            const unsigned slot = atomicAdd(nLongPtr, 1u);
+            if (slot < static_cast<unsigned>(kMaxLong))
+            {
+                longCell[slot] = cell;
+                return;
+            }
+        }
+        // eight entries per round: the loads are issued together (one L2 latency per round, not per entry)
+        for (uint32_t e = eb; e < ee; e += 8)
+        {
+            uint2 kd[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) kd[j] = G.entries[min(e + j, ee - 1)];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (e + j < ee) atomicMin(&smin[kd[j].x], kd[j].y);
+        }
+    };
+    for (int i = threadIdx.x; i < words; i += kThreads)
+    {
+        unsigned bits = bitmap[i];
+        while (bits)
+        {
+            // two cells at a time: their list bounds are independent loads
+            const uint32_t c0 = (static_cast<uint32_t>(i) << 5) + (__ffs(bits) - 1);
+            bits &= bits - 1;
+            uint32_t c1 = c0;
+            if (bits)
+            {
+                c1 = (static_cast<uint32_t>(i) << 5) + (__ffs(bits) - 1);
+                bits &= bits - 1;
+            }
+            const uint32_t b0 = G.offsets[c0], e0 = G.offsets[c0 + 1];
+            const uint32_t b1 = G.offsets[c1], e1 = G.offsets[c1 + 1];
+            foldCell(c0, b0, e0);
+            if (c1 != c0) foldCell(c1, b1, e1);
+        }
+    }
+    __syncthreads();
+    const unsigned nl = min(*nLongPtr, static_cast<unsigned>(kMaxLong));
+    for (unsigned q = 0; q < nl; q++)
+    {
+        const uint32_t cell = longCell[q];
+        const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
+        for (uint32_t e = eb + threadIdx.x; e < ee; e += kThreads)
+        {
+            const uint2 kd = G.entries[e];
+            atomicMin(&smin[kd.x], kd.y);
+        }
+    }
+}
+
 // HAS_BOX: obstacle points outside the node's own world box (float compare, inclusive bounds:
 // ObstacleSource.cpp:29-40) are ignored — the per-query clipping of independent planning queries
 // that share one resident cloud.
@@ -124,6 +198,9 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
     __shared__ uint8_t  chunkCnt[kMaxChunks];
     __shared__ uint32_t insideCell[kMaxInside];
     __shared__ unsigned nInside;
+    __shared__ unsigned ptsTotal;  // points in the bin window: few => sparse form of phase 2
+    __shared__ uint32_t longCell[kMaxLong];
+    __shared__ unsigned nLong;
 
     const int    node = blockIdx.x;
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -162,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
         by1             = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
     }
 
+    int sparseWords = 0;  // > 0: phase 2 of the last group is done in its sparse form after the loop
     for (int gi = 0; any && gi < numGroups; gi++)
     {
         const GridGroupDev& G = groups[gi];
@@ -187,7 +265,12 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
         const int* const      colOut   = G.colOut;
 
         __syncthreads();  // previous group's phase 2 has finished reading the bitmap
-        if (threadIdx.x == 0) nInside = 0;
+        if (threadIdx.x == 0)
+        {
+            nInside  = 0;
+            ptsTotal = 0;
+            nLong    = 0;
+        }
         const int words = ((gnx * gny) >> 5) + 1;
         for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
 
@@ -203,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
                 rowBeg[threadIdx.x]        = b;
                 rowLen[threadIdx.x]        = e - b;
                 rowPrefix[threadIdx.x + 1] = (e - b + 31) >> 5;  // 32-point chunks of this row's run
+                if (e != b) atomicAdd(&ptsTotal, e - b);         // points in the bin window: decides the form of phase 2
             }
             __syncthreads();
             if (warp == 0)
@@ -348,7 +432,16 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
         {
             const unsigned n = min(nInside, static_cast<unsigned>(kMaxInside));
             for (unsigned q = 0; q < n; q++) apply_inside_cell(G, insideCell[q], smin, threadIdx.x, kThreads);
-            if (n) __syncthreads();
+            if (n) __syncthreads();  // the column scan below updates smin without atomics
+        }
+
+        // ---- phase 2, sparse clouds (few points in the bin window): scatter form ----
+        // (only for the last group, after the loop: a call in here would keep the whole kernel state alive across it;
+        // earlier groups of a multi-geometry PTG set take the column scan, which is correct for any density)
+        if (gi == numGroups - 1 && ptsTotal <= static_cast<unsigned>(kScatterMax))
+        {
+            sparseWords = words;
+            break;
         }
 
         // ---- phase 2: per output column, first occupied cell in ascending-d order ----
@@ -388,6 +481,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
             openColumn(base + threadIdx.x + kThreads, B);
         }
     }
+    if (sparseWords) sparse_phase2(groups[numGroups - 1], bitmap, sparseWords, smin, longCell, &nLong);
     __syncthreads();
     float* o = out + static_cast<size_t>(node) * totalPaths;
     for (int i = threadIdx.x; i < totalPaths; i += kThreads) o[i] = __uint_as_float(smin[i]);
