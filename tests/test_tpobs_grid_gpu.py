@@ -164,3 +164,42 @@ def test_mixed_geometry_ptg_groups(capi, orc):
         poses = wl.node_poses(128, 50.0, margin=0.0, seed=seed + 10)
         _check(ctx, orc, optgs, xs, ys, poses, clip=5.0)
     ctx.close()
+
+
+@pytest.mark.parametrize("density", [4.5, 5.5, 6.0, 6.5, 7.5])
+def test_sparse_dense_phase2_boundary(gpu_ctx, orc, oracle_ackermann, density):
+    """Nodes on both sides of the point-count threshold (640 points in the bin window) that selects the scatter form
+    or the column-scan form of phase 2 give the reference's values."""
+    extent = 40.0
+    xs, ys = wl.uniform_cloud(int(density * extent * extent), extent, seed=int(10 * density))
+    poses = wl.node_poses(160, extent, margin=0.5, seed=int(10 * density) + 1)
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+
+
+def test_sparse_cloud_with_points_near_origin(gpu_ctx, orc, oracle_ackermann):
+    """Sparse form with many long by-cell lists: a handful of points right around the robot (cells that carry an entry
+    for almost every path) plus inside-robot points, for many headings."""
+    rng = np.random.default_rng(91)
+    xs = np.concatenate([rng.uniform(19.3, 20.7, 60), rng.uniform(0, 40, 40)]).astype(np.float32)
+    ys = np.concatenate([rng.uniform(19.3, 20.7, 60), rng.uniform(0, 40, 40)]).astype(np.float32)
+    poses = np.array([[20.0 + dx, 20.0 + dy, a] for a in np.linspace(-3.1, 3.1, 9) for dx in (-0.3, 0.0, 0.4)
+                      for dy in (-0.2, 0.1)])
+    got = _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+    assert (got == 0.0).any() and (got == 5.0).any()
+
+
+def test_pinned_and_pageable_buffers_agree(gpu_ctx, capi):
+    """The in-place path (pinned caller buffers, kernels read/write them over PCIe) and the staged-copy path (pageable
+    buffers) return the same rows, for one-node, planner-sized and multi-sub-batch calls."""
+    xs, ys = wl.uniform_cloud(30000, 60.0, seed=17)
+    gpu_ctx.set_obstacles(xs, ys)
+    for n in (1, 37, 1500, 5000):
+        poses = wl.node_poses(n, 60.0, margin=1.0, seed=18 + n)
+        pinned_in = capi.pinned_empty((n, 3), np.float64)
+        pinned_in[:] = poses
+        pinned_out = capi.pinned_empty((n, gpu_ctx.total_paths), np.float32)
+        pinned_out[:] = -1.0
+        a = gpu_ctx.eval_nodes(pinned_in, 5.0, out=pinned_out)
+        b = gpu_ctx.eval_nodes(poses.copy(), 5.0)  # pageable numpy buffers
+        assert a is pinned_out and np.array_equal(a, b)
+        assert (a >= 0).all()
