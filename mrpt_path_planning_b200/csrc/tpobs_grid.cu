@@ -275,7 +275,11 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
         for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
 
         // ---- phase 1: points -> occupancy bitmap ----
+#ifdef MPPB_DBG_SKIP_PHASE1  // timing attribution experiments only
+        for (int rowBase = by0; rowBase <= by1 && clip < 0; rowBase += kRowsPerPass)
+#else
         for (int rowBase = by0; rowBase <= by1; rowBase += kRowsPerPass)
+#endif
         {
             const int nRows = min(kRowsPerPass, by1 - rowBase + 1);
             __syncthreads();  // bitmap cleared / previous pass done with the row tables
@@ -462,7 +466,11 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
             cs.q = next;
             return ++cs.i < cs.end;
         };
+#ifdef MPPB_DBG_SKIP_PHASE2  // timing attribution experiments only
+        for (int base = 0; clip < 0;)
+#else
         for (int base = 0;;)
+#endif
         {
             // a column already blocked at distance 0 by a point inside the robot needs no scan
             bool actA = A.oc >= 0 && smin[A.oc] != 0u;
