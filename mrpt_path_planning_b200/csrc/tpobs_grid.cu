@@ -179,7 +179,7 @@ __device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned
 // ObstacleSource.cpp:29-40) are ignored — the per-query clipping of independent planning queries
 // that share one resident cloud.
 #ifndef MPPB_GRID_MIN_BLOCKS
-#define MPPB_GRID_MIN_BLOCKS 8
+#define MPPB_GRID_MIN_BLOCKS 9  // 56 registers: 9 CTAs per SM (a 4096-node batch is then 3.07 waves of 148 x 9)
 #endif
 template <bool HAS_BOX>
 __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
