@@ -254,6 +254,9 @@ int mppb_set_costmap(mppb_ctx* ctx, int slot, const mppb_costmap_desc* desc);
 int mppb_set_waypoints(mppb_ctx* ctx, int slot, const double* xs, const double* ys, size_t n, double influence_radius,
                        double cost_scale, int use_average);
 int mppb_num_evaluators(const mppb_ctx* ctx);
+/* counter bumped by every mppb_clear_evaluators / mppb_set_costmap / mppb_set_waypoints on this context: lets a caller
+ * that keeps evaluators resident across plans notice that somebody else changed the slots */
+uint64_t mppb_evaluators_epoch(const mppb_ctx* ctx);
 /* Edge e starts at from_xyphi[e] and has the interpolated samples
  * [sample_offsets[e], sample_offsets[e+1]) of rel_xy (poses relative to the start, in time
  * order: MoveEdgeSE2_TPS::interpolatedPath). out[e][slot] = evaluator(edge), row length

@@ -156,6 +156,7 @@ _SIGS = {
     "mppb_set_costmap": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(CostmapDesc)]),
     "mppb_set_waypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
                                      C.c_double, C.c_int]),
+    "mppb_evaluators_epoch": (C.c_uint64, [C.c_void_p]),
     "mppb_num_evaluators": (C.c_int, [C.c_void_p]),
     "mppb_eval_edge_costs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppb_eval_edge_costs_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -686,9 +686,11 @@ int mppb_clear_evaluators(mppb_ctx* ctx)
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < MPPB_MAX_EVALUATORS; i++) ctx->evals[i] = EvaluatorDev{};
     ctx->numEvals = 0;
+    ctx->evalEpoch++;
     return MPPB_OK;
 }
-int mppb_num_evaluators(const mppb_ctx* ctx) { return ctx ? ctx->numEvals : 0; }
+int      mppb_num_evaluators(const mppb_ctx* ctx) { return ctx ? ctx->numEvals : 0; }
+uint64_t mppb_evaluators_epoch(const mppb_ctx* ctx) { return ctx ? ctx->evalEpoch : 0; }
 
 int mppb_set_costmap(mppb_ctx* ctx, int slot, const mppb_costmap_desc* d)
 {
@@ -697,6 +699,7 @@ int mppb_set_costmap(mppb_ctx* ctx, int slot, const mppb_costmap_desc* d)
     if (!d || !d->cells || d->nx <= 0 || d->ny <= 0 || !(d->res > 0))
         return fail(ctx, MPPB_ERR_INVALID_ARG, "bad costmap descriptor");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->evalEpoch++;
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t bytes = static_cast<size_t>(d->nx) * d->ny * sizeof(double);
     MPPB_CUDA(ctx, ctx->evalCells[slot].reserve(bytes));
@@ -721,6 +724,7 @@ int mppb_set_waypoints(mppb_ctx* ctx, int slot, const double* xs, const double* 
     if (slot < 0 || slot >= MPPB_MAX_EVALUATORS) return fail(ctx, MPPB_ERR_INVALID_ARG, "evaluator slot out of range");
     if (n && (!xs || !ys)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null waypoint arrays");
     if (!(influence_radius > 0)) return fail(ctx, MPPB_ERR_INVALID_ARG, "influence radius must be > 0");
+    ctx->evalEpoch++;
     if (n > 0x7fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many waypoints");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

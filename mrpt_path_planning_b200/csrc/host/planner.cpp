@@ -253,6 +253,24 @@ struct TPS_Astar::Impl
     } uploadedCloud;
     bool cloudValid = false;
 
+    // evaluators resident in the context: object, its table and the parameters the device copy depends on.
+    // A CostEvaluatorCostMap / PreferredWaypoint is immutable once built (as in the reference, whose grid and
+    // waypoint map are private), so an unchanged key means the 4.8 MB costmap need not travel again.
+    struct EvalKey
+    {
+        const void* obj  = nullptr;
+        const void* data = nullptr;
+        size_t      n    = 0;
+        double      p[5] = {0, 0, 0, 0, 0};
+        bool        operator==(const EvalKey& o) const
+        {
+            return obj == o.obj && data == o.data && n == o.n && std::memcmp(p, o.p, sizeof(p)) == 0;
+        }
+    };
+    std::vector<EvalKey> uploadedEvals;
+    bool                 evalsValid = false;
+    uint64_t             evalEpoch  = 0;  // the context's evaluator epoch right after our upload
+
     // evaluator slots of the current plan
     std::vector<int> evalSlot;  // per costEvaluators_ entry: GPU slot or -1 (host plugin)
     int              numGpuEvals = 0;
@@ -780,6 +798,32 @@ void TPS_Astar::Impl::uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, 
 
 void TPS_Astar::Impl::uploadEvaluators()
 {
+    // same evaluator objects with the same tables as in the previous plan: nothing to upload
+    std::vector<EvalKey> want;
+    for (const auto& cePtr : self->costEvaluators_)
+    {
+        const CostEvaluator* ce = cePtr.get();
+        EvalKey              k;
+        k.obj = ce;
+        if (auto* cm = dynamic_cast<const CostEvaluatorCostMap*>(ce))
+        {
+            k.data = cm->cells.data();
+            k.n    = cm->cells.size();
+            k.p[0] = cm->x_min, k.p[1] = cm->y_min, k.p[2] = cm->params_.resolution, k.p[3] = cm->size_x;
+            k.p[4] = cm->params_.useAverageOfPath ? 1 : 0;
+        }
+        else if (auto* wp = dynamic_cast<const CostEvaluatorPreferredWaypoint*>(ce))
+        {
+            k.data = wp->waypoints_.data();
+            k.n    = wp->waypoints_.size();
+            k.p[0] = wp->params_.waypointInfluenceRadius, k.p[1] = wp->params_.costScale;
+            k.p[2] = wp->params_.useAverageOfPath ? 1 : 0;
+            for (const auto& w : wp->waypoints_) k.p[3] += w.x, k.p[4] += w.y;  // cheap content check
+        }
+        want.push_back(k);
+    }
+    if (evalsValid && want == uploadedEvals && evalEpoch == mppb_evaluators_epoch(ctx)) return;
+    evalsValid = false;
     ck(ctx, mppb_clear_evaluators(ctx));
     evalSlot.assign(self->costEvaluators_.size(), -1);
     numGpuEvals = 0;
@@ -808,6 +852,9 @@ void TPS_Astar::Impl::uploadEvaluators()
             evalSlot[e] = numGpuEvals++;
         }
     }
+    uploadedEvals = want;
+    evalsValid    = true;
+    evalEpoch     = mppb_evaluators_epoch(ctx);
 }
 
 std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads)

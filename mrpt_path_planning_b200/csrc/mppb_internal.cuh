@@ -244,6 +244,7 @@ struct mppb_ctx
     mppb::DevBuf       evalCells[MPPB_MAX_EVALUATORS], evalWps[MPPB_MAX_EVALUATORS];
     mppb::DevBuf       evalDescs;  // EvaluatorDev[MPPB_MAX_EVALUATORS]
     int                numEvals = 0;
+    uint64_t           evalEpoch = 0;  // bumped by every change of the evaluator slots
 
     mppb::ColgridBuildBufs colgrid;
 
