@@ -203,3 +203,15 @@ def test_pinned_and_pageable_buffers_agree(gpu_ctx, capi):
         b = gpu_ctx.eval_nodes(poses.copy(), 5.0)  # pageable numpy buffers
         assert a is pinned_out and np.array_equal(a, b)
         assert (a >= 0).all()
+
+
+def test_full_size_parity_with_checker(gpu_ctx, orc, oracle_ackermann):
+    """Config C3 at BASELINE's full size — 2^20 points, 4096 nodes, 2 x 121 paths = 991 232 edge evaluations — equals the
+    checker's values bit for bit (the reference build needs ~2 s per 4096 nodes on 16 host threads)."""
+    xs, ys = wl.uniform_cloud(1 << 20, 200.0)
+    poses = wl.node_poses(4096, 200.0)
+    got = _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+    assert got.shape == (4096, 242) and (got < 5.0).mean() > 0.5
+    # the structured variant of SURVEY 8(d): 70 % of the points on wall segments at 0.05 m spacing
+    xs, ys = wl.walls_cloud(1 << 20, 200.0)
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses[:1024])
