@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""Generates the committed regression vectors under tests/golden/ from the CPU oracle.
+"""Generates (or re-checks) the committed vectors under tests/golden/.
 
-The reference itself cannot run in this container (it needs MRPT), so these vectors are ORACLE outputs: they pin
-the oracle (and, through the GPU parity tests, the product) against drift; they are not reference outputs.
-Inputs are regenerated from seeds, only the expected outputs are stored.
+The generator is the REFERENCE BUILD when it is available — the reference's own translation units compiled from
+/root/reference as oracle/_ref/libmpp_ref.so (see oracle/Makefile, target `ref`; MRPT replaced by a stand-in) — and the
+line-by-line restatement (oracle/orc_*.hpp) otherwise; both produce the same arrays (tests/test_oracle_vs_reference.py,
+and tests/test_golden_cpu.py runs against both). Inputs are regenerated from seeds, only expected outputs are stored.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # regenerate in memory and compare with the committed files
+    python tests/golden/make_golden.py --write    # rewrite the files
 """
 import os
 import sys
@@ -18,7 +20,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from mrpt_path_planning_b200 import workloads as wl  # noqa: E402
-from oracle import orc  # noqa: E402
+from oracle import orc as _port, ref as _ref  # noqa: E402
+
+orc = _ref.module() if _ref.available() else _port  # the generator (same interface either way)
 
 GRID_CASE = dict(n=9000, extent=40.0, cloud_seed=101, nodes=48, nodes_seed=102, margin=2.0, clip=5.0)
 HOLO_CASE = dict(n=1500, extent=25.0, cloud_seed=111, nodes=10, seed=112, ks=list(range(0, 191, 10)),
@@ -53,16 +57,17 @@ def holo_inputs():
     return xs, ys, nodes, rel, cn, ck, cs
 
 
-def main():
+def generate():
     from test_oracle_known_answers import C1_PARAMS, C1_TIMESTAMPS, c1_inputs
 
+    files = {}
     xs, ys, poses = grid_inputs()
     free, _ = orc.eval_nodes(orc.ackermann_ptgs(), xs, ys, poses, GRID_CASE["clip"], mode=0, nthreads=0)
-    np.savez_compressed(os.path.join(HERE, "grid_free_distance.npz"), free=free.astype(np.float32))
+    files["grid_free_distance.npz"] = dict(free=free.astype(np.float32))
 
     xs, ys, nodes, rel, cn, ck, cs = holo_inputs()
     raw, fr, _ = orc.eval_candidates(orc.holonomic_ptgs()[0], xs, ys, nodes, rel, cn, ck, cs, HOLO_CASE["clip"])
-    np.savez_compressed(os.path.join(HERE, "holo_candidates.npz"), raw=raw, free=fr)
+    files["holo_candidates.npz"] = dict(raw=raw, free=fr)
 
     xs, ys, start, goal, lo, hi = c1_inputs()
     out = {}
@@ -79,8 +84,26 @@ def main():
         out[name + "_tree"] = pl.tree()
         out[name + "_path_nodes"] = nodes_
         out[name + "_path_edges"] = edges_
-    np.savez_compressed(os.path.join(HERE, "plans.npz"), **out)
-    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+    files["plans.npz"] = out
+    return files
+
+
+def main():
+    files = generate()
+    kind = getattr(orc, "KIND", "port")
+    if "--write" in sys.argv:
+        for fn, arrays in files.items():
+            np.savez_compressed(os.path.join(HERE, fn), **arrays)
+        print("wrote", sorted(files), "from the", kind)
+        return
+    bad = []
+    for fn, arrays in files.items():
+        have = np.load(os.path.join(HERE, fn))
+        for k, v in arrays.items():
+            if k not in have or not np.array_equal(have[k], v):
+                bad.append("%s:%s" % (fn, k))
+    print("generator: %s; committed vectors %s" % (kind, "REPRODUCED" if not bad else "DIFFER: %s" % bad))
+    sys.exit(1 if bad else 0)
 
 
 if __name__ == "__main__":
