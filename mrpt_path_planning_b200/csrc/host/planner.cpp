@@ -103,6 +103,7 @@ struct Candidate
     bool               isTarget;   // direct-to-goal TPS point
     bool               onGrid;     // result lives in the collision-grid row (else in the holo list)
     uint32_t           evalIndex;  // column of the row / index into the query's holo candidates
+    uint32_t           copies;     // how many identical TPS points of the reference this candidate stands for
 };
 struct PendingEdge
 {
@@ -523,16 +524,27 @@ struct TPS_Astar::Impl::Query
                     }
 
             const bool onGrid = ptg.kind() == PtgKind::CollisionGrid;
+            // A trimmable PTG whose paths ignore the trimmed speed yields, for every speed after the first, exact copies
+            // of the first speed's TPS points (same k, step, distance, pose, cell). Copies can never win the strict "<"
+            // of the per-cell selection nor change the goal-cell set, so only the first speed is carried on; `copies`
+            // keeps the reference's count of evaluated points.
+            const bool     dedup  = trimmable && !ptg.pathsDependOnTrimmableSpeed() && speeds.size() > 1;
+            const uint32_t copies = dedup ? static_cast<uint32_t>(speeds.size()) : 1u;
+            // from.state.pose (+) relPose with the heading's cos/sin taken once (TPose2D::operator+ takes them per call)
+            const double fromC = std::cos(from.state.pose.phi), fromS = std::sin(from.state.pose.phi);
             holoIndex.clear();
             for (size_t i = 0; i < tps.size(); i++)
             {
                 const TpsPoint& tp = tps[i];
                 if (tp.step == 0) continue;  // no motion
                 if (trimmable && tp.speed != ptg.trimmableSpeed_) ptg.trimmableSpeed_ = tp.speed;
+                if (dedup && tp.speed != speeds.front()) continue;
                 const uint16_t   k16        = static_cast<uint16_t>(tp.k);
                 const distance_t relTrgDist = ptg.getPathDist(k16, tp.step);
                 const TPose2D    relPose    = ptg.getPathPose(k16, tp.step);
-                const TPose2D    absPose    = from.state.pose + relPose;
+                const TPose2D    absPose(from.state.pose.x + relPose.x * fromC - relPose.y * fromS,
+                                         from.state.pose.y + relPose.x * fromS + relPose.y * fromC,
+                                         wrap_to_pi(from.state.pose.phi + relPose.phi));
                 if (absPose.x < lo.x || absPose.y < lo.y || absPose.phi < lo.phi) continue;
                 if (absPose.x > hi.x - halfCell || absPose.y > hi.y - halfCell || absPose.phi > hi.phi) continue;
                 Candidate c;
@@ -545,6 +557,7 @@ struct TPS_Astar::Impl::Query
                 c.initDist   = ptg.initTPObstacleSingle(k16);
                 c.isTarget   = targetIdx.count(i) != 0;
                 c.onGrid     = onGrid;
+                c.copies     = copies;
                 if (onGrid)
                     c.evalIndex = static_cast<uint32_t>((*columnOffset)[ptgIdx] + tp.k);
                 else
@@ -583,7 +596,7 @@ struct TPS_Astar::Impl::Query
                 goalNodeCoords.clear();  // the reference declares this set inside the per-PTG loop
                 lastPtg = c.ptgIdx;
             }
-            po.tpsPointsEvaluated++;
+            po.tpsPointsEvaluated += c.copies;
             const double     raw          = c.onGrid ? static_cast<double>(gridRow[c.evalIndex]) : holoOut[c.evalIndex];
             const distance_t freeDistance = std::min(c.initDist, raw);
             if (c.relTrgDist >= freeDistance) continue;  // blocked

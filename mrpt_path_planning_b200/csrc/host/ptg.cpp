@@ -419,6 +419,7 @@ class DiffDriveView final : public ptg_t
         return base_->inverseMap_WS2TP(x, y, k, d, tol);
     }
     bool   isSpeedTrimmable() const override { return true; }
+    bool   pathsDependOnTrimmableSpeed() const override { return false; }
     bool   isPointInsideRobotShape(double x, double y) const override { return base_->isPointInsideRobotShape(x, y); }
     double getMaxRobotRadius() const override { return base_->getMaxRobotRadius(); }
     std::unique_ptr<ptg_t> cloneForQuery() const override { return std::make_unique<DiffDriveView>(base_); }

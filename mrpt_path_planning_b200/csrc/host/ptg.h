@@ -63,6 +63,9 @@ class ptg_t
     virtual bool     inverseMap_WS2TP(double x, double y, int& k, double& d, double tol = 0.10) const = 0;
     virtual bool     supportSpeedAtTarget() const { return false; }
     virtual bool     isSpeedTrimmable() const { return false; }
+    /** false for a SpeedTrimmablePTG whose paths ignore trimmableSpeed_ (DiffDrive_C: its steering function does not
+     *  read it, DiffDrive_C.cpp:70-80): the planner's per-speed TPS points are then exact copies of each other. */
+    virtual bool     pathsDependOnTrimmableSpeed() const { return isSpeedTrimmable(); }
     virtual bool     isPointInsideRobotShape(double x, double y) const = 0;
     virtual double   getMaxRobotRadius() const                         = 0;
 
@@ -123,6 +126,7 @@ class DiffDrive_C : public ptg_t
     TTwist2D getPathTwist(uint16_t k, uint32_t step) const override;
     bool     inverseMap_WS2TP(double x, double y, int& k, double& d, double tol = 0.10) const override;
     bool     isSpeedTrimmable() const override { return true; }
+    bool     pathsDependOnTrimmableSpeed() const override { return false; }
     bool     isPointInsideRobotShape(double x, double y) const override;
     double   getMaxRobotRadius() const override { return maxRadius_; }
 
