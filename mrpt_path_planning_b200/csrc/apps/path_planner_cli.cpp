@@ -196,7 +196,7 @@ void do_plan_path(const Args& a)
     };
 
     std::cout << "[PTGs] Initializing PTGs..." << std::endl;
-    pi.ptgs.initFromConfigFile(mpp::ConfigFile(a.get("--ptg-config")), a.get("--config-section", "SelfDriving"));
+    pi.ptgs.initFromConfigFile(mpp::ConfigFile(a.get("--ptg-config")), a.get("--config-section", "SelfDriving"), ctx);
     std::cout << "[PTGs] Done." << std::endl;
 
     const mpp::PlannerOutput plan = planner->plan(pi);

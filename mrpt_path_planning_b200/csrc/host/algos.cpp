@@ -209,7 +209,7 @@ ObstacleSource::Ptr ObstacleSource::FromStaticPointcloud(const PointCloud::Ptr& 
 }
 
 // ---- PTG set from an INI file ------------------------------------------------------------------------
-void TrajectoriesAndRobotShape::initFromConfigFile(const ConfigFile& c, const std::string& s)
+void TrajectoriesAndRobotShape::initFromConfigFile(const ConfigFile& c, const std::string& s, mppb_ctx* buildCtx)
 {
     const int count = c.read_int(s, "PTG_COUNT", 0, true);
     // the reference reads the polygon as float (TrajectoriesAndRobotShape.cpp:25-27)
@@ -240,7 +240,7 @@ void TrajectoriesAndRobotShape::initFromConfigFile(const ConfigFile& c, const st
             if (shape_xs.size() < 3) throw std::runtime_error("PTG " + type + " needs a polygonal robot shape");
             p.shape_x = shape_xs;
             p.shape_y = shape_ys;
-            ptgs.push_back(std::make_shared<DiffDrive_C>(p));
+            ptgs.push_back(std::make_shared<DiffDrive_C>(p, buildCtx));
         }
         else if (type == "mpp::ptg::HolonomicBlend" || type == "HolonomicBlend")
         {

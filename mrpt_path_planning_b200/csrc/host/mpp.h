@@ -288,7 +288,9 @@ struct TrajectoriesAndRobotShape
     std::vector<std::shared_ptr<ptg_t>> ptgs;
     std::vector<double>                 shape_xs, shape_ys;  // polygonal shape (may be empty)
     std::optional<robot_radius_t>       shape_radius;        // circular shape
-    void initFromConfigFile(const ConfigFile& cfg, const std::string& section = "SelfDriving");
+    /** buildCtx (extension): collision grids are built on that context's GPU (mppb_build_collision_grid) instead of
+     *  the host builder; the tables are the same. */
+    void initFromConfigFile(const ConfigFile& cfg, const std::string& section = "SelfDriving", mppb_ctx* buildCtx = nullptr);
     /** extension: adopt already constructed PTG objects */
     void initFromPtgs(std::vector<std::shared_ptr<ptg_t>> list)
     {
