@@ -99,6 +99,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned
+    host buffers the kernels write into over PCIe are allocated on the GPU's own NUMA node."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -342,6 +356,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device — libmpp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 
@@ -408,8 +423,10 @@ def run_ours(args, rank, local_rank, world):
 
     device_steps(args.warmup, False)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # one sampler per node (rank 0, all GPUs of the job in one nvidia-smi process): eight pollers contend for the driver
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local_rank)
+    if rank == 0:
+        sampler.start()
     l0 = ctx.launch_count
     step_ms = device_steps(args.steps, True)
     launches = ctx.launch_count - l0
@@ -432,7 +449,12 @@ def run_ours(args, rank, local_rank, world):
     if world > 1 and not args.no_c5:
         c5 = cloud_sharded_bench(ctx, dev, stream, rank, world, args, d_nodes, d_out, flush)
     c4_s = planner["c4_batch"]["batch_s"] if planner else 0.0
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernel_ms": [float(a[0]) for a in allr], "e2e_ms": [float(a[1]) for a in allr]}
         t = torch.tensor([dev_ms, e2e_ms, c4_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms, c4_s = t.tolist()
@@ -483,7 +505,7 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_poses.nbytes),
                 "d2h_bytes_per_step": int(h_out.nbytes),
                 "note": "mppb_eval_nodes: host cos/sin + H2D(pinned) + kernel + D2H(pinned) + sync; cloud resident"},
-        "gpu_launches": int(launches), "roofline": roofline,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_affinity_cpus": affinity, "per_rank": per_rank,
         "setup": {"ptg_tables_s": t_tables, "ptg_tables_builder": "gpu (mppb_build_collision_grid)",
                   "last_collision_grid": t_grid, "cloud_upload_and_binning_s": t_cloud},
     }
