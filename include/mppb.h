@@ -224,6 +224,10 @@ int mppb_eval_nodes_boxed_device(mppb_ctx* ctx, size_t n_nodes, const double* d_
 /* Fill [n][4] (x, y, cos, sin) from [n][3] (x, y, phi) on the host with the C library. */
 void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, double* out_xycs);
 
+/* Diagnostic switch: on == 0 runs the HolonomicBlend kernel without its geometric pre-filter (every in-window point
+ * goes through the exact FP64 chain). Results are identical either way; the tests compare the two. Default: on. */
+int mppb_set_holo_filter(mppb_ctx* ctx, int on);
+
 /* HolonomicBlend: out[c] = min over the in-window points of node cands[c].node of the
  * TP-space collision distance of candidate c (+INF if unconstrained), in double.
  * freeDistance = min(init, out[c]) with init from mppb_ptg_init_dist (the caller holds it). */

@@ -156,6 +156,7 @@ _SIGS = {
     "mppb_set_costmap": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(CostmapDesc)]),
     "mppb_set_waypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
                                      C.c_double, C.c_int]),
+    "mppb_set_holo_filter": (C.c_int, [C.c_void_p, C.c_int]),
     "mppb_evaluators_epoch": (C.c_uint64, [C.c_void_p]),
     "mppb_num_evaluators": (C.c_int, [C.c_void_p]),
     "mppb_eval_edge_costs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -386,6 +387,10 @@ class Context:
     @property
     def launch_count(self):
         return lib().mppb_launch_count(self.h)
+
+    def set_holo_filter(self, on):
+        """Diagnostic: run tpobs_holo_kernel with (default) or without its geometric pre-filter."""
+        self._ck(lib().mppb_set_holo_filter(self.h, int(on)))
 
     def colgrid_build_stats(self):
         """Timings of the last mppb_build_collision_grid on this context."""

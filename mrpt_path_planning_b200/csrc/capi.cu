@@ -145,6 +145,12 @@ int mppb_sync(mppb_ctx* ctx)
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MPPB_OK;
 }
+int mppb_set_holo_filter(mppb_ctx* ctx, int on)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    ctx->holoFilter = on != 0;
+    return MPPB_OK;
+}
 void*    mppb_stream(mppb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 uint64_t mppb_launch_count(const mppb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -218,6 +218,7 @@ struct mppb_ctx
     int          numSMs    = 0;
     std::string  lastError;
     uint64_t     launches = 0;
+    bool         holoFilter = true;  // geometric pre-filter of tpobs_holo_kernel (mppb_set_holo_filter)
     cudaEvent_t  evBegin = nullptr, evEnd = nullptr;
     // second stream + fork/join events: the host entry points pipeline sub-batches over two streams
     cudaStream_t auxStream = nullptr;

@@ -12,6 +12,16 @@
 // T_ramp) are evaluated on the host exactly as internal_params_from_dir_and_dynstate
 // (HolonomicBlend.cpp:942-973) does, because they involve user expressions and libm cos/sin.
 //
+// Geometric pre-filter: a point can only change the result if it comes within the robot radius of the robot
+// centre's path, i.e. of C = {ramp parabola, t in [0, 1.01 T]} U {cruise line, t >= 0.99 T} (the time ranges the
+// reference accepts roots in, HolonomicBlend.cpp:783-825). The parabola is a quadratic Bezier curve and lies in the
+// triangle of its control points; the cruise part is a ray. Each in-window point is first transformed in FP32
+// (hi/lo split of the node position) and tested against that triangle and ray with a 1 cm safety margin over the
+// radius (FP32 error of the test ~1e-5 m; root-finding slop of the exact path ~1e-12 m); only the few per cent of
+// points that pass are queued per warp and run, 32 at a time, through the exact FP64 chain below. A point the
+// filter drops would have left the minimum untouched, so results are bit-identical to the unfiltered kernel
+// (tests/test_tpobs_holo_gpu.py::test_filter_is_conservative compares the two).
+//
 // Work decomposition: one warp per candidate. The warp walks the bin rows of the cloud index that
 // overlap the node's clipping square; lanes take consecutive points (coalesced 8-byte loads),
 // clip and transform them with the reference's FP64 operation order, round to float as
@@ -144,14 +154,81 @@ __device__ __forceinline__ double update_tp_obstacle(const CandConsts& q, double
     return 0.0;
 }
 
+// conservative FP32 description of the region a colliding obstacle point must lie in (robot frame)
+struct PathHull
+{
+    float ax[3], ay[3], ex[3], ey[3], inv[3];  // triangle edges: start A, vector E, 1/|E|^2 (0 if degenerate)
+    float qx, qy, ux, uy;                      // cruise ray: origin and unit direction
+    float thr2;                                // (R + margin)^2
+    bool  enabled;
+};
+__device__ __forceinline__ PathHull make_hull(const CandConsts& q)
+{
+    PathHull     h;
+    const double tau = q.T101;
+    const double px[3] = {0.0, q.vxi * tau * 0.5, q.vxi * tau + q.k2 * tau * tau};
+    const double py[3] = {0.0, q.vyi * tau * 0.5, q.vyi * tau + q.k4 * tau * tau};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        const int j = (i + 1) % 3;
+        h.ax[i]     = static_cast<float>(px[i]);
+        h.ay[i]     = static_cast<float>(py[i]);
+        h.ex[i]     = static_cast<float>(px[j] - px[i]);
+        h.ey[i]     = static_cast<float>(py[j] - py[i]);
+        const float l2 = h.ex[i] * h.ex[i] + h.ey[i] * h.ey[i];
+        h.inv[i]       = l2 > 1e-12f ? 1.0f / l2 : 0.0f;
+    }
+    // cruise line p(t) = T/2 (vi + vf) + vf (t - T), from t = 0.99 T on
+    h.qx = static_cast<float>(q.TR_2 * (q.vxi + q.vxf) - 0.01 * q.T * q.vxf);
+    h.qy = static_cast<float>(q.TR_2 * (q.vyi + q.vyf) - 0.01 * q.T * q.vyf);
+    const double vn = sqrt(q.vxf * q.vxf + q.vyf * q.vyf);
+    h.ux            = static_cast<float>(vn > 0 ? q.vxf / vn : 0.0);
+    h.uy            = static_cast<float>(vn > 0 ? q.vyf / vn : 0.0);
+    const float thr = static_cast<float>(q.R) + 0.01f;
+    h.thr2          = thr * thr;
+    // degenerate or out-of-range parameters: no filtering (every in-window point takes the exact path)
+    const double big = 1e3;
+    h.enabled = vn > 1e-6 && q.vf > 1e-6 && isfinite(q.T) && q.T > 0 && q.T < big && fabs(q.vxi) < big && fabs(q.vyi) < big &&
+                fabs(q.vxf) < big && fabs(q.vyf) < big && q.R > 0 && q.R < big &&
+                fabs(vn - q.vf) <= 1e-6 * q.vf;  // (vxf, vyf) must be vf * (cos, sin), as the host computes it
+    return h;
+}
+// true if the point (lx, ly) may be within thr of the path (squared distances, FP32)
+__device__ __forceinline__ bool hull_may_hit(const PathHull& h, float lx, float ly)
+{
+    float d2   = FLT_MAX;
+    int   npos = 0, nneg = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        const float rx = lx - h.ax[i], ry = ly - h.ay[i];
+        const float t  = fminf(fmaxf((rx * h.ex[i] + ry * h.ey[i]) * h.inv[i], 0.f), 1.f);
+        const float sx = rx - t * h.ex[i], sy = ry - t * h.ey[i];
+        d2             = fminf(d2, sx * sx + sy * sy);
+        const float cr = h.ex[i] * ry - h.ey[i] * rx;
+        npos += cr > 0.f;
+        nneg += cr < 0.f;
+    }
+    if (npos == 3 || nneg == 3) return true;  // inside the control triangle
+    {
+        const float rx = lx - h.qx, ry = ly - h.qy;
+        const float t  = fmaxf(rx * h.ux + ry * h.uy, 0.f);
+        const float sx = rx - t * h.ux, sy = ry - t * h.uy;
+        d2             = fminf(d2, sx * sx + sy * sy);
+    }
+    return d2 <= h.thr2;
+}
+
 __global__ void __launch_bounds__(kThreads)
     tpobs_holo_kernel(CloudBins bins, const HoloPtgDev* __restrict__ ptgs, const mppb_holo_cand* __restrict__ cands,
                       int nCands, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* NULL or [n] minx,miny,maxx,maxy */, double clip,
-                      double* __restrict__ out)
+                      int useFilter, double* __restrict__ out)
 {
-    const int lane = threadIdx.x & 31;
-    const int ci   = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    __shared__ float2 queue[kWarps][64];  // per warp: points that passed the filter and wait for the exact path
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci   = blockIdx.x * kWarps + warp;
     if (ci >= nCands) return;
     const mppb_holo_cand cd = cands[ci];
     const HoloPtgDev     P  = ptgs[cd.ptg_index];
@@ -184,6 +261,25 @@ __global__ void __launch_bounds__(kThreads)
     const bool   hasBox = boxes != nullptr;
     const float4 box    = hasBox ? boxes[cd.node] : make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // the exact per-point chain of the reference (clip, transform, float rounding, time to collision)
+    auto exact = [&](float2 g, double cur) -> double {
+        const double gx = g.x, gy = g.y;
+        // transform_pc_square_clipping.cpp:30-31
+        if (fabs(gx - x0) > clip || fabs(gy - y0) > clip) return cur;
+        const double ox = (ix + gx * c) + gy * s;
+        const double oy = (iy - gx * s) + gy * c;
+        const float  fx = static_cast<float>(ox), fy = static_cast<float>(oy);  // CPointsMap stores float
+        return update_tp_obstacle(q, static_cast<double>(fx), static_cast<double>(fy), cur);
+    };
+    PathHull    hull   = make_hull(q);
+    const float clipF  = static_cast<float>(clip);
+    const float x0h = static_cast<float>(x0), x0l = static_cast<float>(x0 - static_cast<double>(x0h));
+    const float y0h = static_cast<float>(y0), y0l = static_cast<float>(y0 - static_cast<double>(y0h));
+    const float cf = static_cast<float>(c), sf = static_cast<float>(s);
+    const float clipHi = clipF + 1e-4f * fmaxf(clipF, 1.f);
+    const bool  filter = useFilter && hull.enabled && isfinite(clipF) && clipF < 1e3f;
+    int         qn     = 0;  // queued points of this warp (same value in all lanes)
+
     double best = CUDART_INF;
     if (bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0)
     {
@@ -196,22 +292,63 @@ __global__ void __launch_bounds__(kThreads)
         const int   bx1 = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         const int   by0 = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
         const int   by1 = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
-        for (int row = by0; row <= by1; row++)
+        // One flat loop over (bin row, 32-point chunk); points that pass the filter are queued, and whenever 32 are
+        // waiting (or the cloud is exhausted) the warp runs them through the exact chain — a single call site, so the
+        // FP64 code exists once.
+        int      row = by0;
+        uint32_t p0 = 0, end = 0;
+        bool     rowOpen = false;
+        for (;;)
         {
-            const size_t   r   = static_cast<size_t>(row) * bins.nbx;
-            const uint32_t beg = bins.binStart[r + bx0], end = bins.binStart[r + bx1 + 1];
-            for (uint32_t p = beg + lane; p < end; p += 32)
+            bool haveChunk = false;
+            while (row <= by1)
             {
-                const float2 g  = bins.pts[p];
-                if (hasBox && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) continue;
-                const double gx = g.x, gy = g.y;
-                // transform_pc_square_clipping.cpp:30-31
-                if (fabs(gx - x0) > clip || fabs(gy - y0) > clip) continue;
-                const double ox = (ix + gx * c) + gy * s;
-                const double oy = (iy - gx * s) + gy * c;
-                const float  fx = static_cast<float>(ox), fy = static_cast<float>(oy);  // CPointsMap stores float
-                best            = update_tp_obstacle(q, static_cast<double>(fx), static_cast<double>(fy), best);
+                if (!rowOpen)
+                {
+                    const size_t r = static_cast<size_t>(row) * bins.nbx;
+                    p0             = bins.binStart[r + bx0];
+                    end            = bins.binStart[r + bx1 + 1];
+                    rowOpen        = true;
+                }
+                if (p0 < end)
+                {
+                    haveChunk = true;
+                    break;
+                }
+                rowOpen = false;
+                row++;
             }
+            if (haveChunk)
+            {
+                const uint32_t p    = p0 + lane;
+                bool           pass = false;
+                float2         g    = make_float2(0.f, 0.f);
+                if (p < end)
+                {
+                    g    = bins.pts[p];
+                    pass = !(hasBox && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w));
+                    if (filter)
+                    {
+                        // FP32 transform (|error| < 3e-6 * max(clip,1) m) and the conservative tests
+                        const float dx = (g.x - x0h) - x0l, dy = (g.y - y0h) - y0l;
+                        pass           = pass && fmaxf(fabsf(dx), fabsf(dy)) <= clipHi;
+                        pass           = pass && hull_may_hit(hull, dx * cf + dy * sf, dy * cf - dx * sf);
+                    }
+                }
+                p0 += 32;
+                const unsigned m = __ballot_sync(kFull, pass);
+                if (pass) queue[warp][qn + __popc(m & ((1u << lane) - 1u))] = g;
+                qn += __popc(m);
+            }
+            if (qn >= 32 || (!haveChunk && qn > 0))
+            {
+                __syncwarp();
+                const int take = min(qn, 32);
+                if (lane < take) best = exact(queue[warp][qn - take + lane], best);
+                qn -= take;
+                __syncwarp();
+            }
+            if (!haveChunk && qn == 0) break;
         }
     }
 #pragma unroll
@@ -223,13 +360,14 @@ __global__ void __launch_bounds__(kThreads)
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
                       const float* dBoxes, double clip, double* dOut)
 {
+    const int useFilter = ctx->holoFilter ? 1 : 0;  // off: the unfiltered kernel, for A/B tests (mppb_set_holo_filter)
     if (nCands == 0) return MPPB_OK;
     if (ctx->holos.empty()) return fail(ctx, MPPB_ERR_STATE, "no HolonomicBlend PTG set (mppb_set_ptg_holo)");
     if (nCands > 0x3fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many candidates in one batch");
     const unsigned blocks = static_cast<unsigned>((nCands + kWarps - 1) / kWarps);
     tpobs_holo_kernel<<<blocks, kThreads, 0, ctx->stream>>>(ctx->bins, ctx->holoDescs.as<HoloPtgDev>(), dCands,
                                                             static_cast<int>(nCands), dNodes,
-                                                            reinterpret_cast<const float4*>(dBoxes), clip, dOut);
+                                                            reinterpret_cast<const float4*>(dBoxes), clip, useFilter, dOut);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;

@@ -153,3 +153,27 @@ def test_blocked_decisions_match(holo_ctx, orc):
             assert (d >= min(init_g, got[i])) == (d >= min(init_r, ref[i]))
             n_dec += 1
     assert n_dec > 1000
+
+
+@pytest.mark.parametrize("density,seed", [(1.0, 21), (8.0, 22), (40.0, 23)])
+def test_filter_is_conservative(holo_ctx, density, seed):
+    """The geometric pre-filter only drops points that cannot change the result: the kernel with the filter and the
+    kernel without it (every in-window point through the exact FP64 chain) return the same bits, for every path of the
+    PTG, moving and resting nodes, all three trimmed speeds."""
+    ctx, ptg = holo_ctx
+    extent = 24.0
+    xs, ys = wl.uniform_cloud(int(density * extent * extent), extent, seed=seed)
+    rng = np.random.default_rng(seed + 7)
+    nodes, rel = random_nodes(rng, 10, extent)
+    nodes[::3, 3:] = 0.0  # nodes at rest: degenerate control triangle
+    nodes[1, 3:5] = [1.0, 0.0]
+    cands, *_ = make_candidates(ptg, nodes, rel, [list(range(191))] * len(nodes), (1 / 3, 2 / 3, 1.0))
+    ctx.set_obstacles(xs, ys)
+    try:
+        ctx.set_holo_filter(False)
+        plain = ctx.eval_holo_candidates(nodes[:, :3], cands, 5.0)
+    finally:
+        ctx.set_holo_filter(True)
+    filt = ctx.eval_holo_candidates(nodes[:, :3], cands, 5.0)
+    assert np.array_equal(plain.view(np.uint64), filt.view(np.uint64))
+    assert np.isfinite(plain).any()
