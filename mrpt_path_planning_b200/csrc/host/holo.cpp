@@ -94,12 +94,14 @@ HolonomicBlend::HolonomicBlend(const HolonomicBlendParams& p) : p_(p)
 void HolonomicBlend::onNewNavDynamicState()
 {
     stepCountCache_.assign(numPaths_, -1);
+    memoValid_  = false;
     targetDir_  = target_k_ >= 0 ? index2alpha(static_cast<unsigned>(target_k_)) : .0;
     targetDist_ = dynState_.relTarget.norm();
 }
 
 HolonomicBlend::Internal HolonomicBlend::paramsForDir(double dir) const
 {
+    if (memoValid_ && dir == memoDir_ && trimmableSpeed_ == memoSpeed_) return memoQ_;
     Internal q;
     q.T_ramp = p_.T_ramp_max;
     exprDir_ = dir;
@@ -109,6 +111,10 @@ HolonomicBlend::Internal HolonomicBlend::paramsForDir(double dir) const
     q.vyi    = dynState_.curVelLocal.vy;
     q.vxf    = q.vf * std::cos(dir);
     q.vyf    = q.vf * std::sin(dir);
+    memoQ_     = q;
+    memoDir_   = dir;
+    memoSpeed_ = trimmableSpeed_;
+    memoValid_ = true;
     return q;
 }
 

@@ -533,6 +533,11 @@ struct TPS_Astar::Impl::Query
             // from.state.pose (+) relPose with the heading's cos/sin taken once (TPose2D::operator+ takes them per call)
             const double fromC = std::cos(from.state.pose.phi), fromS = std::sin(from.state.pose.phi);
             holoIndex.clear();
+            // initTPObstacleSingle(k) depends on (k, trimmed speed, PTG state) only: consecutive TPS points of the same
+            // path and speed (the sample timestamps) share it
+            trajectory_index_t initK     = -1;
+            normalized_speed_t initSpeed = -1;
+            distance_t         initVal   = 0;
             for (size_t i = 0; i < tps.size(); i++)
             {
                 const TpsPoint& tp = tps[i];
@@ -554,7 +559,13 @@ struct TPS_Astar::Impl::Query
                 c.relTrgDist = relTrgDist;
                 c.relPose    = relPose;
                 c.nc         = nodeGridCoords(absPose);
-                c.initDist   = ptg.initTPObstacleSingle(k16);
+                if (tp.k != initK || tp.speed != initSpeed)
+                {
+                    initVal   = ptg.initTPObstacleSingle(k16);
+                    initK     = tp.k;
+                    initSpeed = tp.speed;
+                }
+                c.initDist   = initVal;
                 c.isTarget   = targetIdx.count(i) != 0;
                 c.onGrid     = onGrid;
                 c.copies     = copies;

@@ -222,6 +222,12 @@ class HolonomicBlend : public ptg_t
     double                   targetDir_  = 0;
     double                   targetDist_ = 0;
     mutable std::vector<int> stepCountCache_;
+    // paramsForDir() is a pure function of (dir, trimmableSpeed_, dynamic state): the last result is kept, because the
+    // planner asks for the same (k, speed) several times in a row (distance, pose, initial TP-obstacle value, candidate
+    // parameters). Dropped whenever the dynamic state changes.
+    mutable bool     memoValid_ = false;
+    mutable double   memoDir_ = 0, memoSpeed_ = 0;
+    mutable Internal memoQ_{};
 };
 
 }  // namespace mpp
