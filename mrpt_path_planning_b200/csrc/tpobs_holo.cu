@@ -220,7 +220,10 @@ __device__ __forceinline__ bool hull_may_hit(const PathHull& h, float lx, float 
     return d2 <= h.thr2;
 }
 
-__global__ void __launch_bounds__(kThreads)
+#ifndef MPPB_HOLO_MIN_BLOCKS
+#define MPPB_HOLO_MIN_BLOCKS 6  // 80 registers: the FP32 filter loop dominates, the rare exact path may spill
+#endif
+__global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     tpobs_holo_kernel(CloudBins bins, const HoloPtgDev* __restrict__ ptgs, const mppb_holo_cand* __restrict__ cands,
                       int nCands, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* NULL or [n] minx,miny,maxx,maxy */, double clip,
