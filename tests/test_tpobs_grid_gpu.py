@@ -215,3 +215,29 @@ def test_full_size_parity_with_checker(gpu_ctx, orc, oracle_ackermann):
     # the structured variant of SURVEY 8(d): 70 % of the points on wall segments at 0.05 m spacing
     xs, ys = wl.walls_cloud(1 << 20, 200.0)
     _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses[:1024])
+
+
+@pytest.mark.parametrize("offset", [(1.0e5, -2.0e5), (-8191.7, 16384.3), (3.0e6, 3.0e6)])
+def test_large_world_coordinates(gpu_ctx, orc, oracle_ackermann, offset):
+    """Far from the origin the float cloud is coarse (ulp 0.008 m at 1e5 m, 0.25 m at 3e6 m) and the node position
+    needs its hi/lo split in the FP32 filter: values must still be the reference's, bit for bit."""
+    rng = np.random.default_rng(int(abs(offset[0])) % 1000)
+    n = 6000
+    xs = (offset[0] + rng.uniform(0, 30, n)).astype(np.float32)
+    ys = (offset[1] + rng.uniform(0, 30, n)).astype(np.float32)
+    poses = np.c_[offset[0] + rng.uniform(2, 28, 96), offset[1] + rng.uniform(2, 28, 96), rng.uniform(-np.pi, np.pi, 96)]
+    _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+
+
+def test_many_nodes_in_one_batch(gpu_ctx):
+    """A batch far above the sub-batch size and above 65 535 nodes: every row equals the row of its pose evaluated
+    alone in a small batch."""
+    xs, ys = wl.uniform_cloud(40000, 60.0, seed=51)
+    gpu_ctx.set_obstacles(xs, ys)
+    base = wl.node_poses(257, 60.0, margin=1.0, seed=52)
+    rows = gpu_ctx.eval_nodes(base, 5.0)
+    reps = 70000 // len(base) + 1
+    big = np.tile(base, (reps, 1))
+    out = gpu_ctx.eval_nodes(big, 5.0)
+    assert out.shape[0] > 65535
+    assert np.array_equal(out, np.tile(rows, (reps, 1)))
