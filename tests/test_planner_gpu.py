@@ -188,3 +188,30 @@ def test_planner_input_errors(ctx, capi):
         pl.plan([100.0, 0, 0, 0, 0, 0], goal, lo, hi)
     with pytest.raises(capi.MppbError):  # empty world box
         pl.plan(start, goal, lo, lo)
+
+
+@pytest.mark.parametrize("kind", ["holonomic", "ackermann"])
+def test_successive_plans_on_one_planner(ctx, capi, orc, kind, product_ackermann):
+    """Replanning with ONE planner object, as NavEngine does: the PTG objects carry their state (dynamic state, trimmed
+    speed, HolonomicBlend's step-count cache) from plan to plan, the cloud and the evaluators stay resident on the GPU
+    between plans, and an evaluator added later must be picked up. Every plan equals the checker's, which is driven
+    through the same sequence on one planner object of its own."""
+    xs, ys, start, goal, lo, hi = c1_inputs()
+    p_ptgs = capi.holonomic_ptgs() if kind == "holonomic" else product_ackermann
+    o_ptgs = orc.holonomic_ptgs() if kind == "holonomic" else orc.ackermann_ptgs()
+    prod = capi.Planner(ctx, p_ptgs, C1_PARAMS, C1_TIMESTAMPS)
+    ora = orc.Planner(o_ptgs, C1_PARAMS, C1_TIMESTAMPS)
+    for pl in (prod, ora):
+        pl.add_obstacles(xs, ys)
+    prod.add_costmap(xs, ys, 0.04, 0.5, 4.0, False, 15.0, start[:3])
+    ora.add_costmap(orc.CostMap(xs, ys, 0.04, 0.5, 4.0, False, 15.0, start[:3]))
+    goals = [goal, [3.0, -0.5, -1.0, 0, 0, 0], goal, [1.5, 3.0, 2.0, 0, 0, 0]]
+    starts = [start, [4.0, 2.5, 0.8, 0.2, 0.1, 0.0], start, [3.0, -0.5, -1.0, 0, 0, 0]]
+    for i, (s, g) in enumerate(zip(starts, goals)):
+        if i == 2:  # a second evaluator appears between plans
+            prod.add_waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.5, 0.5, True)
+            ora.add_waypoints(orc.Waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.5, 0.5, True))
+        r_p = prod.plan(s, g, lo, hi)
+        r_o = ora.plan(s, g, lo, hi)
+        same_plan(prod, ora, r_p, r_o)
+        assert r_p["expanded"] > 0
