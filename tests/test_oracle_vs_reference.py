@@ -286,3 +286,32 @@ def test_capped_queries_on_wall_map_identical(port, refm, mk, cap):
             pytest.fail(str(e))
         n_nonempty += r["tree_nodes"] > 1
     assert n_nonempty >= 3
+
+
+# [grid_xy, grid_yaw, SE2_metricAngleWeight, heuristic_heading_weight, max_trajs, max_speeds, interp segments, time, cap]
+PARAM_SETS = {
+    "defaults_of_the_class": ([0.20, np.deg2rad(5.0), 1.0, 0.1, 20, 3, 5, 0, 30], [1.0, 3.0, 5.0]),
+    "coarse_two_speeds": ([0.50, np.deg2rad(45.0), 0.3, 0.0, 7, 2, 3, 0, 60], [0.4, 2.0]),
+    "one_speed_many_paths": ([0.30, np.deg2rad(15.0), 0.1, 0.5, 31, 1, 8, 0, 40], [0.25, 0.75, 1.5, 3.0]),
+}
+
+
+@pytest.mark.parametrize("mk", ["holonomic_ptgs", "ackermann_ptgs"])
+@pytest.mark.parametrize("pname", sorted(PARAM_SETS))
+def test_other_planner_parameters_identical(port, refm, mk, pname):
+    """TPS_Astar under other parameter sets than the demo's (lattice resolution, number of trajectories and speeds,
+    sample timestamps, interpolated segments, heuristic weights), with costmap and waypoint evaluators."""
+    params, stamps = PARAM_SETS[pname]
+    obstacles, q = _demo()
+    res = []
+    for M in (port, refm):
+        pl = M.Planner(getattr(M, mk)(), params, stamps)
+        pl.add_obstacles(*obstacles)
+        pl.add_costmap(M.CostMap(obstacles[0], obstacles[1], 0.05, 0.4, 2.0, True, 0.0, None))
+        pl.add_waypoints(M.Waypoints(WAYPOINTS01[0], WAYPOINTS01[1], 1.5, 0.5, False))
+        r = pl.plan(*q)
+        res.append((r, pl.tree()))
+    (ra, ta), (rb, tb) = res
+    for key in ("success", "path_cost", "tree_nodes", "expanded", "tps_points", "edges_costed", "best_node"):
+        assert ra[key] == rb[key], (key, ra[key], rb[key])
+    assert np.array_equal(ta, tb) and ra["expanded"] >= 5

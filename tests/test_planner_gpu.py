@@ -215,3 +215,33 @@ def test_successive_plans_on_one_planner(ctx, capi, orc, kind, product_ackermann
         r_o = ora.plan(s, g, lo, hi)
         same_plan(prod, ora, r_p, r_o)
         assert r_p["expanded"] > 0
+
+
+PARAM_SETS = {
+    "defaults_of_the_class": ([0.20, np.deg2rad(5.0), 1.0, 0.1, 20, 3, 5, 0, 30], [1.0, 3.0, 5.0]),
+    "coarse_two_speeds": ([0.50, np.deg2rad(45.0), 0.3, 0.0, 7, 2, 3, 0, 60], [0.4, 2.0]),
+    "one_speed_many_paths": ([0.30, np.deg2rad(15.0), 0.1, 0.5, 31, 1, 8, 0, 40], [0.25, 0.75, 1.5, 3.0]),
+}
+
+
+@pytest.mark.parametrize("kind", ["holonomic", "ackermann"])
+@pytest.mark.parametrize("pname", sorted(PARAM_SETS))
+def test_other_planner_parameters(ctx, capi, orc, kind, pname, product_ackermann):
+    """Other TPS_Astar parameter sets than the demo's (lattice resolution, trajectories, speeds, sample timestamps,
+    interpolated segments, heuristic weights; averaged costmap, max-combined waypoints): tree and path identical."""
+    params, stamps = PARAM_SETS[pname]
+    xs, ys, start, goal, lo, hi = c1_inputs()
+    p_ptgs = capi.holonomic_ptgs() if kind == "holonomic" else product_ackermann
+    o_ptgs = orc.holonomic_ptgs() if kind == "holonomic" else orc.ackermann_ptgs()
+    prod = capi.Planner(ctx, p_ptgs, params, stamps)
+    ora = orc.Planner(o_ptgs, params, stamps)
+    for pl in (prod, ora):
+        pl.add_obstacles(xs, ys)
+    prod.add_costmap(xs, ys, 0.05, 0.4, 2.0, True, 0.0, None)
+    ora.add_costmap(orc.CostMap(xs, ys, 0.05, 0.4, 2.0, True, 0.0, None))
+    prod.add_waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.5, 0.5, False)
+    ora.add_waypoints(orc.Waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.5, 0.5, False))
+    r_p = prod.plan(start, goal, lo, hi)
+    r_o = ora.plan(start, goal, lo, hi)
+    same_plan(prod, ora, r_p, r_o)
+    assert r_p["expanded"] >= 5
