@@ -315,3 +315,38 @@ def test_other_planner_parameters_identical(port, refm, mk, pname):
     for key in ("success", "path_cost", "tree_nodes", "expanded", "tps_points", "edges_costed", "best_node"):
         assert ra[key] == rb[key], (key, ra[key], rb[key])
     assert np.array_equal(ta, tb) and ra["expanded"] >= 5
+
+
+HOLO_VARIANTS = [
+    # num_paths, ref_distance, T_ramp_max, v_max, w_max, radius, expr_V, expr_W
+    (61, 4.0, 0.5, 0.8, np.deg2rad(90.0), 0.30, "", ""),
+    (101, 6.0, 2.0, 1.5, np.deg2rad(30.0), 0.10, "V_MAX * max(0.2, trimmable_speed) * (1 - 0.3*abs(dir)/PI)",
+     "W_MAX * min(1.0, abs(dir))"),
+]
+
+
+@pytest.mark.parametrize("variant", range(len(HOLO_VARIANTS)))
+def test_holonomic_other_ptg_parameters_identical(port, refm, variant):
+    """HolonomicBlend with other parameters and user expressions than the demo's: candidates and a capped plan."""
+    v = HOLO_VARIANTS[variant]
+    a, b = port.holonomic_blend(*v), refm.holonomic_blend(*v)
+    rng = np.random.default_rng(40 + variant)
+    xs, ys = wl.uniform_cloud(1500, 25.0, seed=41 + variant)
+    B, M = 12, 300
+    nodes = np.c_[rng.uniform(3, 22, B), rng.uniform(3, 22, B), rng.uniform(-np.pi, np.pi, B),
+                  rng.uniform(-0.7, 0.7, B), rng.uniform(-0.7, 0.7, B), rng.uniform(-0.3, 0.3, B)]
+    rel = np.c_[rng.uniform(-6, 6, B), rng.uniform(-6, 6, B), rng.uniform(-3, 3, B)]
+    cn, ck, cs = rng.integers(0, B, M), rng.integers(0, v[0], M), rng.choice([0.5, 1.0], M)
+    ra = port.eval_candidates(a, xs, ys, nodes, rel, cn, ck, cs, v[1])
+    rb = refm.eval_candidates(b, xs, ys, nodes, rel, cn, ck, cs, v[1])
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and np.isfinite(ra[0]).any()
+    obstacles, q = _demo()
+    params = list(wl.DEMO_ASTAR_PARAMS)
+    params[8] = 25
+    res = []
+    for M_, ptg in ((port, a), (refm, b)):
+        pl = M_.Planner([ptg], params, wl.DEMO_ASTAR_TIMESTAMPS)
+        pl.add_obstacles(*obstacles)
+        r = pl.plan(*q)
+        res.append((r["expanded"], r["path_cost"], pl.tree()))
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1] and np.array_equal(res[0][2], res[1][2])

@@ -177,3 +177,37 @@ def test_filter_is_conservative(holo_ctx, density, seed):
     filt = ctx.eval_holo_candidates(nodes[:, :3], cands, 5.0)
     assert np.array_equal(plain.view(np.uint64), filt.view(np.uint64))
     assert np.isfinite(plain).any()
+
+
+HOLO_VARIANTS = [
+    # num_paths, ref_distance, T_ramp_max, v_max, w_max, radius, expr_V, expr_W
+    (61, 4.0, 0.5, 0.8, np.deg2rad(90.0), 0.30, "", ""),
+    (101, 6.0, 2.0, 1.5, np.deg2rad(30.0), 0.10, "V_MAX * max(0.2, trimmable_speed) * (1 - 0.3*abs(dir)/PI)",
+     "W_MAX * min(1.0, abs(dir))"),
+]
+
+
+@pytest.mark.parametrize("variant", range(len(HOLO_VARIANTS)))
+def test_other_ptg_parameters(capi, orc, variant):
+    """HolonomicBlend with other parameters and user expressions than the demo's (ramp time, speeds, radius, path
+    count, clip = its own refDistance): kernel (with its pre-filter) vs the checker, and filter on == filter off."""
+    v = HOLO_VARIANTS[variant]
+    ptg = capi.PTG.holonomic_blend(*v)
+    optg = orc.holonomic_blend(*v)
+    ctx = capi.Context(0)
+    ctx.add_ptg(ptg)
+    rng = np.random.default_rng(60 + variant)
+    xs, ys = wl.uniform_cloud(4000, 25.0, seed=61 + variant)
+    nodes, rel = random_nodes(rng, 8, 25.0)
+    ks = [list(range(0, v[0], 2))] * len(nodes)
+    cands, cn, ck, cs = make_candidates(ptg, nodes, rel, ks, (0.5, 1.0))
+    ctx.set_obstacles(xs, ys)
+    got = ctx.eval_holo_candidates(nodes[:, :3], cands, v[1])
+    ctx.set_holo_filter(False)
+    plain = ctx.eval_holo_candidates(nodes[:, :3], cands, v[1])
+    ctx.close()
+    assert np.array_equal(got.view(np.uint64), plain.view(np.uint64))
+    ref, _, _ = orc.eval_candidates(optg, xs, ys, nodes, rel, cn, ck, cs, v[1], want_free=False)
+    assert np.array_equal(np.isinf(got), np.isinf(ref)) and np.array_equal(got == 0.0, ref == 0.0)
+    fin = np.isfinite(ref)
+    assert fin.any() and (np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-12)).max() <= RTOL
