@@ -9,6 +9,7 @@
 #include <cmath>
 
 #include "mppb_internal.cuh"
+#include "scan.cuh"
 
 namespace mppb
 {
@@ -90,37 +91,6 @@ __global__ void bin_count_kernel(
     }
 }
 
-// Single-CTA exclusive scan (the bin table is small next to the cloud): counts[nb] ->
-// start[nb+1]; counts is zeroed afterwards so it can serve as the scatter cursor.
-__global__ void bin_scan_kernel(uint32_t* counts, uint32_t* start, int nb)
-{
-    __shared__ uint32_t partial[1024];
-    const int           t     = threadIdx.x;
-    const int           chunk = (nb + blockDim.x - 1) / blockDim.x;
-    const int           b0 = t * chunk, b1 = min(nb, b0 + chunk);
-    uint32_t            s = 0;
-    for (int b = b0; b < b1; b++) s += counts[b];
-    partial[t] = s;
-    __syncthreads();
-    // exclusive scan of partial[] by thread 0..: simple Hillis-Steele
-    for (int off = 1; off < blockDim.x; off <<= 1)
-    {
-        uint32_t v = t >= off ? partial[t - off] : 0;
-        __syncthreads();
-        partial[t] += v;
-        __syncthreads();
-    }
-    uint32_t run = partial[t] - s;
-    for (int b = b0; b < b1; b++)
-    {
-        const uint32_t c = counts[b];
-        start[b]         = run;
-        run += c;
-        counts[b] = 0;
-    }
-    if (t == blockDim.x - 1) start[nb] = partial[t];
-}
-
 __global__ void bin_scatter_kernel(
     const float* __restrict__ xs, const float* __restrict__ ys, size_t n, KeepTest keep, float minx, float miny,
     float invBin, int nbx, int nby, const uint32_t* __restrict__ start, uint32_t* cursor, float2* sorted)
@@ -192,7 +162,12 @@ int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize)
     MPPB_CUDA(ctx, cudaMemsetAsync(cs.binCursor.p, 0, static_cast<size_t>(nb) * sizeof(uint32_t), st));
     bin_count_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, keep, b.minx, b.miny, b.invBin, b.nbx, b.nby,
                                                 cs.binCursor.as<uint32_t>());
-    bin_scan_kernel<<<1, 1024, 0, st>>>(cs.binCursor.as<uint32_t>(), cs.binStart.as<uint32_t>(), nb);
+    // counts -> start (exclusive scan, start[nb] = total); the counts are zeroed: they become the scatter cursor
+    MPPB_CUDA(ctx, cs.scanScratch.reserve((4096 + 1) * sizeof(uint32_t)));
+    if (device_exclusive_scan(cs.binCursor.as<uint32_t>(), static_cast<uint32_t>(nb), cs.binStart.as<uint32_t>(),
+                              cs.scanScratch.as<uint32_t>(), cs.binCursor.as<uint32_t>(), st) < 0)
+        return fail(ctx, MPPB_ERR_UNSUPPORTED, "bin table too large");
+    ctx->launches += 2;
     bin_scatter_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, keep, b.minx, b.miny, b.invBin, b.nbx, b.nby,
                                                   cs.binStart.as<uint32_t>(), cs.binCursor.as<uint32_t>(),
                                                   cs.sortedPts.as<float2>());

@@ -16,7 +16,7 @@
 // (200x200 cells = 160 KB: one band on B200's 227 KB); warps take the steps of the path round-robin, lanes take the
 // cell corners of the step's bounding box, hits do shared-memory atomicMin (distances are >= 0, so the unsigned order
 // of the bit patterns is the float order). The band is then written to a dense [K][cells] table; a second pass
-// counts/compacts it per cell into the CSR.
+// counts/compacts it per cell into the CSR (prefix sums by the three-launch scan of scan.cuh).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "mppb_internal.cuh"
+#include "scan.cuh"
 
 namespace mppb
 {
@@ -152,48 +153,6 @@ __global__ void colgrid_count_kernel(const unsigned* __restrict__ dense, int K, 
     counts[cell] = n;
 }
 
-// exclusive scan of counts[0..n) into offsets[0..n], single CTA (n is a few 10^4)
-__global__ void __launch_bounds__(1024) colgrid_scan_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets)
-{
-    __shared__ uint32_t warpSum[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n; base += 1024)
-    {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? counts[i] : 0u;
-        uint32_t       x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += t;
-        }
-        if (lane == 31) warpSum[warp] = x;
-        __syncthreads();
-        if (warp == 0)
-        {
-            uint32_t w = warpSum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            warpSum[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t before = carry + (warp ? warpSum[warp - 1] : 0u) + (x - v);
-        if (i < n) offsets[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) offsets[n] = carry;
-}
-
 __global__ void colgrid_fill_kernel(const unsigned* __restrict__ dense, int K, uint32_t nCells,
                                     const uint32_t* __restrict__ offsets, uint16_t* __restrict__ entryK,
                                     float* __restrict__ entryD)
@@ -291,6 +250,7 @@ extern "C" int mppb_build_collision_grid(mppb_ctx* ctx, const mppb_colgrid_build
     MPPB_CUDA(ctx, B.dDense.reserve(nCells * K * sizeof(unsigned)));
     MPPB_CUDA(ctx, B.dCounts.reserve(nCells * sizeof(uint32_t)));
     MPPB_CUDA(ctx, B.dOffsets.reserve((nCells + 1) * sizeof(uint32_t)));
+    MPPB_CUDA(ctx, B.dScan.reserve((4096 + 1) * sizeof(uint32_t)));
     MPPB_CUDA(ctx, cudaMemcpyAsync(B.dBegin.p, d->path_begin, (K + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     MPPB_CUDA(ctx, cudaMemcpyAsync(B.dX.p, d->x, nSteps * sizeof(float), cudaMemcpyHostToDevice, st));
     MPPB_CUDA(ctx, cudaMemcpyAsync(B.dY.p, d->y, nSteps * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -307,8 +267,10 @@ extern "C" int mppb_build_collision_grid(mppb_ctx* ctx, const mppb_colgrid_build
         rowsPerBand, B.dDense.as<unsigned>());
     const unsigned cblocks = static_cast<unsigned>((nCells + 255) / 256);
     colgrid_count_kernel<<<cblocks, 256, 0, st>>>(B.dDense.as<unsigned>(), K, static_cast<uint32_t>(nCells), B.dCounts.as<uint32_t>());
-    colgrid_scan_kernel<<<1, 1024, 0, st>>>(B.dCounts.as<uint32_t>(), static_cast<uint32_t>(nCells), B.dOffsets.as<uint32_t>());
-    ctx->launches += 3;
+    if (device_exclusive_scan(B.dCounts.as<uint32_t>(), static_cast<uint32_t>(nCells), B.dOffsets.as<uint32_t>(),
+                              B.dScan.as<uint32_t>(), nullptr, st) < 0)
+        return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large");
+    ctx->launches += 5;
     MPPB_CUDA(ctx, cudaGetLastError());
     MPPB_CUDA(ctx, cudaEventRecord(ctx->evEnd, st));
     MPPB_CUDA(ctx, B.hOffsets.reserve((nCells + 1) * sizeof(uint32_t)));

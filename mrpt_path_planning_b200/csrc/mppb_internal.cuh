@@ -147,7 +147,7 @@ struct CloudStore
 {
     DevBuf    rawX, rawY;
     size_t    rawN = 0;
-    DevBuf    sortedPts, binStart, binCursor;
+    DevBuf    sortedPts, binStart, binCursor, scanScratch;
     CloudBins bins;
     double    binSize = 0;
     bool      hasBox  = false;
@@ -159,6 +159,7 @@ struct CloudStore
         sortedPts.release();
         binStart.release();
         binCursor.release();
+        scanScratch.release();
         rawN = 0;
         bins = CloudBins();
     }
@@ -167,12 +168,12 @@ struct CloudStore
 // scratch of mppb_build_collision_grid (colgrid_build.cu); the result's host arrays live here until the next build
 struct ColgridBuildBufs
 {
-    DevBuf    dBegin, dX, dY, dDist, dCs, dDense, dCounts, dOffsets, dEntryK, dEntryD;
+    DevBuf    dBegin, dX, dY, dDist, dCs, dDense, dCounts, dOffsets, dScan, dEntryK, dEntryD;
     PinnedBuf hCs, hOffsets, hEntryK, hEntryD;
     double    stats[4] = {0, 0, 0, 0};
     void      release()
     {
-        for (DevBuf* b : {&dBegin, &dX, &dY, &dDist, &dCs, &dDense, &dCounts, &dOffsets, &dEntryK, &dEntryD}) b->release();
+        for (DevBuf* b : {&dBegin, &dX, &dY, &dDist, &dCs, &dDense, &dCounts, &dOffsets, &dScan, &dEntryK, &dEntryD}) b->release();
         for (PinnedBuf* b : {&hCs, &hOffsets, &hEntryK, &hEntryD}) b->release();
     }
 };
