@@ -114,6 +114,24 @@ void MotionPrimitivesTreeSE2::insert_node_and_edge(TNodeID parentId, TNodeID chi
     n.cost_                       = nodes_.at(parentId).cost_ + e.cost;
     nodes_[childId]               = n;
 }
+void MotionPrimitivesTreeSE2::insert_child_of(TListEdges& parentEdges, const node_t& parentNode, TNodeID parentId, TNodeID childId,
+                                              const SE2_KinState& childData, const MoveEdgeSE2_TPS& e)
+{
+    parentEdges.emplace_back();
+    TEdgeInfo& ei = parentEdges.back();
+    ei.id         = childId;
+    ei.reverse    = false;
+    ei.data       = e;
+    node_t n;
+    static_cast<SE2_KinState&>(n) = childData;
+    n.nodeID_                     = childId;
+    n.parentID_                   = parentId;
+    n.cost_                       = parentNode.cost_ + e.cost;
+    if (nodes_.empty() || childId > nodes_.rbegin()->first)
+        nodes_.emplace_hint(nodes_.end(), childId, n);
+    else
+        nodes_[childId] = n;
+}
 void MotionPrimitivesTreeSE2::rewire_node_parent(TNodeID nodeId, const MoveEdgeSE2_TPS& newEdgeFromParent)
 {
     node_t& node     = nodes_.at(nodeId);

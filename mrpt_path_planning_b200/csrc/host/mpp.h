@@ -245,6 +245,12 @@ class MotionPrimitivesTreeSE2
     void insert_root_node(TNodeID id, const SE2_KinState& data);
     void insert_node_and_edge(TNodeID parentId, TNodeID childId, const SE2_KinState& childData, const MoveEdgeSE2_TPS& e);
     void rewire_node_parent(TNodeID nodeId, const MoveEdgeSE2_TPS& newEdgeFromParent);
+    /** extension: insert_node_and_edge for a caller that adds several children of ONE parent in a row (an A* expansion):
+     *  the parent's edge list and node are looked up once by the caller (`edges_to_children[parentId]`,
+     *  `nodes().at(parentId)`; both stay valid across insertions), and a child id above all present ids goes in with an
+     *  end hint. Same resulting tree as insert_node_and_edge. */
+    void insert_child_of(TListEdges& parentEdges, const node_t& parentNode, TNodeID parentId, TNodeID childId,
+                         const SE2_KinState& childData, const MoveEdgeSE2_TPS& e);
     const MoveEdgeSE2_TPS& edge_to_parent(TNodeID nodeId) const;
     const node_map_t&      nodes() const { return nodes_; }
     SE2_KinState&          node_state(TNodeID id) { return nodes_.at(id); }

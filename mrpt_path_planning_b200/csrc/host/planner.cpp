@@ -80,6 +80,71 @@ struct Node
     bool                   pendingInOpenSet = false;
     bool                   visited          = false;
 };
+// The SE(2) lattice of the reference is a std::unordered_map<NodeCoords, Node> that is only ever indexed, never
+// iterated (TPS_Astar.h:222, TPS_Astar.cpp:514-525), so its container type cannot influence the result. Here: an
+// open-addressing index (linear probing, load <= 1/2) over nodes that live in the query's arena (stable addresses:
+// the open set and cameFrom hold Node pointers).
+class LatticeIndex
+{
+   public:
+    explicit LatticeIndex(std::pmr::monotonic_buffer_resource* arena) : arena_(arena) { slots_.assign(1024, Slot{}); }
+    Node& operator[](const NodeCoords& c)
+    {
+        const int32_t yaw = c.idxYaw.value();  // lattice nodes always carry a heading index
+        for (;;)
+        {
+            const size_t mask = slots_.size() - 1;
+            size_t       h    = mix(c.idxX, c.idxY, yaw) & mask;
+            for (;; h = (h + 1) & mask)
+            {
+                Slot& s = slots_[h];
+                if (!s.node) break;
+                if (s.x == c.idxX && s.y == c.idxY && s.yaw == yaw) return *s.node;
+            }
+            if ((count_ + 1) * 2 > slots_.size())
+            {
+                grow();
+                continue;
+            }
+            Slot& s = slots_[h];
+            s.x = c.idxX, s.y = c.idxY, s.yaw = yaw;
+            s.node = new (arena_->allocate(sizeof(Node), alignof(Node))) Node();
+            count_++;
+            return *s.node;
+        }
+    }
+
+   private:
+    struct Slot
+    {
+        int32_t x = 0, y = 0, yaw = 0;
+        Node*   node = nullptr;
+    };
+    static size_t mix(int32_t x, int32_t y, int32_t yaw)
+    {
+        uint64_t h = static_cast<uint32_t>(x) * 0x9E3779B97F4A7C15ull;
+        h ^= (static_cast<uint64_t>(static_cast<uint32_t>(y)) + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+        h ^= (static_cast<uint64_t>(static_cast<uint32_t>(yaw)) + 0x165667B1ull) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+        return static_cast<size_t>(h * 0x9E3779B97F4A7C15ull >> 20);
+    }
+    void grow()
+    {
+        std::vector<Slot> old(slots_.size() * 2);
+        old.swap(slots_);
+        const size_t mask = slots_.size() - 1;
+        for (const Slot& s : old)
+        {
+            if (!s.node) continue;
+            size_t h = mix(s.x, s.y, s.yaw) & mask;
+            while (slots_[h].node) h = (h + 1) & mask;
+            slots_[h] = s;
+        }
+    }
+    std::pmr::monotonic_buffer_resource* arena_;
+    std::vector<Slot>                    slots_;
+    size_t                               count_ = 0;
+};
 struct PathToNeighbor
 {
     std::optional<size_t>    ptgIndex;
@@ -304,7 +369,7 @@ struct TPS_Astar::Impl::Query
     // lattice and open set live in a per-query arena: node addresses stay stable (node-based containers),
     // allocation is a pointer bump and the whole search state is dropped at once when the query ends
     std::pmr::monotonic_buffer_resource                         searchArena{1 << 16};
-    std::pmr::unordered_map<NodeCoords, Node, NodeCoordsHash>   grid{&searchArena};
+    LatticeIndex                                                grid{&searchArena};
     std::pmr::multimap<distance_t, Node*>                       openSet{&searchArena};
     TNodeID                                                nextFreeId = 0;
     Node*                                                  nodeGoal   = nullptr;
@@ -476,15 +541,21 @@ struct TPS_Astar::Impl::Query
             }
             dynOfPtg[ptgIdx] = ptg.getCurrentNavDynamicState();
 
-            std::pmr::set<trajectory_index_t> trajIdxs(&arena);
-            std::pmr::set<size_t>             targetIdx(&arena);
+            // std::set<trajectory_index_t> of the reference as a sorted vector without duplicates (same iteration order);
+            // the direct-to-goal TPS points are the first nTargets entries of `tps`
+            std::pmr::vector<trajectory_index_t> trajIdxs(&arena);
+            auto insertTraj = [&trajIdxs](trajectory_index_t k) {
+                const auto it = std::lower_bound(trajIdxs.begin(), trajIdxs.end(), k);
+                if (it == trajIdxs.end() || *it != k) trajIdxs.insert(it, k);
+            };
+            size_t nTargets = 0;
             tps.clear();
             MPP_ASSERT(P->max_ptg_trajectories_to_explore >= 2);
             for (size_t i = 0; i < P->max_ptg_trajectories_to_explore; i++)
             {
                 // integer division first, then round (TPS_Astar.cpp:619-623)
                 const size_t q = i * (ptg.getPathCount() - 1) / (P->max_ptg_trajectories_to_explore - 1);
-                trajIdxs.insert(round_i(static_cast<double>(q)));
+                insertTraj(round_i(static_cast<double>(q)));
             }
             std::pmr::vector<normalized_speed_t> speeds(&arena);
             if (trimmable)
@@ -507,9 +578,9 @@ struct TPS_Astar::Impl::Query
                         for (const auto s : speeds)
                         {
                             tps.push_back({goalK, goalStep, s});
-                            targetIdx.insert(tps.size() - 1);
+                            nTargets = tps.size();
                         }
-                    trajIdxs.insert(goalK);
+                    insertTraj(goalK);
                 }
             }
             for (const auto s : speeds)
@@ -566,7 +637,7 @@ struct TPS_Astar::Impl::Query
                     initSpeed = tp.speed;
                 }
                 c.initDist   = initVal;
-                c.isTarget   = targetIdx.count(i) != 0;
+                c.isTarget   = i < nTargets;
                 c.onGrid     = onGrid;
                 c.copies     = copies;
                 if (onGrid)
@@ -670,6 +741,9 @@ struct TPS_Astar::Impl::Query
     void phaseF(const double* gpuCosts, int numGpuEvals, const std::vector<int>& evalSlot)
     {
         auto& tree = po.motionTree;
+        // all tentative edges of this round leave `current`: its edge list and tree node are looked up once
+        MotionPrimitivesTreeSE2::TListEdges*   parentEdges = nullptr;
+        const MotionPrimitivesTreeSE2::node_t* parentNode  = nullptr;
         for (size_t i = 0; i < pending.size(); i++)
         {
             PendingEdge&     pe      = pending[i];
@@ -705,7 +779,14 @@ struct TPS_Astar::Impl::Query
             if (hasToRewire)
                 tree.rewire_node_parent(nbNode.id.value(), newEdge);
             else
-                tree.insert_node_and_edge(newEdge.parentId, nbNode.id.value(), nbNode.state, newEdge);
+            {
+                if (!parentEdges)
+                {
+                    parentEdges = &tree.edges_to_children[newEdge.parentId];
+                    parentNode  = &tree.nodes().at(newEdge.parentId);
+                }
+                tree.insert_child_of(*parentEdges, *parentNode, newEdge.parentId, nbNode.id.value(), nbNode.state, newEdge);
+            }
             if (costToGoal < po.bestNodeIdCostToGoal)
             {
                 po.bestNodeIdCostToGoal = costToGoal;

@@ -226,12 +226,16 @@ bool   DiffDrive_C::getPathStepForDist(uint16_t k, double dist, uint32_t& step) 
 {
     MPP_ASSERT(k < numPaths_);
     const size_t b = pathBegin_[k], n = pathBegin_[k + 1] - b;
-    for (size_t i = 0; i + 1 < n; i++)
-        if (tdist_[b + i + 1] >= dist)
-        {
-            step = static_cast<uint32_t>(i);
-            return true;
-        }
+    // first i with dist(i+1) >= dist (DiffDriveCollisionGridBased.cpp:800-807): the accumulated TP-distance never
+    // decreases along a path, so the reference's linear scan is a lower bound search
+    const float* first = tdist_.data() + b + 1;
+    const float* last  = tdist_.data() + b + n;
+    const float* it    = std::lower_bound(first, last, dist, [](float v, double d) { return !(static_cast<double>(v) >= d); });
+    if (it != last)
+    {
+        step = static_cast<uint32_t>(it - first);
+        return true;
+    }
     step = static_cast<uint32_t>(n - 1);
     return false;
 }
