@@ -321,10 +321,13 @@ static int rebuild_groups(mppb_ctx* ctx)
         if (!ent.empty())
             MPPB_CUDA(ctx, cudaMemcpyAsync(G.entries.p, ent.data(), ent.size() * sizeof(uint2),
                                            cudaMemcpyHostToDevice, ctx->stream));
-        // by-column view: per output column the (cell, d) pairs sorted by ascending d
-        std::vector<uint32_t> colStart(1, 0), colCell;
+        // by-column view (GridGroupDev): per output column the cells in ascending-d order, cut greedily into
+        // chunks that touch at most 4 words of the kernel's tiled occupancy bitmap
+        std::vector<uint32_t> colStart(1, 0), colDBase;
+        std::vector<uint4>    colWord, colMask;
         std::vector<float>    colD;
         std::vector<int>      colOut;
+        const uint32_t        tilesX = static_cast<uint32_t>(grid_tiles_x(g0.nx));
         for (size_t i : m)
         {
             const PtgGridHost&                            g = ctx->grids[i];
@@ -335,30 +338,59 @@ static int rebuild_groups(mppb_ctx* ctx)
             for (int k = 0; k < g.K; k++)
             {
                 std::sort(perK[k].begin(), perK[k].end());
+                uint32_t w[4] = {0, 0, 0, 0}, mk[4] = {0, 0, 0, 0};
+                float    dOf[4][32];
+                int      used = 0;
+                auto     flush = [&]() {
+                    if (!used) return;
+                    colWord.push_back(make_uint4(w[0], w[1], w[2], w[3]));
+                    colMask.push_back(make_uint4(mk[0], mk[1], mk[2], mk[3]));
+                    colDBase.push_back(static_cast<uint32_t>(colD.size()));
+                    for (int sl = 0; sl < used; sl++)
+                        for (int bit = 0; bit < 32; bit++)
+                            if (mk[sl] >> bit & 1u) colD.push_back(dOf[sl][bit]);
+                    used = 0;
+                    for (int sl = 0; sl < 4; sl++) w[sl] = mk[sl] = 0;
+                };
                 for (const auto& dc : perK[k])
                 {
-                    colD.push_back(dc.first);
-                    colCell.push_back(dc.second);
+                    const uint32_t cx = dc.second % static_cast<uint32_t>(g0.nx), cy = dc.second / static_cast<uint32_t>(g0.nx);
+                    const uint32_t word = grid_tile_word(cx, cy, tilesX), bit = grid_tile_bit(cx, cy);
+                    int            sl = 0;
+                    while (sl < used && w[sl] != word) sl++;
+                    if (sl == used)
+                    {
+                        if (used == 4)
+                        {
+                            flush();
+                            sl = 0;
+                        }
+                        w[sl] = word;
+                        used  = sl + 1;
+                    }
+                    mk[sl] |= 1u << bit;
+                    dOf[sl][bit] = dc.first;
                 }
-                // pad to a multiple of 4 entries (16-byte vector loads) with a cell that is never occupied
-                while (colCell.size() % 4)
-                {
-                    colD.push_back(std::numeric_limits<float>::infinity());
-                    colCell.push_back(static_cast<uint32_t>(ncells));
-                }
-                colStart.push_back(static_cast<uint32_t>(colCell.size()));
+                flush();
+                colStart.push_back(static_cast<uint32_t>(colWord.size()));
                 colOut.push_back(g.outOffset + k);
             }
         }
         MPPB_CUDA(ctx, G.colStart.reserve(colStart.size() * sizeof(uint32_t)));
-        MPPB_CUDA(ctx, G.colCell.reserve(std::max<size_t>(colCell.size(), 1) * sizeof(uint32_t)));
+        MPPB_CUDA(ctx, G.colWord.reserve(std::max<size_t>(colWord.size(), 1) * sizeof(uint4)));
+        MPPB_CUDA(ctx, G.colMask.reserve(std::max<size_t>(colMask.size(), 1) * sizeof(uint4)));
+        MPPB_CUDA(ctx, G.colDBase.reserve(std::max<size_t>(colDBase.size(), 1) * sizeof(uint32_t)));
         MPPB_CUDA(ctx, G.colD.reserve(std::max<size_t>(colD.size(), 1) * sizeof(float)));
         MPPB_CUDA(ctx, G.colOut.reserve(colOut.size() * sizeof(int)));
         MPPB_CUDA(ctx, cudaMemcpyAsync(G.colStart.p, colStart.data(), colStart.size() * sizeof(uint32_t),
                                        cudaMemcpyHostToDevice, ctx->stream));
-        if (!colCell.empty())
+        if (!colWord.empty())
         {
-            MPPB_CUDA(ctx, cudaMemcpyAsync(G.colCell.p, colCell.data(), colCell.size() * sizeof(uint32_t),
+            MPPB_CUDA(ctx, cudaMemcpyAsync(G.colWord.p, colWord.data(), colWord.size() * sizeof(uint4),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+            MPPB_CUDA(ctx, cudaMemcpyAsync(G.colMask.p, colMask.data(), colMask.size() * sizeof(uint4),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+            MPPB_CUDA(ctx, cudaMemcpyAsync(G.colDBase.p, colDBase.data(), colDBase.size() * sizeof(uint32_t),
                                            cudaMemcpyHostToDevice, ctx->stream));
             MPPB_CUDA(ctx, cudaMemcpyAsync(G.colD.p, colD.data(), colD.size() * sizeof(float),
                                            cudaMemcpyHostToDevice, ctx->stream));
@@ -370,7 +402,9 @@ static int rebuild_groups(mppb_ctx* ctx)
         std::memset(&v, 0, sizeof(v));
         v.nCols    = static_cast<int>(colOut.size());
         v.colStart = G.colStart.as<uint32_t>();
-        v.colCell  = G.colCell.as<uint32_t>();
+        v.colWord  = G.colWord.as<uint4>();
+        v.colMask  = G.colMask.as<uint4>();
+        v.colDBase = G.colDBase.as<uint32_t>();
         v.colD     = G.colD.as<float>();
         v.colOut   = G.colOut.as<int>();
         v.xmin      = g0.xmin;

@@ -41,17 +41,34 @@ __host__ __device__ inline int bin_coord(float v, float origin, float invBin, in
 // geometry and the robot shape, as the kernel sees it: ONE merged CSR whose entries carry the
 // output column (ptg offset + k) and the float bits of the TP-distance d. Points are mapped to
 // a cell once per group instead of once per PTG.
+// Tiled occupancy bitmap of a collision grid: word and bit of cell (cx, cy); tilesX = grid_tiles_x(nx).
+__host__ __device__ inline int      grid_tiles_x(int nx) { return (nx + 7) >> 3; }
+__host__ __device__ inline int      grid_tiles_y(int ny) { return (ny + 3) >> 2; }
+__host__ __device__ inline uint32_t grid_tile_word(uint32_t cx, uint32_t cy, uint32_t tilesX)
+{
+    return (cy >> 2) * tilesX + (cx >> 3);
+}
+__host__ __device__ inline uint32_t grid_tile_bit(uint32_t cx, uint32_t cy) { return ((cy & 3u) << 3) | (cx & 7u); }
+
 struct GridGroupDev
 {
     double          xmin, ymin, res, invRes;  // CDynamicGrid extents/resolution of the collision grid
     int             nx, ny;
     const uint32_t* offsets;  // by-cell CSR [nx*ny+1]
     const uint2*    entries;  // by-cell entries (output column, float bits of d)
-    // by-column view of the same table: column j of the group owns [colStart[j], colStart[j+1])
-    // of (colCell, colD), sorted by ascending d, and writes output column colOut[j].
+    // by-column view of the same table, for the column scan of tpobs_grid_kernel. The kernel's occupancy bitmap
+    // is tiled: one 32-bit word covers 8 x 4 cells (grid_tile_word / grid_tile_bit below). Column j of the group
+    // owns the CHUNKS [colStart[j], colStart[j+1]) and writes output column colOut[j]. A chunk is a run of the
+    // column's cells in ascending-d order that touches at most 4 bitmap words: colWord[c] holds the 4 word
+    // indices and colMask[c] the cells' bits in each (unused slots: mask 0), so one step of the scan tests the
+    // whole run with 4 loads from shared memory. The d of the cell at (slot s, bit b) of chunk c is
+    // colD[colDBase[c] + popc(mask[0..s-1]) + popc(mask[s] & ((1 << b) - 1))]; all d of chunk c are <= all d of
+    // chunk c+1, so the first chunk with a hit holds the column's minimum.
     int             nCols;
     const uint32_t* colStart;
-    const uint32_t* colCell;
+    const uint4*    colWord;
+    const uint4*    colMask;
+    const uint32_t* colDBase;
     const float*    colD;
     const int*      colOut;
     int             nverts;
@@ -197,13 +214,15 @@ struct PtgGridHost
 struct GridGroupHost
 {
     GridGroupDev dev;
-    DevBuf       offsets, entries, colStart, colCell, colD, colOut;
+    DevBuf       offsets, entries, colStart, colWord, colMask, colDBase, colD, colOut;
     void         release()
     {
         offsets.release();
         entries.release();
         colStart.release();
-        colCell.release();
+        colWord.release();
+        colMask.release();
+        colDBase.release();
         colD.release();
         colOut.release();
     }

@@ -31,10 +31,13 @@
 //    and set the bit of the collision-grid cell they fall in (shared-memory bitmap, one bit per
 //    cell). The rare points inside the robot polygon do not set a bit; their cell's (k,d) list
 //    is applied directly with the BACK_AWAY rule.
-//  Phase 2 (bitmap -> per-path minimum): every output column (PTG, k) owns its (cell, d) list
-//    sorted by ascending d; a warp scans it 32 entries at a time and stops at the first
-//    occupied cell, whose d IS the minimum. Blocked paths exit after a few entries, and no
-//    atomics or variable-length per-point lists remain on the common path.
+//  Phase 2 (bitmap -> per-path minimum): every output column (PTG, k) owns its cells in ascending-d
+//    order, cut into chunks that touch at most 4 words of the bitmap (a word is an 8 x 4 tile of cells,
+//    so the ~25 cells a path sweeps in a few steps share words); a thread scans two columns, one chunk
+//    = 4 shared-memory word tests per step, and stops at the first chunk with an occupied cell, whose
+//    smallest occupied d IS the column's minimum. Blocked paths exit after a chunk or two, a free path
+//    costs ~35 steps, and no atomics or variable-length per-point lists remain on the common path.
+//    Nodes with few points in their bin window scatter the by-cell lists of the occupied cells instead.
 #include <algorithm>
 #include <cfloat>
 
@@ -53,7 +56,7 @@ constexpr int      kRowsPerPass = 64;   // bin rows whose runs are flattened tog
 constexpr int      kMaxChunks   = 512;  // 32-point chunks indexed per pass
 constexpr int      kMaxInside   = 128;  // queued points inside the robot shape per node and group
 #ifndef MPPB_GRID_SCATTER_MAX
-#define MPPB_GRID_SCATTER_MAX 640
+#define MPPB_GRID_SCATTER_MAX 256
 #endif
 constexpr int      kLongList    = 32;   // by-cell lists longer than this are folded by the whole block
 constexpr int      kMaxLong     = 128;  // queue of such cells per node and group
@@ -110,6 +113,28 @@ __device__ __forceinline__ void apply_inside_cell(const GridGroupDev& G, uint32_
     }
 }
 
+// Minimum d (as float bits; d >= 0, so unsigned order is float order) over the occupied cells h0..h3 of a chunk of
+// a by-column list (GridGroupDev): d values are stored by (slot, rank of the bit within the slot's mask).
+__device__ __noinline__ unsigned chunk_min_d(const float* __restrict__ d, uint4 m, unsigned h0, unsigned h1,
+                                             unsigned h2, unsigned h3)
+{
+    unsigned best = kInfBits;
+    auto     fold = [&](unsigned h, unsigned mask, unsigned base) {
+        while (h)
+        {
+            const unsigned b = __ffs(h) - 1;
+            h &= h - 1;
+            best = min(best, __float_as_uint(d[base + __popc(mask & ((1u << b) - 1u))]));
+        }
+    };
+    const unsigned b1 = __popc(m.x), b2 = b1 + __popc(m.y), b3 = b2 + __popc(m.z);
+    fold(h0, m.x, 0);
+    fold(h1, m.y, b1);
+    fold(h2, m.z, b2);
+    fold(h3, m.w, b3);
+    return best;
+}
+
 // Phase 2 for sparse clouds: scatter the (column, d) lists of the few occupied cells.
 // A column scan walks a whole ascending-d list (hundreds of dependent steps) when nothing blocks the path; with few
 // occupied cells it is far cheaper to visit those cells' by-cell lists instead: every thread walks its share of the
@@ -141,19 +166,26 @@ __device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned
                 if (e + j < ee) atomicMin(&smin[kd[j].x], kd[j].y);
         }
     };
+    const uint32_t gnx = static_cast<uint32_t>(G.nx), tilesX = static_cast<uint32_t>(grid_tiles_x(G.nx));
     for (int i = threadIdx.x; i < words; i += kThreads)
     {
         unsigned bits = bitmap[i];
+        if (!bits) continue;
+        // word i is the 8 x 4 tile (i % tilesX, i / tilesX); bit b of it is cell (b & 7, b >> 3) of the tile
+        const uint32_t ty = static_cast<uint32_t>(i) / tilesX, tx = static_cast<uint32_t>(i) - ty * tilesX;
+        const uint32_t cellBase = (ty << 2) * gnx + (tx << 3);
         while (bits)
         {
             // two cells at a time: their list bounds are independent loads
-            const uint32_t c0 = (static_cast<uint32_t>(i) << 5) + (__ffs(bits) - 1);
+            uint32_t b = __ffs(bits) - 1;
             bits &= bits - 1;
-            uint32_t c1 = c0;
+            const uint32_t c0 = cellBase + (b >> 3) * gnx + (b & 7u);
+            uint32_t       c1 = c0;
             if (bits)
             {
-                c1 = (static_cast<uint32_t>(i) << 5) + (__ffs(bits) - 1);
+                b = __ffs(bits) - 1;
                 bits &= bits - 1;
+                c1 = cellBase + (b >> 3) * gnx + (b & 7u);
             }
             const uint32_t b0 = G.offsets[c0], e0 = G.offsets[c0 + 1];
             const uint32_t b1 = G.offsets[c1], e1 = G.offsets[c1 + 1];
@@ -190,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
 {
     extern __shared__ unsigned smem[];
     unsigned*           smin   = smem;               // [totalPaths] float bits
-    unsigned*           bitmap = smem + totalPaths;  // [bitmapWords] one bit per grid cell (+1 never-set bit)
+    unsigned*           bitmap = smem + totalPaths;  // [bitmapWords] one bit per grid cell, in 8 x 4 tiles per word
     __shared__ uint32_t rowBeg[kRowsPerPass];
     __shared__ uint32_t rowPrefix[kRowsPerPass + 1];
     __shared__ uint32_t rowLen[kRowsPerPass];
@@ -259,9 +291,10 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
         // (their rounding adds < 2e-7 * q to the error, inside the 3e-7 * n term of mq)
         const float cq = cf * ginvf, sq = sf * ginvf, offx = -gxminf * ginvf, offy = -gyminf * ginvf;
         const float halfMinusMq = 0.5f - mq;
+        const uint32_t        tilesX   = static_cast<uint32_t>(grid_tiles_x(gnx));
         const uint32_t* const colStart = G.colStart;
-        const uint4* const    colCell4 = reinterpret_cast<const uint4*>(G.colCell);
-        const float* const    colD     = G.colD;
+        const uint4* const    colWord  = G.colWord;
+        const uint4* const    colMask  = G.colMask;
         const int* const      colOut   = G.colOut;
 
         __syncthreads();  // previous group's phase 2 has finished reading the bitmap
@@ -271,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
             ptsTotal = 0;
             nLong    = 0;
         }
-        const int words = ((gnx * gny) >> 5) + 1;
+        const int words = grid_tiles_x(gnx) * grid_tiles_y(gny);
         for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
 
         // ---- phase 1: points -> occupancy bitmap ----
@@ -372,8 +405,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
                             const unsigned cx = static_cast<unsigned>(__float2int_rz(qx));
                             const unsigned cy = static_cast<unsigned>(__float2int_rz(qy));
                             if (cx >= static_cast<unsigned>(gnx) || cy >= static_cast<unsigned>(gny)) continue;
-                            const uint32_t cell = cx + cy * gnx;
-                            atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
+                            atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
                             continue;
                         }
                     }
@@ -403,29 +435,30 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
                             continue;
                         }
                     }
-                    atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
+                    atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
                 }
             }
         }
-        // Phase 2 works on two columns per thread at a time (two independent load chains). Their first
-        // four cells do not depend on the bitmap: request them before the barrier that ends phase 1,
-        // so that the L2 latency overlaps the barrier wait and phase 1b.
+        // Phase 2 works on two columns per thread at a time (independent load chains). Their first chunks do
+        // not depend on the bitmap: request them before the barrier that ends phase 1, so that the L2 latency
+        // overlaps the barrier wait and phase 1b.
         struct ColScan
         {
-            uint32_t i, end;
-            uint4    q;
-            int      oc;  // output column, -1 = nothing to scan
+            uint32_t i, end;  // current / one-past-last chunk of the column
+            uint4    w, m;    // the current chunk: 4 bitmap words and the column's cells in each
+            int      oc;      // output column, -1 = nothing to scan
         };
         auto openColumn = [&](int col, ColScan& cs) {
             cs.oc = -1;
             cs.i = cs.end = 0;
-            cs.q          = make_uint4(0, 0, 0, 0);
+            cs.w = cs.m = make_uint4(0, 0, 0, 0);
             if (col >= nCols) return;
-            cs.i   = colStart[col] >> 2;  // lists are padded to x4
-            cs.end = colStart[col + 1] >> 2;
+            cs.i   = colStart[col];
+            cs.end = colStart[col + 1];
             if (cs.i >= cs.end) return;
             cs.oc = colOut[col];
-            cs.q  = colCell4[cs.i];
+            cs.w  = colWord[cs.i];
+            cs.m  = colMask[cs.i];
         };
         ColScan A, B;
         openColumn(threadIdx.x, A);
@@ -448,23 +481,22 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
             break;
         }
 
-        // ---- phase 2: per output column, first occupied cell in ascending-d order ----
-        // one step of a column scan: test the 4 cells in hand, else move on to the prefetched 4
-        auto step = [&](ColScan& cs, const uint4& next) -> bool {
-            const uint4    q  = cs.q;
-            const unsigned h0 = (bitmap[q.x >> 5] >> (q.x & 31)) & 1u;
-            const unsigned h1 = (bitmap[q.y >> 5] >> (q.y & 31)) & 1u;
-            const unsigned h2 = (bitmap[q.z >> 5] >> (q.z & 31)) & 1u;
-            const unsigned h3 = (bitmap[q.w >> 5] >> (q.w & 31)) & 1u;
-            const unsigned m  = h0 | (h1 << 1) | (h2 << 2) | (h3 << 3);
-            if (m)
+        // ---- phase 2: per output column, the first chunk (ascending d) with an occupied cell ----
+        // one step of a column scan: test the chunk in hand (4 words of the bitmap against the column's cells in
+        // them); on a hit the minimum d over the occupied cells of the chunk is the column's result
+        auto step = [&](ColScan& cs) -> bool {
+            const unsigned h0 = bitmap[cs.w.x] & cs.m.x, h1 = bitmap[cs.w.y] & cs.m.y;
+            const unsigned h2 = bitmap[cs.w.z] & cs.m.z, h3 = bitmap[cs.w.w] & cs.m.w;
+            if (h0 | h1 | h2 | h3)
             {
-                const unsigned v = __float_as_uint(colD[4 * cs.i + __ffs(m) - 1]);
+                const unsigned v = chunk_min_d(G.colD + G.colDBase[cs.i], cs.m, h0, h1, h2, h3);
                 if (v < smin[cs.oc]) smin[cs.oc] = v;  // this thread is the only writer of the column now
                 return false;
             }
-            cs.q = next;
-            return ++cs.i < cs.end;
+            if (++cs.i >= cs.end) return false;
+            cs.w = colWord[cs.i];
+            cs.m = colMask[cs.i];
+            return true;
         };
 #ifdef MPPB_DBG_SKIP_PHASE2  // timing attribution experiments only
         for (int base = 0; clip < 0;)
@@ -477,11 +509,8 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
             bool actB = B.oc >= 0 && smin[B.oc] != 0u;
             while (actA || actB)
             {
-                uint4 nA = A.q, nB = B.q;
-                if (actA) nA = colCell4[min(A.i + 1, A.end - 1)];
-                if (actB) nB = colCell4[min(B.i + 1, B.end - 1)];
-                if (actA) actA = step(A, nA);
-                if (actB) actB = step(B, nB);
+                if (actA) actA = step(A);
+                if (actB) actB = step(B);
             }
             base += 2 * kThreads;
             if (base >= nCols) break;
@@ -504,7 +533,7 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     if (nNodes > 0x7fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many nodes in one batch");
     size_t words = 1;
     for (const auto& g : ctx->groups)
-        words = std::max(words, (static_cast<size_t>(g.dev.nx) * g.dev.ny) / 32 + 1);
+        words = std::max(words, static_cast<size_t>(grid_tiles_x(g.dev.nx)) * grid_tiles_y(g.dev.ny));
     const size_t smem = (static_cast<size_t>(ctx->totalPaths) + words) * sizeof(unsigned);
     if (smem > 200 * 1024)
         return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");

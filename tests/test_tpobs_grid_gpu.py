@@ -152,13 +152,15 @@ def test_mixed_geometry_ptg_groups(capi, orc):
     from oracle.orc import ACKERMANN_SHAPE_X as X, ACKERMANN_SHAPE_Y as Y
 
     w = 60.0 * np.pi / 180.0
-    specs = [(121, 5.0, 0.05, 1.0, w, +1.0), (31, 3.0, 0.1, 0.8, 1.3 * w, -1.0), (61, 5.0, 0.05, 1.0, w, -1.0)]
+    # the last one has a 47 x 47 grid: partial 8 x 4 tiles of the occupancy bitmap on both axes
+    specs = [(121, 5.0, 0.05, 1.0, w, +1.0), (31, 3.0, 0.1, 0.8, 1.3 * w, -1.0), (61, 5.0, 0.05, 1.0, w, -1.0),
+             (25, 2.35, 0.1, 0.6, 1.1 * w, +1.0)]
     optgs = [orc.diffdrive_c(n, rd, res, v, ww, K, X, Y) for (n, rd, res, v, ww, K) in specs]
     pptgs = [capi.PTG.diffdrive_c(n, rd, res, v, ww, K, X, Y) for (n, rd, res, v, ww, K) in specs]
     ctx = capi.Context(0)
     for p in pptgs:
         ctx.add_ptg(p)
-    assert ctx.total_paths == 121 + 31 + 61
+    assert ctx.total_paths == 121 + 31 + 61 + 25
     for density, seed in ((0.3, 81), (8.0, 82)):
         xs, ys = wl.uniform_cloud(int(density * 50 * 50), 50.0, seed=seed)
         poses = wl.node_poses(128, 50.0, margin=0.0, seed=seed + 10)
@@ -166,9 +168,9 @@ def test_mixed_geometry_ptg_groups(capi, orc):
     ctx.close()
 
 
-@pytest.mark.parametrize("density", [4.5, 5.5, 6.0, 6.5, 7.5])
+@pytest.mark.parametrize("density", [1.6, 2.1, 2.4, 2.7, 3.2, 6.0])
 def test_sparse_dense_phase2_boundary(gpu_ctx, orc, oracle_ackermann, density):
-    """Nodes on both sides of the point-count threshold (640 points in the bin window) that selects the scatter form
+    """Nodes on both sides of the point-count threshold (256 points in the bin window) that selects the scatter form
     or the column-scan form of phase 2 give the reference's values."""
     extent = 40.0
     xs, ys = wl.uniform_cloud(int(density * extent * extent), extent, seed=int(10 * density))
