@@ -207,6 +207,32 @@ def test_pinned_and_pageable_buffers_agree(gpu_ctx, capi):
         assert (a >= 0).all()
 
 
+def test_large_batch_with_pinned_buffers(gpu_ctx, capi, orc, oracle_ackermann):
+    """More than 1024 nodes with pinned buffers (the pipelined sub-batch path whose kernels store their rows straight
+    into the caller's buffer): same values as the checker, also next to rows whose pose is not finite, repeatedly on
+    the same buffers (rows of the previous call must not survive)."""
+    xs, ys = wl.uniform_cloud(40000, 60.0, seed=27)
+    gpu_ctx.set_obstacles(xs, ys)
+    n = 3000
+    pinned_in = capi.pinned_empty((n, 3), np.float64)
+    pinned_out = capi.pinned_empty((n, gpu_ctx.total_paths), np.float32)
+    for rep in range(3):
+        poses = wl.node_poses(n, 60.0, margin=1.0, seed=28 + rep)
+        poses[5, 2] = np.nan
+        poses[77, 2] = np.inf
+        poses[2999, 0] = np.nan
+        pinned_in[:] = poses
+        pinned_out[:] = -1.0
+        got = gpu_ctx.eval_nodes(pinned_in, 5.0, out=pinned_out)
+        assert got is pinned_out
+        for i in (5, 77, 2999):  # no obstacle can be placed relative to such a node: nothing constrains its paths
+            assert np.isinf(got[i]).all()
+        sel = np.r_[0:40, 1000:1040, 2960:2999]
+        want, _ = orc.eval_nodes(oracle_ackermann, xs, ys, poses[sel], 5.0, mode=1, nthreads=0)
+        assert np.array_equal(free_dist(got[sel], oracle_ackermann), want)
+        assert np.array_equal(got, gpu_ctx.eval_nodes(poses.copy(), 5.0))  # staged-copy path, pageable buffers
+
+
 def test_full_size_parity_with_checker(gpu_ctx, orc, oracle_ackermann):
     """Config C3 at BASELINE's full size — 2^20 points, 4096 nodes, 2 x 121 paths = 991 232 edge evaluations — equals the
     checker's values bit for bit (the reference build needs ~2 s per 4096 nodes on 16 host threads)."""
