@@ -506,13 +506,14 @@ def run_ours(args, rank, local_rank, world):
                 "frac": work["hbm_bytes"] / kernel_s / 1e9 / peaks.get("hbm_gbs", 1)},
         "fp64_peak_tflops": fp64_peak, "traffic": None,
     }
-    tpath = os.path.join(ROOT, "profiles", "r1m_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1n_traffic.json")
     if os.path.exists(tpath) and B == 4096 and args.points == (1 << 20):
         t = json.load(open(tpath))["tpobs_grid_kernel"]
         roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]  # bytes per launch, from the ncu capture
-        roofline["traffic_source"] = "profiles/r1m_grid_ncu_full.txt"
-        roofline["limiter"] = ("instruction issue: %.0f %% issue-slot utilisation at %.0f %% occupancy, %.1f M warp "
-                               "instructions per launch (ncu); neither HBM nor FMA throughput bounds this kernel" % (
+        roofline["traffic_source"] = "profiles/r1n_grid_ncu_full.txt"
+        roofline["limiter"] = ("instruction issue and per-CTA latency: %.0f %% issue-slot utilisation at %.0f %% occupancy "
+                               "(9 CTAs per SM, register-bound), %.1f M warp instructions per launch (ncu); neither HBM "
+                               "nor FMA throughput bounds this kernel" % (
                                    t["issue_active_pct"], t["warps_active_pct"], t["warp_instructions"] / 1e6))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
