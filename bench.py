@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
     value = sample * N_PTGS * K_PATHS / (ms * 1e-3)
     desc = "%d of %d nodes per step vs the full %d-point cloud, %d host threads" % (
         sample, args.nodes, args.points, threads)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -547,9 +547,18 @@ def run_ours(args, rank, local_rank, world):
             "sample": "first %d of %d nodes vs the full %d-point cloud (%.1f s on %d host threads)" % (
                 done, B, args.points, secs, threads),
             "parity_on_sample": bool(np.array_equal(got, ref_out))}
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -569,6 +578,12 @@ def main():
     ap.add_argument("--c5-points-per-gpu", type=int, default=1 << 23)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints
+    # its version banner there) are pointed at stderr, the JSON line goes to a private copy of the real stdout
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
