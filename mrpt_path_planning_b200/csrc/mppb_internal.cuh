@@ -243,6 +243,8 @@ struct mppb_ctx
     // second stream + fork/join events: the host entry points pipeline sub-batches over two streams
     cudaStream_t auxStream = nullptr;
     cudaEvent_t  evFork = nullptr, evJoin = nullptr;
+    cudaStream_t auxMore[2] = {nullptr, nullptr};  // sub-batch streams 3 and 4 of mppb_eval_nodes
+    cudaEvent_t  evJoinMore[2] = {nullptr, nullptr};
 
     // obstacle cloud: raw SoA (concatenated sources) + bin index
     mppb::CloudStore cloud;
