@@ -345,9 +345,15 @@ static int rebuild_groups(mppb_ctx* ctx)
                 std::sort(perK[k].begin(), perK[k].end());
                 uint32_t w[4] = {0, 0, 0, 0}, mk[4] = {0, 0, 0, 0};
                 float    dOf[4][32];
-                int      used = 0;
-                auto     flush = [&]() {
+                int      used = 0, cells = 0, chunkOfColumn = 0;
+                // The first chunk of a column is kept short (16 cells): on a dense cloud the scan ends in it, and the
+                // kernel looks up the d of every occupied cell of the chunk that ends the scan (2^23-point cloud:
+                // 0.427 -> 0.400 ms per 4096 nodes; C3 unchanged; caps of 4/8/16 or 8/16 cost C3 1.5-3 %).
+                auto cellCap = [&]() { return chunkOfColumn == 0 ? 16 : 1 << 30; };
+                auto flush   = [&]() {
                     if (!used) return;
+                    chunkOfColumn++;
+                    cells = 0;
                     colWord.push_back(make_uint4(w[0], w[1], w[2], w[3]));
                     colMask.push_back(make_uint4(mk[0], mk[1], mk[2], mk[3]));
                     colDBase.push_back(static_cast<uint32_t>(colD.size()));
@@ -363,18 +369,19 @@ static int rebuild_groups(mppb_ctx* ctx)
                     const uint32_t word = grid_tile_word(cx, cy, tilesX), bit = grid_tile_bit(cx, cy);
                     int            sl = 0;
                     while (sl < used && w[sl] != word) sl++;
+                    if (cells == cellCap() || (sl == used && used == 4))
+                    {
+                        flush();
+                        sl = 0;
+                    }
                     if (sl == used)
                     {
-                        if (used == 4)
-                        {
-                            flush();
-                            sl = 0;
-                        }
                         w[sl] = word;
                         used  = sl + 1;
                     }
                     mk[sl] |= 1u << bit;
                     dOf[sl][bit] = dc.first;
+                    cells++;
                 }
                 flush();
                 colStart.push_back(static_cast<uint32_t>(colWord.size()));
