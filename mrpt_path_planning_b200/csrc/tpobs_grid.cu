@@ -40,6 +40,7 @@
 //    Nodes with few points in their bin window scatter the by-cell lists of the occupied cells instead.
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "mppb_internal.cuh"
 
@@ -61,6 +62,9 @@ constexpr int      kMaxInside   = 128;  // queued points inside the robot shape 
 constexpr int      kLongList    = 32;   // by-cell lists longer than this are folded by the whole block
 constexpr int      kMaxLong     = 128;  // queue of such cells per node and group
 constexpr int      kScatterMax  = MPPB_GRID_SCATTER_MAX;  // <= this many points in the bin window: sparse phase 2
+constexpr int      kSplit         = 16;  // CTAs per node of a small batch
+constexpr int      kSplitMaxNodes = 32;  // batches of at most this many nodes are split
+const bool         g_noSplit      = std::getenv("MPPB_NO_SPLIT") != nullptr;  // A/B measurements only
 constexpr unsigned kInfBits = 0x7f800000u;
 constexpr unsigned kFull    = 0xffffffffu;
 
@@ -213,8 +217,13 @@ __device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned
 #ifndef MPPB_GRID_MIN_BLOCKS
 #define MPPB_GRID_MIN_BLOCKS 9  // 56 registers: 9 CTAs per SM (a 4096-node batch is then 3.07 waves of 148 x 9)
 #endif
-template <bool HAS_BOX>
-__global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
+// SPLIT > 1 (small batches, e.g. the single node of one A* expansion): SPLIT CTAs per node. Each repeats phase 1 (a
+// few microseconds for one node) and takes a contiguous 1/SPLIT of the output columns in phase 2, eight lanes per column looking
+// at eight consecutive chunks at a time. A lone CTA is bound by the latency of its dependent loads (a free path is
+// ~35 chunk loads in a row, a sparse window a chain of by-cell lists: 13-27 us measured on the reference's demo
+// map); split, the whole scan is a handful of load round trips and there is no communication between the CTAs.
+template <bool HAS_BOX, int SPLIT>
+__global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
@@ -234,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
     __shared__ uint32_t longCell[kMaxLong];
     __shared__ unsigned nLong;
 
-    const int    node = blockIdx.x;
+    const int    node = SPLIT > 1 ? blockIdx.x / SPLIT : blockIdx.x;
+    const int    part = SPLIT > 1 ? blockIdx.x % SPLIT : 0;  // this CTA's share of the output columns
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double x0 = nodes[4 * node + 0], y0 = nodes[4 * node + 1];
     const double c = nodes[4 * node + 2], s = nodes[4 * node + 3];
@@ -439,6 +449,63 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
                 }
             }
         }
+        if constexpr (SPLIT > 1)
+        {
+            __syncthreads();  // end of phase 1
+            const unsigned nIn = min(nInside, static_cast<unsigned>(kMaxInside));
+            for (unsigned q = 0; q < nIn; q++) apply_inside_cell(G, insideCell[q], smin, threadIdx.x, kThreads);
+            if (nIn) __syncthreads();
+            // ---- phase 2, column-split form: 8 lanes per column, 16 columns per pass ----
+            constexpr int  kLanes = 8, kColsPerPass = kThreads / kLanes;
+            const int      sub = threadIdx.x & (kLanes - 1), grp = threadIdx.x / kLanes;
+            const unsigned grpShift = lane & ~(kLanes - 1);  // where the group's lanes sit in a warp ballot
+            // this CTA's columns: a contiguous block (its part of the output row is then contiguous too)
+            const int perPart = (nCols + SPLIT - 1) / SPLIT;
+            const int colEnd  = min(nCols, (part + 1) * perPart);
+            for (int c0 = part * perPart; c0 < colEnd; c0 += kColsPerPass)
+            {
+                const int col = c0 + grp;
+                uint32_t  i = 0, end = 0;
+                int       oc = 0;
+                if (col < colEnd)
+                {
+                    i   = colStart[col];
+                    end = colStart[col + 1];
+                    oc  = colOut[col];
+                    if (smin[oc] == 0u) end = i;  // already blocked at distance 0 by a point inside the robot
+                }
+                bool open = i < end;  // (uniform over the 8 lanes of the column)
+                i += sub;
+                while (__any_sync(kFull, open))
+                {
+                    unsigned h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+                    uint4    m  = make_uint4(0, 0, 0, 0);
+                    if (open && i < end)
+                    {
+                        const uint4 w = colWord[i];
+                        m             = colMask[i];
+                        h0 = bitmap[w.x] & m.x, h1 = bitmap[w.y] & m.y, h2 = bitmap[w.z] & m.z, h3 = bitmap[w.w] & m.w;
+                    }
+                    const unsigned hits = (__ballot_sync(kFull, (h0 | h1 | h2 | h3) != 0u) >> grpShift) & 0xffu;
+                    if (hits)
+                    {
+                        // chunks are in ascending-d order: the lowest lane with a hit holds the column's minimum
+                        if (open && sub == __ffs(hits) - 1)
+                        {
+                            const unsigned v = chunk_min_d(G.colD + G.colDBase[i], m, h0, h1, h2, h3);
+                            if (v < smin[oc]) smin[oc] = v;  // the only writer of this column
+                        }
+                        open = false;
+                    }
+                    else
+                    {
+                        i += kLanes;
+                        if (i - sub >= end) open = false;
+                    }
+                }
+            }
+            continue;  // next group
+        }
         // Phase 2 works on two columns per thread at a time (independent load chains). Their first chunks do
         // not depend on the bitmap: request them before the barrier that ends phase 1, so that the L2 latency
         // overlaps the barrier wait and phase 1b.
@@ -521,7 +588,23 @@ __global__ void __launch_bounds__(kThreads, MPPB_GRID_MIN_BLOCKS)
     if (sparseWords) sparse_phase2(groups[numGroups - 1], bitmap, sparseWords, smin, longCell, &nLong);
     __syncthreads();
     float* o = out + static_cast<size_t>(node) * totalPaths;
-    for (int i = threadIdx.x; i < totalPaths; i += kThreads) o[i] = __uint_as_float(smin[i]);
+    if constexpr (SPLIT > 1)
+    {
+        // this CTA's columns of the row (the other CTAs of the node write theirs)
+        for (int gi = 0; gi < numGroups; gi++)
+        {
+            const GridGroupDev& G       = groups[gi];
+            const int           perPart = (G.nCols + SPLIT - 1) / SPLIT;
+            const int           colEnd  = min(G.nCols, (part + 1) * perPart);
+            for (int col = part * perPart + static_cast<int>(threadIdx.x); col < colEnd; col += kThreads)
+            {
+                const int oc = G.colOut[col];
+                o[oc]        = __uint_as_float(smin[oc]);
+            }
+        }
+    }
+    else
+        for (int i = threadIdx.x; i < totalPaths; i += kThreads) o[i] = __uint_as_float(smin[i]);
 }
 }  // namespace
 
@@ -537,21 +620,22 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     const size_t smem = (static_cast<size_t>(ctx->totalPaths) + words) * sizeof(unsigned);
     if (smem > 200 * 1024)
         return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
-    if (smem > 48 * 1024)
-    {
-        MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
-        MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
-    }
-    if (dBoxes)
-        tpobs_grid_kernel<true><<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
+    // small batches: kSplit CTAs per node (see the kernel), else one
+    const bool split = nNodes <= static_cast<size_t>(kSplitMaxNodes) && !g_noSplit;
+    auto       launch = [&](auto kernel, unsigned ctasPerNode) -> int {
+        if (smem > 48 * 1024)
+            MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<static_cast<unsigned>(nNodes) * ctasPerNode, kThreads, smem, ctx->stream>>>(
             ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
             static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut);
+        return MPPB_OK;
+    };
+    int rc;
+    if (split)
+        rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit>, kSplit) : launch(tpobs_grid_kernel<false, kSplit>, kSplit);
     else
-        tpobs_grid_kernel<false><<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
-            ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
-            static_cast<int>(words), dNodes, nullptr, clip, dOut);
+        rc = dBoxes ? launch(tpobs_grid_kernel<true, 1>, 1) : launch(tpobs_grid_kernel<false, 1>, 1);
+    if (rc != MPPB_OK) return rc;
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;
