@@ -867,7 +867,7 @@ int mppb_eval_edge_costs(mppb_ctx* ctx, size_t n_edges, const double* from_xyphi
         MPPB_CUDA(ctx, ctx->dStage3.reserve(outBytes));
         dOut = ctx->dStage3.as<double>();
     }
-    const int rc = launch_edge_costs(ctx, n_edges, dFrom, dOff, dRel, dOut);
+    const int rc = launch_edge_costs(ctx, n_edges, dFrom, dOff, dRel, dOut, m);
     if (rc != MPPB_OK) return rc;
     if (!outInPlace) MPPB_CUDA(ctx, cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -19,6 +19,9 @@
 // costmap (4.8 MB at config C2) stays L2-resident; nothing here is bandwidth-bound.
 #include <math_constants.h>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "mppb_internal.cuh"
 
 namespace mppb
@@ -102,6 +105,85 @@ __global__ void __launch_bounds__(128)
     out[t] = cost / static_cast<double>(n);
 }
 
+// Small batches (the tentative edges of ONE A* expansion: a few dozen edges): one CTA. The general kernel walks an
+// edge's samples one by one — for inputs read in place from pinned host memory that is a PCIe read plus a costmap read
+// per sample, one after the other (≈12 us for 7 samples). Here the CTA first copies the whole input into shared
+// memory (coalesced, one PCIe round trip), then every thread issues the evaluator look-ups of all samples of its edge
+// together and folds them in time order afterwards. Same arithmetic, same results.
+constexpr int kSmallMaxPairs   = 1024;  // (edge, evaluator) pairs = threads of the CTA
+constexpr int kSmallMaxEdges   = 512;
+constexpr int kSmallMaxSamples = 1024;
+constexpr int kSmallRound      = 8;  // samples whose look-ups are in flight together
+__global__ void __launch_bounds__(kSmallMaxPairs)
+    edge_cost_small_kernel(const EvaluatorDev* __restrict__ evals, int nEvals, int nEdges, int nSamples,
+                           const double* __restrict__ from /* [n][4] x,y,cos,sin */,
+                           const uint32_t* __restrict__ offsets, const double* __restrict__ rel, double* __restrict__ out)
+{
+    extern __shared__ double sm[];
+    double*   sFrom = sm;
+    double*   sRel  = sm + 4 * nEdges;
+    uint32_t* sOff  = reinterpret_cast<uint32_t*>(sRel + 2 * nSamples);
+    // four loads per thread in flight per round (a load-store loop would wait for every PCIe read in turn)
+    auto stage = [&](auto* dst, const auto* src, int n) {
+        for (int base = threadIdx.x; base < n; base += 4 * blockDim.x)
+        {
+            std::remove_reference_t<decltype(dst[0])> r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (base + j * static_cast<int>(blockDim.x) < n) r[j] = src[base + j * blockDim.x];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (base + j * static_cast<int>(blockDim.x) < n) dst[base + j * blockDim.x] = r[j];
+        }
+    };
+    stage(sFrom, from, 4 * nEdges);
+    stage(sRel, rel, 2 * nSamples);
+    stage(sOff, offsets, nEdges + 1);
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= nEdges * nEvals) return;
+    const int           e = t / nEvals, slot = t - e * nEvals;
+    const EvaluatorDev& E = evals[slot];
+    const double        x0 = sFrom[4 * e + 0], y0 = sFrom[4 * e + 1], c = sFrom[4 * e + 2], s = sFrom[4 * e + 3];
+    const uint32_t      first = sOff[e], n = sOff[e + 1] - first;
+    const bool          isMap = E.kind == 1, average = E.useAverage != 0;
+    double              cost = .0;
+    unsigned            cnt  = 0;
+    for (uint32_t base = 0; base < n; base += kSmallRound)
+    {
+        double v[kSmallRound];
+#pragma unroll
+        for (int j = 0; j < kSmallRound; j++)
+        {
+            v[j] = .0;
+            if (base + j < n)
+            {
+                const double bx = sRel[2 * (first + base + j)], by = sRel[2 * (first + base + j) + 1];
+                // TPose2D::operator+ : x + b.x*cos - b.y*sin ; y + b.x*sin + b.y*cos
+                const double px = x0 + bx * c - by * s;
+                const double py = y0 + bx * s + by * c;
+                v[j]            = isMap ? costmap_at(E, px, py) : waypoints_at(E, px, py);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kSmallRound; j++)
+        {
+            if (base + j >= n) break;
+            if (average)
+            {
+                cost += v[j];
+                ++cnt;
+            }
+            else if (v[j] >= cost)
+            {
+                cost = v[j];
+                cnt  = 1;
+            }
+        }
+    }
+    out[t] = cost / static_cast<double>(cnt);
+}
+
 // costmap builder: nearest float squared distance from each cell centre to the cloud
 // (CostEvaluatorCostMap.cpp:91-97 with nanoflann's float L2: dx*dx + dy*dy)
 __global__ void __launch_bounds__(256)
@@ -141,11 +223,23 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const uint32_t* dOffsets, const double* dRel,
-                      double* dOut)
+                      double* dOut, size_t nSamples)
 {
     if (nEdges == 0 || ctx->numEvals == 0) return MPPB_OK;
     const size_t total = nEdges * static_cast<size_t>(ctx->numEvals);
     if (total > 0x7fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many edges in one batch");
+    if (nSamples > 0 && total <= kSmallMaxPairs && nEdges <= kSmallMaxEdges && nSamples <= kSmallMaxSamples)
+    {
+        // one A* expansion's worth of edges: the single-CTA kernel (sample count known to the caller)
+        const size_t   smem    = (4 * nEdges + 2 * nSamples) * sizeof(double) + (nEdges + 1) * sizeof(uint32_t);
+        const unsigned threads = std::max(256u, static_cast<unsigned>((total + 31) / 32 * 32));  // >= 256 for the staging
+        edge_cost_small_kernel<<<1, threads, smem, ctx->stream>>>(ctx->evalDescs.as<EvaluatorDev>(), ctx->numEvals,
+                                                                  static_cast<int>(nEdges), static_cast<int>(nSamples),
+                                                                  dFrom, dOffsets, dRel, dOut);
+        ctx->launches++;
+        MPPB_CUDA(ctx, cudaGetLastError());
+        return MPPB_OK;
+    }
     const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
     edge_cost_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->evalDescs.as<EvaluatorDev>(), ctx->numEvals,
                                                       static_cast<int>(nEdges), dFrom, dOffsets, dRel, dOut);

@@ -294,8 +294,9 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
                       float* dOut);
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
                       const float* dBoxes, double clip, double* dOut);
+// nSamples = dOffsets[nEdges] if the caller knows it (selects the small-batch kernel), 0 otherwise
 int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const uint32_t* dOffsets, const double* dRel,
-                      double* dOut);
+                      double* dOut, size_t nSamples = 0);
 int launch_costmap_d2(mppb_ctx* ctx, const CloudStore& cs, double xmin, double ymin, double res, int nx, int ny,
                       float clearance, float* dOut);
 
