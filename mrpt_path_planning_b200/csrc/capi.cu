@@ -723,7 +723,7 @@ int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double*
         MPPB_CUDA(ctx, ctx->dStage2.reserve(outBytes));
         dOut = ctx->dStage2.as<double>();
     }
-    const int rc = launch_tpobs_holo(ctx, n_cands, dCands, dNodes, dBoxes, clip_dist, dOut);
+    const int rc = launch_tpobs_holo(ctx, n_cands, dCands, dNodes, dBoxes, clip_dist, dOut, n_nodes);
     if (rc != MPPB_OK) return rc;
     if (!outInPlace) MPPB_CUDA(ctx, cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -292,8 +292,9 @@ void set_global_error(const std::string& msg);
 int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize);
 int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
                       float* dOut);
+// nNodes = rows of dNodes if the caller knows it (1 lets the kernel fetch the row early), 0 otherwise
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
-                      const float* dBoxes, double clip, double* dOut);
+                      const float* dBoxes, double clip, double* dOut, size_t nNodes = 0);
 // nSamples = dOffsets[nEdges] if the caller knows it (selects the small-batch kernel), 0 otherwise
 int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const uint32_t* dOffsets, const double* dRel,
                       double* dOut, size_t nSamples = 0);

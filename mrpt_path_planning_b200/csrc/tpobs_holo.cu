@@ -225,7 +225,7 @@ __device__ __forceinline__ bool hull_may_hit(const PathHull& h, float lx, float 
 #endif
 __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     tpobs_holo_kernel(CloudBins bins, const HoloPtgDev* __restrict__ ptgs, const mppb_holo_cand* __restrict__ cands,
-                      int nCands, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
+                      int nCands, int nNodes, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* NULL or [n] minx,miny,maxx,maxy */, double clip,
                       int useFilter, double* __restrict__ out)
 {
@@ -233,6 +233,11 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ci   = blockIdx.x * kWarps + warp;
     if (ci >= nCands) return;
+    // one node (a single query's expansion): its row does not have to wait for the candidate record, which, like the
+    // row, may sit in pinned host memory (two PCIe round trips in a row otherwise)
+    double row0[4] = {0, 0, 0, 0};
+    if (nNodes == 1)
+        for (int j = 0; j < 4; j++) row0[j] = nodes[j];
     const mppb_holo_cand cd = cands[ci];
     const HoloPtgDev     P  = ptgs[cd.ptg_index];
 
@@ -255,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     q.qb              = (q.k2 * q.vxi * 2.0 + q.k4 * q.vyi * 2.0);
     q.distAtT         = ramp_distance(q.k2, q.k4, q.vxi, q.vyi, q.T);
 
-    const double x0 = nodes[4 * cd.node + 0], y0 = nodes[4 * cd.node + 1];
-    const double c = nodes[4 * cd.node + 2], s = nodes[4 * cd.node + 3];
+    const double x0 = nNodes == 1 ? row0[0] : nodes[4 * cd.node + 0], y0 = nNodes == 1 ? row0[1] : nodes[4 * cd.node + 1];
+    const double c = nNodes == 1 ? row0[2] : nodes[4 * cd.node + 2], s = nNodes == 1 ? row0[3] : nodes[4 * cd.node + 3];
     const double ix = -x0 * c - y0 * s;  // CPose2D unary minus
     const double iy = x0 * s - y0 * c;
 
@@ -295,38 +300,66 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
         const int   bx1 = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         const int   by0 = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
         const int   by1 = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
-        // One flat loop over (bin row, 32-point chunk); points that pass the filter are queued, and whenever 32 are
-        // waiting (or the cloud is exhausted) the warp runs them through the exact chain — a single call site, so the
-        // FP64 code exists once.
-        int      row = by0;
-        uint32_t p0 = 0, end = 0;
-        bool     rowOpen = false;
+        // The window's points, 32 at a time across bin rows: the runs of up to 32 rows are fetched together (one
+        // row per lane, so their binStart reads are ONE round trip instead of one per row — on a sparse map the
+        // rows hold a dozen points each and a row-by-row loop is a chain of dependent loads), a warp scan of the
+        // run lengths gives every flat index its (row, offset), and lanes load consecutive flat indices. Points
+        // that pass the filter are queued, and whenever 32 are waiting (or the window is exhausted) the warp runs
+        // them through the exact chain — a single call site, so the FP64 code exists once.
+        int      rowBase = by0;
+        uint32_t f0 = 0, total = 0, runBeg = 0, excl = 0;
+        bool     groupOpen = false;
         for (;;)
         {
             bool haveChunk = false;
-            while (row <= by1)
+            while (rowBase <= by1)
             {
-                if (!rowOpen)
+                if (!groupOpen)
                 {
-                    const size_t r = static_cast<size_t>(row) * bins.nbx;
-                    p0             = bins.binStart[r + bx0];
-                    end            = bins.binStart[r + bx1 + 1];
-                    rowOpen        = true;
+                    const int nRows  = min(32, by1 - rowBase + 1);
+                    uint32_t  runLen = 0;
+                    runBeg           = 0;
+                    if (lane < nRows)
+                    {
+                        const size_t r = static_cast<size_t>(rowBase + lane) * bins.nbx;
+                        runBeg         = bins.binStart[r + bx0];
+                        runLen         = bins.binStart[r + bx1 + 1] - runBeg;
+                    }
+                    uint32_t incl = runLen;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    total     = __shfl_sync(kFull, incl, 31);
+                    excl      = incl - runLen;
+                    f0        = 0;
+                    groupOpen = true;
                 }
-                if (p0 < end)
+                if (f0 < total)
                 {
                     haveChunk = true;
                     break;
                 }
-                rowOpen = false;
-                row++;
+                groupOpen = false;
+                rowBase += 32;
             }
             if (haveChunk)
             {
-                const uint32_t p    = p0 + lane;
+                const uint32_t f = f0 + lane;
+                // the last row whose first flat index is <= f (empty rows share their successor's index and lose)
+                int row = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                {
+                    const uint32_t v = __shfl_sync(kFull, excl, row + step);
+                    if (v <= f) row += step;
+                }
+                const uint32_t p = __shfl_sync(kFull, runBeg, row) + (f - __shfl_sync(kFull, excl, row));
                 bool           pass = false;
                 float2         g    = make_float2(0.f, 0.f);
-                if (p < end)
+                if (f < total)
                 {
                     g    = bins.pts[p];
                     pass = !(hasBox && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w));
@@ -338,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
                         pass           = pass && hull_may_hit(hull, dx * cf + dy * sf, dy * cf - dx * sf);
                     }
                 }
-                p0 += 32;
+                f0 += 32;
                 const unsigned m = __ballot_sync(kFull, pass);
                 if (pass) queue[warp][qn + __popc(m & ((1u << lane) - 1u))] = g;
                 qn += __popc(m);
@@ -361,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
 }  // namespace
 
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
-                      const float* dBoxes, double clip, double* dOut)
+                      const float* dBoxes, double clip, double* dOut, size_t nNodes)
 {
     const int useFilter = ctx->holoFilter ? 1 : 0;  // off: the unfiltered kernel, for A/B tests (mppb_set_holo_filter)
     if (nCands == 0) return MPPB_OK;
@@ -369,7 +402,7 @@ int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands
     if (nCands > 0x3fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many candidates in one batch");
     const unsigned blocks = static_cast<unsigned>((nCands + kWarps - 1) / kWarps);
     tpobs_holo_kernel<<<blocks, kThreads, 0, ctx->stream>>>(ctx->bins, ctx->holoDescs.as<HoloPtgDev>(), dCands,
-                                                            static_cast<int>(nCands), dNodes,
+                                                            static_cast<int>(nCands), nNodes == 1 ? 1 : 0, dNodes,
                                                             reinterpret_cast<const float4*>(dBoxes), clip, useFilter, dOut);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
