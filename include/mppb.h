@@ -221,6 +221,13 @@ int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyp
                           double clip_dist, float* out);
 int mppb_eval_nodes_boxed_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, const float* d_node_boxes,
                                  double clip_dist, float* d_out);
+/* Split form of the host call, for callers that have host work of their own to do while the GPU
+ * evaluates (TPS_Astar reconstructs the end poses of its candidate TPS points, TPS_Astar.cpp:725-736,
+ * which need the node pose only): _begin enqueues the same work as mppb_eval_nodes_boxed and returns;
+ * mppb_sync(ctx) completes it. Until then poses_xyphi, node_boxes and out must stay alive and
+ * untouched, and no second _begin of the same entry point may be issued on the context. */
+int mppb_eval_nodes_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                double clip_dist, float* out);
 /* Fill [n][4] (x, y, cos, sin) from [n][3] (x, y, phi) on the host with the C library. */
 void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, double* out_xycs);
 
@@ -242,6 +249,10 @@ int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double*
 int mppb_eval_holo_candidates_boxed_device(mppb_ctx* ctx, size_t n_cands, const mppb_holo_cand* d_cands,
                                            const double* d_nodes_xycs, const float* d_node_boxes, double clip_dist,
                                            double* d_out);
+/* split form (see mppb_eval_nodes_boxed_begin); may be in flight together with one mppb_eval_nodes_boxed_begin */
+int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi,
+                                          const float* node_boxes, size_t n_cands, const mppb_holo_cand* cands,
+                                          double clip_dist, double* out);
 
 /* ---- stage (c): cost evaluators ---------------------------------------------------------
  * Evaluator slots are evaluated in slot order, like Planner::costEvaluators_ (Planner.cpp:22-26). */

@@ -172,6 +172,10 @@ _SIGS = {
     "mppb_eval_nodes_boxed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "mppb_eval_nodes_boxed_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
                                                C.c_void_p]),
+    "mppb_eval_nodes_boxed_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double,
+                                              C.c_void_p]),
+    "mppb_eval_holo_candidates_boxed_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                        C.c_void_p, C.c_double, C.c_void_p]),
     "mppb_eval_holo_candidates_boxed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                                   C.c_void_p, C.c_double, C.c_void_p]),
     "mppb_eval_holo_candidates_boxed_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -541,6 +545,28 @@ class Context:
         self._ck(lib().mppb_eval_holo_candidates_boxed(self.h, poses.shape[0], _ptr(poses), _ptr(boxes), len(cands),
                                                        _ptr(cands), clip_dist, _ptr(out)))
         return out
+
+    def eval_both_split(self, poses, boxes, cands, clip_dist):
+        """Collision-grid rows and HolonomicBlend candidates of the same nodes through the split entry points
+        (mppb_eval_nodes_boxed_begin + mppb_eval_holo_candidates_boxed_begin, both in flight, one mppb_sync).
+        boxes may be None; either result is None when the context has no PTG of that kind / cands is empty."""
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+        if boxes is not None:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+        rows = hout = None
+        if self.total_paths > 0:
+            rows = np.empty((poses.shape[0], self.total_paths), dtype=np.float32)
+            self._ck(lib().mppb_eval_nodes_boxed_begin(self.h, poses.shape[0], _ptr(poses),
+                                                       _ptr(boxes) if boxes is not None else None, clip_dist,
+                                                       _ptr(rows)))
+        if cands is not None and len(cands):
+            cands = np.ascontiguousarray(cands, dtype=HOLO_CAND_DTYPE)
+            hout = np.empty(len(cands), dtype=np.float64)
+            self._ck(lib().mppb_eval_holo_candidates_boxed_begin(self.h, poses.shape[0], _ptr(poses),
+                                                                 _ptr(boxes) if boxes is not None else None,
+                                                                 len(cands), _ptr(cands), clip_dist, _ptr(hout)))
+        self.sync()
+        return rows, hout
 
     def eval_nodes_device(self, n, d_nodes_xycs, clip_dist, d_out):
         self._ck(lib().mppb_eval_nodes_device(self.h, n, _ptr(d_nodes_xycs), clip_dist, _ptr(d_out)))

@@ -122,6 +122,9 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     ctx->hNodes.release();
     ctx->hOut.release();
     ctx->hStage.release();
+    ctx->hNodesHolo.release();
+    ctx->dNodesHolo.release();
+    ctx->dBoxesHolo.release();
     ctx->dNodes.release();
     ctx->dOut.release();
     ctx->dStage.release();
@@ -549,8 +552,21 @@ int mppb_eval_nodes(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, do
     return mppb_eval_nodes_boxed(ctx, n_nodes, poses_xyphi, nullptr, clip_dist, out);
 }
 
+static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                 double clip_dist, float* out, bool wait);
 int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
                           double clip_dist, float* out)
+{
+    return eval_nodes_boxed_impl(ctx, n_nodes, poses_xyphi, node_boxes, clip_dist, out, true);
+}
+int mppb_eval_nodes_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                double clip_dist, float* out)
+{
+    return eval_nodes_boxed_impl(ctx, n_nodes, poses_xyphi, node_boxes, clip_dist, out, false);
+}
+
+static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                 double clip_dist, float* out, bool wait)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n_nodes == 0) return MPPB_OK;
@@ -646,7 +662,7 @@ int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyp
             cudaStreamWaitEvent(ctx->stream, evs[i - 1], 0);
         }
     }
-    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (wait) MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // _begin: the caller's mppb_sync() completes the call
     return rc;
 }
 
@@ -672,8 +688,24 @@ int mppb_eval_holo_candidates(mppb_ctx* ctx, size_t n_nodes, const double* poses
     return mppb_eval_holo_candidates_boxed(ctx, n_nodes, poses_xyphi, nullptr, n_cands, cands, clip_dist, out);
 }
 
+static int eval_holo_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                size_t n_cands, const mppb_holo_cand* cands, double clip_dist, double* out, bool wait);
 int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
                                     size_t n_cands, const mppb_holo_cand* cands, double clip_dist, double* out)
+{
+    return eval_holo_boxed_impl(ctx, n_nodes, poses_xyphi, node_boxes, n_cands, cands, clip_dist, out, true);
+}
+int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi,
+                                          const float* node_boxes, size_t n_cands, const mppb_holo_cand* cands,
+                                          double clip_dist, double* out)
+{
+    return eval_holo_boxed_impl(ctx, n_nodes, poses_xyphi, node_boxes, n_cands, cands, clip_dist, out, false);
+}
+
+// (node rows and boxes are staged in buffers of their own, so that a collision-grid call and a HolonomicBlend call
+// of the same expansion can be in flight together)
+static int eval_holo_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi, const float* node_boxes,
+                                size_t n_cands, const mppb_holo_cand* cands, double clip_dist, double* out, bool wait)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     if (n_cands == 0) return MPPB_OK;
@@ -690,19 +722,19 @@ int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double*
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nodeBytes = n_nodes * 4 * sizeof(double), candBytes = n_cands * sizeof(mppb_holo_cand);
     const size_t outBytes  = n_cands * sizeof(double);
-    MPPB_CUDA(ctx, ctx->hNodes.reserve(nodeBytes));
-    mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodes.as<double>());
+    MPPB_CUDA(ctx, ctx->hNodesHolo.reserve(nodeBytes));
+    mppb_nodes_xycs_from_poses(n_nodes, poses_xyphi, ctx->hNodesHolo.as<double>());
     // small batch with pinned caller buffers: the kernel works on them in place (no staging copies)
     const bool            small  = nodeBytes + candBytes <= kZeroCopyInputBytes;
-    const double*         dNodes = small ? mapped_alias(ctx->hNodes.as<double>()) : nullptr;
+    const double*         dNodes = small ? mapped_alias(ctx->hNodesHolo.as<double>()) : nullptr;
     const mppb_holo_cand* dCands = small ? mapped_alias(cands) : nullptr;
     const float*          dBoxes = (small && node_boxes) ? mapped_alias(node_boxes) : nullptr;
     double*               dOut   = mapped_alias(out);
     if (!dNodes)
     {
-        MPPB_CUDA(ctx, ctx->dNodes.reserve(nodeBytes));
-        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodes.p, ctx->hNodes.p, nodeBytes, cudaMemcpyHostToDevice, ctx->stream));
-        dNodes = ctx->dNodes.as<double>();
+        MPPB_CUDA(ctx, ctx->dNodesHolo.reserve(nodeBytes));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dNodesHolo.p, ctx->hNodesHolo.p, nodeBytes, cudaMemcpyHostToDevice, ctx->stream));
+        dNodes = ctx->dNodesHolo.as<double>();
     }
     if (!dCands)
     {
@@ -712,10 +744,10 @@ int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double*
     }
     if (node_boxes && !dBoxes)
     {
-        MPPB_CUDA(ctx, ctx->dBoxes.reserve(n_nodes * 4 * sizeof(float)));
-        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxes.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
+        MPPB_CUDA(ctx, ctx->dBoxesHolo.reserve(n_nodes * 4 * sizeof(float)));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dBoxesHolo.p, node_boxes, n_nodes * 4 * sizeof(float), cudaMemcpyHostToDevice,
                                        ctx->stream));
-        dBoxes = ctx->dBoxes.as<float>();
+        dBoxes = ctx->dBoxesHolo.as<float>();
     }
     const bool outInPlace = dOut != nullptr;
     if (!outInPlace)
@@ -726,7 +758,7 @@ int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double*
     const int rc = launch_tpobs_holo(ctx, n_cands, dCands, dNodes, dBoxes, clip_dist, dOut, n_nodes);
     if (rc != MPPB_OK) return rc;
     if (!outInPlace) MPPB_CUDA(ctx, cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
-    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (wait) MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // _begin: the caller's mppb_sync() completes the call
     return MPPB_OK;
 }
 

@@ -5,6 +5,7 @@
 // :514-533, inverseMap_WS2TP_with_Tramp :309-484, internal_params_from_dir_and_dynstate :942-973).
 // The arithmetic keeps the reference's operation order: these values decide lattice cells and
 // the free/blocked comparison, so they must round identically.
+#include <cstring>
 #include <algorithm>
 #include <limits>
 
@@ -88,20 +89,25 @@ HolonomicBlend::HolonomicBlend(const HolonomicBlendParams& p) : p_(p)
     }
     exprV_.compile(p_.expr_V.empty() ? "V_MAX" : p_.expr_V);
     exprW_.compile(p_.expr_W.empty() ? "W_MAX" : p_.expr_W);
+    memoGen_++;
     initialized_ = true;
 }
 
 void HolonomicBlend::onNewNavDynamicState()
 {
     stepCountCache_.assign(numPaths_, -1);
-    memoValid_  = false;
+    memoGen_++;  // drops every memoised paramsForDir() result
     targetDir_  = target_k_ >= 0 ? index2alpha(static_cast<unsigned>(target_k_)) : .0;
     targetDist_ = dynState_.relTarget.norm();
 }
 
 HolonomicBlend::Internal HolonomicBlend::paramsForDir(double dir) const
 {
-    if (memoValid_ && dir == memoDir_ && trimmableSpeed_ == memoSpeed_) return memoQ_;
+    uint64_t db, sb;
+    std::memcpy(&db, &dir, sizeof(db));
+    std::memcpy(&sb, &trimmableSpeed_, sizeof(sb));
+    Memo& m = memo_[((db * 0x9E3779B97F4A7C15ull) ^ (sb * 0xC2B2AE3D27D4EB4Full)) >> 58];
+    if (m.gen == memoGen_ && dir == m.dir && trimmableSpeed_ == m.speed) return m.q;
     Internal q;
     q.T_ramp = p_.T_ramp_max;
     exprDir_ = dir;
@@ -111,10 +117,10 @@ HolonomicBlend::Internal HolonomicBlend::paramsForDir(double dir) const
     q.vyi    = dynState_.curVelLocal.vy;
     q.vxf    = q.vf * std::cos(dir);
     q.vyf    = q.vf * std::sin(dir);
-    memoQ_     = q;
-    memoDir_   = dir;
-    memoSpeed_ = trimmableSpeed_;
-    memoValid_ = true;
+    m.q      = q;
+    m.dir    = dir;
+    m.speed  = trimmableSpeed_;
+    m.gen    = memoGen_;
     return q;
 }
 

@@ -16,6 +16,7 @@
 // multimap open set with its stale keys, node-id assignment order) is kept as in the reference,
 // and every PTG object sees the same sequence of state changes, so a query produces the same tree
 // whether it runs alone (plan) or interleaved with thousands of others (plan_batch).
+#include <cstdlib>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -504,26 +505,40 @@ struct TPS_Astar::Impl::Query
     }
 
     // ---- phase A: candidate TPS points of `current` (TPS_Astar.cpp:549-736) ----
-    void phaseA()
+    // In two parts, so that the GPU can work while the host finishes: phaseAPrepare() lists the TPS points of every
+    // PTG and collects what the collision kernels need (the HolonomicBlend candidate records; the collision-grid
+    // kernel needs the node pose only); phaseACandidates() then reconstructs the end poses and lattice cells. The
+    // PTG objects see the same sequence of state changes as in the reference's single loop.
+    struct TpsPoint
+    {
+        trajectory_index_t k;
+        ptg_step_t         step;
+        normalized_speed_t speed;
+        uint32_t           evalIndex;  // HolonomicBlend: index into holoCands
+    };
+    struct TpsRange  // the TPS points of one PTG inside tpsAll
+    {
+        size_t             begin = 0, end = 0, nTargets = 0;
+        bool               trimmable = false, dedup = false;
+        uint32_t           copies     = 1;
+        normalized_speed_t firstSpeed = 1.0;
+    };
+    std::vector<TpsPoint> tpsAll;
+    std::vector<TpsRange> tpsOfPtg;
+
+    void phaseAPrepare()
     {
         cands.clear();
         holoCands.clear();
+        tpsAll.clear();
+        tpsOfPtg.assign(trs.ptgs.size(), TpsRange());
         dynOfPtg.assign(trs.ptgs.size(), TNavDynamicState());
         const Node&      from        = *current;
         const NodeCoords iGoalCoords = goalCellIndices;
         const TPose2D    relGoal     = in->stateGoal.asSE2KinState().pose - from.state.pose;
-        const double     halfCell    = P->grid_resolution_xy * 0.5;
-        const TPose2D&   lo = in->worldBboxMin, &hi = in->worldBboxMax;
 
-        struct TpsPoint
-        {
-            trajectory_index_t k;
-            ptg_step_t         step;
-            normalized_speed_t speed;
-        };
         arena.release();  // phase scratch of the previous expansion
-        std::pmr::vector<TpsPoint>                                         tps(&arena);
-        std::pmr::map<std::pair<trajectory_index_t, double>, uint32_t>     holoIndex(&arena);
+        std::pmr::map<std::pair<trajectory_index_t, double>, uint32_t> holoIndex(&arena);
 
         for (size_t ptgIdx = 0; ptgIdx < trs.ptgs.size(); ptgIdx++)
         {
@@ -542,14 +557,15 @@ struct TPS_Astar::Impl::Query
             dynOfPtg[ptgIdx] = ptg.getCurrentNavDynamicState();
 
             // std::set<trajectory_index_t> of the reference as a sorted vector without duplicates (same iteration order);
-            // the direct-to-goal TPS points are the first nTargets entries of `tps`
+            // the direct-to-goal TPS points are the first nTargets entries of the PTG's range
             std::pmr::vector<trajectory_index_t> trajIdxs(&arena);
             auto insertTraj = [&trajIdxs](trajectory_index_t k) {
                 const auto it = std::lower_bound(trajIdxs.begin(), trajIdxs.end(), k);
                 if (it == trajIdxs.end() || *it != k) trajIdxs.insert(it, k);
             };
-            size_t nTargets = 0;
-            tps.clear();
+            TpsRange& R = tpsOfPtg[ptgIdx];
+            R.begin     = tpsAll.size();
+            R.trimmable = trimmable;
             MPP_ASSERT(P->max_ptg_trajectories_to_explore >= 2);
             for (size_t i = 0; i < P->max_ptg_trajectories_to_explore; i++)
             {
@@ -577,8 +593,8 @@ struct TPS_Astar::Impl::Query
                     if (ptg.getPathStepForDist(static_cast<uint16_t>(goalK), goalD, goalStep))
                         for (const auto s : speeds)
                         {
-                            tps.push_back({goalK, goalStep, s});
-                            nTargets = tps.size();
+                            tpsAll.push_back({goalK, goalStep, s, 0u});
+                            R.nTargets = tpsAll.size() - R.begin;
                         }
                     insertTraj(goalK);
                 }
@@ -591,30 +607,67 @@ struct TPS_Astar::Impl::Query
                         const size_t     maxSteps = ptg.getPathStepCount(static_cast<uint16_t>(k));
                         MPP_ASSERT(maxSteps >= 1);
                         if (step >= maxSteps) continue;
-                        tps.push_back({k, step, s});
+                        tpsAll.push_back({k, step, s, 0u});
                     }
+            R.end = tpsAll.size();
 
-            const bool onGrid = ptg.kind() == PtgKind::CollisionGrid;
             // A trimmable PTG whose paths ignore the trimmed speed yields, for every speed after the first, exact copies
             // of the first speed's TPS points (same k, step, distance, pose, cell). Copies can never win the strict "<"
             // of the per-cell selection nor change the goal-cell set, so only the first speed is carried on; `copies`
             // keeps the reference's count of evaluated points.
-            const bool     dedup  = trimmable && !ptg.pathsDependOnTrimmableSpeed() && speeds.size() > 1;
-            const uint32_t copies = dedup ? static_cast<uint32_t>(speeds.size()) : 1u;
-            // from.state.pose (+) relPose with the heading's cos/sin taken once (TPose2D::operator+ takes them per call)
-            const double fromC = std::cos(from.state.pose.phi), fromS = std::sin(from.state.pose.phi);
+            R.dedup      = trimmable && !ptg.pathsDependOnTrimmableSpeed() && speeds.size() > 1;
+            R.copies     = R.dedup ? static_cast<uint32_t>(speeds.size()) : 1u;
+            R.firstSpeed = speeds.front();
+
+            if (ptg.kind() == PtgKind::CollisionGrid) continue;
+            // HolonomicBlend: one candidate record per (k, trimmed speed) of the PTG's TPS points. (Records are made
+            // before the world-box test of phaseACandidates(): a point that fails it leaves an unused record.)
             holoIndex.clear();
+            for (size_t i = R.begin; i < R.end; i++)
+            {
+                TpsPoint& tp = tpsAll[i];
+                if (tp.step == 0) continue;  // no motion
+                if (trimmable && tp.speed != ptg.trimmableSpeed_) ptg.trimmableSpeed_ = tp.speed;
+                const auto key = std::make_pair(tp.k, tp.speed);
+                auto       it  = holoIndex.find(key);
+                if (it == holoIndex.end())
+                {
+                    mppb_holo_cand hc;
+                    static_cast<const HolonomicBlend&>(ptg).holoParams(static_cast<uint16_t>(tp.k), hc);
+                    hc.node      = 0;  // position in the round's node batch: filled in when the batch is assembled
+                    hc.ptg_index = static_cast<int32_t>(ptgIdx);
+                    holoCands.push_back(hc);
+                    it = holoIndex.emplace(key, static_cast<uint32_t>(holoCands.size() - 1)).first;
+                }
+                tp.evalIndex = it->second;
+            }
+        }
+    }
+
+    void phaseACandidates()
+    {
+        const Node&    from     = *current;
+        const double   halfCell = P->grid_resolution_xy * 0.5;
+        const TPose2D& lo = in->worldBboxMin, &hi = in->worldBboxMax;
+        // from.state.pose (+) relPose with the heading's cos/sin taken once (TPose2D::operator+ takes them per call)
+        const double fromC = std::cos(from.state.pose.phi), fromS = std::sin(from.state.pose.phi);
+        for (size_t ptgIdx = 0; ptgIdx < trs.ptgs.size(); ptgIdx++)
+        {
+            ptg_t&          ptg       = *trs.ptgs[ptgIdx];
+            const TpsRange& R         = tpsOfPtg[ptgIdx];
+            const bool      trimmable = R.trimmable, dedup = R.dedup;
+            const bool      onGrid    = ptg.kind() == PtgKind::CollisionGrid;
             // initTPObstacleSingle(k) depends on (k, trimmed speed, PTG state) only: consecutive TPS points of the same
             // path and speed (the sample timestamps) share it
             trajectory_index_t initK     = -1;
             normalized_speed_t initSpeed = -1;
             distance_t         initVal   = 0;
-            for (size_t i = 0; i < tps.size(); i++)
+            for (size_t i = R.begin; i < R.end; i++)
             {
-                const TpsPoint& tp = tps[i];
+                const TpsPoint& tp = tpsAll[i];
                 if (tp.step == 0) continue;  // no motion
                 if (trimmable && tp.speed != ptg.trimmableSpeed_) ptg.trimmableSpeed_ = tp.speed;
-                if (dedup && tp.speed != speeds.front()) continue;
+                if (dedup && tp.speed != R.firstSpeed) continue;
                 const uint16_t   k16        = static_cast<uint16_t>(tp.k);
                 const distance_t relTrgDist = ptg.getPathDist(k16, tp.step);
                 const TPose2D    relPose    = ptg.getPathPose(k16, tp.step);
@@ -637,26 +690,10 @@ struct TPS_Astar::Impl::Query
                     initSpeed = tp.speed;
                 }
                 c.initDist   = initVal;
-                c.isTarget   = i < nTargets;
+                c.isTarget   = i - R.begin < R.nTargets;
                 c.onGrid     = onGrid;
-                c.copies     = copies;
-                if (onGrid)
-                    c.evalIndex = static_cast<uint32_t>((*columnOffset)[ptgIdx] + tp.k);
-                else
-                {
-                    const auto key = std::make_pair(tp.k, tp.speed);
-                    auto       it  = holoIndex.find(key);
-                    if (it == holoIndex.end())
-                    {
-                        mppb_holo_cand hc;
-                        static_cast<const HolonomicBlend&>(ptg).holoParams(k16, hc);
-                        hc.node      = 0;  // position in the round's node batch: filled in when the batch is assembled
-                        hc.ptg_index = static_cast<int32_t>(ptgIdx);
-                        holoCands.push_back(hc);
-                        it = holoIndex.emplace(key, static_cast<uint32_t>(holoCands.size() - 1)).first;
-                    }
-                    c.evalIndex = it->second;
-                }
+                c.copies     = R.copies;
+                c.evalIndex  = onGrid ? static_cast<uint32_t>((*columnOffset)[ptgIdx] + tp.k) : tp.evalIndex;
                 cands.push_back(c);
             }
         }
@@ -1022,6 +1059,11 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     {
         auto tl = Clock::now();
         // ---- per query, no barrier in between: F of the previous round, pop, A of this round ----
+        // A single query overlaps the second half of A (end poses and lattice cells of the candidate TPS points, host)
+        // with phase B (GPU): the collision calls are issued in their split form right after phaseAPrepare() and
+        // completed once phaseACandidates() is done. A batch of queries keeps A whole inside the parallel section.
+        static const bool noOverlap = std::getenv("MPPB_NO_OVERLAP") != nullptr;  // A/B measurements only
+        const bool        overlapAB = Q == 1 && !noOverlap;
         pool.run(Q, [&](size_t i) {
             Query& q = *qs[i];
             q.active = false;
@@ -1032,7 +1074,11 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
                 q.needF = false;
             }
             q.active = q.popNext();
-            if (q.active) q.phaseA();
+            if (q.active)
+            {
+                q.phaseAPrepare();
+                if (!overlapAB) q.phaseACandidates();
+            }
         });
         active.clear();
         for (size_t i = 0; i < Q; i++)
@@ -1059,7 +1105,10 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         if (cols > 0)
         {
             rows = hRows.reserve(static_cast<size_t>(cols) * A);
-            ck(ctx, mppb_eval_nodes_boxed(ctx, A, poses, boxes, qs[active[0]]->MAX_XY_DIST, rows));
+            if (overlapAB)
+                ck(ctx, mppb_eval_nodes_boxed_begin(ctx, A, poses, boxes, qs[active[0]]->MAX_XY_DIST, rows));
+            else
+                ck(ctx, mppb_eval_nodes_boxed(ctx, A, poses, boxes, qs[active[0]]->MAX_XY_DIST, rows));
         }
         double* holoOut = nullptr;
         if (holoBase[A] > 0)
@@ -1073,7 +1122,15 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
                 for (size_t j = 0; j < v.size(); j++) hc[holoBase[a] + j].node = static_cast<int32_t>(a);
             }
             holoOut = hHoloOut.reserve(holoBase[A]);
-            ck(ctx, mppb_eval_holo_candidates_boxed(ctx, A, poses, boxes, holoBase[A], hc, qs[active[0]]->MAX_XY_DIST, holoOut));
+            if (overlapAB)
+                ck(ctx, mppb_eval_holo_candidates_boxed_begin(ctx, A, poses, boxes, holoBase[A], hc, qs[active[0]]->MAX_XY_DIST, holoOut));
+            else
+                ck(ctx, mppb_eval_holo_candidates_boxed(ctx, A, poses, boxes, holoBase[A], hc, qs[active[0]]->MAX_XY_DIST, holoOut));
+        }
+        if (overlapAB)
+        {
+            qs[active[0]]->phaseACandidates();  // host work while the GPU evaluates
+            ck(ctx, mppb_sync(ctx));
         }
         st.gpuSeconds += seconds_since(tB);
         st.collisionBatches++;

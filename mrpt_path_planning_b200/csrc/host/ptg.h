@@ -6,6 +6,7 @@
 // The per-point collision arithmetic (updateTPObstacleSingle) is NOT implemented on the
 // host: it lives in the CUDA kernels, which consume the tables these classes build.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -222,12 +223,19 @@ class HolonomicBlend : public ptg_t
     double                   targetDir_  = 0;
     double                   targetDist_ = 0;
     mutable std::vector<int> stepCountCache_;
-    // paramsForDir() is a pure function of (dir, trimmableSpeed_, dynamic state): the last result is kept, because the
-    // planner asks for the same (k, speed) several times in a row (distance, pose, initial TP-obstacle value, candidate
-    // parameters). Dropped whenever the dynamic state changes.
-    mutable bool     memoValid_ = false;
-    mutable double   memoDir_ = 0, memoSpeed_ = 0;
-    mutable Internal memoQ_{};
+    // paramsForDir() is a pure function of (dir, trimmableSpeed_, dynamic state) and costs two user expressions: its
+    // results are kept in a small direct-mapped table, because the planner asks for the same (k, speed) several times
+    // per expansion (candidate parameters, then distance, pose and initial TP-obstacle value of every sample
+    // timestamp). A slot that another (dir, speed) took is simply recomputed. Dropped (generation counter) whenever
+    // the dynamic state changes.
+    struct Memo
+    {
+        double   dir = 0, speed = 0;
+        Internal q{};
+        uint32_t gen = 0;
+    };
+    mutable std::array<Memo, 64> memo_{};
+    mutable uint32_t             memoGen_ = 1;
 };
 
 }  // namespace mpp

@@ -272,8 +272,8 @@ struct mppb_ctx
     mppb::ColgridBuildBufs colgrid;
 
     // staging for the host entry points
-    mppb::PinnedBuf hNodes, hOut, hStage;
-    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes;
+    mppb::PinnedBuf hNodes, hOut, hStage, hNodesHolo;
+    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes, dNodesHolo, dBoxesHolo;
 };
 
 namespace mppb

@@ -211,3 +211,37 @@ def test_other_ptg_parameters(capi, orc, variant):
     assert np.array_equal(np.isinf(got), np.isinf(ref)) and np.array_equal(got == 0.0, ref == 0.0)
     fin = np.isfinite(ref)
     assert fin.any() and (np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-12)).max() <= RTOL
+
+
+@pytest.mark.parametrize("n_nodes,boxed", [(1, False), (1, True), (7, True), (300, False)])
+def test_split_calls_equal_blocking_calls(capi, product_ackermann, n_nodes, boxed):
+    """mppb_eval_nodes_boxed_begin + mppb_eval_holo_candidates_boxed_begin in flight together, one mppb_sync: the
+    same bits as the two blocking calls (one context holding both PTG kinds, as a mixed planner would)."""
+    ptg = capi.holonomic_ptgs()[0]
+    ctx = capi.Context(0)
+    for p in product_ackermann:
+        ctx.add_ptg(p)
+    holo_index = ctx.num_ptgs
+    ctx.add_ptg(ptg)
+    rng = np.random.default_rng(100 + n_nodes)
+    xs, ys = wl.uniform_cloud(40000, 40.0, seed=31)
+    ctx.set_obstacles(xs, ys)
+    nodes, rel = random_nodes(rng, n_nodes, 40.0)
+    ks = [rng.choice(ptg.num_paths, 9, replace=False) for _ in range(n_nodes)]
+    cands, _, _, _ = make_candidates(ptg, nodes, rel, ks, (1 / 3, 1.0))
+    cands["ptg_index"] = holo_index
+    poses = nodes[:, :3]
+    boxes = None
+    if boxed:
+        boxes = np.stack([poses[:, 0] - 3.0, poses[:, 1] - 2.5, poses[:, 0] + 4.0, poses[:, 1] + 3.5], 1).astype(np.float32)
+        want_rows = ctx.eval_nodes_boxed(poses, boxes, 5.0)
+        want_holo = ctx.eval_holo_candidates_boxed(poses, boxes, cands, 5.0)
+    else:
+        want_rows = ctx.eval_nodes(poses, 5.0)
+        want_holo = ctx.eval_holo_candidates(poses, cands, 5.0)
+    assert np.isfinite(want_holo).any() and np.isfinite(want_rows).any()
+    for _ in range(3):  # back to back: the staging buffers are reused
+        rows, hout = ctx.eval_both_split(poses, boxes, cands, 5.0)
+        assert np.array_equal(rows, want_rows)
+        assert np.array_equal(hout, want_holo)
+    ctx.close()
