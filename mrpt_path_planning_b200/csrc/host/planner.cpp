@@ -179,12 +179,16 @@ struct PendingEdge
 };
 
 // ---- persistent host thread pool for the per-query phases --------------------------------------------
+// Items are handed out with affinity: worker t owns the t-th contiguous slice of [0,count) and only helps with the
+// slices of others once its own is done. The planner runs the same per-query phases round after round, so a query's
+// search state (lattice, open set, PTG clones, arenas) stays in the caches of one core instead of moving to whichever
+// thread happened to ask next.
 class Workers
 {
    public:
-    explicit Workers(int n) : n_(std::max(1, n))
+    explicit Workers(int n) : n_(std::max(1, n)), slices_(static_cast<size_t>(std::max(1, n)))
     {
-        for (int i = 1; i < n_; i++) threads_.emplace_back([this]() { loop(); });
+        for (int i = 1; i < n_; i++) threads_.emplace_back([this, i]() { loop(i); });
     }
     ~Workers()
     {
@@ -208,14 +212,17 @@ class Workers
         {
             std::lock_guard<std::mutex> lk(m_);
             fn_      = &fn;
-            count_   = count;
-            next_    = 0;
             pending_ = n_ - 1;
             err_.clear();
+            for (int t = 0; t < n_; t++)
+            {
+                slices_[t].next.store(count * t / n_, std::memory_order_relaxed);
+                slices_[t].end = count * (t + 1) / n_;
+            }
             gen_++;
         }
         cv_.notify_all();
-        work();
+        work(0);
         std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [this]() { return pending_ == 0; });
         fn_ = nullptr;
@@ -223,24 +230,34 @@ class Workers
     }
 
    private:
-    void work()
+    struct alignas(64) Slice
     {
-        for (;;)
+        std::atomic<size_t> next{0};
+        size_t              end = 0;
+    };
+    void work(int self)
+    {
+        static const bool noAffinity = std::getenv("MPPB_POOL_NO_AFFINITY") != nullptr;  // A/B measurements only
+        for (int v = 0; v < n_; v++)
         {
-            const size_t i = next_.fetch_add(1);
-            if (i >= count_) break;
-            try
+            Slice& sl = slices_[noAffinity ? v : (self + v) % n_];  // own slice first, then the others'
+            for (;;)
             {
-                (*fn_)(i);
-            }
-            catch (const std::exception& e)
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                if (err_.empty()) err_ = e.what();
+                const size_t i = sl.next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= sl.end) break;
+                try
+                {
+                    (*fn_)(i);
+                }
+                catch (const std::exception& e)
+                {
+                    std::lock_guard<std::mutex> lk(m_);
+                    if (err_.empty()) err_ = e.what();
+                }
             }
         }
     }
-    void loop()
+    void loop(int self)
     {
         uint64_t seen = 0;
         for (;;)
@@ -251,7 +268,7 @@ class Workers
                 if (stop_) return;
                 seen = gen_;
             }
-            work();
+            work(self);
             {
                 std::lock_guard<std::mutex> lk(m_);
                 pending_--;
@@ -261,13 +278,12 @@ class Workers
     }
     int                                n_;
     std::vector<std::thread>           threads_;
+    std::vector<Slice>                 slices_;
     std::mutex                         m_;
     std::condition_variable            cv_, done_;
     bool                               stop_ = false;
     uint64_t                           gen_  = 0;
     const std::function<void(size_t)>* fn_   = nullptr;
-    size_t                             count_ = 0;
-    std::atomic<size_t>                next_{0};
     int                                pending_ = 0;
     std::string                        err_;
 };
@@ -382,6 +398,7 @@ struct TPS_Astar::Impl::Query
     bool                                                   active      = false;  // expands a node this round
     bool                                                   needF       = false;  // tentative edges wait for relaxation
     size_t                                                 costBase    = 0;      // first row of this query in the cost batch
+    size_t                                                 slot        = 0;      // position in the round's node batch
     float                                                  box[4]      = {0, 0, 0, 0};
 
     // phase scratch
@@ -1082,7 +1099,11 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         });
         active.clear();
         for (size_t i = 0; i < Q; i++)
-            if (qs[i]->active) active.push_back(i);
+            if (qs[i]->active)
+            {
+                qs[i]->slot = active.size();
+                active.push_back(i);
+            }
         if (active.empty()) break;
         const size_t A = active.size();
         lap(tl, 1);
@@ -1139,8 +1160,10 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         lap(tl, 2);
 
         // ---- phases C + D ----
-        pool.run(A, [&](size_t a) {
-            Query& q = *qs[active[a]];
+        pool.run(Q, [&](size_t i) {  // over the queries, not the active list: a query stays with its worker
+            Query& q = *qs[i];
+            if (!q.active) return;
+            const size_t a = q.slot;
             q.phaseCD(rows ? rows + static_cast<size_t>(cols) * a : nullptr, holoOut ? holoOut + holoBase[a] : nullptr);
             q.needF = true;
         });
