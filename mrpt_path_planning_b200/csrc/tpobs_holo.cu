@@ -64,6 +64,29 @@ __device__ __forceinline__ double ramp_integral_numeric(double T, double a, doub
     }
     return d;
 }
+// The same sum, bit for bit, by a whole warp whose lanes hold the same arguments (the candidate prologue): the 21
+// square roots — the expensive part of the scalar loop, 1.8 us per candidate — are taken by 21 lanes at once; the
+// abscissae and the sum are still accumulated in the reference's order.
+__device__ __forceinline__ double ramp_integral_numeric_warp(double T, double a, double b, double c, int lane)
+{
+    const double At = T / 20;
+    double       t = .0, tMine = .0;
+#pragma unroll
+    for (int i = 0; i < 20; i++)
+    {
+        t += At;
+        if (i + 1 == lane) tMine = t;  // lane i+1 takes the i-th step's f1; lane 0 takes f(0) = sqrt(c)
+    }
+    double dd = lane == 0 ? c : a * tMine * tMine + b * tMine + c;
+    if (lane != 0 && dd < 0) dd = .0;
+    const double f     = sqrt(dd);
+    const double fPrev = __shfl_up_sync(kFull, f, 1);
+    const double term  = At * (fPrev + f) * 0.5;  // lanes 1..20: the i-th step's increment, i = lane - 1
+    double       d     = .0;
+#pragma unroll
+    for (int i = 1; i <= 20; i++) d += __shfl_sync(kFull, term, i);
+    return d;
+}
 // HolonomicBlend.cpp:150-180
 __device__ __forceinline__ double ramp_distance(double k2, double k4, double vxi, double vyi, double t)
 {
@@ -74,6 +97,20 @@ __device__ __forceinline__ double ramp_distance(double k2, double k4, double vxi
         const double b = (k2 * vxi * 4.0 + k4 * vyi * 4.0);
         if (fabs(b) < kEps && fabs(c) < kEps) return sqrt(a) * (t * t) * 0.5;
         return ramp_integral_numeric(t, a, b, c);
+    }
+    return sqrt(c) * t;
+}
+
+// ramp_distance() evaluated by a warp with uniform arguments (same branches, same value in every lane)
+__device__ __forceinline__ double ramp_distance_warp(double k2, double k4, double vxi, double vyi, double t, int lane)
+{
+    const double c = (vxi * vxi + vyi * vyi);
+    if (fabs(k2) > kEps || fabs(k4) > kEps)
+    {
+        const double a = ((k2 * k2) * 4.0 + (k4 * k4) * 4.0);
+        const double b = (k2 * vxi * 4.0 + k4 * vyi * 4.0);
+        if (fabs(b) < kEps && fabs(c) < kEps) return sqrt(a) * (t * t) * 0.5;
+        return ramp_integral_numeric_warp(t, a, b, c, lane);
     }
     return sqrt(c) * t;
 }
@@ -258,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     q.k4              = (q.vyf - q.vyi) * TR2_;
     q.qa              = (q.k2 * q.k2 + q.k4 * q.k4);
     q.qb              = (q.k2 * q.vxi * 2.0 + q.k4 * q.vyi * 2.0);
-    q.distAtT         = ramp_distance(q.k2, q.k4, q.vxi, q.vyi, q.T);
+    q.distAtT         = ramp_distance_warp(q.k2, q.k4, q.vxi, q.vyi, q.T, lane);
 
     const double x0 = nNodes == 1 ? row0[0] : nodes[4 * cd.node + 0], y0 = nNodes == 1 ? row0[1] : nodes[4 * cd.node + 1];
     const double c = nNodes == 1 ? row0[2] : nodes[4 * cd.node + 2], s = nNodes == 1 ? row0[3] : nodes[4 * cd.node + 3];
