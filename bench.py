@@ -229,7 +229,9 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
         d = {"plan_ms": 1e3 * min(ts), "success": bool(r["success"]), "nodes_expanded": int(r["expanded"]),
              "tps_points": int(r["tps_points"]), "edges_costed": int(r["edges_costed"]),
              "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_ms": 1e3 * st["gpu_seconds"],
-             "phase_ms": {k: 1e3 * v for k, v in st["phase_seconds"].items()}, "costmap_build_ms": 1e3 * t_cm}
+             "phase_ms": {k: 1e3 * v for k, v in st["phase_seconds"].items()}, "costmap_build_ms": 1e3 * t_cm,
+             "phase_note": "B_collision_gpu and gpu_ms include the host's second half of phase A, which runs while the "
+                           "collision kernels do (split entry points + mppb_sync)"}
         if with_cpu:
             optgs = orc.holonomic_ptgs() if name.startswith("c1") else orc.ackermann_ptgs()
             opl = orc.Planner(optgs, wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
@@ -506,11 +508,11 @@ def run_ours(args, rank, local_rank, world):
                 "frac": work["hbm_bytes"] / kernel_s / 1e9 / peaks.get("hbm_gbs", 1)},
         "fp64_peak_tflops": fp64_peak, "traffic": None,
     }
-    tpath = os.path.join(ROOT, "profiles", "r1n_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1p_traffic.json")
     if os.path.exists(tpath) and B == 4096 and args.points == (1 << 20):
         t = json.load(open(tpath))["tpobs_grid_kernel"]
         roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]  # bytes per launch, from the ncu capture
-        roofline["traffic_source"] = "profiles/r1n_grid_ncu_full.txt"
+        roofline["traffic_source"] = "profiles/r1p_grid_ncu_full.txt"
         roofline["limiter"] = ("instruction issue and per-CTA latency: %.0f %% issue-slot utilisation at %.0f %% occupancy "
                                "(9 CTAs per SM, register-bound), %.1f M warp instructions per launch (ncu); neither HBM "
                                "nor FMA throughput bounds this kernel" % (
