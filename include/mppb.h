@@ -439,6 +439,10 @@ int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample
  * calls, then wall seconds per phase: pop, A enumerate, B collision (GPU), C+D select/build, E assemble,
  * E cost (GPU), F relax */
 int mppb_planner_gpu_stats(const mppb_planner* p, double* out13);
+/* Host self-test (no GPU) of the worker pool behind plan_batch: `rounds` times every index of [0,count) must run
+ * exactly once on n_threads workers, and an exception thrown by a work item must reach the caller. Returns the number
+ * of indices that did not (0 = correct), negative on a lost exception. */
+int mppb_selftest_worker_pool(int n_threads, size_t count, int rounds);
 
 #ifdef __cplusplus
 }

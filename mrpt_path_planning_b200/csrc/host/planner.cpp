@@ -313,6 +313,42 @@ struct Pinned
 };
 }  // namespace
 
+// Host self-test of the worker pool (no GPU): `rounds` times, fn(i) for i in [0,count) on n_threads workers; returns the
+// number of indices that were not executed exactly once per round (0 = correct), or -1 if an exception thrown by a
+// work item is not rethrown to the caller.
+int selftest_worker_pool(int n_threads, size_t count, int rounds)
+{
+    Workers                        pool(n_threads);
+    std::vector<std::atomic<int>> hits(count);
+    int                            bad = 0;
+    for (int r = 0; r < rounds; r++)
+    {
+        for (auto& h : hits) h.store(0);
+        pool.run(count, [&](size_t i) { hits[i].fetch_add(1); });
+        for (auto& h : hits) bad += h.load() != 1;
+    }
+    if (count > 1)
+    {
+        bool thrown = false;
+        try
+        {
+            pool.run(count, [&](size_t i) {
+                if (i == count / 2) throw std::runtime_error("selftest");
+            });
+        }
+        catch (const std::runtime_error&)
+        {
+            thrown = true;
+        }
+        if (!thrown) return -1;
+        // the pool is usable after an exception
+        for (auto& h : hits) h.store(0);
+        pool.run(count, [&](size_t i) { hits[i].fetch_add(1); });
+        for (auto& h : hits) bad += h.load() != 1;
+    }
+    return bad;
+}
+
 // ======================================================================================================
 struct TPS_Astar::Impl
 {

@@ -46,7 +46,24 @@ void require(bool cond, const char* msg)
 }
 }  // namespace
 
+namespace mpp
+{
+int selftest_worker_pool(int n_threads, size_t count, int rounds);  // planner.cpp
+}
+
 extern "C" {
+
+int mppb_selftest_worker_pool(int n_threads, size_t count, int rounds)
+{
+    try
+    {
+        return mpp::selftest_worker_pool(n_threads, count, rounds);
+    }
+    catch (const std::exception&)
+    {
+        return -2;
+    }
+}
 
 int mppb_planner_create(mppb_ctx* ctx, mppb_planner** out)
 {

@@ -55,3 +55,39 @@ def test_cli_binary_is_built(capi):
 
     capi.lib()
     assert os.access(build.CLI_PATH, os.X_OK)
+
+
+def test_worker_pool_runs_every_item_once(capi):
+    """the pool behind plan_batch (slices with affinity + helping): every index exactly once per round, for counts
+    below, at and far above the worker count; an exception in a work item reaches the caller and the pool survives"""
+    for n_threads, count in ((1, 5), (4, 1), (4, 3), (4, 4), (7, 50), (16, 512), (3, 1000)):
+        assert capi.lib().mppb_selftest_worker_pool(n_threads, count, 20) == 0, (n_threads, count)
+
+
+def test_holo_direction_memo_is_transparent(capi, orc):
+    """HolonomicBlend keeps its per-direction parameters in a small direct-mapped memo per dynamic state: any order of
+    (k, trimmed speed) queries — slot collisions included — gives the oracle's values"""
+    h = capi.holonomic_ptgs()[0]
+    o = orc.holonomic_ptgs()[0]
+    rng = np.random.default_rng(5)
+    for state in range(4):
+        vel = rng.uniform(-0.8, 0.8, 3)
+        tgt = [rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3, 3)]
+        for p in (h, o):
+            p.update_dyn_state(vel, tgt, 0.0, force=True)
+        for _ in range(1500):
+            sp = float(rng.choice([1 / 3, 2 / 3, 1.0, 0.37, 0.81]))
+            k, st = int(rng.integers(0, 191)), int(rng.integers(1, 300))
+            for p in (h, o):
+                p.set_trim_speed(sp)
+            assert np.array_equal(h.path_pose(k, st), o.path_pose(k, st))
+            assert h.init_dist(k) == o.init_dist(k)
+        # a fresh PTG (empty memo) agrees on the candidate records
+        f = capi.holonomic_ptgs()[0]
+        f.update_dyn_state(vel, tgt, 0.0, force=True)
+        for k in range(0, 191, 7):
+            for sp in (1 / 3, 1.0):
+                h.set_trim_speed(sp)
+                f.set_trim_speed(sp)
+                a, b = h.holo_params(k), f.holo_params(k)
+                assert (a.T_ramp, a.vxi, a.vyi, a.vxf, a.vyf, a.vf) == (b.T_ramp, b.vxi, b.vyi, b.vxf, b.vyf, b.vf)
