@@ -20,6 +20,13 @@ class RuntimeExpr
 {
    public:
     void bind(const std::string& name, const double* var) { vars_[lower(name)] = var; }
+    /** true if the compiled program reads the bound variable `var` */
+    bool references(const double* var) const
+    {
+        for (const Tok& t : prog_)
+            if (t.kind == Tok::VAR && t.var == var) return true;
+        return false;
+    }
 
     void compile(const std::string& text)
     {

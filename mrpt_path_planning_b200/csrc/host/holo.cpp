@@ -89,6 +89,14 @@ HolonomicBlend::HolonomicBlend(const HolonomicBlendParams& p) : p_(p)
     }
     exprV_.compile(p_.expr_V.empty() ? "V_MAX" : p_.expr_V);
     exprW_.compile(p_.expr_W.empty() ? "W_MAX" : p_.expr_W);
+    // do |V| and |omega| read the dynamic state? If not (the shipped configurations: functions of dir and the trimmed
+    // speed only), memoised results stay valid when the state changes
+    exprsReadDynState_ = false;
+    for (const RuntimeExpr* e : {&exprV_, &exprW_})
+        for (const double* v : {&targetDir_, &targetDist_, &dynState_.relTarget.x, &dynState_.relTarget.y,
+                                &dynState_.relTarget.phi, &dynState_.curVelLocal.vx, &dynState_.curVelLocal.vy,
+                                &dynState_.curVelLocal.omega, &dynState_.targetRelSpeed})
+            if (e->references(v)) exprsReadDynState_ = true;
     memoGen_++;
     initialized_ = true;
 }
@@ -96,7 +104,7 @@ HolonomicBlend::HolonomicBlend(const HolonomicBlendParams& p) : p_(p)
 void HolonomicBlend::onNewNavDynamicState()
 {
     stepCountCache_.assign(numPaths_, -1);
-    memoGen_++;  // drops every memoised paramsForDir() result
+    if (exprsReadDynState_) memoGen_++;  // drops every memoised paramsForDir() result
     targetDir_  = target_k_ >= 0 ? index2alpha(static_cast<unsigned>(target_k_)) : .0;
     targetDist_ = dynState_.relTarget.norm();
 }
@@ -106,8 +114,14 @@ HolonomicBlend::Internal HolonomicBlend::paramsForDir(double dir) const
     uint64_t db, sb;
     std::memcpy(&db, &dir, sizeof(db));
     std::memcpy(&sb, &trimmableSpeed_, sizeof(sb));
-    Memo& m = memo_[((db * 0x9E3779B97F4A7C15ull) ^ (sb * 0xC2B2AE3D27D4EB4Full)) >> 58];
-    if (m.gen == memoGen_ && dir == m.dir && trimmableSpeed_ == m.speed) return m.q;
+    Memo& m = memo_[((db * 0x9E3779B97F4A7C15ull) ^ (sb * 0xC2B2AE3D27D4EB4Full)) >> 55];
+    if (m.gen == memoGen_ && dir == m.dir && trimmableSpeed_ == m.speed)
+    {
+        Internal q = m.q;  // vf, wf, vxf, vyf, T_ramp; the initial velocity is the current state's
+        q.vxi      = dynState_.curVelLocal.vx;
+        q.vyi      = dynState_.curVelLocal.vy;
+        return q;
+    }
     Internal q;
     q.T_ramp = p_.T_ramp_max;
     exprDir_ = dir;

@@ -223,19 +223,22 @@ class HolonomicBlend : public ptg_t
     double                   targetDir_  = 0;
     double                   targetDist_ = 0;
     mutable std::vector<int> stepCountCache_;
-    // paramsForDir() is a pure function of (dir, trimmableSpeed_, dynamic state) and costs two user expressions: its
-    // results are kept in a small direct-mapped table, because the planner asks for the same (k, speed) several times
-    // per expansion (candidate parameters, then distance, pose and initial TP-obstacle value of every sample
-    // timestamp). A slot that another (dir, speed) took is simply recomputed. Dropped (generation counter) whenever
-    // the dynamic state changes.
+    // paramsForDir() costs two user expressions plus cos/sin of the direction, and the planner asks for the same
+    // (k, speed) several times per expansion (candidate parameters, then distance, pose and initial TP-obstacle value
+    // of every sample timestamp) and for the same few dozen (k, speed) in every expansion. Its results are kept in a
+    // direct-mapped table keyed by (dir, trimmableSpeed_); a slot that another key took is simply recomputed. The
+    // initial velocity is not part of an entry (it is the current state's). If the expressions read the dynamic
+    // state, every entry is dropped (generation counter) when the state changes; the shipped configurations
+    // (functions of dir and the trimmed speed) keep theirs for the lifetime of the object.
     struct Memo
     {
         double   dir = 0, speed = 0;
         Internal q{};
         uint32_t gen = 0;
     };
-    mutable std::array<Memo, 64> memo_{};
-    mutable uint32_t             memoGen_ = 1;
+    mutable std::array<Memo, 512> memo_{};
+    mutable uint32_t              memoGen_ = 1;
+    bool                          exprsReadDynState_ = true;
 };
 
 }  // namespace mpp

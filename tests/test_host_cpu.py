@@ -91,3 +91,31 @@ def test_holo_direction_memo_is_transparent(capi, orc):
                 f.set_trim_speed(sp)
                 a, b = h.holo_params(k), f.holo_params(k)
                 assert (a.T_ramp, a.vxi, a.vyi, a.vxf, a.vyf, a.vf) == (b.T_ramp, b.vxi, b.vyi, b.vxf, b.vyf, b.vf)
+
+
+def test_holo_memo_with_state_reading_expressions(capi, orc):
+    """|V| and |omega| formulas that read the dynamic state (target, current velocity): memoised parameters must be
+    dropped at every state change; formulas of dir and the trimmed speed only keep theirs. Either way the values
+    are the oracle's over a sequence of state changes with repeated (k, speed) queries."""
+    variants = [
+        (61, 4.0, 0.5, 0.8, np.deg2rad(90.0), 0.30, "V_MAX * trimmable_speed * min(1.0, 0.3 + target_dist/4)",
+         "W_MAX * min(1.0, abs(dir - target_dir) + 0.2*abs(vxi) + 0.1*target_rel_speed)"),
+        (61, 4.0, 0.5, 0.8, np.deg2rad(90.0), 0.30, "V_MAX * max(0.2, trimmable_speed) * (1 - 0.3*abs(dir)/PI)",
+         "W_MAX * min(1.0, abs(dir))"),
+    ]
+    rng = np.random.default_rng(11)
+    for v in variants:
+        h, o = capi.PTG.holonomic_blend(*v), orc.holonomic_blend(*v)
+        queries = [(int(rng.integers(0, 61)), float(rng.choice([0.5, 1.0])), int(rng.integers(1, 200))) for _ in range(40)]
+        for state in range(12):
+            vel = rng.uniform(-0.6, 0.6, 3)
+            tgt = [rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(-3, 3)]
+            trs = float(rng.uniform(0, 1))
+            for p in (h, o):
+                p.update_dyn_state(vel, tgt, trs)
+            for k, sp, st in queries + queries[::-1]:
+                for p in (h, o):
+                    p.set_trim_speed(sp)
+                assert np.array_equal(h.path_pose(k, st), o.path_pose(k, st)), (v[6], state, k, sp, st)
+                assert h.init_dist(k) == o.init_dist(k)
+                assert h.step_for_dist(k, 1.1) == o.step_for_dist(k, 1.1)
