@@ -437,6 +437,43 @@ struct TPS_Astar::Impl::Query
     size_t                                                 slot        = 0;      // position in the round's node batch
     float                                                  box[4]      = {0, 0, 0, 0};
 
+    // Tree insertions of phase F do not influence the search (open set, g/f scores and node states do): a single
+    // query queues them and applies them, in order, while the GPU evaluates the next expansion's collisions.
+    struct TreeOp
+    {
+        bool            rewire = false;
+        TNodeID         parent = 0, child = 0;
+        SE2_KinState    state;
+        MoveEdgeSE2_TPS edge;
+    };
+    std::vector<TreeOp> treeOps;
+    bool                deferTreeOps = false;
+    void flushTreeOps()
+    {
+        if (treeOps.empty()) return;
+        auto&                                  tree        = po.motionTree;
+        MotionPrimitivesTreeSE2::TListEdges*   parentEdges = nullptr;
+        const MotionPrimitivesTreeSE2::node_t* parentNode  = nullptr;
+        TNodeID                                curParent   = 0;
+        for (TreeOp& op : treeOps)
+        {
+            if (op.rewire)
+            {
+                tree.rewire_node_parent(op.child, op.edge);
+                continue;
+            }
+            // the children of one expansion share their parent: its edge list and tree node are looked up once
+            if (!parentEdges || op.parent != curParent)
+            {
+                parentEdges = &tree.edges_to_children[op.parent];
+                parentNode  = &tree.nodes().at(op.parent);
+                curParent   = op.parent;
+            }
+            tree.insert_child_of(*parentEdges, *parentNode, op.parent, op.child, op.state, op.edge);
+        }
+        treeOps.clear();
+    }
+
     // phase scratch
     std::pmr::monotonic_buffer_resource arena{16384};
     std::vector<Candidate>        cands;
@@ -520,6 +557,7 @@ struct TPS_Astar::Impl::Query
         Node& cur = *openSet.begin()->second;
         if (nodeGridCoords(cur.state.pose).sameLocation(goalCellIndices))
         {
+            flushTreeOps();
             // snap the node onto the exact goal; refine_trajectory() fixes the last edge later
             if (in->stateGoal.state.isPoint())
             {
@@ -550,6 +588,7 @@ struct TPS_Astar::Impl::Query
 
     void finish()
     {
+        flushTreeOps();
         done       = true;
         current    = nullptr;
         po.success = po.goalNodeId == po.bestNodeId;
@@ -866,7 +905,17 @@ struct TPS_Astar::Impl::Query
                 openSet.insert({nbNode.fScore, &nbNode});
             }
             nbNode.state = pe.x_i;
-            if (hasToRewire)
+            if (deferTreeOps)
+            {
+                TreeOp op;
+                op.rewire = hasToRewire;
+                op.parent = newEdge.parentId;
+                op.child  = nbNode.id.value();
+                op.state  = nbNode.state;
+                op.edge   = std::move(newEdge);  // `pending` is cleared below
+                treeOps.push_back(std::move(op));
+            }
+            else if (hasToRewire)
                 tree.rewire_node_parent(nbNode.id.value(), newEdge);
             else
             {
@@ -894,6 +943,7 @@ struct TPS_Astar::Impl::Query
         if (planner->progressCallback_ && (tNow - tLastCallback) > planner->progressCallbackCallPeriod_ && po.bestNodeId)
         {
             tLastCallback = tNow;
+            flushTreeOps();
             auto [foundPath, pathEdges] = tree.backtrack_path(*po.bestNodeId);
             ProgressCallbackData pcd;
             pcd.bestCostFromStart = tree.nodes().at(*po.bestNodeId).cost_;
@@ -1085,6 +1135,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         q.trs               = ins[i]->ptgs;
         if (Q > 1)  // interleaved queries must not share mutable PTG state
             for (auto& p : q.trs.ptgs) p = std::shared_ptr<ptg_t>(p->cloneForQuery());
+        q.deferTreeOps = Q == 1 && std::getenv("MPPB_NO_OVERLAP") == nullptr;
         q.start();
     }
     // obstacles: one query -> clipped to its world box at upload (ObstacleSource::apply_clipping_box);
@@ -1187,6 +1238,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         if (overlapAB)
         {
             qs[active[0]]->phaseACandidates();  // host work while the GPU evaluates
+            qs[active[0]]->flushTreeOps();      // (the previous expansion's tree insertions)
             ck(ctx, mppb_sync(ctx));
         }
         st.gpuSeconds += seconds_since(tB);
