@@ -117,16 +117,22 @@ void MotionPrimitivesTreeSE2::insert_node_and_edge(TNodeID parentId, TNodeID chi
 void MotionPrimitivesTreeSE2::insert_child_of(TListEdges& parentEdges, const node_t& parentNode, TNodeID parentId, TNodeID childId,
                                               const SE2_KinState& childData, const MoveEdgeSE2_TPS& e)
 {
+    insert_child_of(parentEdges, parentNode, parentId, childId, childData, MoveEdgeSE2_TPS(e));
+}
+void MotionPrimitivesTreeSE2::insert_child_of(TListEdges& parentEdges, const node_t& parentNode, TNodeID parentId, TNodeID childId,
+                                              const SE2_KinState& childData, MoveEdgeSE2_TPS&& e)
+{
     parentEdges.emplace_back();
     TEdgeInfo& ei = parentEdges.back();
     ei.id         = childId;
     ei.reverse    = false;
-    ei.data       = e;
+    const cost_t edgeCost = e.cost;
+    ei.data               = std::move(e);
     node_t n;
     static_cast<SE2_KinState&>(n) = childData;
     n.nodeID_                     = childId;
     n.parentID_                   = parentId;
-    n.cost_                       = parentNode.cost_ + e.cost;
+    n.cost_                       = parentNode.cost_ + edgeCost;
     if (nodes_.empty() || childId > nodes_.rbegin()->first)
         nodes_.emplace_hint(nodes_.end(), childId, n);
     else

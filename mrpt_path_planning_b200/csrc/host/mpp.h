@@ -251,6 +251,9 @@ class MotionPrimitivesTreeSE2
      *  end hint. Same resulting tree as insert_node_and_edge. */
     void insert_child_of(TListEdges& parentEdges, const node_t& parentNode, TNodeID parentId, TNodeID childId,
                          const SE2_KinState& childData, const MoveEdgeSE2_TPS& e);
+    /** same, taking the edge over (its interpolated path is not copied) */
+    void insert_child_of(TListEdges& parentEdges, const node_t& parentNode, TNodeID parentId, TNodeID childId,
+                         const SE2_KinState& childData, MoveEdgeSE2_TPS&& e);
     const MoveEdgeSE2_TPS& edge_to_parent(TNodeID nodeId) const;
     const node_map_t&      nodes() const { return nodes_; }
     SE2_KinState&          node_state(TNodeID id) { return nodes_.at(id); }

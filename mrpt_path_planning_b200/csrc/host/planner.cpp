@@ -423,7 +423,38 @@ struct TPS_Astar::Impl::Query
     // allocation is a pointer bump and the whole search state is dropped at once when the query ends
     std::pmr::monotonic_buffer_resource                         searchArena{1 << 16};
     LatticeIndex                                                grid{&searchArena};
-    std::pmr::multimap<distance_t, Node*>                       openSet{&searchArena};
+    // The reference's open set is a std::multimap<cost, Node*> that is only ever inserted into and popped at begin()
+    // (keys go stale, nothing is erased elsewhere). A binary heap ordered by (key, insertion number) pops in exactly the
+    // multimap's order — equal keys leave in insertion order, as multimap::insert places them at the upper bound of
+    // their range — without a node allocation and a cold pointer chase per insertion.
+    struct OpenSet
+    {
+        struct Item
+        {
+            distance_t f;
+            uint64_t   seq;
+            Node*      node;
+        };
+        struct Later
+        {
+            bool operator()(const Item& a, const Item& b) const { return a.f > b.f || (a.f == b.f && a.seq > b.seq); }
+        };
+        std::vector<Item> heap;
+        uint64_t          nextSeq = 0;
+        bool              empty() const { return heap.empty(); }
+        Node*             top() const { return heap.front().node; }
+        void              insert(distance_t f, Node* n)
+        {
+            heap.push_back(Item{f, nextSeq++, n});
+            std::push_heap(heap.begin(), heap.end(), Later());
+        }
+        void pop()
+        {
+            std::pop_heap(heap.begin(), heap.end(), Later());
+            heap.pop_back();
+        }
+    };
+    OpenSet                                                     openSet;
     TNodeID                                                nextFreeId = 0;
     Node*                                                  nodeGoal   = nullptr;
     NodeCoords                                             goalCellIndices;
@@ -469,7 +500,7 @@ struct TPS_Astar::Impl::Query
                 parentNode  = &tree.nodes().at(op.parent);
                 curParent   = op.parent;
             }
-            tree.insert_child_of(*parentEdges, *parentNode, op.parent, op.child, op.state, op.edge);
+            tree.insert_child_of(*parentEdges, *parentNode, op.parent, op.child, op.state, std::move(op.edge));
         }
         treeOps.clear();
     }
@@ -535,7 +566,7 @@ struct TPS_Astar::Impl::Query
             n.gScore           = 0;
             n.fScore           = planner->heuristic(n.state, in->stateGoal);
             n.pendingInOpenSet = true;
-            openSet.insert({n.fScore, &n});
+            openSet.insert(n.fScore, &n);
         }
         nodeGoal      = &getOrCreateNodeByPose(in->stateGoal.asSE2KinState());
         po.goalNodeId = nodeGoal->id.value();
@@ -554,7 +585,7 @@ struct TPS_Astar::Impl::Query
             finish();
             return false;
         }
-        Node& cur = *openSet.begin()->second;
+        Node& cur = *openSet.top();
         if (nodeGridCoords(cur.state.pose).sameLocation(goalCellIndices))
         {
             flushTreeOps();
@@ -580,7 +611,7 @@ struct TPS_Astar::Impl::Query
         }
         cur.pendingInOpenSet = false;
         cur.visited          = true;
-        openSet.erase(openSet.begin());
+        openSet.pop();
         current = &cur;
         po.nodesExpanded++;
         return true;
@@ -902,7 +933,7 @@ struct TPS_Astar::Impl::Query
             if (!nbNode.pendingInOpenSet)
             {
                 nbNode.pendingInOpenSet = true;
-                openSet.insert({nbNode.fScore, &nbNode});
+                openSet.insert(nbNode.fScore, &nbNode);
             }
             nbNode.state = pe.x_i;
             if (deferTreeOps)
@@ -924,7 +955,9 @@ struct TPS_Astar::Impl::Query
                     parentEdges = &tree.edges_to_children[newEdge.parentId];
                     parentNode  = &tree.nodes().at(newEdge.parentId);
                 }
-                tree.insert_child_of(*parentEdges, *parentNode, newEdge.parentId, nbNode.id.value(), nbNode.state, newEdge);
+                // (the edge moves into the tree: `pending` is cleared below)
+                tree.insert_child_of(*parentEdges, *parentNode, newEdge.parentId, nbNode.id.value(), nbNode.state,
+                                     std::move(newEdge));
             }
             if (costToGoal < po.bestNodeIdCostToGoal)
             {
