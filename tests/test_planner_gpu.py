@@ -245,3 +245,34 @@ def test_other_planner_parameters(ctx, capi, orc, kind, pname, product_ackermann
     r_o = ora.plan(start, goal, lo, hi)
     same_plan(prod, ora, r_p, r_o)
     assert r_p["expanded"] >= 5
+
+
+@pytest.mark.parametrize("kind", ["ackermann", "holonomic"])
+def test_batch_without_evaluators_equals_single_plans_and_oracle(ctx, capi, orc, kind, product_ackermann, oracle_ackermann):
+    """No cost evaluator on the GPU (the shape of config C4: no cost batch at all, relaxation straight after C/D).
+    Batch == one by one == oracle; queries that finish early must not disturb the others."""
+    extent = 40.0
+    xs, ys = wl.walls_cloud(6000, extent, wall_fraction=0.8, seed=35)
+    qs = _random_queries(np.random.default_rng(36), 7, extent, 2.0, 9.0)
+    params = list(C1_PARAMS)
+    params[8] = 45
+    p_ptgs = product_ackermann if kind == "ackermann" else capi.holonomic_ptgs()
+    o_ptgs = oracle_ackermann if kind == "ackermann" else orc.holonomic_ptgs()
+    prod = capi.Planner(ctx, p_ptgs, params, C1_TIMESTAMPS)
+    prod.add_obstacles(xs, ys)
+    batch = prod.plan_many(qs, n_threads=3)
+    trees = [prod.tree(i) for i in range(len(qs))]
+    assert sum(r["expanded"] for r in batch) > 50
+    for i, q in enumerate(qs):
+        single = capi.Planner(ctx, p_ptgs, params, C1_TIMESTAMPS)
+        single.add_obstacles(xs, ys)
+        r1 = single.plan(*q[:4])
+        for key in ("success", "path_cost", "tree_nodes", "expanded", "edges_costed", "best_node"):
+            assert r1[key] == batch[i][key], (i, key)
+        assert np.array_equal(single.tree(), trees[i])
+        if i < 4:
+            ora = orc.Planner(o_ptgs, params, C1_TIMESTAMPS)
+            ora.add_obstacles(xs, ys)
+            r_o = ora.plan(*q[:4])
+            assert r_o["path_cost"] == batch[i]["path_cost"] and r_o["expanded"] == batch[i]["expanded"]
+            assert np.array_equal(ora.tree(), trees[i])
