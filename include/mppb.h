@@ -436,8 +436,9 @@ int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t ca
 /* plan_to_trajectory + save_to_txt text (src/algos/trajectories.cpp:15-106); returns the text length */
 int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample_period, char* buf, int64_t cap);
 /* Work of the last plan, out13 = collision batches, cost batches, nodes, holo candidates, edges, seconds in GPU
- * calls, then wall seconds per phase: pop, A enumerate, B collision (GPU), C+D select/build, E assemble,
- * E cost (GPU), F relax */
+ * calls, then wall seconds per phase: set-up, F relax + pop + A enumerate, B collision (GPU; for a single query it
+ * includes the second half of A, which the host runs while the kernels do), C+D select/build, E assemble,
+ * E cost (GPU), teardown */
 int mppb_planner_gpu_stats(const mppb_planner* p, double* out13);
 /* Host self-test (no GPU) of the worker pool behind plan_batch: `rounds` times every index of [0,count) must run
  * exactly once on n_threads workers, and an exception thrown by a work item must reach the caller. Returns the number
