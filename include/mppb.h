@@ -444,6 +444,11 @@ int mppb_planner_gpu_stats(const mppb_planner* p, double* out13);
  * exactly once on n_threads workers, and an exception thrown by a work item must reach the caller. Returns the number
  * of indices that did not (0 = correct), negative on a lost exception. */
 int mppb_selftest_worker_pool(int n_threads, size_t count, int rounds);
+/* Host self-test (no GPU) of the planner's open set, a binary heap ordered by (key, insertion number) that stands in
+ * for the reference's std::multimap<cost, Node*> (TPS_Astar.cpp: inserted into and popped at begin() only): `ops`
+ * random insertions with frequent equal keys, interleaved with pops. Returns the number of pops that differ from a
+ * std::multimap driven the same way (0 = same order). */
+int mppb_selftest_open_set(uint64_t seed, size_t ops, int distinct_keys);
 
 #ifdef __cplusplus
 }

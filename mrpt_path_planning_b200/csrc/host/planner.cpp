@@ -18,6 +18,7 @@
 // whether it runs alone (plan) or interleaved with thousands of others (plan_batch).
 #include <cstdlib>
 #include <algorithm>
+#include <map>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -178,6 +179,40 @@ struct PendingEdge
     MoveEdgeSE2_TPS edge;
 };
 
+// The reference's open set is a std::multimap<cost, Node*> that is only ever inserted into and popped at begin()
+// (keys go stale, nothing is erased elsewhere). A binary heap ordered by (key, insertion number) pops in exactly the
+// multimap's order — equal keys leave in insertion order, as multimap::insert places them at the upper bound of
+// their range — without a node allocation and a cold pointer chase per insertion.
+// (selftest_open_set() below checks the equivalence against a std::multimap; tests/test_host_cpu.py runs it.)
+template <class T>
+struct OpenSetT
+{
+    struct Item
+    {
+        distance_t f;
+        uint64_t   seq;
+        T*         node;
+    };
+    struct Later
+    {
+        bool operator()(const Item& a, const Item& b) const { return a.f > b.f || (a.f == b.f && a.seq > b.seq); }
+    };
+    std::vector<Item> heap;
+    uint64_t          nextSeq = 0;
+    bool              empty() const { return heap.empty(); }
+    T*                top() const { return heap.front().node; }
+    void              insert(distance_t f, T* n)
+    {
+        heap.push_back(Item{f, nextSeq++, n});
+        std::push_heap(heap.begin(), heap.end(), Later());
+    }
+    void pop()
+    {
+        std::pop_heap(heap.begin(), heap.end(), Later());
+        heap.pop_back();
+    }
+};
+
 // ---- persistent host thread pool for the per-query phases --------------------------------------------
 // Items are handed out with affinity: worker t owns the t-th contiguous slice of [0,count) and only helps with the
 // slices of others once its own is done. The planner runs the same per-query phases round after round, so a query's
@@ -313,6 +348,44 @@ struct Pinned
 };
 }  // namespace
 
+// Host self-test of the open set (no GPU): `ops` random insertions (keys drawn from `distinct_keys` values, so that
+// equal keys are frequent) interleaved with pops; returns the number of pops that differ from a std::multimap
+// driven the same way (0 = same order).
+int selftest_open_set(uint64_t seed, size_t ops, int distinct_keys)
+{
+    std::vector<int>                    payload(ops);
+    OpenSetT<int>                       heap;
+    std::multimap<distance_t, int*>     ref;
+    uint64_t                            x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto                                rnd = [&x]() {
+        x ^= x << 13;
+        x ^= x >> 7;
+        x ^= x << 17;
+        return x;
+    };
+    int    bad = 0;
+    size_t next = 0;
+    while (next < ops || !ref.empty())
+    {
+        const bool doInsert = next < ops && (ref.empty() || rnd() % 3 != 0);
+        if (doInsert)
+        {
+            const distance_t key = 0.25 * static_cast<double>(rnd() % static_cast<uint64_t>(std::max(1, distinct_keys)));
+            payload[next]        = static_cast<int>(next);
+            heap.insert(key, &payload[next]);
+            ref.insert({key, &payload[next]});
+            next++;
+        }
+        else
+        {
+            if (heap.empty() || heap.top() != ref.begin()->second) bad++;
+            if (!heap.empty()) heap.pop();
+            ref.erase(ref.begin());
+        }
+    }
+    return bad + (heap.empty() ? 0 : 1);
+}
+
 // Host self-test of the worker pool (no GPU): `rounds` times, fn(i) for i in [0,count) on n_threads workers; returns the
 // number of indices that were not executed exactly once per round (0 = correct), or -1 if an exception thrown by a
 // work item is not rethrown to the caller.
@@ -423,38 +496,7 @@ struct TPS_Astar::Impl::Query
     // allocation is a pointer bump and the whole search state is dropped at once when the query ends
     std::pmr::monotonic_buffer_resource                         searchArena{1 << 16};
     LatticeIndex                                                grid{&searchArena};
-    // The reference's open set is a std::multimap<cost, Node*> that is only ever inserted into and popped at begin()
-    // (keys go stale, nothing is erased elsewhere). A binary heap ordered by (key, insertion number) pops in exactly the
-    // multimap's order — equal keys leave in insertion order, as multimap::insert places them at the upper bound of
-    // their range — without a node allocation and a cold pointer chase per insertion.
-    struct OpenSet
-    {
-        struct Item
-        {
-            distance_t f;
-            uint64_t   seq;
-            Node*      node;
-        };
-        struct Later
-        {
-            bool operator()(const Item& a, const Item& b) const { return a.f > b.f || (a.f == b.f && a.seq > b.seq); }
-        };
-        std::vector<Item> heap;
-        uint64_t          nextSeq = 0;
-        bool              empty() const { return heap.empty(); }
-        Node*             top() const { return heap.front().node; }
-        void              insert(distance_t f, Node* n)
-        {
-            heap.push_back(Item{f, nextSeq++, n});
-            std::push_heap(heap.begin(), heap.end(), Later());
-        }
-        void pop()
-        {
-            std::pop_heap(heap.begin(), heap.end(), Later());
-            heap.pop_back();
-        }
-    };
-    OpenSet                                                     openSet;
+    OpenSetT<Node>                                              openSet;  // see OpenSetT
     TNodeID                                                nextFreeId = 0;
     Node*                                                  nodeGoal   = nullptr;
     NodeCoords                                             goalCellIndices;

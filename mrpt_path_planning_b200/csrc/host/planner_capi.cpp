@@ -49,6 +49,7 @@ void require(bool cond, const char* msg)
 namespace mpp
 {
 int selftest_worker_pool(int n_threads, size_t count, int rounds);  // planner.cpp
+int selftest_open_set(uint64_t seed, size_t ops, int distinct_keys);  // planner.cpp
 }
 
 extern "C" {
@@ -58,6 +59,18 @@ int mppb_selftest_worker_pool(int n_threads, size_t count, int rounds)
     try
     {
         return mpp::selftest_worker_pool(n_threads, count, rounds);
+    }
+    catch (const std::exception&)
+    {
+        return -2;
+    }
+}
+
+int mppb_selftest_open_set(uint64_t seed, size_t ops, int distinct_keys)
+{
+    try
+    {
+        return mpp::selftest_open_set(seed, ops, distinct_keys);
     }
     catch (const std::exception&)
     {

@@ -119,3 +119,10 @@ def test_holo_memo_with_state_reading_expressions(capi, orc):
                 assert np.array_equal(h.path_pose(k, st), o.path_pose(k, st)), (v[6], state, k, sp, st)
                 assert h.init_dist(k) == o.init_dist(k)
                 assert h.step_for_dist(k, 1.1) == o.step_for_dist(k, 1.1)
+
+
+def test_open_set_pops_in_multimap_order(capi):
+    """the planner's heap open set leaves in the order of the reference's std::multimap (smallest key first, equal
+    keys in insertion order), whatever the mix of insertions and pops"""
+    for seed, ops, keys in ((1, 10, 1), (2, 1000, 3), (3, 20000, 50), (4, 20000, 100000), (5, 5000, 2)):
+        assert capi.lib().mppb_selftest_open_set(seed, ops, keys) == 0, (seed, ops, keys)
