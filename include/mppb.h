@@ -449,6 +449,11 @@ int mppb_selftest_worker_pool(int n_threads, size_t count, int rounds);
  * random insertions with frequent equal keys, interleaved with pops. Returns the number of pops that differ from a
  * std::multimap driven the same way (0 = same order). */
 int mppb_selftest_open_set(uint64_t seed, size_t ops, int distinct_keys);
+/* Host self-test (no GPU) of the planner's SE(2) lattice index, an open-addressing table over arena nodes that
+ * stands in for the reference's std::unordered_map<NodeCoords, Node> (TPS_Astar.h:222; only ever indexed): `ops`
+ * look-ups of random coordinates in [-range/2, range/2) through several table growths; every coordinate must keep
+ * returning the node it got the first time, distinct coordinates distinct nodes. Returns the number of violations. */
+int mppb_selftest_lattice_index(uint64_t seed, size_t ops, int range);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@
 // whether it runs alone (plan) or interleaved with thousands of others (plan_batch).
 #include <cstdlib>
 #include <algorithm>
+#include <tuple>
 #include <map>
 #include <atomic>
 #include <chrono>
@@ -347,6 +348,52 @@ struct Pinned
     }
 };
 }  // namespace
+
+// Host self-test of the lattice index (no GPU): `ops` look-ups of random lattice coordinates (a small range, so that
+// repeats are frequent, through several table growths); every coordinate must keep returning the node it was given
+// the first time (stable address, same tag) and distinct coordinates distinct nodes. Returns the number of
+// look-ups that did not (0 = correct).
+int selftest_lattice_index(uint64_t seed, size_t ops, int range)
+{
+    std::pmr::monotonic_buffer_resource                       arena{1 << 16};
+    LatticeIndex                                              grid{&arena};
+    std::map<std::tuple<int32_t, int32_t, int32_t>, Node*>    ref;
+    uint64_t                                                  x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto                                                      rnd = [&x]() {
+        x ^= x << 13;
+        x ^= x >> 7;
+        x ^= x << 17;
+        return x;
+    };
+    const uint64_t r   = static_cast<uint64_t>(std::max(1, range));
+    int            bad = 0;
+    TNodeID        next = 0;
+    for (size_t i = 0; i < ops; i++)
+    {
+        const int32_t cx = static_cast<int32_t>(rnd() % r) - static_cast<int32_t>(r / 2);
+        const int32_t cy = static_cast<int32_t>(rnd() % r) - static_cast<int32_t>(r / 2);
+        const int32_t cw = static_cast<int32_t>(rnd() % 16) - 8;
+        Node&         n  = grid[NodeCoords(cx, cy, cw)];
+        const auto    key = std::make_tuple(cx, cy, cw);
+        const auto    it  = ref.find(key);
+        if (it == ref.end())
+        {
+            if (n.id.has_value()) bad++;  // a fresh node must be untouched
+            n.id     = next++;
+            ref[key] = &n;
+        }
+        else if (it->second != &n)
+            bad++;
+    }
+    // every node still holds its own tag (no two coordinates share a node)
+    std::vector<char> seen(static_cast<size_t>(next), 0);
+    for (const auto& kv : ref)
+    {
+        const Node* n = kv.second;
+        if (!n->id.has_value() || *n->id >= next || seen[static_cast<size_t>(*n->id)]++) bad++;
+    }
+    return bad;
+}
 
 // Host self-test of the open set (no GPU): `ops` random insertions (keys drawn from `distinct_keys` values, so that
 // equal keys are frequent) interleaved with pops; returns the number of pops that differ from a std::multimap

@@ -50,6 +50,7 @@ namespace mpp
 {
 int selftest_worker_pool(int n_threads, size_t count, int rounds);  // planner.cpp
 int selftest_open_set(uint64_t seed, size_t ops, int distinct_keys);  // planner.cpp
+int selftest_lattice_index(uint64_t seed, size_t ops, int range);     // planner.cpp
 }
 
 extern "C" {
@@ -71,6 +72,18 @@ int mppb_selftest_open_set(uint64_t seed, size_t ops, int distinct_keys)
     try
     {
         return mpp::selftest_open_set(seed, ops, distinct_keys);
+    }
+    catch (const std::exception&)
+    {
+        return -2;
+    }
+}
+
+int mppb_selftest_lattice_index(uint64_t seed, size_t ops, int range)
+{
+    try
+    {
+        return mpp::selftest_lattice_index(seed, ops, range);
     }
     catch (const std::exception&)
     {

@@ -126,3 +126,10 @@ def test_open_set_pops_in_multimap_order(capi):
     keys in insertion order), whatever the mix of insertions and pops"""
     for seed, ops, keys in ((1, 10, 1), (2, 1000, 3), (3, 20000, 50), (4, 20000, 100000), (5, 5000, 2)):
         assert capi.lib().mppb_selftest_open_set(seed, ops, keys) == 0, (seed, ops, keys)
+
+
+def test_lattice_index_is_a_stable_map(capi):
+    """the planner's open-addressing lattice index behaves like the reference's unordered_map<NodeCoords, Node> under
+    indexing: one node per coordinate, stable addresses through table growth"""
+    for seed, ops, rng_ in ((1, 100, 2), (2, 50000, 40), (3, 200000, 400), (4, 3000, 100000)):
+        assert capi.lib().mppb_selftest_lattice_index(seed, ops, rng_) == 0, (seed, ops, rng_)
