@@ -1,0 +1,274 @@
+// TEST INFRASTRUCTURE — not part of the product, never shipped, never loaded by the product.
+//
+// A stand-in for the DEVICE entry points of include/mppb.h (the ones libmpp_b200's host code reaches through the PLT)
+// that answers them on the CPU with the oracle (oracle/_build/liboracle.so). Pre-loaded (LD_PRELOAD) into a test
+// process it lets the product's HOST logic — mpp::TPS_Astar's phases A, C, D, F, its open set, lattice, motion tree,
+// the split collision calls, the deferred tree insertions — run without a GPU, so that `-m "not gpu"` can compare the
+// product planner's motion tree with the oracle's. Nothing here is a CPU fallback of the product: libmpp_b200.so itself
+// still fails loudly without CUDA (mppb_ctx_create), and the GPU parity of the kernels is the `-m gpu` tests' job.
+//
+// Supported: collision-grid PTGs (answered by orc_eval_nodes on oracle PTG objects the harness registers), cost
+// evaluators (orc_eval_edge_costs on oracle evaluators the harness registers per slot), one obstacle cloud with the
+// ObstacleSource.cpp:29-40 clipping box. HolonomicBlend candidates are not supported (the candidate record does not
+// say which (k, speed) it is).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/mppb.h"
+
+extern "C" {
+// oracle/oracle_capi.cpp
+double orc_eval_nodes(void** ptgs, int nptg, const float* xs, const float* ys, size_t n, const double* poses_xyphi,
+                      size_t B, double clip, double* out, int mode, int nthreads);
+int    orc_eval_edge_costs(void* evaluator, int kind, size_t nEdges, const double* from_xyphi,
+                           const uint32_t* sample_offsets, const double* rel_xy, double* out_cost);
+}
+
+struct mppb_ctx
+{
+    std::string        lastError;
+    std::vector<int>   numPaths;  // per uploaded collision-grid PTG
+    std::vector<float> xs, ys;    // the (clipped) cloud
+    bool               haveBox = false;
+    float              box[4]  = {0, 0, 0, 0};
+    int                numEvals = 0;
+    uint64_t           evalEpoch = 0;
+    uint64_t           calls[4]  = {0, 0, 0, 0};  // eval_nodes, eval_nodes_begin, eval_edge_costs, sync
+};
+
+namespace
+{
+std::vector<void*> g_oraclePtgs;
+void*              g_oracleEval[MPPB_MAX_EVALUATORS]     = {};
+int                g_oracleEvalKind[MPPB_MAX_EVALUATORS] = {};
+std::string        g_globalError;
+mppb_ctx*          g_lastCtx = nullptr;
+
+int fail(mppb_ctx* ctx, const char* msg)
+{
+    if (ctx) ctx->lastError = msg;
+    g_globalError = msg;
+    return MPPB_ERR_STATE;
+}
+int eval_nodes(mppb_ctx* ctx, size_t n, const double* poses, const float* boxes, double clip, float* out)
+{
+    if (g_oraclePtgs.size() != ctx->numPaths.size()) return fail(ctx, "mppb_sim: register the oracle PTGs first");
+    size_t cols = 0;
+    for (int k : ctx->numPaths) cols += static_cast<size_t>(k);
+    std::vector<double> tmp(n * cols);
+    const int           nptg = static_cast<int>(g_oraclePtgs.size());
+    if (!boxes)
+    {
+        if (orc_eval_nodes(g_oraclePtgs.data(), nptg, ctx->xs.data(), ctx->ys.data(), ctx->xs.size(), poses, n, clip,
+                           tmp.data(), 1, 1) < 0)
+            return fail(ctx, "mppb_sim: orc_eval_nodes failed");
+    }
+    else
+    {
+        // per-node world box (ObstacleSource.cpp:29-40 applied per query): the node sees the points inside its box
+        std::vector<float> bx, by;
+        for (size_t i = 0; i < n; i++)
+        {
+            const float* b = boxes + 4 * i;
+            bx.clear();
+            by.clear();
+            for (size_t p = 0; p < ctx->xs.size(); p++)
+            {
+                const float x = ctx->xs[p], y = ctx->ys[p];
+                if (x < b[0] || x > b[2] || y < b[1] || y > b[3]) continue;
+                bx.push_back(x);
+                by.push_back(y);
+            }
+            if (orc_eval_nodes(g_oraclePtgs.data(), nptg, bx.data(), by.data(), bx.size(), poses + 3 * i, 1, clip,
+                               tmp.data() + i * cols, 1, 1) < 0)
+                return fail(ctx, "mppb_sim: orc_eval_nodes failed");
+        }
+    }
+    // the oracle returns min(init_k, c): 0, a table float or the reference distance — all exact in float; the
+    // planner applies min(init_k, .) again, which changes nothing
+    for (size_t i = 0; i < tmp.size(); i++) out[i] = static_cast<float>(tmp[i]);
+    return MPPB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// ---- harness controls ----
+void mppbsim_set_oracle_ptgs(void** handles, int n) { g_oraclePtgs.assign(handles, handles + n); }
+void mppbsim_set_oracle_evaluator(int slot, void* handle, int kind)
+{
+    g_oracleEval[slot]     = handle;
+    g_oracleEvalKind[slot] = kind;
+}
+void mppbsim_call_counts(uint64_t* out4)
+{
+    for (int i = 0; i < 4; i++) out4[i] = g_lastCtx ? g_lastCtx->calls[i] : 0;
+}
+
+// ---- device entry points of include/mppb.h ----
+const char* mppb_last_global_error(void) { return g_globalError.c_str(); }
+int         mppb_ctx_create(int, void*, mppb_ctx** out)
+{
+    *out      = new mppb_ctx();
+    g_lastCtx = *out;
+    return MPPB_OK;
+}
+void mppb_ctx_destroy(mppb_ctx* ctx)
+{
+    if (g_lastCtx == ctx) g_lastCtx = nullptr;
+    delete ctx;
+}
+const char* mppb_last_error(const mppb_ctx* ctx) { return ctx ? ctx->lastError.c_str() : ""; }
+int         mppb_sync(mppb_ctx* ctx)
+{
+    ctx->calls[3]++;
+    return MPPB_OK;
+}
+int mppb_host_alloc(size_t bytes, void** out)
+{
+    return posix_memalign(out, 256, bytes ? bytes : 256) == 0 ? MPPB_OK : MPPB_ERR_STATE;
+}
+int mppb_host_free(void* p)
+{
+    free(p);
+    return MPPB_OK;
+}
+
+int mppb_set_obstacles_clipped(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double, int append,
+                               const float* box)
+{
+    if (!append)
+    {
+        ctx->xs.clear();
+        ctx->ys.clear();
+        ctx->haveBox = box != nullptr;
+        if (box) std::memcpy(ctx->box, box, sizeof(ctx->box));
+    }
+    for (size_t i = 0; i < n; i++)
+    {
+        const float x = xs[i], y = ys[i];
+        if (!std::isfinite(x) || !std::isfinite(y)) continue;
+        if (ctx->haveBox && (x < ctx->box[0] || x > ctx->box[2] || y < ctx->box[1] || y > ctx->box[3])) continue;
+        ctx->xs.push_back(x);
+        ctx->ys.push_back(y);
+    }
+    return MPPB_OK;
+}
+int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin, int append)
+{
+    return mppb_set_obstacles_clipped(ctx, xs, ys, n, bin, append, nullptr);
+}
+
+int mppb_clear_ptgs(mppb_ctx* ctx)
+{
+    ctx->numPaths.clear();
+    return MPPB_OK;
+}
+int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* desc)
+{
+    if (ptg_index != static_cast<int>(ctx->numPaths.size())) return fail(ctx, "mppb_sim: PTGs must be set in order");
+    ctx->numPaths.push_back(desc->num_paths);
+    return MPPB_OK;
+}
+int mppb_set_ptg_holo(mppb_ctx* ctx, int, const mppb_ptg_holo_desc*)
+{
+    return fail(ctx, "mppb_sim: HolonomicBlend PTGs are not supported");
+}
+int mppb_num_ptgs(const mppb_ctx* ctx) { return static_cast<int>(ctx->numPaths.size()); }
+int mppb_total_paths(const mppb_ctx* ctx)
+{
+    int s = 0;
+    for (int k : ctx->numPaths) s += k;
+    return s;
+}
+int mppb_ptg_column_offset(const mppb_ctx* ctx, int ptg_index)
+{
+    int s = 0;
+    for (int i = 0; i < ptg_index && i < static_cast<int>(ctx->numPaths.size()); i++) s += ctx->numPaths[i];
+    return s;
+}
+
+int mppb_eval_nodes_boxed(mppb_ctx* ctx, size_t n, const double* poses, const float* boxes, double clip, float* out)
+{
+    ctx->calls[0]++;
+    return eval_nodes(ctx, n, poses, boxes, clip, out);
+}
+int mppb_eval_nodes_boxed_begin(mppb_ctx* ctx, size_t n, const double* poses, const float* boxes, double clip,
+                                float* out)
+{
+    ctx->calls[1]++;
+    return eval_nodes(ctx, n, poses, boxes, clip, out);  // complete at once; mppb_sync is then a no-op
+}
+int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t, const double*, const float*, size_t, const mppb_holo_cand*,
+                                    double, double*)
+{
+    return fail(ctx, "mppb_sim: HolonomicBlend candidates are not supported");
+}
+int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t, const double*, const float*, size_t,
+                                          const mppb_holo_cand*, double, double*)
+{
+    return fail(ctx, "mppb_sim: HolonomicBlend candidates are not supported");
+}
+
+int mppb_clear_evaluators(mppb_ctx* ctx)
+{
+    ctx->numEvals = 0;
+    ctx->evalEpoch++;
+    return MPPB_OK;
+}
+int mppb_set_costmap(mppb_ctx* ctx, int slot, const mppb_costmap_desc*)
+{
+    ctx->numEvals = std::max(ctx->numEvals, slot + 1);
+    ctx->evalEpoch++;
+    return MPPB_OK;
+}
+int mppb_set_waypoints(mppb_ctx* ctx, int slot, const double*, const double*, size_t, double, double, int)
+{
+    ctx->numEvals = std::max(ctx->numEvals, slot + 1);
+    ctx->evalEpoch++;
+    return MPPB_OK;
+}
+int      mppb_num_evaluators(const mppb_ctx* ctx) { return ctx->numEvals; }
+uint64_t mppb_evaluators_epoch(const mppb_ctx* ctx) { return ctx->evalEpoch; }
+int      mppb_eval_edge_costs(mppb_ctx* ctx, size_t n_edges, const double* from, const uint32_t* off, const double* rel,
+                              double* out)
+{
+    ctx->calls[2]++;
+    const int           E = ctx->numEvals;
+    std::vector<double> col(n_edges);
+    for (int s = 0; s < E; s++)
+    {
+        if (!g_oracleEval[s]) return fail(ctx, "mppb_sim: register an oracle evaluator for every slot");
+        if (orc_eval_edge_costs(g_oracleEval[s], g_oracleEvalKind[s], n_edges, from, off, rel, col.data()) != 0)
+            return fail(ctx, "mppb_sim: orc_eval_edge_costs failed");
+        for (size_t e = 0; e < n_edges; e++) out[e * E + s] = col[e];
+    }
+    return MPPB_OK;
+}
+// Only used by the product's host costmap construction, whose cells this stand-in never reads (costs come from the
+// registered oracle evaluators): a plain nearest search, exact below the clearance like the kernel's.
+int mppb_costmap_nearest_d2(mppb_ctx*, const float* xs, const float* ys, size_t n, double x_min, double y_min, double res,
+                            int nx, int ny, float, float* out)
+{
+    for (int cy = 0; cy < ny; cy++)
+        for (int cx = 0; cx < nx; cx++)
+        {
+            const float x = static_cast<float>(x_min + (cx + 0.5) * res), y = static_cast<float>(y_min + (cy + 0.5) * res);
+            float       best = std::numeric_limits<float>::infinity();
+            for (size_t i = 0; i < n; i++)
+            {
+                const float dx = x - xs[i], dy = y - ys[i], d2 = dx * dx + dy * dy;
+                best = d2 < best ? d2 : best;
+            }
+            out[cx + static_cast<size_t>(cy) * nx] = best;
+        }
+    return MPPB_OK;
+}
+
+}  // extern "C"
