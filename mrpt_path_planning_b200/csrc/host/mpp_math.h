@@ -51,9 +51,10 @@ struct TTwist2D
     TTwist2D() = default;
     TTwist2D(double vx_, double vy_, double w_) : vx(vx_), vy(vy_), omega(w_) {}
     /** rotate the linear part by `ang` radians */
-    void rotate(double ang)
+    void rotate(double ang) { rotateCS(std::cos(ang), std::sin(ang)); }
+    /** rotate() with the angle's cosine and sine taken by the caller (the same angle for many twists) */
+    void rotateCS(double c, double s)
     {
-        const double c = std::cos(ang), s = std::sin(ang);
         const double nx = vx * c - vy * s, ny = vx * s + vy * c;
         vx = nx;
         vy = ny;
@@ -67,9 +68,10 @@ struct TPose2D
     TPose2D() = default;
     TPose2D(double x_, double y_, double phi_) : x(x_), y(y_), phi(phi_) {}
     /** pose composition this (+) b */
-    TPose2D operator+(const TPose2D& b) const
+    TPose2D operator+(const TPose2D& b) const { return composeCS(std::cos(phi), std::sin(phi), b); }
+    /** operator+ with cos(phi), sin(phi) of this pose taken by the caller (one pose composed with many) */
+    TPose2D composeCS(double c, double s, const TPose2D& b) const
     {
-        const double c = std::cos(phi), s = std::sin(phi);
         return {x + b.x * c - b.y * s, y + b.x * s + b.y * c, wrap_to_pi(phi + b.phi)};
     }
     /** inverse composition this (-) b: this pose as seen from b */

@@ -949,6 +949,10 @@ struct TPS_Astar::Impl::Query
 
         pending.clear();
         const TPose2D& lo = in->worldBboxMin, &hi = in->worldBboxMax;
+        // every neighbour is reached from `current`: the cos/sin of its heading (pose composition, twist rotation) and
+        // the goal as seen from it are taken once, not once per neighbour (same libm calls on the same argument)
+        const double  curC = std::cos(current->state.pose.phi), curS = std::sin(current->state.pose.phi);
+        const TPose2D goalFromCurrent = in->stateGoal.asSE2KinState().pose - current->state.pose;
         for (const auto& kv : bestPaths)  // unordered_map order, as in the reference
         {
             const PathToNeighbor& nb = kv.second;
@@ -956,11 +960,11 @@ struct TPS_Astar::Impl::Query
             ptg_t& ptg = *trs.ptgs.at(*nb.ptgIndex);
             ptg.updateNavDynamicState(nb.ptgDynState);
             if (ptg.isSpeedTrimmable()) ptg.trimmableSpeed_ = nb.ptgTrimmableSpeed;
-            const TPose2D  q_i      = current->state.pose + nb.relReconstrPose;
+            const TPose2D  q_i      = current->state.pose.composeCS(curC, curS, nb.relReconstrPose);
             const TTwist2D relTwist = ptg.getPathTwist(static_cast<uint16_t>(nb.ptgTrajIndex), nb.relTrgStep);
             SE2_KinState   x_i;
             x_i.pose = q_i;
-            (x_i.vel = relTwist).rotate(current->state.pose.phi);
+            (x_i.vel = relTwist).rotateCS(curC, curS);
             if (q_i.x < lo.x || q_i.y < lo.y || q_i.phi < lo.phi) continue;
             if (q_i.x > hi.x || q_i.y > hi.y || q_i.phi > hi.phi) continue;
             Node& neighborNode = getOrCreateNodeByPose(x_i);
@@ -976,7 +980,7 @@ struct TPS_Astar::Impl::Query
             e.ptgPathIndex         = static_cast<int16_t>(nb.ptgTrajIndex);
             e.ptgTrimmableSpeed    = nb.ptgTrimmableSpeed;
             e.ptgFinalGoalRelSpeed = 0;
-            e.ptgFinalRelativeGoal = in->stateGoal.asSE2KinState().pose - current->state.pose;
+            e.ptgFinalRelativeGoal = goalFromCurrent;
             e.stateFrom            = current->state;
             e.stateTo              = x_i;
             e.ptgStep              = nb.relTrgStep;
