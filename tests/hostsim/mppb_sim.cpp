@@ -9,8 +9,10 @@
 //
 // Supported: collision-grid PTGs (answered by orc_eval_nodes on oracle PTG objects the harness registers), cost
 // evaluators (orc_eval_edge_costs on oracle evaluators the harness registers per slot), one obstacle cloud with the
-// ObstacleSource.cpp:29-40 clipping box. HolonomicBlend candidates are not supported (the candidate record does not
-// say which (k, speed) it is).
+// ObstacleSource.cpp:29-40 clipping box, and HolonomicBlend candidates: the harness registers a table
+// (vxf, vyf, vf) -> (k, trimmed speed) made with the product's host PTG, the candidate record is matched against it bit
+// for bit, and an oracle HolonomicBlend object of the stand-in's own (not the oracle planner's) is put into the
+// candidate's initial velocity and trimmed speed and folded over the node's local obstacles.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -28,6 +30,11 @@ double orc_eval_nodes(void** ptgs, int nptg, const float* xs, const float* ys, s
                       size_t B, double clip, double* out, int mode, int nthreads);
 int    orc_eval_edge_costs(void* evaluator, int kind, size_t nEdges, const double* from_xyphi,
                            const uint32_t* sample_offsets, const double* rel_xy, double* out_cost);
+long   orc_local_obstacles(const float* xs, const float* ys, size_t n, const double* pose_xyphi, double clip, float* out_x,
+                           float* out_y);
+int    orc_ptg_update_dyn_state(void* h, const double* dyn7, int force);
+void   orc_ptg_set_trim_speed(void* h, double s);
+double orc_ptg_update_tpobs_single(void* h, double ox, double oy, int k, double tp_obstacle_k);
 }
 
 struct mppb_ctx
@@ -37,6 +44,7 @@ struct mppb_ctx
     std::vector<float> xs, ys;    // the (clipped) cloud
     bool               haveBox = false;
     float              box[4]  = {0, 0, 0, 0};
+    int                holoPtgs = 0;
     int                numEvals = 0;
     uint64_t           evalEpoch = 0;
     uint64_t           calls[4]  = {0, 0, 0, 0};  // eval_nodes, eval_nodes_begin, eval_edge_costs, sync
@@ -47,6 +55,13 @@ namespace
 std::vector<void*> g_oraclePtgs;
 void*              g_oracleEval[MPPB_MAX_EVALUATORS]     = {};
 int                g_oracleEvalKind[MPPB_MAX_EVALUATORS] = {};
+struct HoloKey
+{
+    double vxf, vyf, vf, speed;
+    int    k;
+};
+std::vector<HoloKey> g_holoTable;
+void*                g_oracleHolo = nullptr;  // the stand-in's own oracle HolonomicBlend
 std::string        g_globalError;
 mppb_ctx*          g_lastCtx = nullptr;
 
@@ -58,7 +73,8 @@ int fail(mppb_ctx* ctx, const char* msg)
 }
 int eval_nodes(mppb_ctx* ctx, size_t n, const double* poses, const float* boxes, double clip, float* out)
 {
-    if (g_oraclePtgs.size() != ctx->numPaths.size()) return fail(ctx, "mppb_sim: register the oracle PTGs first");
+    if (g_oraclePtgs.size() + ctx->holoPtgs != ctx->numPaths.size())
+        return fail(ctx, "mppb_sim: register the oracle PTGs first");
     size_t cols = 0;
     for (int k : ctx->numPaths) cols += static_cast<size_t>(k);
     std::vector<double> tmp(n * cols);
@@ -100,6 +116,13 @@ int eval_nodes(mppb_ctx* ctx, size_t n, const double* poses, const float* boxes,
 extern "C" {
 
 // ---- harness controls ----
+void mppbsim_set_holo(void* oracle_holo_ptg, size_t n, const double* vxf, const double* vyf, const double* vf,
+                      const int* k, const double* speed)
+{
+    g_oracleHolo = oracle_holo_ptg;
+    g_holoTable.clear();
+    for (size_t i = 0; i < n; i++) g_holoTable.push_back(HoloKey{vxf[i], vyf[i], vf[i], speed[i], k[i]});
+}
 void mppbsim_set_oracle_ptgs(void** handles, int n) { g_oraclePtgs.assign(handles, handles + n); }
 void mppbsim_set_oracle_evaluator(int slot, void* handle, int kind)
 {
@@ -167,6 +190,7 @@ int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n
 
 int mppb_clear_ptgs(mppb_ctx* ctx)
 {
+    ctx->holoPtgs = 0;
     ctx->numPaths.clear();
     return MPPB_OK;
 }
@@ -176,9 +200,12 @@ int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* de
     ctx->numPaths.push_back(desc->num_paths);
     return MPPB_OK;
 }
-int mppb_set_ptg_holo(mppb_ctx* ctx, int, const mppb_ptg_holo_desc*)
+int mppb_set_ptg_holo(mppb_ctx* ctx, int ptg_index, const mppb_ptg_holo_desc*)
 {
-    return fail(ctx, "mppb_sim: HolonomicBlend PTGs are not supported");
+    if (ptg_index != static_cast<int>(ctx->numPaths.size())) return fail(ctx, "mppb_sim: PTGs must be set in order");
+    ctx->numPaths.push_back(0);  // no columns in the collision-grid rows
+    ctx->holoPtgs++;
+    return MPPB_OK;
 }
 int mppb_num_ptgs(const mppb_ctx* ctx) { return static_cast<int>(ctx->numPaths.size()); }
 int mppb_total_paths(const mppb_ctx* ctx)
@@ -205,15 +232,65 @@ int mppb_eval_nodes_boxed_begin(mppb_ctx* ctx, size_t n, const double* poses, co
     ctx->calls[1]++;
     return eval_nodes(ctx, n, poses, boxes, clip, out);  // complete at once; mppb_sync is then a no-op
 }
-int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t, const double*, const float*, size_t, const mppb_holo_cand*,
-                                    double, double*)
+static int eval_holo(mppb_ctx* ctx, size_t n_nodes, const double* poses, const float* boxes, size_t n_cands,
+                     const mppb_holo_cand* cands, double clip, double* out)
 {
-    return fail(ctx, "mppb_sim: HolonomicBlend candidates are not supported");
+    if (!g_oracleHolo) return fail(ctx, "mppb_sim: register the oracle HolonomicBlend and its table first");
+    std::vector<float> lx(ctx->xs.size() + 1), ly(ctx->xs.size() + 1), bx, by;
+    long               nLocal = 0;
+    int                localOf = -1;
+    for (size_t c = 0; c < n_cands; c++)
+    {
+        const mppb_holo_cand& cd = cands[c];
+        if (cd.node < 0 || static_cast<size_t>(cd.node) >= n_nodes) return fail(ctx, "mppb_sim: bad candidate node");
+        const HoloKey* key = nullptr;
+        for (const HoloKey& h : g_holoTable)
+            if (h.vxf == cd.vxf && h.vyf == cd.vyf && h.vf == cd.vf) key = &h;
+        if (!key) return fail(ctx, "mppb_sim: candidate parameters are not in the registered (k, speed) table");
+        if (cd.node != localOf)  // candidates come grouped by node
+        {
+            const float *px = ctx->xs.data(), *py = ctx->ys.data();
+            size_t       np = ctx->xs.size();
+            if (boxes)
+            {
+                const float* b = boxes + 4 * cd.node;
+                bx.clear();
+                by.clear();
+                for (size_t p = 0; p < np; p++)
+                    if (!(px[p] < b[0] || px[p] > b[2] || py[p] < b[1] || py[p] > b[3]))
+                    {
+                        bx.push_back(px[p]);
+                        by.push_back(py[p]);
+                    }
+                px = bx.data(), py = by.data(), np = bx.size();
+            }
+            nLocal = orc_local_obstacles(px, py, np, poses + 3 * cd.node, clip, lx.data(), ly.data());
+            if (nLocal < 0) return fail(ctx, "mppb_sim: orc_local_obstacles failed");
+            localOf = cd.node;
+        }
+        // the oracle object computes its parameters from (k, trimmed speed, initial velocity): put it into the
+        // candidate's (the |V|, |omega| formulas of the tested configurations read nothing else)
+        const double dyn[7] = {cd.vxi, cd.vyi, 0.0, 1.0, 0.0, 0.0, 0.0};  // (some target: it is not read)
+        orc_ptg_set_trim_speed(g_oracleHolo, key->speed);
+        if (orc_ptg_update_dyn_state(g_oracleHolo, dyn, 1) != 0) return fail(ctx, "mppb_sim: oracle dyn state failed");
+        orc_ptg_set_trim_speed(g_oracleHolo, key->speed);
+        double raw = std::numeric_limits<double>::infinity();
+        for (long i = 0; i < nLocal; i++) raw = orc_ptg_update_tpobs_single(g_oracleHolo, lx[i], ly[i], key->k, raw);
+        out[c] = raw;
+    }
+    return MPPB_OK;
 }
-int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t, const double*, const float*, size_t,
-                                          const mppb_holo_cand*, double, double*)
+int mppb_eval_holo_candidates_boxed(mppb_ctx* ctx, size_t n_nodes, const double* poses, const float* boxes, size_t n_cands,
+                                    const mppb_holo_cand* cands, double clip, double* out)
 {
-    return fail(ctx, "mppb_sim: HolonomicBlend candidates are not supported");
+    ctx->calls[0]++;
+    return eval_holo(ctx, n_nodes, poses, boxes, n_cands, cands, clip, out);
+}
+int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* poses, const float* boxes,
+                                          size_t n_cands, const mppb_holo_cand* cands, double clip, double* out)
+{
+    ctx->calls[1]++;
+    return eval_holo(ctx, n_nodes, poses, boxes, n_cands, cands, clip, out);
 }
 
 int mppb_clear_evaluators(mppb_ctx* ctx)

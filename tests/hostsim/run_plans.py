@@ -43,6 +43,32 @@ def register_evaluator(slot, handle, kind):
     sim.mppbsim_set_oracle_evaluator(slot, handle.h if handle is not None else None, kind)
 
 
+def register_holo(product_ptg, oracle_ptg, n_speeds=3):
+    """table (vxf, vyf, vf) -> (k, trimmed speed) from the product's host PTG (its |V|, |omega| formulas read dir and
+    the trimmed speed only), and the oracle HolonomicBlend object the stand-in evaluates with"""
+    inc = 1.0 / n_speeds
+    speeds, sp = [], inc
+    while sp < 1.001:  # TPS_Astar.cpp:636-640
+        speeds.append(sp)
+        sp += inc
+    rows = []
+    product_ptg.update_dyn_state((0.0, 0.0, 0.0), (1.0, 0.0, 0.0), 0.0, force=True)
+    for sp in speeds:
+        product_ptg.set_trim_speed(sp)
+        for k in range(product_ptg.num_paths):
+            c = product_ptg.holo_params(k)
+            rows.append((c.vxf, c.vyf, c.vf, k, sp))
+    a = np.array(rows)
+    vxf, vyf, vf = (np.ascontiguousarray(a[:, i]) for i in range(3))
+    ks = np.ascontiguousarray(a[:, 3].astype(np.int32))
+    sps = np.ascontiguousarray(a[:, 4])
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    sim.mppbsim_set_holo.argtypes = [C.c_void_p, C.c_size_t, dp, dp, dp, ip, dp]
+    sim.mppbsim_set_holo(oracle_ptg.h, len(rows), vxf.ctypes.data_as(dp), vyf.ctypes.data_as(dp), vf.ctypes.data_as(dp),
+                         ks.ctypes.data_as(ip), sps.ctypes.data_as(dp))
+    return (vxf, vyf, vf, ks, sps)  # keep alive until copied (the stand-in copies at once)
+
+
 def call_counts():
     v = (C.c_uint64 * 4)()
     sim.mppbsim_call_counts(v)
@@ -153,6 +179,41 @@ def main():
         total += int(r_o["expanded"])
     assert total > 50
     out["batch"] = dict(queries=len(qs), expansions=total)
+    prod.close()
+    # --- C1: HolonomicBlend PTG with the obstacle costmap (candidate records, direction memo, split calls) ---
+    ph = capi.holonomic_ptgs()
+    oh = orc.holonomic_ptgs()
+    sim_holo = orc.holonomic_ptgs()[0]  # the stand-in's own oracle object (the oracle planner keeps its own state)
+    register_ptgs([])
+    register_holo(capi.holonomic_ptgs()[0], sim_holo)
+    register_evaluator(0, cm, 0)
+    register_evaluator(1, None, 0)
+    prod = capi.Planner(ctx, ph, C1_PARAMS, C1_TIMESTAMPS)
+    prod.add_obstacles(xs, ys)
+    prod.add_costmap(xs, ys, 0.04, 0.5, 4.0, False, 15.0, start[:3])
+    ora = orc.Planner(oh, C1_PARAMS, C1_TIMESTAMPS)
+    ora.add_obstacles(xs, ys)
+    ora.add_costmap(cm)
+    r_p, r_o = prod.plan(start, goal, lo, hi), ora.plan(start, goal, lo, hi)
+    same_plan(prod, ora, r_p, r_o)
+    assert r_p["success"] == 1.0 and r_p["expanded"] > 20
+    out["c1"] = dict(expanded=int(r_p["expanded"]), tree_nodes=int(r_p["tree_nodes"]))
+    for s_, g_ in (([4.0, 2.5, 0.8, 0.2, 0.1, 0.0], [3.0, -0.5, -1.0, 0, 0, 0]), (start, [1.5, 3.0, 2.0, 0, 0, 0])):
+        r_p, r_o = prod.plan(s_, g_, lo, hi), ora.plan(s_, g_, lo, hi)
+        same_plan(prod, ora, r_p, r_o)
+    prod.close()
+    # a holonomic batch in lock-step (per-node boxes, private PTG clones), no evaluators
+    register_evaluator(0, None, 0)
+    params = list(C1_PARAMS)
+    params[8] = 15
+    prod = capi.Planner(ctx, ph, params, C1_TIMESTAMPS)
+    prod.add_obstacles(mx, my)
+    batch = prod.plan_many(qs[:4], n_threads=2)
+    for i, q in enumerate(qs[:4]):
+        ora = orc.Planner(orc.holonomic_ptgs(), params, C1_TIMESTAMPS)
+        ora.add_obstacles(mx, my)
+        same_plan(prod, ora, batch[i], ora.plan(*q[:4]), query=i)
+    out["holonomic_batch"] = True
     prod.close()
     print(json.dumps(out))
 
