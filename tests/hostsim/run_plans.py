@@ -215,6 +215,41 @@ def main():
         same_plan(prod, ora, batch[i], ora.plan(*q[:4]), query=i)
     out["holonomic_batch"] = True
     prod.close()
+    # --- other TPS_Astar parameter sets (lattice resolution, trajectories, speeds, sample timestamps, interpolated
+    #     segments, heuristic weights; averaged costmap, max-combined waypoints), both PTG kinds ---
+    param_sets = {
+        "defaults_of_the_class": ([0.20, np.deg2rad(5.0), 1.0, 0.1, 20, 3, 5, 0, 30], [1.0, 3.0, 5.0]),
+        "coarse_two_speeds": ([0.50, np.deg2rad(45.0), 0.3, 0.0, 7, 2, 3, 0, 60], [0.4, 2.0]),
+        "one_speed_many_paths": ([0.30, np.deg2rad(15.0), 0.1, 0.5, 31, 1, 8, 0, 40], [0.25, 0.75, 1.5, 3.0]),
+    }
+    cm2 = orc.CostMap(xs, ys, 0.05, 0.4, 2.0, True, 0.0, None)
+    wp3 = orc.Waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.5, 0.5, False)
+    register_evaluator(0, cm2, 0)
+    register_evaluator(1, wp3, 1)
+    done = []
+    for pname, (params, stamps) in sorted(param_sets.items()):
+        for kind in ("ackermann", "holonomic"):
+            if kind == "ackermann":
+                register_ptgs(o_ptgs)
+                pp, oo = p_ptgs, o_ptgs
+            else:
+                register_ptgs([])
+                register_holo(capi.holonomic_ptgs()[0], sim_holo, n_speeds=int(params[5]))
+                pp, oo = capi.holonomic_ptgs(), orc.holonomic_ptgs()
+            prod = capi.Planner(ctx, pp, params, stamps)
+            ora = orc.Planner(oo, params, stamps)
+            for pl in (prod, ora):
+                pl.add_obstacles(xs, ys)
+            prod.add_costmap(xs, ys, 0.05, 0.4, 2.0, True, 0.0, None)
+            ora.add_costmap(cm2)
+            prod.add_waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.5, 0.5, False)
+            ora.add_waypoints(wp3)
+            r_p, r_o = prod.plan(start, goal, lo, hi), ora.plan(start, goal, lo, hi)
+            same_plan(prod, ora, r_p, r_o)
+            assert r_p["expanded"] >= 5
+            done.append(pname + "/" + kind)
+            prod.close()
+    out["parameter_sets"] = done
     print(json.dumps(out))
 
 
