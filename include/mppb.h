@@ -78,6 +78,8 @@ const char* mppb_last_error(const mppb_ctx* ctx);
 int         mppb_sync(mppb_ctx* ctx);
 /* the cudaStream_t the context enqueues on */
 void*       mppb_stream(mppb_ctx* ctx);
+/* the CUDA ordinal the context is bound to (-1 for a null context) */
+int         mppb_ctx_device(const mppb_ctx* ctx);
 /* number of kernels this context has launched so far (for launch accounting) */
 uint64_t    mppb_launch_count(const mppb_ctx* ctx);
 
@@ -111,6 +113,10 @@ int mppb_set_obstacles_clipped(mppb_ctx* ctx, const float* xs, const float* ys, 
                                int append, const float* box);
 /* number of finite (and in-box) points currently indexed */
 size_t mppb_num_obstacles(const mppb_ctx* ctx);
+/* counter bumped by every mppb_set_obstacles* call on this context: lets a caller that keeps the cloud resident
+ * across plans (the reference re-reads ObstacleSource::obstacles() on every plan(), TPS_Astar.cpp:125-137) notice
+ * that somebody else replaced it */
+uint64_t mppb_obstacles_epoch(const mppb_ctx* ctx);
 
 /* ---- PTG tables: collision-grid family ------------------------------------------------
  * One descriptor per PTG of the DiffDriveCollisionGridBased family. All arrays are host
@@ -172,6 +178,8 @@ int mppb_clear_ptgs(mppb_ctx* ctx);
 /* ptg_index must be the next free index (0,1,2,...) over PTGs of all kinds */
 int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* desc);
 int mppb_num_ptgs(const mppb_ctx* ctx);
+/* counter bumped by mppb_clear_ptgs and every mppb_set_ptg_* call (same purpose as mppb_obstacles_epoch) */
+uint64_t mppb_ptgs_epoch(const mppb_ctx* ctx);
 /* sum over the collision-grid PTGs of num_paths = row length of the mppb_eval_nodes output */
 int mppb_total_paths(const mppb_ctx* ctx);
 /* first output column of collision-grid PTG ptg_index, or -1 if it is of another kind */
@@ -412,6 +420,9 @@ int         mppb_planner_set_params(mppb_planner* p, const mppb_astar_params* pa
 int mppb_planner_add_ptg(mppb_planner* p, mppb_ptg* ptg);
 /* one static obstacle source (ObstacleSource::FromStaticPointcloud); the points are copied */
 int mppb_planner_add_obstacles(mppb_planner* p, const float* xs, const float* ys, size_t n);
+/* new points for obstacle source #source, written into the source's existing cloud object (the next plan sees
+ * them, as the reference re-reads ObstacleSource::obstacles() on every plan(), TPS_Astar.cpp:125-137) */
+int mppb_planner_update_obstacles(mppb_planner* p, size_t source, const float* xs, const float* ys, size_t n);
 /* CostEvaluatorCostMap::FromStaticPointObstacles + push_back into costEvaluators_ */
 int mppb_planner_add_costmap(mppb_planner* p, const float* xs, const float* ys, size_t n, double resolution,
                              double preferred_clearance, double max_cost, int use_average, double max_radius_from_robot,

@@ -118,6 +118,9 @@ _SIGS = {
     "mppb_set_obstacles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int]),
     "mppb_set_obstacles_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int]),
     "mppb_num_obstacles": (C.c_size_t, [C.c_void_p]),
+    "mppb_obstacles_epoch": (C.c_uint64, [C.c_void_p]),
+    "mppb_ptgs_epoch": (C.c_uint64, [C.c_void_p]),
+    "mppb_ctx_device": (C.c_int, [C.c_void_p]),
     "mppb_clear_ptgs": (C.c_int, [C.c_void_p]),
     "mppb_set_ptg_grid": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GridDesc)]),
     "mppb_num_ptgs": (C.c_int, [C.c_void_p]),
@@ -189,6 +192,7 @@ _SIGS = {
     "mppb_planner_set_params": (C.c_int, [C.c_void_p, C.POINTER(AstarParams)]),
     "mppb_planner_add_ptg": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppb_planner_add_obstacles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mppb_planner_update_obstacles": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),
     "mppb_planner_add_costmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double,
                                            C.c_double, C.c_int, C.c_double, C.c_void_p]),
     "mppb_planner_costmap_cells": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -587,20 +591,30 @@ def free_distance(out_row_f32, init_dists):
     return np.minimum(np.asarray(init_dists, dtype=np.float64), out_row_f32.astype(np.float64))
 
 
+class _PinnedBlock:
+    """Owner of one mppb_host_alloc block: exposes it through the array interface (numpy keeps this object as the
+    base of every view) and returns it with mppb_host_free when the last view is collected."""
+
+    def __init__(self, nbytes):
+        self._p = C.c_void_p()
+        if lib().mppb_host_alloc(nbytes, C.byref(self._p)) != 0:
+            raise MppbError(lib().mppb_last_global_error().decode())
+        self._free = lib().mppb_host_free  # bound now: module globals may be gone at interpreter shutdown
+        self.__array_interface__ = {"shape": (max(1, nbytes),), "typestr": "|u1", "data": (self._p.value, False),
+                                    "version": 3}
+
+    def __del__(self):
+        p, self._p = self._p, None
+        if p is not None and p.value:
+            self._free(p)
+
+
 def pinned_empty(shape, dtype):
-    """numpy array over pinned host memory from mppb_host_alloc (freed when the array is collected)."""
+    """numpy array over pinned host memory from mppb_host_alloc (freed when the array and its views are collected)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape))
-    p = C.c_void_p()
-    if lib().mppb_host_alloc(n * dtype.itemsize, C.byref(p)) != 0:
-        raise MppbError(lib().mppb_last_global_error().decode())
-    buf = (C.c_byte * (n * dtype.itemsize)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _PINNED[arr.ctypes.data] = p
-    return arr
-
-
-_PINNED = {}
+    block = _PinnedBlock(n * dtype.itemsize)
+    return np.asarray(block)[:n * dtype.itemsize].view(dtype).reshape(shape)
 
 
 # PTG set of share/ptgs_ackermann_vehicle.ini (values typed here as data). The reference reads
@@ -667,6 +681,11 @@ class Planner:
         xs = np.ascontiguousarray(xs, dtype=np.float32)
         ys = np.ascontiguousarray(ys, dtype=np.float32)
         self._ck(lib().mppb_planner_add_obstacles(self.h, _ptr(xs), _ptr(ys), xs.size))
+
+    def update_obstacles(self, source, xs, ys):
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        self._ck(lib().mppb_planner_update_obstacles(self.h, source, _ptr(xs), _ptr(ys), xs.size))
 
     def add_costmap(self, xs, ys, resolution, clearance, max_cost, use_average, max_radius_from_robot, robot_pose):
         xs = np.ascontiguousarray(xs, dtype=np.float32)

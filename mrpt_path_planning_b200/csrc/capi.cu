@@ -160,6 +160,7 @@ int mppb_set_holo_filter(mppb_ctx* ctx, int on)
     return MPPB_OK;
 }
 void*    mppb_stream(mppb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+int      mppb_ctx_device(const mppb_ctx* ctx) { return ctx ? ctx->device : -1; }
 uint64_t mppb_launch_count(const mppb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int mppb_host_alloc(size_t bytes, void** out_ptr)
@@ -198,6 +199,7 @@ static int set_cloud(mppb_ctx* ctx, CloudStore& cs, const float* xs, const float
 {
     if (n > 0 && (!xs || !ys)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null cloud pointers");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (&cs == &ctx->cloud) ctx->cloudEpoch++;  // whatever happens below, the resident cloud is no longer the old one
     const size_t keep  = append ? cs.rawN : 0;
     const size_t total = keep + n;
     if (!append)
@@ -255,7 +257,9 @@ int mppb_set_obstacles_clipped(mppb_ctx* ctx, const float* xs, const float* ys, 
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     return set_cloud(ctx, ctx->cloud, xs, ys, n, bin_size, append, box, cudaMemcpyHostToDevice);
 }
-size_t mppb_num_obstacles(const mppb_ctx* ctx) { return ctx ? ctx->bins.n : 0; }
+size_t   mppb_num_obstacles(const mppb_ctx* ctx) { return ctx ? ctx->bins.n : 0; }
+uint64_t mppb_obstacles_epoch(const mppb_ctx* ctx) { return ctx ? ctx->cloudEpoch : 0; }
+uint64_t mppb_ptgs_epoch(const mppb_ctx* ctx) { return ctx ? ctx->ptgEpoch : 0; }
 
 // ---- PTG tables -------------------------------------------------------------------------
 static void release_groups(mppb_ctx* ctx)
@@ -268,6 +272,7 @@ int mppb_clear_ptgs(mppb_ctx* ctx)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ptgEpoch++;
     release_groups(ctx);
     ctx->grids.clear();
     ctx->holos.clear();
@@ -472,6 +477,7 @@ int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* d)
         if (!(d->entry_d[i] >= 0.f)) return fail(ctx, MPPB_ERR_INVALID_ARG, "entry_d must be >= 0");
     }
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->ptgEpoch++;
     PtgGridHost g;
     g.K         = d->num_paths;
     g.outOffset = ctx->totalPaths;
@@ -513,6 +519,7 @@ int mppb_set_ptg_holo(mppb_ctx* ctx, int ptg_index, const mppb_ptg_holo_desc* d)
     if (!(d->robot_radius > 0) || !(d->v_max > 0) || d->num_paths <= 0)
         return fail(ctx, MPPB_ERR_INVALID_ARG, "bad HolonomicBlend constants");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->ptgEpoch++;
     ctx->ptgKinds.push_back(1);
     ctx->holos.push_back(HoloPtgDev{d->robot_radius, d->v_max});
     HoloPtgDev table[MPPB_MAX_PTGS] = {};

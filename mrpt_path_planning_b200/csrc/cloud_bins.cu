@@ -133,9 +133,11 @@ int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize)
     int h[4];
     MPPB_CUDA(ctx, cudaMemcpyAsync(h, ctx->bboxScratch.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     MPPB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h[0] == INT32_MAX) return MPPB_OK;  // no finite point at all
     const float minx = from_ordered_int(h[0]), miny = from_ordered_int(h[1]);
     const float maxx = from_ordered_int(h[2]), maxy = from_ordered_int(h[3]);
+    // No point kept (all non-finite, or all outside the clipping box): every warp still folded its neutral
+    // FLT_MAX / -FLT_MAX into the scratch, so the test is on the decoded box, not on the initial pattern.
+    if (h[0] == INT32_MAX || !(minx <= maxx) || !(miny <= maxy)) return MPPB_OK;  // cs.bins stays empty (n == 0)
 
     // 2) bin grid: at most 2^24 bins
     double s = binSize;

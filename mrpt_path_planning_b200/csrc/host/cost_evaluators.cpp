@@ -4,6 +4,7 @@
 // Reference: src/algos/CostEvaluatorCostMap.cpp:54-162, src/algos/CostEvaluatorPreferredWaypoint.cpp:49-120,
 // src/algos/Planner.cpp:15-29.
 #include <cmath>
+#include <cstring>
 
 #include "mpp.h"
 
@@ -36,6 +37,24 @@ struct EdgeSamples
         offsets.push_back(static_cast<uint32_t>(e.interpolatedPath.size()));
     }
 };
+// the evaluator's private context, created on first use on the device of `like`
+mppb_ctx* private_ctx(detail::EvaluatorGpu& g, mppb_ctx* like)
+{
+    if (!g.ctx)
+    {
+        if (mppb_ctx_create(mppb_ctx_device(like), nullptr, &g.ctx) != MPPB_OK)
+            throw std::runtime_error(std::string("cost evaluator: no CUDA context: ") + mppb_last_global_error());
+        g.uploaded = false;
+    }
+    return g.ctx;
+}
+// true if the resident copy was made from these parameters; records them otherwise
+bool same_key(detail::EvaluatorGpu& g, const double (&k)[6])
+{
+    if (g.uploaded && std::memcmp(g.key, k, sizeof(k)) == 0) return true;
+    std::memcpy(g.key, k, sizeof(k));
+    return false;
+}
 }  // namespace
 
 // ---- CostEvaluatorCostMap ----------------------------------------------------------------------------
@@ -112,12 +131,20 @@ CostEvaluatorCostMap::Ptr CostEvaluatorCostMap::FromStaticPointObstacles(mppb_ct
 double CostEvaluatorCostMap::operator()(const MoveEdgeSE2_TPS& edge) const
 {
     if (!ctx_) throw std::runtime_error("CostEvaluatorCostMap is not bound to a libmpp_b200 context");
-    const EdgeSamples s(edge);
-    mppb_costmap_desc d{x_min, y_min, params_.resolution, size_x, size_y, cells.data(), params_.useAverageOfPath ? 1 : 0};
-    ck(ctx_, mppb_clear_evaluators(ctx_));
-    ck(ctx_, mppb_set_costmap(ctx_, 0, &d));
+    const EdgeSamples           s(edge);
+    std::lock_guard<std::mutex> lk(gpu_->m);
+    mppb_ctx*                   c = private_ctx(*gpu_, ctx_);
+    const double key[6] = {x_min, y_min, params_.resolution, static_cast<double>(size_x) * size_y,
+                           params_.useAverageOfPath ? 1.0 : 0.0, static_cast<double>(reinterpret_cast<uintptr_t>(cells.data()))};
+    if (!same_key(*gpu_, key))  // the grid travels once (it is immutable once built by FromStaticPointObstacles)
+    {
+        mppb_costmap_desc d{x_min, y_min, params_.resolution, size_x, size_y, cells.data(), params_.useAverageOfPath ? 1 : 0};
+        ck(c, mppb_clear_evaluators(c));
+        ck(c, mppb_set_costmap(c, 0, &d));
+        gpu_->uploaded = true;
+    }
     double out = 0;
-    ck(ctx_, mppb_eval_edge_costs(ctx_, 1, s.from, s.offsets.data(), s.rel.data(), &out));
+    ck(c, mppb_eval_edge_costs(c, 1, s.from, s.offsets.data(), s.rel.data(), &out));
     return out;
 }
 
@@ -135,19 +162,35 @@ CostEvaluatorPreferredWaypoint::Parameters CostEvaluatorPreferredWaypoint::Param
 double CostEvaluatorPreferredWaypoint::operator()(const MoveEdgeSE2_TPS& edge) const
 {
     if (!ctx_) throw std::runtime_error("CostEvaluatorPreferredWaypoint is not bound to a libmpp_b200 context");
-    const EdgeSamples   s(edge);
-    std::vector<double> xs, ys;
-    for (const auto& w : waypoints_)
+    const EdgeSamples           s(edge);
+    std::lock_guard<std::mutex> lk(gpu_->m);
+    mppb_ctx*                   c = private_ctx(*gpu_, ctx_);
+    double key[6] = {params_.waypointInfluenceRadius, params_.costScale, params_.useAverageOfPath ? 1.0 : 0.0,
+                     static_cast<double>(waypoints_.size()), 0, 0};
+    for (const auto& w : waypoints_) key[4] += w.x, key[5] += w.y;
+    if (!same_key(*gpu_, key))
     {
-        xs.push_back(w.x);
-        ys.push_back(w.y);
+        std::vector<double> xs, ys;
+        for (const auto& w : waypoints_)
+        {
+            xs.push_back(w.x);
+            ys.push_back(w.y);
+        }
+        ck(c, mppb_clear_evaluators(c));
+        ck(c, mppb_set_waypoints(c, 0, xs.data(), ys.data(), xs.size(), params_.waypointInfluenceRadius,
+                                 params_.costScale, params_.useAverageOfPath ? 1 : 0));
+        gpu_->uploaded = true;
     }
-    ck(ctx_, mppb_clear_evaluators(ctx_));
-    ck(ctx_, mppb_set_waypoints(ctx_, 0, xs.data(), ys.data(), xs.size(), params_.waypointInfluenceRadius,
-                                params_.costScale, params_.useAverageOfPath ? 1 : 0));
     double out = 0;
-    ck(ctx_, mppb_eval_edge_costs(ctx_, 1, s.from, s.offsets.data(), s.rel.data(), &out));
+    ck(c, mppb_eval_edge_costs(c, 1, s.from, s.offsets.data(), s.rel.data(), &out));
     return out;
+}
+
+void CostEvaluatorPreferredWaypoint::setPreferredWaypoints(const std::vector<TPoint2D>& pts)
+{
+    std::lock_guard<std::mutex> lk(gpu_->m);
+    waypoints_     = pts;
+    gpu_->uploaded = false;
 }
 
 std::vector<TPoint2D> waypoint_targets_from_yaml(const Yaml& y)

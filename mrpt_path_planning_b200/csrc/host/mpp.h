@@ -20,6 +20,7 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <string>
 #include <vector>
@@ -346,6 +347,25 @@ class CostEvaluator
     virtual double operator()(const MoveEdgeSE2_TPS& edge) const    = 0;
 };
 
+namespace detail
+{
+/** The private one-edge GPU context behind operator() of the two built-in evaluators. A planner keeps ITS evaluator
+ *  slots resident in its own context; a direct operator() call (a user calling the plugin, Planner::cost_path_segment,
+ *  or the planner's host-plugin path for evaluators beyond MPPB_MAX_EVALUATORS) must not disturb them, and may come
+ *  from any thread: it runs on a context of its own, created on first use on the same device, behind a mutex. */
+struct EvaluatorGpu
+{
+    std::mutex m;
+    mppb_ctx*  ctx      = nullptr;
+    bool       uploaded = false;
+    double     key[6]   = {0, 0, 0, 0, 0, 0};  // the public parameters the resident copy was made from
+    ~EvaluatorGpu()
+    {
+        if (ctx) mppb_ctx_destroy(ctx);
+    }
+};
+}  // namespace detail
+
 class CostEvaluatorCostMap : public CostEvaluator
 {
    public:
@@ -365,7 +385,10 @@ class CostEvaluatorCostMap : public CostEvaluator
     double              x_min = 0, y_min = 0, x_max = 0, y_max = 0;
     int                 size_x = 0, size_y = 0;
     std::vector<double> cells;  // row-major [size_y][size_x]
-    mppb_ctx*           ctx_ = nullptr;
+    mppb_ctx*           ctx_ = nullptr;  // the context the table was built on (tells operator() which device to use)
+
+   private:
+    std::shared_ptr<detail::EvaluatorGpu> gpu_ = std::make_shared<detail::EvaluatorGpu>();
 };
 
 class CostEvaluatorPreferredWaypoint : public CostEvaluator
@@ -379,12 +402,15 @@ class CostEvaluatorPreferredWaypoint : public CostEvaluator
         static Parameters FromYAML(const Yaml& c);
     };
     explicit CostEvaluatorPreferredWaypoint(mppb_ctx* ctx) : ctx_(ctx) {}
-    void   setPreferredWaypoints(const std::vector<TPoint2D>& pts) { waypoints_ = pts; }
+    void   setPreferredWaypoints(const std::vector<TPoint2D>& pts);
     double operator()(const MoveEdgeSE2_TPS& edge) const override;  // one-edge GPU batch
 
     Parameters            params_;
     std::vector<TPoint2D> waypoints_;
-    mppb_ctx*             ctx_ = nullptr;
+    mppb_ctx*             ctx_ = nullptr;  // tells operator() which device to use
+
+   private:
+    std::shared_ptr<detail::EvaluatorGpu> gpu_ = std::make_shared<detail::EvaluatorGpu>();
 };
 
 /** reads the `target: [x, y]` entries of a waypoint-sequence YAML (src/data/Waypoints.cpp:85-105) */

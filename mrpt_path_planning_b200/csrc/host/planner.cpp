@@ -476,21 +476,28 @@ struct TPS_Astar::Impl
     mppb_ctx*  ctx    = nullptr;
     bool       ownCtx = false;
 
-    // what is resident in the context
-    std::vector<const ptg_t*> uploadedPtgs;
+    // what is resident in the context. Each kind of resident data carries the context's epoch counter as it was
+    // right after our upload: another planner on the same context, or a direct mppb_set_* call, bumps it.
+    std::vector<std::pair<const ptg_t*, uint64_t>> uploadedPtgs;  // (object, ptg_t::revision())
+    uint64_t                  ptgEpoch = 0;
     std::vector<int>          columnOffset;  // per PTG: first column of its collision-grid row, or -1
+    // The reference re-reads ObstacleSource::obstacles() on every plan() (TPS_Astar.cpp:125-137). The cloud stays
+    // resident here only while its CONTENT is unchanged: the key holds a hash of every coordinate (a cloud updated
+    // in place — clear() plus the same number of insertPoint() calls, a freed buffer reallocated at the same
+    // address — changes it), not buffer addresses.
     struct CloudKey
     {
-        std::vector<const void*> data;
-        std::vector<size_t>      sizes;
-        bool                     hasBox = false;
-        float                    box[4] = {0, 0, 0, 0};
-        bool                     operator==(const CloudKey& o) const
+        std::vector<size_t>   sizes;
+        std::vector<uint64_t> hashes;
+        bool                  hasBox = false;
+        float                 box[4] = {0, 0, 0, 0};
+        bool                  operator==(const CloudKey& o) const
         {
-            return data == o.data && sizes == o.sizes && hasBox == o.hasBox && std::memcmp(box, o.box, sizeof(box)) == 0;
+            return sizes == o.sizes && hashes == o.hashes && hasBox == o.hasBox && std::memcmp(box, o.box, sizeof(box)) == 0;
         }
     } uploadedCloud;
-    bool cloudValid = false;
+    bool     cloudValid = false;
+    uint64_t cloudEpoch = 0;
 
     // evaluators resident in the context: object, its table and the parameters the device copy depends on.
     // A CostEvaluatorCostMap / PreferredWaypoint is immutable once built (as in the reference, whose grid and
@@ -912,7 +919,7 @@ struct TPS_Astar::Impl::Query
     }
 
     // ---- phases C + D: neighbour selection and tentative edges (TPS_Astar.cpp:738-814, 269-341) ----
-    void phaseCD(const float* gridRow, const double* holoOut)
+    void phaseCD(const float* gridRow, uint32_t gridCols, const double* holoOut)
     {
         // same containers and hash as the reference (their iteration order decides node ids), fed from a
         // per-expansion arena: the allocator does not influence bucket layout or iteration order
@@ -928,6 +935,7 @@ struct TPS_Astar::Impl::Query
                 lastPtg = c.ptgIdx;
             }
             po.tpsPointsEvaluated += c.copies;
+            MPP_ASSERT(!c.onGrid || c.evalIndex < gridCols);
             const double     raw          = c.onGrid ? static_cast<double>(gridRow[c.evalIndex]) : holoOut[c.evalIndex];
             const distance_t freeDistance = std::min(c.initDist, raw);
             if (c.relTrgDist >= freeDistance) continue;  // blocked
@@ -1111,9 +1119,9 @@ void TPS_Astar::Impl::ensureContext()
 
 void TPS_Astar::Impl::uploadPtgs(const TrajectoriesAndRobotShape& trs)
 {
-    std::vector<const ptg_t*> want;
-    for (const auto& p : trs.ptgs) want.push_back(p.get());
-    if (want == uploadedPtgs && static_cast<int>(want.size()) == mppb_num_ptgs(ctx)) return;
+    std::vector<std::pair<const ptg_t*, uint64_t>> want;
+    for (const auto& p : trs.ptgs) want.emplace_back(p.get(), p->revision());
+    if (want == uploadedPtgs && ptgEpoch == mppb_ptgs_epoch(ctx) && static_cast<int>(want.size()) == mppb_num_ptgs(ctx)) return;
     ck(ctx, mppb_clear_ptgs(ctx));
     uploadedPtgs.clear();
     columnOffset.clear();
@@ -1135,7 +1143,33 @@ void TPS_Astar::Impl::uploadPtgs(const TrajectoriesAndRobotShape& trs)
         columnOffset.push_back(mppb_ptg_column_offset(ctx, static_cast<int>(i)));
     }
     uploadedPtgs = want;
+    ptgEpoch     = mppb_ptgs_epoch(ctx);
 }
+
+namespace
+{
+// 64-bit content hash of a float array, four independent multiply-xor lanes (memory-bound: ~0.3 ms per 2^20 points)
+uint64_t hash_floats(const float* p, size_t n, uint64_t seed)
+{
+    uint64_t     h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull, seed ^ 0x27D4EB2F165667C5ull};
+    const size_t n8   = n / 8;
+    for (size_t i = 0; i < n8; i++)
+    {
+        uint64_t w[4];
+        std::memcpy(w, p + 8 * i, sizeof(w));
+        for (int j = 0; j < 4; j++) h[j] = (h[j] ^ w[j]) * 0x100000001B3ull + (h[j] >> 29);
+    }
+    for (size_t i = 8 * n8; i < n; i++)
+    {
+        uint32_t w;
+        std::memcpy(&w, p + i, sizeof(w));
+        h[i & 3] = (h[i & 3] ^ w) * 0x100000001B3ull + (h[i & 3] >> 29);
+    }
+    uint64_t r = n;
+    for (int j = 0; j < 4; j++) r = (r ^ h[j]) * 0xD6E8FEB86659FD93ull, r ^= r >> 32;
+    return r;
+}
+}  // namespace
 
 void TPS_Astar::Impl::uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, const float* box)
 {
@@ -1147,12 +1181,15 @@ void TPS_Astar::Impl::uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, 
         if (!os) continue;
         clouds.push_back(os->obstacles());
         dynamic = dynamic || os->dynamic();
-        key.data.push_back(clouds.back() ? clouds.back()->xs.data() : nullptr);
-        key.sizes.push_back(clouds.back() ? clouds.back()->size() : 0);
+        const PointCloud* c = clouds.back().get();
+        if (c) MPP_ASSERT(c->xs.size() == c->ys.size());
+        key.sizes.push_back(c ? c->size() : 0);
+        key.hashes.push_back(c ? hash_floats(c->xs.data(), c->size(), 1) ^ hash_floats(c->ys.data(), c->size(), 2) : 0);
     }
     key.hasBox = box != nullptr;
     if (box) std::memcpy(key.box, box, sizeof(key.box));
-    if (cloudValid && !dynamic && key == uploadedCloud) return;  // still resident from the previous plan
+    // still resident from the previous plan: same content, and nobody else touched the context's cloud since
+    if (cloudValid && !dynamic && key == uploadedCloud && cloudEpoch == mppb_obstacles_epoch(ctx)) return;
     bool first = true;
     for (const auto& c : clouds)
     {
@@ -1165,6 +1202,7 @@ void TPS_Astar::Impl::uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, 
     if (first) ck(ctx, mppb_set_obstacles_clipped(ctx, nullptr, nullptr, 0, 0.0, 0, box));
     uploadedCloud = key;
     cloudValid    = true;
+    cloudEpoch    = mppb_obstacles_epoch(ctx);
 }
 
 void TPS_Astar::Impl::uploadEvaluators()
@@ -1378,7 +1416,8 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
             Query& q = *qs[i];
             if (!q.active) return;
             const size_t a = q.slot;
-            q.phaseCD(rows ? rows + static_cast<size_t>(cols) * a : nullptr, holoOut ? holoOut + holoBase[a] : nullptr);
+            q.phaseCD(rows ? rows + static_cast<size_t>(cols) * a : nullptr, static_cast<uint32_t>(cols),
+                      holoOut ? holoOut + holoBase[a] : nullptr);
             q.needF = true;
         });
         lap(tl, 3);

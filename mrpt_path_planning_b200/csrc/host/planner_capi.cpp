@@ -13,6 +13,7 @@ struct mppb_planner
     std::unique_ptr<mpp::TPS_Astar>              planner;
     mpp::TrajectoriesAndRobotShape               trs;
     std::vector<mpp::ObstacleSource::Ptr>        obstacles;
+    std::vector<mpp::PointCloud::Ptr>            clouds;  // the clouds behind `obstacles`, same order
     std::vector<mpp::PlannerInput>               inputs;
     std::vector<mpp::PlannerOutput>              outputs;
     std::vector<mpp::MotionPrimitivesTreeSE2::path_t>          paths;
@@ -143,6 +144,19 @@ int mppb_planner_add_obstacles(mppb_planner* p, const float* xs, const float* ys
         pc->xs.assign(xs, xs + n);
         pc->ys.assign(ys, ys + n);
         p->obstacles.push_back(mpp::ObstacleSource::FromStaticPointcloud(pc));
+        p->clouds.push_back(pc);
+    });
+}
+
+int mppb_planner_update_obstacles(mppb_planner* p, size_t source, const float* xs, const float* ys, size_t n)
+{
+    if (!p || (n && (!xs || !ys))) return MPPB_ERR_INVALID_ARG;
+    return guarded(p, [&]() {
+        require(source < p->clouds.size(), "obstacle source index out of range");
+        // in place: with an unchanged point count the buffers keep their addresses, as a fixed-size scan does
+        mpp::PointCloud& pc = *p->clouds[source];
+        pc.xs.assign(xs, xs + n);
+        pc.ys.assign(ys, ys + n);
     });
 }
 
@@ -223,6 +237,10 @@ int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* 
             in.obstacles     = p->obstacles;
             in.ptgs          = p->trs;
         }
+        // results of the previous call go first: paths/pathEdges hold raw pointers into the trees of `outputs`, and
+        // a plan that throws must not leave them dangling behind a non-empty `outputs`
+        p->paths.clear();
+        p->pathEdges.clear();
         if (p->outputs.size() > 16)
         {
             // the previous batch's motion trees are hundreds of thousands of small nodes: drop them on several
@@ -235,11 +253,9 @@ int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* 
                 });
             for (auto& t : ts) t.join();
         }
+        p->outputs.clear();
         if (n_queries == 1)
-        {
-            p->outputs.clear();
             p->outputs.push_back(p->planner->plan(p->inputs[0]));
-        }
         else
             p->outputs = p->planner->plan_batch(p->inputs, n_threads);
         p->paths.assign(n_queries, {});
@@ -269,7 +285,7 @@ int mppb_planner_refine(mppb_planner* p, size_t query)
 {
     if (!p) return MPPB_ERR_INVALID_ARG;
     return guarded(p, [&]() {
-        require(query < p->outputs.size(), "query index out of range");
+        require(query < p->outputs.size() && query < p->paths.size(), "query index out of range");
         mpp::refine_trajectory(p->paths[query], p->pathEdges[query], p->inputs[query].ptgs);
     });
 }
@@ -278,7 +294,7 @@ int mppb_planner_path(mppb_planner* p, size_t query, double* nodes, double* edge
 {
     if (!p) return MPPB_ERR_INVALID_ARG;
     return guarded(p, [&]() {
-        require(query < p->outputs.size(), "query index out of range");
+        require(query < p->outputs.size() && query < p->paths.size(), "query index out of range");
         size_t i = 0;
         if (nodes)
             for (const auto& n : p->paths[query])
@@ -337,7 +353,7 @@ int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t ca
 
 int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample_period, char* buf, int64_t cap)
 {
-    if (!p || query >= p->outputs.size()) return -1;
+    if (!p || query >= p->outputs.size() || query >= p->pathEdges.size()) return -1;
     const int rc = guarded(p, [&]() {
         auto traj = mpp::plan_to_trajectory(p->pathEdges[query], p->inputs[query].ptgs, sample_period);
         // the trajectory is relative to the start pose; path-planner-cli re-bases it (path-planner-cli.cpp:396-399)

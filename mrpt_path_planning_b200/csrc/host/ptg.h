@@ -7,6 +7,7 @@
 // host: it lives in the CUDA kernels, which consume the tables these classes build.
 #pragma once
 #include <array>
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -87,6 +88,11 @@ class ptg_t
      *  so that they can run interleaved / concurrently; `this` must outlive the clone. */
     virtual std::unique_ptr<ptg_t> cloneForQuery() const = 0;
 
+    /** Process-wide unique id of this object's tables: every constructed PTG object draws a fresh one, so a new
+     *  object that happens to live at the address of a destroyed one is never mistaken for it by a planner that
+     *  keeps tables resident on the GPU. */
+    uint64_t revision() const { return revision_; }
+
    protected:
     virtual void     onNewNavDynamicState() {}
     unsigned         numPaths_    = 0;
@@ -94,6 +100,14 @@ class ptg_t
     bool             initialized_ = false;
     TNavDynamicState dynState_;
     int              target_k_ = -1;
+
+   private:
+    static uint64_t newRevision()
+    {
+        static std::atomic<uint64_t> next{1};
+        return next.fetch_add(1);
+    }
+    uint64_t revision_ = newRevision();
 };
 
 /** Parameters of mpp::ptg::DiffDrive_C (ini keys of share/ptgs_ackermann_vehicle.ini). */

@@ -268,6 +268,8 @@ struct mppb_ctx
     mppb::DevBuf       evalDescs;  // EvaluatorDev[MPPB_MAX_EVALUATORS]
     int                numEvals = 0;
     uint64_t           evalEpoch = 0;  // bumped by every change of the evaluator slots
+    uint64_t           cloudEpoch = 0; // bumped by every change of the resident obstacle cloud (mppb_set_obstacles*)
+    uint64_t           ptgEpoch   = 0; // bumped by mppb_clear_ptgs / mppb_set_ptg_*
 
     mppb::ColgridBuildBufs colgrid;
 

@@ -46,7 +46,7 @@ struct mppb_ctx
     float              box[4]  = {0, 0, 0, 0};
     int                holoPtgs = 0;
     int                numEvals = 0;
-    uint64_t           evalEpoch = 0;
+    uint64_t           evalEpoch = 0, cloudEpoch = 0, ptgEpoch = 0;
     uint64_t           calls[4]  = {0, 0, 0, 0};  // eval_nodes, eval_nodes_begin, eval_edge_costs, sync
 };
 
@@ -166,6 +166,7 @@ int mppb_host_free(void* p)
 int mppb_set_obstacles_clipped(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double, int append,
                                const float* box)
 {
+    ctx->cloudEpoch++;
     if (!append)
     {
         ctx->xs.clear();
@@ -188,8 +189,13 @@ int mppb_set_obstacles(mppb_ctx* ctx, const float* xs, const float* ys, size_t n
     return mppb_set_obstacles_clipped(ctx, xs, ys, n, bin, append, nullptr);
 }
 
+uint64_t mppb_obstacles_epoch(const mppb_ctx* ctx) { return ctx->cloudEpoch; }
+uint64_t mppb_ptgs_epoch(const mppb_ctx* ctx) { return ctx->ptgEpoch; }
+int      mppb_ctx_device(const mppb_ctx*) { return 0; }
+
 int mppb_clear_ptgs(mppb_ctx* ctx)
 {
+    ctx->ptgEpoch++;
     ctx->holoPtgs = 0;
     ctx->numPaths.clear();
     return MPPB_OK;
@@ -197,12 +203,14 @@ int mppb_clear_ptgs(mppb_ctx* ctx)
 int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* desc)
 {
     if (ptg_index != static_cast<int>(ctx->numPaths.size())) return fail(ctx, "mppb_sim: PTGs must be set in order");
+    ctx->ptgEpoch++;
     ctx->numPaths.push_back(desc->num_paths);
     return MPPB_OK;
 }
 int mppb_set_ptg_holo(mppb_ctx* ctx, int ptg_index, const mppb_ptg_holo_desc*)
 {
     if (ptg_index != static_cast<int>(ctx->numPaths.size())) return fail(ctx, "mppb_sim: PTGs must be set in order");
+    ctx->ptgEpoch++;
     ctx->numPaths.push_back(0);  // no columns in the collision-grid rows
     ctx->holoPtgs++;
     return MPPB_OK;

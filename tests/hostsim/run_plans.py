@@ -143,6 +143,31 @@ def main():
         same_plan(prod, ora, r_p, r_o)
     prod.close()
 
+    # --- obstacles changed between plans: in place (same count, same buffers) and by another planner on the context ---
+    for slot in (0, 1):
+        register_evaluator(slot, None, 0)
+    rng = np.random.default_rng(5)
+    xs2 = (xs + rng.uniform(-0.3, 0.3, xs.size)).astype(np.float32)
+    ys2 = (ys + rng.uniform(-0.3, 0.3, ys.size)).astype(np.float32)
+    pa = capi.Planner(ctx, p_ptgs, C1_PARAMS, C1_TIMESTAMPS)
+    pb = capi.Planner(ctx, p_ptgs, C1_PARAMS, C1_TIMESTAMPS)
+    pa.add_obstacles(xs, ys)
+    pb.add_obstacles(xs2, ys2)
+    oa = orc.Planner(o_ptgs, C1_PARAMS, C1_TIMESTAMPS)
+    ob = orc.Planner(o_ptgs, C1_PARAMS, C1_TIMESTAMPS)
+    oa.add_obstacles(xs, ys)
+    ob.add_obstacles(xs2, ys2)
+    ra, rb = oa.plan(start, goal, lo, hi), ob.plan(start, goal, lo, hi)
+    assert not np.array_equal(oa.tree(), ob.tree())  # the two clouds do give different searches
+    for _ in range(2):  # interleaved on ONE context: each planner must notice that the other replaced the cloud
+        same_plan(pa, oa, pa.plan(start, goal, lo, hi), ra)
+        same_plan(pb, ob, pb.plan(start, goal, lo, hi), rb)
+    pa.update_obstacles(0, xs2, ys2)  # same point count: the cloud's buffers keep their addresses
+    same_plan(pa, ob, pa.plan(start, goal, lo, hi), rb)
+    pa.close()
+    pb.close()
+    out["obstacles_changed_between_plans"] = True
+
     # --- no evaluators, expansion cap and point goal ---
     for slot in (0, 1):
         register_evaluator(slot, None, 0)

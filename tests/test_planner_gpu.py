@@ -276,3 +276,71 @@ def test_batch_without_evaluators_equals_single_plans_and_oracle(ctx, capi, orc,
             r_o = ora.plan(*q[:4])
             assert r_o["path_cost"] == batch[i]["path_cost"] and r_o["expanded"] == batch[i]["expanded"]
             assert np.array_equal(ora.tree(), trees[i])
+
+
+def test_obstacles_changed_between_plans_and_interleaved_planners(ctx, capi, orc, product_ackermann, oracle_ackermann):
+    """The reference re-reads ObstacleSource::obstacles() on every plan() (TPS_Astar.cpp:125-137). The product keeps
+    the cloud resident on the GPU; it must notice (a) a cloud updated in place — same point count, same buffers —
+    and (b) another planner on the same context that replaced the resident cloud in between."""
+    xs, ys, start, goal, lo, hi = c1_inputs()
+    rng = np.random.default_rng(5)
+    xs2 = (xs + rng.uniform(-0.3, 0.3, xs.size)).astype(np.float32)
+    ys2 = (ys + rng.uniform(-0.3, 0.3, ys.size)).astype(np.float32)
+    pa = capi.Planner(ctx, product_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    pb = capi.Planner(ctx, product_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    pa.add_obstacles(xs, ys)
+    pb.add_obstacles(xs2, ys2)
+    oa = orc.Planner(oracle_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    ob = orc.Planner(oracle_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    oa.add_obstacles(xs, ys)
+    ob.add_obstacles(xs2, ys2)
+    ra, rb = oa.plan(start, goal, lo, hi), ob.plan(start, goal, lo, hi)
+    assert not np.array_equal(oa.tree(), ob.tree())
+    for _ in range(2):
+        same_plan(pa, oa, pa.plan(start, goal, lo, hi), ra)
+        same_plan(pb, ob, pb.plan(start, goal, lo, hi), rb)
+    pa.update_obstacles(0, xs2, ys2)
+    same_plan(pa, ob, pa.plan(start, goal, lo, hi), rb)
+    pa.close()
+    pb.close()
+
+
+def test_interleaved_planners_with_different_ptg_tables_on_one_context(ctx, capi, orc, product_ackermann, oracle_ackermann):
+    """Two planners on one context whose PTG sets have the same count but different tables: each plan must run on
+    its own planner's tables (a PTG epoch on the context tells a planner that somebody else replaced them)."""
+    xs, ys, start, goal, lo, hi = c1_inputs()
+    p_small, o_small = capi.ackermann_ptgs(num_paths=61, ref_distance=4.0), orc.ackermann_ptgs(num_paths=61, ref_distance=4.0)
+    pa = capi.Planner(ctx, product_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    pb = capi.Planner(ctx, p_small, C1_PARAMS, C1_TIMESTAMPS)
+    oa = orc.Planner(oracle_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    ob = orc.Planner(o_small, C1_PARAMS, C1_TIMESTAMPS)
+    for pl in (pa, pb, oa, ob):
+        pl.add_obstacles(xs, ys)
+    ra, rb = oa.plan(start, goal, lo, hi), ob.plan(start, goal, lo, hi)
+    for _ in range(2):
+        same_plan(pa, oa, pa.plan(start, goal, lo, hi), ra)
+        same_plan(pb, ob, pb.plan(start, goal, lo, hi), rb)
+    pa.close()
+    pb.close()
+
+
+def test_more_than_max_evaluators_and_direct_plugin_calls_leave_the_planner_intact(ctx, capi, orc, product_ackermann,
+                                                                                   oracle_ackermann):
+    """Evaluators beyond MPPB_MAX_EVALUATORS run as host plugins through operator(), which uses a private context:
+    the planner's resident slots stay as they are and the costs are the reference's."""
+    xs, ys, start, goal, lo, hi = c1_inputs()
+    prod = capi.Planner(ctx, product_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    ora = orc.Planner(oracle_ackermann, C1_PARAMS, C1_TIMESTAMPS)
+    prod.add_obstacles(xs, ys)
+    ora.add_obstacles(xs, ys)
+    cm = orc.CostMap(xs, ys, 0.05, 0.4, 1.0, False, 0.0, None)
+    for i in range(6):  # 4 GPU slots + 2 host-plugin evaluators
+        if i % 2 == 0:
+            prod.add_costmap(xs, ys, 0.05, 0.4, 1.0, False, 0.0, None)
+            ora.add_costmap(cm)
+        else:
+            prod.add_waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.0 + 0.25 * i, 0.5, True)
+            ora.add_waypoints(orc.Waypoints(WAYPOINTS[0], WAYPOINTS[1], 1.0 + 0.25 * i, 0.5, True))
+    r_p, r_o = prod.plan(start, goal, lo, hi), ora.plan(start, goal, lo, hi)
+    same_plan(prod, ora, r_p, r_o)
+    prod.close()

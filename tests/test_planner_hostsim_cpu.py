@@ -38,5 +38,6 @@ def test_product_planner_host_logic_equals_oracle_planner(capi):
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["c2"]["expanded"] > 5 and out["cap_and_point_goal"] and out["batch"]["expansions"] > 50
+    assert out["obstacles_changed_between_plans"] is True
     assert out["c1"]["expanded"] > 20 and out["holonomic_batch"] and len(out["parameter_sets"]) == 6
     assert out["real_context_available"] is False or os.path.exists("/dev/nvidiactl")  # no CPU path in the product
