@@ -30,6 +30,11 @@
  *                               FromStaticPointObstacles (CostEvaluatorCostMap.cpp:91-97)
  *   mppb_set_obstacles_clipped <- ObstacleSource::apply_clipping_box (src/interfaces/
  *                               ObstacleSource.cpp:19-42)
+ *   mppb_set_ptg_paths / mppb_expand_nodes
+ *                            <- the candidate set, end poses, blocked test, per-cell selection and edge costs of
+ *                               TPS_Astar::find_feasible_paths_to_neighbors (src/algos/TPS_Astar.cpp:538-826) and
+ *                               of the per-neighbour block of plan() (:269-345), over the sampled PTG paths
+ *                               (src/ptgs/DiffDriveCollisionGridBased.cpp:766-811)
  *   mppb_planner_*           <- mpp::TPS_Astar::plan (src/algos/TPS_Astar.cpp:86-475) behind the
  *                               mpp::Planner interface (include/mpp/algos/Planner.h:23-62)
  *
@@ -262,6 +267,83 @@ int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const d
                                           const float* node_boxes, size_t n_cands, const mppb_holo_cand* cands,
                                           double clip_dist, double* out);
 
+/* ---- one A* expansion per node on the device (collision-grid PTGs) ------------------------
+ * Everything TPS_Astar::find_feasible_paths_to_neighbors (src/algos/TPS_Astar.cpp:538-826) and the per-neighbour
+ * block of TPS_Astar::plan (:269-345) compute for an expanded node that does not depend on the search state:
+ *   - the candidate TPS points in the reference's order (:614-697): per PTG the direct-to-goal point first, then
+ *     for k in (k-subset + goal k, ascending) / for t in ptg_sample_timestamps, with trjStep = round(t / dt);
+ *   - end pose, world-box test and lattice cell of each (:725-736; getPathPose/getPathDist are look-ups into the
+ *     sampled paths, DiffDriveCollisionGridBased.cpp:766-811);
+ *   - blocked iff relTrgDist >= freeDistance against the node's collision row (:749), computed by the same call;
+ *   - goal-cell rule (:765-778) and the best candidate per reached lattice cell, strict < (:783-796);
+ *   - per reached cell: neighbour pose, twist (getPathTwist rotated into the global frame, :290-297), the
+ *     neighbour's own world-box test (:303-308), the interpolated samples (edge_interpolated_path.cpp:51-72) and
+ *     cost_path_segment = estimatedExecTime + evaluators in slot order (Planner.cpp:15-29).
+ * What stays with the caller is what depends on the search: the insertion into its per-expansion hash map (whose
+ * iteration order assigns node ids), the visited test, relaxation, open set and tree. Results are returned per node
+ * in the order in which the reference's map would see each cell for the first time.
+ * Requires: every PTG of the context is of the collision-grid kind and has its sampled paths set. */
+typedef struct mppb_ptg_paths_desc
+{
+    int32_t         num_paths;
+    const uint32_t* path_begin;   /* [num_paths+1]: path k owns steps [path_begin[k], path_begin[k+1]) */
+    const float*    x;            /* TCPoint::x, y, phi, dist, v, w per step (DiffDriveCollisionGridBased.h:18-28) */
+    const float*    y;
+    const float*    phi;
+    const float*    dist;
+    const float*    v;
+    const float*    w;
+    const double*   cos_phi;      /* cos / sin of (double)phi per step, taken with the host C library */
+    const double*   sin_phi;
+    double          step_duration; /* getPathStepDuration() */
+    double          ref_distance;
+} mppb_ptg_paths_desc;
+/* sampled paths of PTG ptg_index, which must already be set as a collision-grid PTG (mppb_set_ptg_grid) */
+int mppb_set_ptg_paths(mppb_ctx* ctx, int ptg_index, const mppb_ptg_paths_desc* desc);
+
+#define MPPB_MAX_TIMESTAMPS 8
+#define MPPB_MAX_EXPLORE_PATHS 64
+struct mppb_astar_params;
+/* planner parameters the expansion depends on: grid_resolution_xy/yaw, max_ptg_trajectories_to_explore,
+ * ptg_sample_timestamps, path_interpolated_segments (the other fields are ignored) */
+int mppb_set_expand_params(mppb_ctx* ctx, const struct mppb_astar_params* params);
+/* upper bound of neighbours per node with the current PTGs and parameters = row length of mppb_expand_nodes' output;
+ * 0 if the expansion is not available (PTG of another kind, paths or parameters missing, limits exceeded) */
+uint32_t mppb_expand_max_neighbors(const mppb_ctx* ctx);
+
+typedef struct mppb_expand_node
+{
+    double   pose[3];                    /* x y phi of the node */
+    double   bbox_min[3], bbox_max[3];   /* world box of the node's query: x y phi */
+    int32_t  goal_k[MPPB_MAX_PTGS];      /* per PTG: path straight to the goal if inverseMap_WS2TP is exact, else -1 */
+    uint32_t goal_step[MPPB_MAX_PTGS];   /* its step if getPathStepForDist found one, else 0xffffffff */
+} mppb_expand_node;
+
+typedef struct mppb_neighbor
+{
+    int32_t  cell[3];    /* lattice cell x, y, yaw (TPS_Astar.h:224-230) */
+    uint8_t  ptg_index;
+    uint8_t  in_bbox;    /* the neighbour pose passes the test of TPS_Astar.cpp:303-308 */
+    uint16_t k;          /* chosen path */
+    uint32_t step;       /* relTrgStep */
+    float    ptg_dist;   /* relTrgDist: a float of the path table */
+    double   pose[3];    /* x_i.pose */
+    double   vel[3];     /* x_i.vel (global frame) */
+    double   cost;       /* cost_path_segment of the edge */
+} mppb_neighbor;
+
+/* out: [n_nodes][mppb_expand_max_neighbors()] records, of which the first out_counts[2*i] are valid for node i;
+ * out_counts[2*i+1] = TPS points evaluated for node i (with the reference's count of per-speed copies).
+ * use_node_boxes != 0: obstacle points outside a node's world box are ignored for it, as in mppb_eval_nodes_boxed
+ * (box = bbox_min/max narrowed to float). Host pointers; pinned buffers are used in place. */
+int mppb_expand_nodes(mppb_ctx* ctx, size_t n_nodes, const mppb_expand_node* nodes, int use_node_boxes, double clip_dist,
+                      mppb_neighbor* out, uint32_t* out_counts);
+/* split form: enqueues and returns; mppb_sync() completes it (buffers must stay alive and untouched until then) */
+int mppb_expand_nodes_begin(mppb_ctx* ctx, size_t n_nodes, const mppb_expand_node* nodes, int use_node_boxes,
+                            double clip_dist, mppb_neighbor* out, uint32_t* out_counts);
+/* the collision rows [n_nodes][mppb_total_paths] of the last mppb_expand_nodes call (device -> host copy; for tests) */
+int mppb_expand_last_rows(mppb_ctx* ctx, size_t n_nodes, float* out_rows);
+
 /* ---- stage (c): cost evaluators ---------------------------------------------------------
  * Evaluator slots are evaluated in slot order, like Planner::costEvaluators_ (Planner.cpp:22-26). */
 typedef struct mppb_costmap_desc
@@ -346,7 +428,10 @@ double mppb_ptg_init_dist(const mppb_ptg* ptg, int k);
 /* collision-grid tables (pointers stay valid while the PTG object lives); error if the PTG
  * is not of the collision-grid family */
 int mppb_ptg_grid_export(const mppb_ptg* ptg, mppb_ptg_grid_desc* out_desc);
-/* upload this PTG's tables as the next PTG of the context */
+/* sampled paths of a collision-grid PTG object (pointers stay valid while the PTG object lives); the descriptor type
+ * is declared with mppb_set_ptg_paths */
+int mppb_ptg_paths_export(const mppb_ptg* ptg, mppb_ptg_paths_desc* out_desc);
+/* upload this PTG's tables (collision grid and sampled paths) as the next PTG of the context */
 int mppb_ctx_add_ptg(mppb_ctx* ctx, const mppb_ptg* ptg);
 
 typedef struct mppb_holo_params

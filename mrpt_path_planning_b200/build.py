@@ -26,6 +26,7 @@ LINK_FLAGS = ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
 PER_FILE_FLAGS = {
     "tpobs_holo.cu": ["-fmad=false"],
     "edge_cost.cu": ["-fmad=false"],
+    "expand.cu": ["-fmad=false"],
 }
 OBJ_DIR = os.path.join(HERE, "lib", "obj")
 BIN_DIR = os.path.join(HERE, "bin")

@@ -87,6 +87,23 @@ class AstarParams(C.Structure):
                 ("max_expansions", C.c_uint64), ("ptg_sample_timestamps", c_double_p), ("num_timestamps", C.c_uint32)]
 
 
+MAX_PTGS = 8
+
+
+class PathsDesc(C.Structure):
+    _fields_ = [("num_paths", C.c_int32), ("path_begin", c_u32_p), ("x", c_float_p), ("y", c_float_p),
+                ("phi", c_float_p), ("dist", c_float_p), ("v", c_float_p), ("w", c_float_p), ("cos_phi", c_double_p),
+                ("sin_phi", c_double_p), ("step_duration", C.c_double), ("ref_distance", C.c_double)]
+
+
+EXPAND_NODE_DTYPE = np.dtype([("pose", np.float64, 3), ("bbox_min", np.float64, 3), ("bbox_max", np.float64, 3),
+                              ("goal_k", np.int32, MAX_PTGS), ("goal_step", np.uint32, MAX_PTGS)])
+NEIGHBOR_DTYPE = np.dtype([("cell", np.int32, 3), ("ptg_index", np.uint8), ("in_bbox", np.uint8), ("k", np.uint16),
+                           ("step", np.uint32), ("ptg_dist", np.float32), ("pose", np.float64, 3),
+                           ("vel", np.float64, 3), ("cost", np.float64)])
+assert EXPAND_NODE_DTYPE.itemsize == 136 and NEIGHBOR_DTYPE.itemsize == 80
+
+
 class PlanQuery(C.Structure):
     _fields_ = [("start", C.c_double * 6), ("goal", C.c_double * 6), ("goal_is_point", C.c_int32),
                 ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3)]
@@ -204,6 +221,14 @@ _SIGS = {
     "mppb_planner_tree": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64]),
     "mppb_planner_trajectory_txt": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int64]),
     "mppb_planner_gpu_stats": (C.c_int, [C.c_void_p, c_double_p]),
+    "mppb_set_ptg_paths": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PathsDesc)]),
+    "mppb_ptg_paths_export": (C.c_int, [C.c_void_p, C.POINTER(PathsDesc)]),
+    "mppb_set_expand_params": (C.c_int, [C.c_void_p, C.POINTER(AstarParams)]),
+    "mppb_expand_max_neighbors": (C.c_uint32, [C.c_void_p]),
+    "mppb_expand_nodes": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "mppb_expand_nodes_begin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double, C.c_void_p,
+                                          C.c_void_p]),
+    "mppb_expand_last_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 
@@ -348,6 +373,13 @@ class PTG:
 
     def init_dists(self):
         return np.array([self.init_dist(k) for k in range(self.num_paths)])
+
+    def paths_desc(self):
+        """mppb_ptg_paths_desc of a collision-grid PTG (pointers into this object's tables)"""
+        d = PathsDesc()
+        if lib().mppb_ptg_paths_export(self.h, C.byref(d)) != 0:
+            raise MppbError(lib().mppb_ptg_last_error().decode())
+        return d
 
     def grid(self):
         d = GridDesc()
@@ -501,6 +533,35 @@ class Context:
     def eval_holo_candidates_device(self, n_cands, d_cands, d_nodes_xycs, clip_dist, d_out):
         self._ck(lib().mppb_eval_holo_candidates_device(self.h, n_cands, _ptr(d_cands), _ptr(d_nodes_xycs),
                                                         clip_dist, _ptr(d_out)))
+
+    # -- one A* expansion per node on the device --
+    def set_expand_params(self, params, timestamps):
+        """params: the 9-list of workloads.DEMO_ASTAR_PARAMS (grid xy, grid yaw, ..., trajectories, speeds, segments)"""
+        ts = np.ascontiguousarray(timestamps, dtype=np.float64)
+        a = AstarParams(params[0], params[1], params[2], params[3], int(params[4]), int(params[5]), int(params[6]),
+                        0.0, 0, ts.ctypes.data_as(c_double_p), len(ts))
+        self._ck(lib().mppb_set_expand_params(self.h, C.byref(a)))
+
+    @property
+    def expand_max_neighbors(self):
+        return lib().mppb_expand_max_neighbors(self.h)
+
+    def expand_nodes(self, nodes, clip_dist, use_node_boxes=False):
+        """nodes: structured array (EXPAND_NODE_DTYPE) -> (neighbors [n][stride] NEIGHBOR_DTYPE, counts [n][2] uint32)"""
+        nodes = np.ascontiguousarray(nodes, dtype=EXPAND_NODE_DTYPE)
+        stride = self.expand_max_neighbors
+        if stride == 0:
+            raise MppbError("device expansion not available: " + lib().mppb_last_error(self.h).decode())
+        out = np.zeros((len(nodes), stride), dtype=NEIGHBOR_DTYPE)
+        counts = np.zeros((len(nodes), 2), dtype=np.uint32)
+        self._ck(lib().mppb_expand_nodes(self.h, len(nodes), _ptr(nodes), int(use_node_boxes), clip_dist, _ptr(out),
+                                         _ptr(counts)))
+        return out, counts
+
+    def expand_last_rows(self, n):
+        out = np.empty((n, self.total_paths), dtype=np.float32)
+        self._ck(lib().mppb_expand_last_rows(self.h, n, _ptr(out)))
+        return out
 
     # -- stage (c) --
     def clear_evaluators(self):

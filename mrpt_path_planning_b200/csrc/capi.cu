@@ -119,6 +119,12 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     }
     ctx->evalDescs.release();
     ctx->colgrid.release();
+    for (auto& t : ctx->pathTables) t.release();
+    ctx->expandDev.release();
+    for (mppb::DevBuf* b : {&ctx->dExpandIn, &ctx->dExpandRows, &ctx->dExpandOut, &ctx->dExpandCounts, &ctx->dExpandNodes, &ctx->dExpandBoxes})
+        b->release();
+    ctx->hExpandNodes.release();
+    ctx->hExpandBoxes.release();
     ctx->hNodes.release();
     ctx->hOut.release();
     ctx->hStage.release();
@@ -273,6 +279,8 @@ int mppb_clear_ptgs(mppb_ctx* ctx)
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->ptgEpoch++;
+    expand_invalidate(ctx);
+    for (auto& t : ctx->pathTables) t.release();
     release_groups(ctx);
     ctx->grids.clear();
     ctx->holos.clear();
@@ -478,6 +486,7 @@ int mppb_set_ptg_grid(mppb_ctx* ctx, int ptg_index, const mppb_ptg_grid_desc* d)
     }
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->ptgEpoch++;
+    expand_invalidate(ctx);
     PtgGridHost g;
     g.K         = d->num_paths;
     g.outOffset = ctx->totalPaths;
@@ -520,6 +529,7 @@ int mppb_set_ptg_holo(mppb_ctx* ctx, int ptg_index, const mppb_ptg_holo_desc* d)
         return fail(ctx, MPPB_ERR_INVALID_ARG, "bad HolonomicBlend constants");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->ptgEpoch++;
+    expand_invalidate(ctx);
     ctx->ptgKinds.push_back(1);
     ctx->holos.push_back(HoloPtgDev{d->robot_radius, d->v_max});
     HoloPtgDev table[MPPB_MAX_PTGS] = {};

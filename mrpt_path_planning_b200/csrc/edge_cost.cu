@@ -22,55 +22,13 @@
 #include <algorithm>
 #include <type_traits>
 
+#include "evaluators.cuh"
 #include "mppb_internal.cuh"
 
 namespace mppb
 {
 namespace
 {
-__device__ __forceinline__ double costmap_at(const EvaluatorDev& E, double x, double y)
-{
-    // CDynamicGrid::cellByPos -> x2idx = int((x - x_min) / res), null outside [0,size)
-    const int cx = static_cast<int>((x - E.xmin) / E.res);
-    const int cy = static_cast<int>((y - E.ymin) / E.res);
-    if (cx < 0 || cx >= E.nx || cy < 0 || cy >= E.ny) return .0;
-    return E.cells[cx + static_cast<size_t>(cy) * E.nx];
-}
-
-__device__ __forceinline__ double waypoints_at(const EvaluatorDev& E, double x, double y)
-{
-    const float qx = static_cast<float>(x), qy = static_cast<float>(y);
-    double      cost    = E.scale;
-    float       last    = -1.f;  // squared distance of the previous match
-    int         lastIdx = -1;
-    for (;;)
-    {
-        // next match in ascending (distance, index) order
-        float best    = 0.f;
-        int   bestIdx = -1;
-        for (int i = 0; i < E.nWps; i++)
-        {
-            const float2 w  = E.wps[i];
-            const float  dx = qx - w.x, dy = qy - w.y;
-            const float  d2 = dx * dx + dy * dy;
-            if (!(d2 < E.radiusSqrF)) continue;
-            if (!(d2 > last || (d2 == last && i > lastIdx))) continue;
-            if (bestIdx < 0 || d2 < best)
-            {
-                best    = d2;
-                bestIdx = i;
-            }
-        }
-        if (bestIdx < 0) break;
-        last             = best;
-        lastIdx          = bestIdx;
-        const float dist = sqrtf(best);
-        if (dist > E.radius || dist < 0) continue;
-        cost -= E.scale * (1.0 - sqrt(static_cast<double>(dist) / E.radius));
-    }
-    return cost > .0 ? cost : .0;
-}
-
 __global__ void __launch_bounds__(128)
     edge_cost_kernel(const EvaluatorDev* __restrict__ evals, int nEvals, int nEdges,
                      const double* __restrict__ from /* [n][4] x,y,cos,sin */,

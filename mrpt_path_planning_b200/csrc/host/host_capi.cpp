@@ -117,6 +117,16 @@ int mppb_ptg_grid_export(const mppb_ptg* p, mppb_ptg_grid_desc* out)
     return MPPB_OK;
     HOST_CATCH(MPPB_ERR_UNSUPPORTED)
 }
+int mppb_ptg_paths_export(const mppb_ptg* p, mppb_ptg_paths_desc* out)
+{
+    HOST_TRY
+    if (!p || !out) throw std::runtime_error("bad argument");
+    auto* dd = dynamic_cast<const mpp::DiffDrive_C*>(p->obj.get());
+    if (!dd) throw std::runtime_error("PTG is not of the collision-grid family");
+    *out = dd->pathsDesc();
+    return MPPB_OK;
+    HOST_CATCH(MPPB_ERR_UNSUPPORTED)
+}
 int mppb_ctx_add_ptg(mppb_ctx* ctx, const mppb_ptg* p)
 {
     if (!ctx || !p) return MPPB_ERR_INVALID_ARG;
@@ -128,7 +138,12 @@ int mppb_ctx_add_ptg(mppb_ctx* ctx, const mppb_ptg* p)
     mppb_ptg_grid_desc d;
     int                rc = mppb_ptg_grid_export(p, &d);
     if (rc != MPPB_OK) return rc;
-    return mppb_set_ptg_grid(ctx, mppb_num_ptgs(ctx), &d);
+    const int idx = mppb_num_ptgs(ctx);
+    rc            = mppb_set_ptg_grid(ctx, idx, &d);
+    if (rc != MPPB_OK) return rc;
+    // the sampled paths too: the device-side expansion (mppb_expand_nodes) looks end poses and distances up in them
+    const mppb_ptg_paths_desc pd = static_cast<const mpp::DiffDrive_C*>(p->obj.get())->pathsDesc();
+    return mppb_set_ptg_paths(ctx, idx, &pd);
 }
 
 int mppb_ptg_create_holo(const mppb_holo_params* p, mppb_ptg** out)

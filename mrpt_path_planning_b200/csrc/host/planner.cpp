@@ -117,6 +117,13 @@ class LatticeIndex
         }
     }
 
+    /** warm the cache line the look-up of (x, y, yaw) will start at (the search state of many interleaved queries is
+     *  far larger than the caches) */
+    void prefetch(int32_t x, int32_t y, int32_t yaw) const
+    {
+        __builtin_prefetch(&slots_[mix(x, y, yaw) & (slots_.size() - 1)]);
+    }
+
    private:
     struct Slot
     {
@@ -521,6 +528,15 @@ struct TPS_Astar::Impl
     std::vector<int> evalSlot;  // per costEvaluators_ entry: GPU slot or -1 (host plugin)
     int              numGpuEvals = 0;
 
+    // device-side expansion (mppb_expand_nodes): available when every PTG is of the collision-grid kind and every cost
+    // evaluator lives in a GPU slot; then phases A (second half), C, D and E leave the host altogether
+    bool                     useExpand = false;
+    uint32_t                 expandStride = 0;  // neighbour records per node in hNeighbors
+    Pinned<mppb_expand_node> hExpandIn;
+    Pinned<mppb_neighbor>    hNeighbors;
+    Pinned<uint32_t>         hExpandCounts;
+    void                     setupExpand();
+
     Pinned<double>         hPoses, hHoloOut, hFrom, hRel, hCost;
     Pinned<float>          hRows, hBoxes;
     Pinned<mppb_holo_cand> hCands;
@@ -600,6 +616,36 @@ struct TPS_Astar::Impl::Query
         }
         treeOps.clear();
     }
+
+    // ---- device-side expansion path: what the host still does per expansion, and the compact log of the search ----
+    // The motion tree does not influence the search, so the expansion path does not touch it while searching: every
+    // accepted relaxation is appended to a log (80 bytes, no allocation), and the tree — one map node, one list node
+    // with a 600-byte edge and its interpolated samples per TREE NODE — is built once, when the query ends, from each
+    // node's last entry. That is the reference's tree: a node is expanded at most once (visited nodes are never
+    // relaxed again), so a parent's cost is final when its children are logged, a node's tree cost equals its gScore,
+    // and a parent's edge list is its surviving children in log order.
+    bool             useExpand = false;
+    mppb_expand_node expIn{};  // this round's record for mppb_expand_nodes
+    struct ExpansionRec
+    {
+        TNodeID      parent;
+        SE2_KinState stateFrom;
+        TPose2D      goalRel;  // the goal as seen from the parent (MoveEdgeSE2_TPS::ptgFinalRelativeGoal)
+    };
+    struct EdgeRec
+    {
+        uint32_t     expansion;  // index into expansions
+        uint32_t     step;
+        TNodeID      child;
+        SE2_KinState stateTo;
+        double       cost;
+        float        ptgDist;
+        uint16_t     k;
+        uint8_t      ptg;
+    };
+    std::vector<ExpansionRec>               expansions;
+    std::vector<EdgeRec>                    edgeLog;
+    std::optional<std::pair<TNodeID, TPose2D>> goalSnap;  // node whose pose popNext() moved onto the exact goal
 
     // phase scratch
     std::pmr::monotonic_buffer_resource arena{16384};
@@ -701,7 +747,10 @@ struct TPS_Astar::Impl::Query
                 cur.state.pose          = in->stateGoal.state.pose();
                 po.bestNodeIdCostToGoal = 0;
             }
-            po.motionTree.node_state(*cur.id).pose = cur.state.pose;
+            if (useExpand)
+                goalSnap = std::make_pair(*cur.id, cur.state.pose);  // applied when the tree is built
+            else
+                po.motionTree.node_state(*cur.id).pose = cur.state.pose;
             finish();
             return false;
         }
@@ -716,6 +765,7 @@ struct TPS_Astar::Impl::Query
     void finish()
     {
         flushTreeOps();
+        if (useExpand) buildTreeFromLog(po.motionTree);
         done       = true;
         current    = nullptr;
         po.success = po.goalNodeId == po.bestNodeId;
@@ -1090,6 +1140,178 @@ struct TPS_Astar::Impl::Query
             planner->progressCallback_(pcd);
         }
     }
+
+    // ======== device-side expansion path ========
+    // ---- phase A, what is left of it: PTG state, and the path straight to the goal per PTG (TPS_Astar.cpp:587-611,
+    // :650-677; inverseMap_WS2TP takes atan2 from the host C library) ----
+    void phaseAExpand()
+    {
+        const Node&   from    = *current;
+        const TPose2D relGoal = in->stateGoal.asSE2KinState().pose - from.state.pose;
+        expansions.push_back(ExpansionRec{from.id.value(), from.state, relGoal});
+        for (int i = 0; i < 3; i++)
+        {
+            const double* lo = &in->worldBboxMin.x;  // (x, y, phi are consecutive doubles of TPose2D)
+            const double* hi = &in->worldBboxMax.x;
+            expIn.bbox_min[i] = lo[i];
+            expIn.bbox_max[i] = hi[i];
+        }
+        expIn.pose[0] = from.state.pose.x;
+        expIn.pose[1] = from.state.pose.y;
+        expIn.pose[2] = from.state.pose.phi;
+        const auto itSpeed = nodesWithDesiredSpeed.find(goalCellIndices);
+        for (size_t ptgIdx = 0; ptgIdx < trs.ptgs.size(); ptgIdx++)
+        {
+            ptg_t& ptg = *trs.ptgs[ptgIdx];
+            {
+                TNavDynamicState ds;
+                (ds.curVelLocal = from.state.vel).rotate(-from.state.pose.phi);
+                ds.relTarget      = relGoal;
+                ds.targetRelSpeed = itSpeed != nodesWithDesiredSpeed.end() ? itSpeed->second : 0;
+                ptg.updateNavDynamicState(ds);
+            }
+            if (ptg.isSpeedTrimmable()) ptg.trimmableSpeed_ = 1.0;  // where the reference's loops leave it (:721-722, :282-284)
+            int    goalK = 0;
+            double goalD = 0;
+            expIn.goal_k[ptgIdx]    = -1;
+            expIn.goal_step[ptgIdx] = 0xffffffffu;
+            if (ptg.inverseMap_WS2TP(relGoal.x, relGoal.y, goalK, goalD, P->grid_resolution_xy))
+            {
+                expIn.goal_k[ptgIdx] = goalK;
+                ptg_step_t goalStep  = 0;
+                // the reference passes the normalised distance here (TPS_Astar.cpp:658)
+                if (ptg.getPathStepForDist(static_cast<uint16_t>(goalK), goalD, goalStep)) expIn.goal_step[ptgIdx] = goalStep;
+            }
+        }
+    }
+
+    // ---- what phases C, D and F leave to the host (TPS_Astar.cpp:783-814, :303-314, :343-451): the reference's hash
+    // map decides the ORDER in which the reached cells become nodes (its iteration order assigns node ids), then the
+    // visited test and the relaxation of each neighbour. recs: the node's reached cells in first-insertion order. ----
+    void consumeNeighbors(const mppb_neighbor* recs, uint32_t n, uint32_t tpsPoints)
+    {
+        po.tpsPointsEvaluated += tpsPoints;
+        arena.release();
+        std::pmr::unordered_map<NodeCoords, uint32_t, NodeCoordsHash> bestPaths(&arena);
+        for (uint32_t i = 0; i < n; i++)
+        {
+            const mppb_neighbor& r = recs[i];
+            bestPaths[NodeCoords(r.cell[0], r.cell[1], r.cell[2])] = i;
+            grid.prefetch(r.cell[0], r.cell[1], r.cell[2]);
+        }
+        const uint32_t expIdx = static_cast<uint32_t>(expansions.size() - 1);
+        for (const auto& kv : bestPaths)  // unordered_map order, as in the reference
+        {
+            const mppb_neighbor& r = recs[kv.second];
+            if (!r.in_bbox) continue;
+            Node& nbNode = grid[kv.first];
+            if (!nbNode.id.has_value())
+            {
+                nbNode.id         = nextFreeId++;
+                nbNode.state.pose = TPose2D(r.pose[0], r.pose[1], r.pose[2]);
+                nbNode.state.vel  = TTwist2D(r.vel[0], r.vel[1], r.vel[2]);
+            }
+            if (nbNode.visited) continue;
+            const cost_t edgeCost = r.cost;
+            po.edgesCosted++;
+            MPP_ASSERT(edgeCost > .0);
+            const cost_t tentative_gScore = current->gScore + edgeCost;
+            if (tentative_gScore >= nbNode.gScore) continue;
+            nbNode.cameFrom = current;
+            nbNode.gScore   = tentative_gScore;
+            // NOTE: the heuristic is taken at the node's previous state, before it is overwritten
+            const cost_t costToGoal = planner->heuristic(nbNode.state, in->stateGoal);
+            nbNode.fScore           = tentative_gScore + costToGoal;
+            if (!nbNode.pendingInOpenSet)
+            {
+                nbNode.pendingInOpenSet = true;
+                openSet.insert(nbNode.fScore, &nbNode);
+            }
+            nbNode.state.pose = TPose2D(r.pose[0], r.pose[1], r.pose[2]);
+            nbNode.state.vel  = TTwist2D(r.vel[0], r.vel[1], r.vel[2]);
+            edgeLog.push_back(EdgeRec{expIdx, r.step, nbNode.id.value(), nbNode.state, edgeCost, r.ptg_dist, r.k, r.ptg_index});
+            if (costToGoal < po.bestNodeIdCostToGoal)
+            {
+                po.bestNodeIdCostToGoal = costToGoal;
+                po.bestNodeId           = nbNode.id.value();
+            }
+        }
+        const double tNow = seconds_since(t0);
+        if (tNow > P->maximumComputationTime || po.nodesExpanded >= P->maxExpansions)
+        {
+            finish();  // timeout: the best node so far is the result
+            return;
+        }
+        if (planner->progressCallback_ && (tNow - tLastCallback) > planner->progressCallbackCallPeriod_ && po.bestNodeId)
+        {
+            tLastCallback = tNow;
+            MotionPrimitivesTreeSE2 tree;  // the tree as it stands now
+            buildTreeFromLog(tree);
+            auto [foundPath, pathEdges] = tree.backtrack_path(*po.bestNodeId);
+            ProgressCallbackData pcd;
+            pcd.bestCostFromStart = tree.nodes().at(*po.bestNodeId).cost_;
+            pcd.bestCostToGoal    = po.bestNodeIdCostToGoal;
+            pcd.bestFinalNode     = po.bestNodeId;
+            pcd.bestPath          = std::move(pathEdges);
+            pcd.costEvaluators    = &planner->costEvaluators_;
+            pcd.originalPlanInput = in;
+            pcd.tree              = &tree;
+            planner->progressCallback_(pcd);
+        }
+    }
+
+    // The motion tree of the reference from the log: see the comment at `edgeLog`.
+    void buildTreeFromLog(MotionPrimitivesTreeSE2& tree) const
+    {
+        if (tree.nodes().empty())
+        {
+            tree.root = po.motionTree.root;
+            tree.insert_root_node(tree.root, in->stateStart);
+        }
+        // last entry of every node = its edge, parent and cost; FIRST entry = its state in the tree (the reference's
+        // rewire_node_parent updates parent and cost only, MotionPrimitivesTree.h:173-215)
+        std::vector<uint32_t> lastOf(static_cast<size_t>(nextFreeId), 0xffffffffu), firstOf(static_cast<size_t>(nextFreeId), 0xffffffffu);
+        for (size_t i = 0; i < edgeLog.size(); i++)
+        {
+            const size_t c = static_cast<size_t>(edgeLog[i].child);
+            lastOf[c]      = static_cast<uint32_t>(i);
+            if (firstOf[c] == 0xffffffffu) firstOf[c] = static_cast<uint32_t>(i);
+        }
+        MotionPrimitivesTreeSE2::TListEdges*   parentEdges = nullptr;
+        const MotionPrimitivesTreeSE2::node_t* parentNode  = nullptr;
+        uint32_t                               curExp      = 0xffffffffu;
+        for (size_t i = 0; i < edgeLog.size(); i++)
+        {
+            const EdgeRec& r = edgeLog[i];
+            if (r.expansion != curExp)
+            {
+                // (a parent whose children were all re-parented later still owns an — empty — edge list, as after
+                // the reference's rewire_node_parent)
+                const ExpansionRec& x = expansions[r.expansion];
+                parentEdges           = &tree.edges_to_children[x.parent];
+                parentNode            = &tree.nodes().at(x.parent);
+                curExp                = r.expansion;
+            }
+            if (lastOf[static_cast<size_t>(r.child)] != i) continue;  // superseded by a later, cheaper edge
+            const ExpansionRec& x = expansions[r.expansion];
+            MoveEdgeSE2_TPS     e;
+            e.parentId             = x.parent;
+            e.ptgDist              = r.ptgDist;
+            e.ptgIndex             = static_cast<int8_t>(r.ptg);
+            e.ptgPathIndex         = static_cast<int16_t>(r.k);
+            e.ptgTrimmableSpeed    = 1.0;  // never assigned by the reference's neighbour search: stays 1.0
+            e.ptgFinalGoalRelSpeed = 0;
+            e.ptgFinalRelativeGoal = x.goalRel;
+            e.stateFrom            = x.stateFrom;
+            e.stateTo              = r.stateTo;
+            e.ptgStep              = r.step;
+            e.cost                 = r.cost;
+            edge_interpolated_path(e, trs, trs.ptgs[r.ptg]->getPathPose(r.k, r.step), r.step, P->pathInterpolatedSegments);
+            tree.insert_child_of(*parentEdges, *parentNode, x.parent, r.child,
+                                 edgeLog[firstOf[static_cast<size_t>(r.child)]].stateTo, std::move(e));
+        }
+        if (goalSnap) tree.node_state(goalSnap->first).pose = goalSnap->second;
+    }
 };
 
 // ======================================================================================================
@@ -1132,6 +1354,8 @@ void TPS_Astar::Impl::uploadPtgs(const TrajectoriesAndRobotShape& trs)
         {
             const mppb_ptg_grid_desc d = dd->gridDesc();
             ck(ctx, mppb_set_ptg_grid(ctx, static_cast<int>(i), &d));
+            const mppb_ptg_paths_desc pd = dd->pathsDesc();
+            ck(ctx, mppb_set_ptg_paths(ctx, static_cast<int>(i), &pd));
         }
         else if (auto* hb = dynamic_cast<const HolonomicBlend*>(p))
         {
@@ -1266,6 +1490,34 @@ void TPS_Astar::Impl::uploadEvaluators()
     evalEpoch     = mppb_evaluators_epoch(ctx);
 }
 
+// Decide whether this plan can use the device-side expansion and hand the planner parameters to the context.
+void TPS_Astar::Impl::setupExpand()
+{
+    useExpand                = false;
+    expandStride             = 0;
+    static const bool disabled = std::getenv("MPPB_NO_EXPAND") != nullptr;  // A/B measurements and tests of the host phases
+    if (disabled) return;
+    for (int c : columnOffset)
+        if (c < 0) return;  // a PTG of another kind (HolonomicBlend: its candidates need the host's expressions and libm)
+    for (int slot : evalSlot)
+        if (slot < 0) return;  // an evaluator that runs as a host plugin needs the edge on the host
+    const TPS_Astar_Parameters& P = self->params_;
+    if (P.ptg_sample_timestamps.empty() || P.ptg_sample_timestamps.size() > MPPB_MAX_TIMESTAMPS) return;
+    mppb_astar_params a{};
+    a.grid_resolution_xy              = P.grid_resolution_xy;
+    a.grid_resolution_yaw             = P.grid_resolution_yaw;
+    a.SE2_metricAngleWeight           = P.SE2_metricAngleWeight;
+    a.heuristic_heading_weight        = P.heuristic_heading_weight;
+    a.max_ptg_trajectories_to_explore = P.max_ptg_trajectories_to_explore;
+    a.max_ptg_speeds_to_explore       = P.max_ptg_speeds_to_explore;
+    a.path_interpolated_segments      = static_cast<uint32_t>(P.pathInterpolatedSegments);
+    a.ptg_sample_timestamps           = P.ptg_sample_timestamps.data();
+    a.num_timestamps                  = static_cast<uint32_t>(P.ptg_sample_timestamps.size());
+    if (mppb_set_expand_params(ctx, &a) != MPPB_OK) return;
+    expandStride = mppb_expand_max_neighbors(ctx);  // 0: outside the kernel's limits -> host phases
+    useExpand    = expandStride > 0;
+}
+
 std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads)
 {
     ensureContext();
@@ -1286,6 +1538,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     auto tSetup = Clock::now();
     uploadPtgs(ins[0]->ptgs);
     uploadEvaluators();
+    setupExpand();
 
     std::vector<std::unique_ptr<Query>> qs(Q);
     for (size_t i = 0; i < Q; i++)
@@ -1300,6 +1553,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         if (Q > 1)  // interleaved queries must not share mutable PTG state
             for (auto& p : q.trs.ptgs) p = std::shared_ptr<ptg_t>(p->cloneForQuery());
         q.deferTreeOps = Q == 1 && std::getenv("MPPB_NO_OVERLAP") == nullptr;
+        q.useExpand    = useExpand;
         q.start();
     }
     // obstacles: one query -> clipped to its world box at upload (ObstacleSource::apply_clipping_box);
@@ -1322,8 +1576,52 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         t = now;
     };
     lap(tSetup, 0);
+    // ---- device-side expansion: per round ONE parallel host section (relaxation of the previous round's neighbours,
+    // pop, goal direction per PTG) and ONE GPU call (collision rows + expansion of every current node) ----
+    for (; useExpand;)
+    {
+        auto tl = Clock::now();
+        const mppb_neighbor* nbrs   = hNeighbors.p;
+        const uint32_t*      counts = hExpandCounts.p;
+        pool.run(Q, [&](size_t i) {
+            Query& q = *qs[i];
+            q.active = false;
+            if (q.done) return;
+            if (q.needF)
+            {
+                q.consumeNeighbors(nbrs + q.slot * expandStride, counts[2 * q.slot], counts[2 * q.slot + 1]);
+                q.needF = false;
+            }
+            q.active = q.popNext();
+            if (q.active) q.phaseAExpand();
+        });
+        active.clear();
+        for (size_t i = 0; i < Q; i++)
+            if (qs[i]->active) active.push_back(i);
+        if (active.empty()) break;
+        const size_t      A  = active.size();
+        mppb_expand_node* in = hExpandIn.reserve(A);
+        mppb_neighbor*    nb = hNeighbors.reserve(A * expandStride);
+        uint32_t*         ct = hExpandCounts.reserve(2 * A);
+        for (size_t a = 0; a < A; a++)
+        {
+            Query& q = *qs[active[a]];
+            q.slot   = a;
+            q.needF  = true;
+            in[a]    = q.expIn;
+        }
+        lap(tl, 1);
+        const auto tB = Clock::now();
+        ck(ctx, mppb_expand_nodes_begin(ctx, A, in, sharedCloud ? 1 : 0, qs[active[0]]->MAX_XY_DIST, nb, ct));
+        ck(ctx, mppb_sync(ctx));
+        st.gpuSeconds += seconds_since(tB);
+        st.collisionBatches++;
+        st.nodesEvaluated += A;
+        for (size_t a = 0; a < A; a++) st.edgesCosted += ct[2 * a];
+        lap(tl, 2);
+    }
     double* costs = nullptr;  // evaluator values of the previous round's tentative edges (pinned buffer)
-    for (;;)
+    for (; !useExpand;)
     {
         auto tl = Clock::now();
         // ---- per query, no barrier in between: F of the previous round, pop, A of this round ----

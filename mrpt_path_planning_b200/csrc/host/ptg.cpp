@@ -207,6 +207,27 @@ void DiffDrive_C::simulate()
         tw_.insert(tw_.end(), P.w.begin(), P.w.end());
         pathBegin_.push_back(tx_.size());
     }
+    pathBegin32_.assign(pathBegin_.begin(), pathBegin_.end());
+    // heading cos/sin per step (TTwist2D::rotate(phi) of getPathTwist takes them of the float heading widened to double)
+    tcos_.resize(total);
+    tsin_.resize(total);
+    std::atomic<size_t> nextBlock{0};
+    auto                trig = [&]() {
+        for (;;)
+        {
+            const size_t b = nextBlock.fetch_add(1) * 8192;
+            if (b >= total) break;
+            for (size_t i = b; i < std::min(total, b + 8192); i++)
+            {
+                tcos_[i] = std::cos(static_cast<double>(tphi_[i]));
+                tsin_[i] = std::sin(static_cast<double>(tphi_[i]));
+            }
+        }
+    };
+    th.clear();
+    for (unsigned i = 1; i < nth; i++) th.emplace_back(trig);
+    trig();
+    for (auto& t : th) t.join();
 }
 
 size_t DiffDrive_C::at(uint16_t k, uint32_t step) const
@@ -243,7 +264,7 @@ TTwist2D DiffDrive_C::getPathTwist(uint16_t k, uint32_t step) const
 {
     const size_t i = at(k, step);
     TTwist2D     tw(tv_[i], 0, tw_[i]);
-    tw.rotate(tphi_[i]);
+    tw.rotateCS(tcos_[i], tsin_[i]);  // rotate(phi) with the tabulated cos/sin of the same argument
     return tw;
 }
 bool DiffDrive_C::isPointInsideRobotShape(double x, double y) const
@@ -434,6 +455,25 @@ class DiffDriveView final : public ptg_t
 }  // namespace
 
 std::unique_ptr<ptg_t> DiffDrive_C::cloneForQuery() const { return std::make_unique<DiffDriveView>(this); }
+
+mppb_ptg_paths_desc DiffDrive_C::pathsDesc() const
+{
+    mppb_ptg_paths_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.num_paths     = static_cast<int32_t>(numPaths_);
+    d.path_begin    = pathBegin32_.data();
+    d.x             = tx_.data();
+    d.y             = ty_.data();
+    d.phi           = tphi_.data();
+    d.dist          = tdist_.data();
+    d.v             = tv_.data();
+    d.w             = tw_.data();
+    d.cos_phi       = tcos_.data();
+    d.sin_phi       = tsin_.data();
+    d.step_duration = stepDuration_;
+    d.ref_distance  = refDistance_;
+    return d;
+}
 
 mppb_ptg_grid_desc DiffDrive_C::gridDesc() const
 {

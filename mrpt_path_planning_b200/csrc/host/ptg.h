@@ -147,6 +147,8 @@ class DiffDrive_C : public ptg_t
 
     /** descriptor of the collision grid for mppb_set_ptg_grid (pointers owned by this object) */
     mppb_ptg_grid_desc gridDesc() const;
+    /** descriptor of the sampled trajectories for mppb_set_ptg_paths (pointers owned by this object) */
+    mppb_ptg_paths_desc pathsDesc() const;
     std::unique_ptr<ptg_t> cloneForQuery() const override;
 
     const DiffDriveCParams& params() const { return p_; }
@@ -163,6 +165,10 @@ class DiffDrive_C : public ptg_t
     // trajectories: flat SoA, path k owns [pathBegin_[k], pathBegin_[k+1])
     std::vector<size_t> pathBegin_;
     std::vector<float>  tx_, ty_, tphi_, tdist_, tv_, tw_;
+    std::vector<uint32_t> pathBegin32_;
+    // cos/sin of every step's heading, (double)phi through the C library: getPathTwist() rotates the step's (v, 0, w) by
+    // it, and the GPU expansion kernel needs the same values (device cos/sin differ from glibc's in the last bits)
+    std::vector<double> tcos_, tsin_;
     // collision grid (CDynamicGrid geometry) in CSR form, entries sorted by k inside a cell
     double                gxmin_ = 0, gymin_ = 0, gres_ = 0;
     int                   gnx_ = 0, gny_ = 0;

@@ -101,6 +101,29 @@ struct EvaluatorDev
     float         radiusSqrF;
 };
 
+// Sampled paths of one collision-grid PTG as the expansion kernel sees them (expand.cu)
+struct PathTableDev
+{
+    const uint32_t* begin;     // [K+1]
+    const float *   x, *y, *phi, *dist, *v, *w;
+    const double *  cs, *sn;   // cos / sin of (double)phi, host libm
+    const double*   initDist;  // [K] initTPObstacleSingle: min(refDistance, dist of the last step)
+    int             K, colOffset;
+    double          dt;
+};
+// Everything of TPS_Astar_Parameters + PTG set that shapes the candidate set of an expansion
+struct ExpandParamsDev
+{
+    double       resXY, resYaw, halfCell;
+    int          nSeg, nPtgs, nT, maxCand;
+    int          nK[MPPB_MAX_PTGS];       // size of the k subset per PTG
+    int          candBase[MPPB_MAX_PTGS + 1];  // first candidate slot of each PTG: 1 + (nK + 1) * nT slots per PTG
+    int          copies[MPPB_MAX_PTGS];   // identical per-speed copies each TPS point stands for
+    uint16_t     kSubset[MPPB_MAX_PTGS][MPPB_MAX_EXPLORE_PATHS];  // ascending, no duplicates
+    uint32_t     tsStep[MPPB_MAX_PTGS][MPPB_MAX_TIMESTAMPS];      // round(t / dt)
+    PathTableDev paths[MPPB_MAX_PTGS];
+};
+
 // ---------------------------------------------------------------------------------------
 // Host-side context
 // ---------------------------------------------------------------------------------------
@@ -211,6 +234,20 @@ struct PtgGridHost
                maxRadius == o.maxRadius && shapeX == o.shapeX && shapeY == o.shapeY;
     }
 };
+// device copy of one PTG's sampled paths
+struct PathTableHost
+{
+    bool   set = false;
+    int    K   = 0;
+    double dt = 0, refDistance = 0;
+    DevBuf begin, x, y, phi, dist, v, w, cs, sn, initDist;
+    std::vector<uint32_t> hostBegin;  // step counts are needed on the host to size the candidate set
+    void   release()
+    {
+        for (DevBuf* b : {&begin, &x, &y, &phi, &dist, &v, &w, &cs, &sn, &initDist}) b->release();
+        set = false;
+    }
+};
 struct GridGroupHost
 {
     GridGroupDev dev;
@@ -273,6 +310,18 @@ struct mppb_ctx
 
     mppb::ColgridBuildBufs colgrid;
 
+    // device-side expansion (expand.cu): sampled paths per PTG index, the planner parameters, staging
+    mppb::PathTableHost  pathTables[MPPB_MAX_PTGS];
+    bool                 expandParamsSet = false;
+    mppb_astar_params    expandParams{};
+    double               expandTimestamps[MPPB_MAX_TIMESTAMPS] = {};
+    mppb::ExpandParamsDev expandHost{};   // what was last uploaded
+    bool                 expandReady = false;  // expandDev matches PTGs + parameters
+    mppb::DevBuf         expandDev;       // ExpandParamsDev on the device
+    mppb::DevBuf         dExpandIn, dExpandRows, dExpandOut, dExpandCounts, dExpandNodes, dExpandBoxes;
+    mppb::PinnedBuf      hExpandNodes, hExpandBoxes;
+    size_t               expandRowsNodes = 0;  // rows held by dExpandRows (mppb_expand_last_rows)
+
     // staging for the host entry points
     mppb::PinnedBuf hNodes, hOut, hStage, hNodesHolo;
     mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes, dNodesHolo, dBoxesHolo;
@@ -302,5 +351,9 @@ int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const u
                       double* dOut, size_t nSamples = 0);
 int launch_costmap_d2(mppb_ctx* ctx, const CloudStore& cs, double xmin, double ymin, double res, int nx, int ny,
                       float clearance, float* dOut);
+// expansion kernel over the collision rows dRows [n][totalPaths] (expand.cu)
+int launch_expand(mppb_ctx* ctx, size_t nNodes, const mppb_expand_node* dIn, const double* dNodes4, const float* dRows,
+                  mppb_neighbor* dOut, uint32_t* dCounts);
+void expand_invalidate(mppb_ctx* ctx);  // PTGs or parameters changed: the device parameter block must be rebuilt
 
 }  // namespace mppb

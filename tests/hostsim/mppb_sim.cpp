@@ -19,7 +19,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/mppb.h"
@@ -48,6 +51,22 @@ struct mppb_ctx
     int                numEvals = 0;
     uint64_t           evalEpoch = 0, cloudEpoch = 0, ptgEpoch = 0;
     uint64_t           calls[4]  = {0, 0, 0, 0};  // eval_nodes, eval_nodes_begin, eval_edge_costs, sync
+    uint64_t           expandCalls = 0, expandNodes = 0;
+    // device-side expansion: the product's sampled paths (copied at mppb_set_ptg_paths) and the planner parameters
+    struct Paths
+    {
+        bool                  set = false;
+        int                   K   = 0;
+        double                dt = 0, refDistance = 0;
+        std::vector<uint32_t> begin;
+        std::vector<float>    x, y, phi, dist, v, w;
+        std::vector<double>   cs, sn;
+    } paths[MPPB_MAX_PTGS];
+    bool                paramsSet = false;
+    double              resXY = 0, resYaw = 0;
+    unsigned            M = 0, S = 0, nSeg = 0;
+    std::vector<double> timestamps;
+    std::vector<float>  lastRows;
 };
 
 namespace
@@ -354,6 +373,248 @@ int mppb_costmap_nearest_d2(mppb_ctx*, const float* xs, const float* ys, size_t 
             out[cx + static_cast<size_t>(cy) * nx] = best;
         }
     return MPPB_OK;
+}
+
+// ---- device-side expansion (include/mppb.h, "one A* expansion per node"), answered on the CPU in the REFERENCE's own
+// sequential form: std::set of trajectory indices, TPS points in a vector, the goal-cell set, a map of best paths with
+// the order of first insertion, std::map of time-keyed samples (TPS_Astar.cpp:538-826, :269-345,
+// edge_interpolated_path.cpp:51-72). Collision rows and evaluator values come from the oracle.
+int mppb_set_ptg_paths(mppb_ctx* ctx, int ptg_index, const mppb_ptg_paths_desc* d)
+{
+    if (ptg_index < 0 || ptg_index >= static_cast<int>(ctx->numPaths.size())) return fail(ctx, "mppb_sim: bad ptg_index");
+    mppb_ctx::Paths& P = ctx->paths[ptg_index];
+    const size_t     K = static_cast<size_t>(d->num_paths), n = d->path_begin[K];
+    P.K                = d->num_paths;
+    P.dt               = d->step_duration;
+    P.refDistance      = d->ref_distance;
+    P.begin.assign(d->path_begin, d->path_begin + K + 1);
+    P.x.assign(d->x, d->x + n);
+    P.y.assign(d->y, d->y + n);
+    P.phi.assign(d->phi, d->phi + n);
+    P.dist.assign(d->dist, d->dist + n);
+    P.v.assign(d->v, d->v + n);
+    P.w.assign(d->w, d->w + n);
+    P.cs.assign(d->cos_phi, d->cos_phi + n);
+    P.sn.assign(d->sin_phi, d->sin_phi + n);
+    P.set = true;
+    return MPPB_OK;
+}
+int mppb_set_expand_params(mppb_ctx* ctx, const mppb_astar_params* a)
+{
+    ctx->resXY  = a->grid_resolution_xy;
+    ctx->resYaw = a->grid_resolution_yaw;
+    ctx->M      = a->max_ptg_trajectories_to_explore;
+    ctx->S      = a->max_ptg_speeds_to_explore;
+    ctx->nSeg   = a->path_interpolated_segments;
+    ctx->timestamps.assign(a->ptg_sample_timestamps, a->ptg_sample_timestamps + a->num_timestamps);
+    ctx->paramsSet = true;
+    return MPPB_OK;
+}
+static bool sim_expand_available(const mppb_ctx* ctx)
+{
+    if (!ctx->paramsSet || ctx->numPaths.empty() || ctx->holoPtgs > 0) return false;
+    if (std::getenv("MPPBSIM_NO_EXPAND")) return false;
+    for (size_t p = 0; p < ctx->numPaths.size(); p++)
+        if (!ctx->paths[p].set) return false;
+    return true;
+}
+uint32_t mppb_expand_max_neighbors(const mppb_ctx* ctx)
+{
+    if (!sim_expand_available(ctx)) return 0;
+    uint32_t n = 0;
+    for (size_t p = 0; p < ctx->numPaths.size(); p++) n += 1 + (ctx->M + 1) * static_cast<uint32_t>(ctx->timestamps.size());
+    return n;
+}
+
+namespace
+{
+double sim_wrap_2pi(double a)
+{
+    const bool neg = a < 0;
+    a              = std::fmod(a, 2.0 * M_PI);
+    return neg ? a + 2.0 * M_PI : a;
+}
+double sim_wrap_pi(double a) { return sim_wrap_2pi(a + M_PI) - M_PI; }
+using Cell = std::tuple<int32_t, int32_t, int32_t>;
+}  // namespace
+
+int mppb_expand_nodes(mppb_ctx* ctx, size_t n_nodes, const mppb_expand_node* nodes, int use_node_boxes, double clip,
+                      mppb_neighbor* out, uint32_t* out_counts)
+{
+    if (!sim_expand_available(ctx)) return fail(ctx, "mppb_sim: expansion not available");
+    ctx->expandCalls++;
+    ctx->expandNodes += n_nodes;
+    const uint32_t stride = mppb_expand_max_neighbors(ctx);
+    size_t         cols   = 0;
+    for (int k : ctx->numPaths) cols += static_cast<size_t>(k);
+    ctx->lastRows.assign(n_nodes * cols, 0.f);
+    const int nP = static_cast<int>(ctx->numPaths.size());
+    for (size_t i = 0; i < n_nodes; i++)
+    {
+        const mppb_expand_node& N = nodes[i];
+        float* row = ctx->lastRows.data() + i * cols;
+        float  box[4] = {static_cast<float>(N.bbox_min[0]), static_cast<float>(N.bbox_min[1]),
+                         static_cast<float>(N.bbox_max[0]), static_cast<float>(N.bbox_max[1])};
+        if (eval_nodes(ctx, 1, N.pose, use_node_boxes ? box : nullptr, clip, row) != MPPB_OK) return MPPB_ERR_STATE;
+        const double fromC = std::cos(N.pose[2]), fromS = std::sin(N.pose[2]);
+        const double halfCell = ctx->resXY * 0.5;
+        struct Best
+        {
+            int      ptg = -1, k = -1;
+            uint32_t step = 0;
+            double   dist = std::numeric_limits<double>::max();
+            double   rel[3] = {0, 0, 0};
+        };
+        std::map<Cell, Best> bestPaths;
+        std::vector<Cell>    order;  // cells in the order of their first insertion into bestPaths
+        uint32_t             tps = 0;
+        size_t               colBase = 0;
+        for (int p = 0; p < nP; p++)
+        {
+            const mppb_ctx::Paths& T = ctx->paths[p];
+            std::set<int>          trajIdxs;
+            for (size_t m = 0; m < ctx->M; m++)
+            {
+                const size_t q = m * static_cast<size_t>(T.K - 1) / (ctx->M - 1);
+                trajIdxs.insert(static_cast<int>(std::lrint(static_cast<double>(q))));
+            }
+            unsigned nSpeeds = 0;
+            for (double sp = 1.0 / ctx->S; sp < 1.001; sp += 1.0 / ctx->S) nSpeeds++;
+            struct Tps
+            {
+                int      k;
+                uint32_t step;
+                bool     target;
+            };
+            std::vector<Tps> pts;
+            if (N.goal_k[p] >= 0)
+            {
+                if (N.goal_step[p] != 0xffffffffu) pts.push_back({N.goal_k[p], N.goal_step[p], true});
+                trajIdxs.insert(N.goal_k[p]);
+            }
+            // (the per-speed copies of a DiffDrive_C TPS point are identical: one is evaluated, nSpeeds are counted)
+            for (int k : trajIdxs)
+                for (double t : ctx->timestamps)
+                {
+                    const uint32_t step = static_cast<uint32_t>(static_cast<int>(std::lrint(t / T.dt)));
+                    if (step >= T.begin[k + 1] - T.begin[k]) continue;
+                    pts.push_back({k, step, false});
+                }
+            std::set<Cell> goalNodeCoords;
+            for (const Tps& tp : pts)
+            {
+                if (tp.step == 0) continue;
+                const size_t idx = static_cast<size_t>(T.begin[tp.k]) + tp.step;
+                const double relTrgDist = T.dist[idx];
+                const double rx = T.x[idx], ry = T.y[idx], rphi = T.phi[idx];
+                const double ax = N.pose[0] + rx * fromC - ry * fromS, ay = N.pose[1] + rx * fromS + ry * fromC;
+                const double aphi = sim_wrap_pi(N.pose[2] + rphi);
+                if (ax < N.bbox_min[0] || ay < N.bbox_min[1] || aphi < N.bbox_min[2]) continue;
+                if (ax > N.bbox_max[0] - halfCell || ay > N.bbox_max[1] - halfCell || aphi > N.bbox_max[2]) continue;
+                tps += nSpeeds;
+                const double init = std::min(T.refDistance, static_cast<double>(T.dist[T.begin[tp.k + 1] - 1]));
+                const double freeDistance = std::min(init, static_cast<double>(row[colBase + tp.k]));
+                if (relTrgDist >= freeDistance) continue;
+                // TPS_Astar.h:224-230
+                const float fx = static_cast<float>(ax), fy = static_cast<float>(ay), fyaw = static_cast<float>(aphi);
+                const float pi = static_cast<float>(M_PI), twoPi = static_cast<float>(2.0 * M_PI);
+                float       a   = fyaw + pi;
+                const bool  neg = a < 0;
+                a               = std::fmod(a, twoPi);
+                if (neg) a += twoPi;
+                const Cell nc(static_cast<int32_t>(fx / ctx->resXY), static_cast<int32_t>(fy / ctx->resXY),
+                              static_cast<int32_t>((a - pi) / ctx->resYaw));
+                if (tp.target)
+                    goalNodeCoords.insert(nc);
+                else if (goalNodeCoords.count(nc))
+                    continue;
+                auto it = bestPaths.find(nc);
+                if (it == bestPaths.end())
+                {
+                    it = bestPaths.emplace(nc, Best()).first;
+                    order.push_back(nc);
+                }
+                if (relTrgDist < it->second.dist)
+                {
+                    Best& b = it->second;
+                    b.dist = relTrgDist, b.ptg = p, b.k = tp.k, b.step = tp.step;
+                    b.rel[0] = rx, b.rel[1] = ry, b.rel[2] = rphi;
+                }
+            }
+            colBase += static_cast<size_t>(T.K);
+        }
+        if (order.size() > stride) return fail(ctx, "mppb_sim: more neighbours than the row holds");
+        mppb_neighbor* o = out + i * stride;
+        for (size_t j = 0; j < order.size(); j++)
+        {
+            const Best&            b = bestPaths.at(order[j]);
+            const mppb_ctx::Paths& T = ctx->paths[b.ptg];
+            const size_t           base = T.begin[b.k], idx = base + b.step;
+            mppb_neighbor          r{};
+            r.cell[0] = std::get<0>(order[j]), r.cell[1] = std::get<1>(order[j]), r.cell[2] = std::get<2>(order[j]);
+            r.ptg_index = static_cast<uint8_t>(b.ptg);
+            r.k         = static_cast<uint16_t>(b.k);
+            r.step      = b.step;
+            r.ptg_dist  = static_cast<float>(b.dist);
+            r.pose[0]   = N.pose[0] + b.rel[0] * fromC - b.rel[1] * fromS;
+            r.pose[1]   = N.pose[1] + b.rel[0] * fromS + b.rel[1] * fromC;
+            r.pose[2]   = sim_wrap_pi(N.pose[2] + b.rel[2]);
+            const double v = T.v[idx], w = T.w[idx];
+            const double lx = v * T.cs[idx] - 0.0 * T.sn[idx], ly = v * T.sn[idx] + 0.0 * T.cs[idx];
+            r.vel[0] = lx * fromC - ly * fromS;
+            r.vel[1] = lx * fromS + ly * fromC;
+            r.vel[2] = w;
+            r.in_bbox = !(r.pose[0] < N.bbox_min[0] || r.pose[1] < N.bbox_min[1] || r.pose[2] < N.bbox_min[2] ||
+                          r.pose[0] > N.bbox_max[0] || r.pose[1] > N.bbox_max[1] || r.pose[2] > N.bbox_max[2]);
+            // edge_interpolated_path: a std::map keyed by time, later assignments overwrite
+            std::map<double, std::pair<double, double>> ip;
+            ip[0 * T.dt] = {0.0, 0.0};
+            for (size_t s2 = 0; s2 < ctx->nSeg; s2++)
+            {
+                const size_t iStep = ((s2 + 1) * static_cast<size_t>(b.step)) / (ctx->nSeg + 2);
+                ip[iStep * T.dt]   = {T.x[base + iStep], T.y[base + iStep]};
+            }
+            ip[static_cast<size_t>(b.step) * T.dt] = {b.rel[0], b.rel[1]};
+            std::vector<double> rel;
+            for (const auto& kv : ip)
+            {
+                rel.push_back(kv.second.first);
+                rel.push_back(kv.second.second);
+            }
+            const uint32_t off[2] = {0, static_cast<uint32_t>(ip.size())};
+            double         cost   = static_cast<size_t>(b.step) * T.dt;
+            for (int e = 0; e < ctx->numEvals; e++)
+            {
+                if (!g_oracleEval[e]) return fail(ctx, "mppb_sim: register an oracle evaluator for every slot");
+                double c1 = 0;
+                if (orc_eval_edge_costs(g_oracleEval[e], g_oracleEvalKind[e], 1, N.pose, off, rel.data(), &c1) != 0)
+                    return fail(ctx, "mppb_sim: orc_eval_edge_costs failed");
+                cost += c1;
+            }
+            r.cost = cost;
+            o[j]   = r;
+        }
+        out_counts[2 * i + 0] = static_cast<uint32_t>(order.size());
+        out_counts[2 * i + 1] = tps;
+    }
+    return MPPB_OK;
+}
+int mppb_expand_nodes_begin(mppb_ctx* ctx, size_t n_nodes, const mppb_expand_node* nodes, int use_node_boxes, double clip,
+                            mppb_neighbor* out, uint32_t* out_counts)
+{
+    return mppb_expand_nodes(ctx, n_nodes, nodes, use_node_boxes, clip, out, out_counts);
+}
+int mppb_expand_last_rows(mppb_ctx* ctx, size_t n_nodes, float* out_rows)
+{
+    size_t cols = 0;
+    for (int k : ctx->numPaths) cols += static_cast<size_t>(k);
+    std::memcpy(out_rows, ctx->lastRows.data(), n_nodes * cols * sizeof(float));
+    return MPPB_OK;
+}
+void mppbsim_expand_counts(mppb_ctx* ctx, uint64_t* out2)
+{
+    out2[0] = ctx->expandCalls;
+    out2[1] = ctx->expandNodes;
 }
 
 }  // extern "C"

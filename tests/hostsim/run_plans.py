@@ -75,6 +75,18 @@ def call_counts():
     return dict(eval_nodes=v[0], eval_nodes_begin=v[1], eval_edge_costs=v[2], sync=v[3])
 
 
+# the product planner uses the device-side expansion for collision-grid PTG sets unless MPPB_NO_EXPAND is set; the
+# test runs this script once each way, so that both the slim host path and the full host phases are compared
+EXPAND = os.environ.get("MPPB_NO_EXPAND") is None
+
+
+def expand_counts(ctx):
+    v = (C.c_uint64 * 2)()
+    sim.mppbsim_expand_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    sim.mppbsim_expand_counts(ctx.h, v)
+    return (v[0], v[1])
+
+
 def same_plan(prod, ora, r_p, r_o, query=0):
     for key in ("success", "tree_nodes", "tree_parents", "expanded", "tps_points", "edges_costed", "best_node",
                 "goal_node"):
@@ -136,7 +148,12 @@ def main():
     assert np.array_equal(n_p, n_o) and np.array_equal(e_p, e_o)
     out["c2"] = dict(expanded=int(r_p["expanded"]), tree_nodes=int(r_p["tree_nodes"]), success=bool(r_p["success"]))
     cc = call_counts()
-    assert cc["eval_nodes_begin"] == r_p["expanded"] and cc["sync"] >= r_p["expanded"], cc  # split form used
+    if EXPAND:  # device-side expansion: one expansion call (and one sync) per A* iteration, no separate cost batches
+        assert cc["eval_nodes_begin"] == 0 and cc["eval_edge_costs"] == 0 and cc["sync"] >= r_p["expanded"], cc
+        assert expand_counts(ctx) == (r_p["expanded"], r_p["expanded"])
+    else:
+        assert cc["eval_nodes_begin"] == r_p["expanded"] and cc["sync"] >= r_p["expanded"], cc  # split form used
+        assert expand_counts(ctx) == (0, 0)
     # replanning on the same objects, other start/goal (PTG state carried over on both sides)
     for s, g in (([4.0, 2.5, 0.8, 0.2, 0.1, 0.0], [3.0, -0.5, -1.0, 0, 0, 0]), (start, [1.5, 3.0, 2.0, 0, 0, 0])):
         r_p, r_o = prod.plan(s, g, lo, hi), ora.plan(s, g, lo, hi)
@@ -275,6 +292,7 @@ def main():
             done.append(pname + "/" + kind)
             prod.close()
     out["parameter_sets"] = done
+    out["expand"] = EXPAND
     print(json.dumps(out))
 
 

@@ -30,13 +30,23 @@ def build_sim():
     return SIM_LIB
 
 
-def test_product_planner_host_logic_equals_oracle_planner(capi):
+import pytest
+
+
+@pytest.mark.parametrize("expand", [True, False], ids=["device_expansion", "host_phases"])
+def test_product_planner_host_logic_equals_oracle_planner(capi, expand):
+    """expand=True: collision-grid PTG sets go through mppb_expand_nodes (answered by the stand-in in the reference's
+    sequential form) and the host does relaxation only; expand=False (MPPB_NO_EXPAND): the full host phases A, C, D, F."""
     capi.lib()  # the product library is built and loads
     env = dict(os.environ, LD_PRELOAD=build_sim())
+    env.pop("MPPB_NO_EXPAND", None)
+    if not expand:
+        env["MPPB_NO_EXPAND"] = "1"
     r = subprocess.run([sys.executable, os.path.join(HERE, "hostsim", "run_plans.py")], env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["expand"] is expand
     assert out["c2"]["expanded"] > 5 and out["cap_and_point_goal"] and out["batch"]["expansions"] > 50
     assert out["obstacles_changed_between_plans"] is True
     assert out["c1"]["expanded"] > 20 and out["holonomic_batch"] and len(out["parameter_sets"]) == 6
