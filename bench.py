@@ -179,14 +179,14 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, sample_nodes=sample),
+        "config": config_dict(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-C4_MAX_EXPANSIONS = 400
+C4_COSTMAP = (0.10, 0.5, 4.0)  # resolution, preferredClearanceDistance, maxCost
 WAYPOINTS01 = ([3.0, 5.0, 9.0, 20.0, 26.0], [2.0, 5.0, 8.0, 7.0, 3.0])  # share/mvsim-demo-waypoints01.yaml targets
 
 
@@ -248,35 +248,66 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
         pl.close()
         out[name] = d
 
-    # C4: independent queries on a 200x200 m wall map (2^20 points on ~8 km of wall segments)
-    nq = args.queries
-    mx, my = wl.walls_cloud(args.points, EXTENT, wall_fraction=1.0, spacing=0.008, seed=wl.C3_WALLS_SEED)
-    allq = wl.planning_queries(nq * world)
-    mine = [allq[i] for i in range(rank, nq * world, world)]
+    # C4: 4096 independent queries in total (strong scaling: 4096 / N per rank, by query id) on a synthetic 200x200 m
+    # map of 2^20 points (round pillars: workloads.pillars_map), demo planner parameters, the obstacle costmap as cost
+    # evaluator (share/costmap-obstacles.yaml values at 0.10 m cells: one map for the whole world), per-query world box
+    # = start/goal +- 4 m, an expansion cap instead of a time limit
+    nq_total = args.queries
+    mx, my, pillars = wl.pillars_map(args.points, EXTENT)
+    allq = wl.planning_queries_free(nq_total, pillars, EXTENT)
+    mine = [allq[i] for i in range(rank, nq_total, world)]
     params = list(wl.DEMO_ASTAR_PARAMS)
-    params[8] = C4_MAX_EXPANSIONS
+    params[8] = args.c4_max_expansions
     ptgs = capi.ackermann_ptgs()
     pl = capi.Planner(ctx, ptgs, params, wl.DEMO_ASTAR_TIMESTAMPS)
     pl.add_obstacles(mx, my)
-    n_threads = max(1, (os.cpu_count() or 1) // world)
-    pl.plan_many(mine[:8], n_threads=n_threads)  # warm-up
     t0 = time.perf_counter()
-    res = pl.plan_many(mine, n_threads=n_threads)
-    t_batch = time.perf_counter() - t0
-    st = pl.gpu_stats()
-    d = {"queries_per_gpu": nq, "max_expansions": C4_MAX_EXPANSIONS, "batch_s": t_batch,
-         "expansions": int(sum(r["expanded"] for r in res)), "successes": int(sum(r["success"] for r in res)),
-         "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_s": st["gpu_seconds"],
-         "phase_seconds": st["phase_seconds"], "host_threads": n_threads}
+    pl.add_costmap(mx, my, C4_COSTMAP[0], C4_COSTMAP[1], C4_COSTMAP[2], False, 0.0, None)
+    t_cm = time.perf_counter() - t0
+    cpus = os.cpu_count() or 1
+    try:
+        import torch
+
+        gpus_on_box = max(world, torch.cuda.device_count())
+    except Exception:
+        gpus_on_box = world
+    runs = {}
+    # (a) every host thread this rank may use; (b) the share of the host a rank has when all GPUs of the box are busy
+    # (cpu_count / GPUs on the box, the same number at every N): the figure to compare across N
+    # (the fixed-thread run takes every fourth query of this rank's share: with an eighth of the host it would
+    # otherwise take minutes)
+    for label, n_threads, qsel in (("all_threads", max(1, cpus // world), mine),
+                                   ("fixed_threads", max(1, cpus // max(8, gpus_on_box)), mine[::4])):
+        pl.plan_many(mine[:16], n_threads=n_threads)  # warm-up
+        t0 = time.perf_counter()
+        res = pl.plan_many(qsel, n_threads=n_threads)
+        t_batch = time.perf_counter() - t0
+        st = pl.gpu_stats()
+        runs[label] = {"host_threads": n_threads, "batch_s": t_batch, "queries": len(qsel),
+                       "expansions": int(sum(r["expanded"] for r in res)), "successes": int(sum(r["success"] for r in res)),
+                       "gpu_batches": st["collision_batches"] + st["cost_batches"], "gpu_s": st["gpu_seconds"],
+                       "phase_seconds": st["phase_seconds"]}
+    d = dict(runs["all_threads"])
+    d.update({"queries_total": nq_total, "queries_this_rank": len(mine), "max_expansions": args.c4_max_expansions,
+              "map": "workloads.pillars_map: %d points on %d round pillars (r 0.5-1.5 m), 200x200 m" % (len(mx), len(pillars)),
+              "cost_evaluators": "CostEvaluatorCostMap %.2f m cells, clearance %.1f m, maxCost %.0f (whole map, %d s build)" % (
+                  C4_COSTMAP[0], C4_COSTMAP[1], C4_COSTMAP[2], round(t_cm)),
+              "costmap_build_s": t_cm, "scaling": "strong (queries_total fixed)", "fixed_threads": runs["fixed_threads"],
+              "tree_nodes": int(sum(r["tree_nodes"] for r in res)),
+              "max_rss_gb": __import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0})
     if with_cpu:
-        # bounded CPU sample: a few of the same queries through the oracle planner, one per host thread
+        # bounded CPU sample: a few of the same queries through the reference planner, one per host thread
         from concurrent.futures import ThreadPoolExecutor
 
-        optgs_pool = [orc.ackermann_ptgs() for _ in range(min(4, os.cpu_count() or 1))]
+        t0 = time.perf_counter()
+        ocm = orc.CostMap(mx, my, C4_COSTMAP[0], C4_COSTMAP[1], C4_COSTMAP[2], False, 0.0, None)
+        d["cpu_costmap_build_s"] = time.perf_counter() - t0
+        optgs_pool = [orc.ackermann_ptgs() for _ in range(min(4, cpus))]
 
         def one(i):
             opl = orc.Planner(optgs_pool[i % len(optgs_pool)], params, wl.DEMO_ASTAR_TIMESTAMPS)
             opl.add_obstacles(mx, my)
+            opl.add_costmap(ocm)
             return opl.plan(*mine[i][:4]), opl.tree()
 
         n_cpu = len(optgs_pool)
@@ -468,19 +499,34 @@ def run_ours(args, rank, local_rank, world):
     if world > 1 and not args.no_c5:
         c5 = cloud_sharded_bench(ctx, dev, stream, rank, world, args, d_nodes, d_out, flush)
     c4_s = planner["c4_batch"]["batch_s"] if planner else 0.0
+    c4f_s = planner["c4_batch"]["fixed_threads"]["batch_s"] if planner else 0.0
+    c4_exp = float(planner["c4_batch"]["expansions"]) if planner else 0.0
+    c4f_exp = float(planner["c4_batch"]["fixed_threads"]["expansions"]) if planner else 0.0
+    c4_succ = float(planner["c4_batch"]["successes"]) if planner else 0.0
+    c4f_q = float(planner["c4_batch"]["fixed_threads"]["queries"]) if planner else 0.0
     per_rank = None
     if world > 1:
         mine = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = {"kernel_ms": [float(a[0]) for a in allr], "e2e_ms": [float(a[1]) for a in allr]}
-        t = torch.tensor([dev_ms, e2e_ms, c4_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_ms, c4_s, c4f_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, c4_s = t.tolist()
+        dev_ms, e2e_ms, c4_s, c4f_s = t.tolist()
+        t = torch.tensor([c4_exp, c4f_exp, c4_succ, c4f_q], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        c4_exp, c4f_exp, c4_succ, c4f_q = t.tolist()
     if planner:
         c4 = planner["c4_batch"]
-        c4["plans_per_s"] = world * c4["queries_per_gpu"] / c4_s
+        c4["plans_per_s"] = c4["queries_total"] / c4_s
         c4["batch_s_max_over_ranks"] = c4_s
+        c4["expansions_per_s"] = c4_exp / c4_s
+        c4["successes_total"] = int(c4_succ)
+        c4["success_rate"] = c4_succ / c4["queries_total"]
+        c4["fixed_threads"]["plans_per_s"] = c4f_q / c4f_s
+        c4["fixed_threads"]["queries_total"] = int(c4f_q)
+        c4["fixed_threads"]["expansions_per_s"] = c4f_exp / c4f_s
+        c4["fixed_threads"]["batch_s_max_over_ranks"] = c4f_s
     edges_total = world * B * cols
     value = edges_total / (dev_ms * 1e-3)
     e2e_value = edges_total / (e2e_ms * 1e-3)
@@ -576,7 +622,9 @@ def main():
     ap.add_argument("--no-planner", action="store_true", help="skip the planner-level (C1/C2/C4) measurements")
     ap.add_argument("--no-structured", action="store_true", help="skip the structured (wall map) variant of C3")
     ap.add_argument("--no-c5", action="store_true", help="skip the cloud-sharded (C5) measurement at N > 1")
-    ap.add_argument("--queries", type=int, default=512, help="C4: planning queries per GPU")
+    ap.add_argument("--queries", type=int, default=4096, help="C4: planning queries in total (split over the ranks)")
+    ap.add_argument("--c4-max-expansions", type=int, default=5000,
+                    help="C4: expansion cap per query (5000: >= 90 %% of the queries reach their goal)")
     ap.add_argument("--c5-points-per-gpu", type=int, default=1 << 23)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -551,6 +551,12 @@ int mppb_selftest_open_set(uint64_t seed, size_t ops, int distinct_keys);
  * returning the node it got the first time, distinct coordinates distinct nodes. Returns the number of violations. */
 int mppb_selftest_lattice_index(uint64_t seed, size_t ops, int range);
 
+/* Host self-test (no GPU) of the planner's replay of the ORDER in which the reference's std::unordered_map of reached
+ * cells (TPS_Astar.cpp:565-566, 806-814) is iterated — the order that assigns node ids: `trials` random sets of up to
+ * max_keys distinct lattice cells are fed to the replay and to a real std::unordered_map with the reference's hash.
+ * Returns the number of sets iterated in a different order (0 = identical). */
+int mppb_selftest_cell_order(uint64_t seed, size_t trials, int max_keys);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(kMaxCand)
     __syncthreads();
 
     // ---- the winners write their cell's record at the position of the cell's first appearance ----
-    mppb_neighbor* o = out + static_cast<size_t>(node) * P.maxCand;
+    // (records are assembled in shared memory and leave with 16-byte stores of consecutive threads: the destination
+    // may be pinned host memory, where field-by-field stores of single threads would each be a PCIe transaction)
+    extern __shared__ uint4 sRecRaw[];
+    mppb_neighbor* const    o = reinterpret_cast<mppb_neighbor*>(sRecRaw);
     if (winner)
     {
         int pos = 0;
@@ -312,6 +315,13 @@ __global__ void __launch_bounds__(kMaxCand)
         for (int s = 0; s < nEvals; s++) cc += sVal[e * nEvals + s];
         o[e].cost = cc;
     }
+    __syncthreads();
+    {
+        static_assert(sizeof(mppb_neighbor) % sizeof(uint4) == 0, "records leave in 16-byte words");
+        constexpr int kWordsPerRec = sizeof(mppb_neighbor) / sizeof(uint4);
+        uint4*        dst          = reinterpret_cast<uint4*>(out + static_cast<size_t>(node) * P.maxCand);
+        for (int i = c; i < nOut * kWordsPerRec; i += blockDim.x) dst[i] = sRecRaw[i];
+    }
     if (c == 0)
     {
         counts[2 * node + 0] = static_cast<uint32_t>(nOut);
@@ -401,8 +411,11 @@ int launch_expand(mppb_ctx* ctx, size_t nNodes, const mppb_expand_node* dIn, con
                   mppb_neighbor* dOut, uint32_t* dCounts)
 {
     if (nNodes == 0) return MPPB_OK;
-    const int threads = std::min(kMaxCand, (ctx->expandHost.maxCand + 31) / 32 * 32);
-    expand_kernel<<<static_cast<unsigned>(nNodes), threads, 0, ctx->stream>>>(
+    const int    threads = std::min(kMaxCand, (ctx->expandHost.maxCand + 31) / 32 * 32);
+    const size_t smem    = static_cast<size_t>(ctx->expandHost.maxCand) * sizeof(mppb_neighbor);
+    if (smem > 16 * 1024)  // (static shared memory of the kernel: ~30 KB)
+        MPPB_CUDA(ctx, cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    expand_kernel<<<static_cast<unsigned>(nNodes), threads, smem, ctx->stream>>>(
         ctx->expandDev.as<ExpandParamsDev>(), ctx->evalDescs.as<EvaluatorDev>(), ctx->numEvals, dIn, dNodes4, dRows,
         ctx->totalPaths, dOut, dCounts);
     ctx->launches++;

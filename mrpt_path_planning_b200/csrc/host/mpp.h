@@ -334,6 +334,20 @@ struct PlannerOutput
     MotionPrimitivesTreeSE2 motionTree;
     /** extension: work counters of this plan */
     size_t nodesExpanded = 0, tpsPointsEvaluated = 0, edgesCosted = 0;
+    /** extension: size of the motion tree and nodes on the path root -> best node (valid whether or not motionTree has
+     *  been built yet) */
+    size_t treeNodes = 0, treeParents = 0, pathLength = 0;
+    /** extension: TPS_Astar::plan_batch(..., materializeTrees = false) leaves motionTree empty — a search of thousands
+     *  of queries holds tens of millions of tree nodes that most callers never look at — and puts a builder here;
+     *  materializeTree() runs it once. plan() and plan_batch() by default return with the tree built. */
+    std::function<void(PlannerOutput&)> treeBuilder;
+    void materializeTree()
+    {
+        if (!treeBuilder) return;
+        auto f      = std::move(treeBuilder);
+        treeBuilder = nullptr;
+        f(*this);
+    }
 };
 
 // ---- cost evaluators -----------------------------------------------------------------------------
@@ -483,7 +497,7 @@ class TPS_Astar : public Planner
     /** Many independent queries over the SAME obstacle sources, advanced in lock-step: one GPU
      *  batch per A* iteration covers the current node of every unfinished query. Results are
      *  identical to calling plan() on each input alone. nThreads host threads (0 = all). */
-    std::vector<PlannerOutput> plan_batch(const std::vector<PlannerInput>& ins, int nThreads = 0);
+    std::vector<PlannerOutput> plan_batch(const std::vector<PlannerInput>& ins, int nThreads = 0, bool materializeTrees = true);
 
     void        params_from_yaml(const Yaml& c) override { params_.load_from_yaml(c); }
     std::string params_as_yaml_text() const override { return params_.as_yaml_text(); }

@@ -16,6 +16,8 @@
 // multimap open set with its stale keys, node-id assignment order) is kept as in the reference,
 // and every PTG object sees the same sequence of state changes, so a query produces the same tree
 // whether it runs alone (plan) or interleaved with thousands of others (plan_batch).
+#include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <algorithm>
 #include <tuple>
@@ -38,6 +40,35 @@ namespace mpp
 {
 namespace
 {
+#ifdef MPPB_PROFILE  // host-phase attribution experiments only (build with MPPB_EXTRA_NVCC=-DMPPB_PROFILE)
+#include <x86intrin.h>
+struct ProfCounters
+{
+    std::atomic<uint64_t> t[8] = {}, n[8] = {};
+    ~ProfCounters()
+    {
+        static const char* names[8] = {"pop", "A", "order+prefetch", "find+prefetch", "relax loop", "heuristic", "heap insert", "-"};
+        for (int i = 0; i < 8; i++)
+            if (n[i]) fprintf(stderr, "[mppb prof] %-16s %12llu calls %8.1f cycles/call %10.3f Gcycles\n", names[i],
+                              (unsigned long long)n[i].load(), double(t[i].load()) / double(n[i].load()), double(t[i].load()) * 1e-9);
+    }
+};
+static ProfCounters g_prof;
+struct ProfScope
+{
+    int      i;
+    uint64_t t0;
+    explicit ProfScope(int i_) : i(i_), t0(__rdtsc()) {}
+    ~ProfScope()
+    {
+        g_prof.t[i].fetch_add(__rdtsc() - t0, std::memory_order_relaxed);
+        g_prof.n[i].fetch_add(1, std::memory_order_relaxed);
+    }
+};
+#define MPPB_PROF(i) ProfScope profScope##i(i)
+#else
+#define MPPB_PROF(i)
+#endif
 using Clock = std::chrono::steady_clock;
 double seconds_since(const Clock::time_point& t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
 
@@ -73,16 +104,38 @@ struct NodeCoordsHash
         return res;
     }
 };
-struct Node
+// One lattice node. With thousands of interleaved queries the search state is far larger than the caches and every
+// neighbour of an expansion is a cache miss, so the fields are ordered by use: the first 64-byte line holds everything
+// the common case reads (a neighbour that exists already and is not improved: id, visited, gScore), the second what an
+// accepted relaxation overwrites, the third what only the tree builder reads.
+struct alignas(64) Node
 {
+    // ---- line 1 ----
     std::optional<TNodeID> id;
-    SE2_KinState           state;
     cost_t                 gScore = std::numeric_limits<cost_t>::max();
     cost_t                 fScore = std::numeric_limits<cost_t>::max();
     const Node*            cameFrom         = nullptr;
     bool                   pendingInOpenSet = false;
     bool                   visited          = false;
+    // Device-expansion path: the node's place in the motion tree, kept here instead of in a tree that is mutated
+    // while searching. A node is expanded at most once (visited nodes are never relaxed again), so when a relaxation
+    // is accepted its parent's cost and state are final: the node's tree cost IS its gScore, its edge is described by
+    // the edge* fields, and a parent's edge list is its surviving children in the order of their accepting
+    // relaxations (edgeSeq). The reference's rewire_node_parent leaves the node's own state as first inserted
+    // (MotionPrimitivesTree.h:173-215): firstState.
+    bool     everParent = false;  // some relaxation out of this node was accepted (it owns an edge list)
+    uint8_t  edgePtg    = 0;
+    uint16_t edgeK      = 0;
+    uint32_t edgeStep   = 0;
+    uint32_t edgeSeq    = 0;  // number of the accepting relaxation within the query
+    float    edgeDist   = 0;
+    // ---- line 2 ----
+    alignas(64) SE2_KinState state;
+    cost_t edgeCost = 0;
+    // ---- line 3 ----
+    alignas(64) SE2_KinState firstState;
 };
+static_assert(sizeof(Node) == 192 && offsetof(Node, state) == 64 && offsetof(Node, firstState) == 128, "Node layout");
 // The SE(2) lattice of the reference is a std::unordered_map<NodeCoords, Node> that is only ever indexed, never
 // iterated (TPS_Astar.h:222, TPS_Astar.cpp:514-525), so its container type cannot influence the result. Here: an
 // open-addressing index (linear probing, load <= 1/2) over nodes that live in the query's arena (stable addresses:
@@ -117,6 +170,24 @@ class LatticeIndex
         }
     }
 
+    /** the node of (x, y, yaw) if it exists, else nullptr (nothing is created) */
+    Node* find(int32_t x, int32_t y, int32_t yaw) const
+    {
+        const size_t mask = slots_.size() - 1;
+        for (size_t h = mix(x, y, yaw) & mask;; h = (h + 1) & mask)
+        {
+            const Slot& s = slots_[h];
+            if (!s.node) return nullptr;
+            if (s.x == x && s.y == y && s.yaw == yaw) return s.node;
+        }
+    }
+    /** every node of the lattice (any order) */
+    template <class F>
+    void forEachNode(F&& f) const
+    {
+        for (const Slot& s : slots_)
+            if (s.node) f(*s.node);
+    }
     /** warm the cache line the look-up of (x, y, yaw) will start at (the search state of many interleaved queries is
      *  far larger than the caches) */
     void prefetch(int32_t x, int32_t y, int32_t yaw) const
@@ -155,6 +226,127 @@ class LatticeIndex
     std::vector<Slot>                    slots_;
     size_t                               count_ = 0;
 };
+// The order in which the reference visits the cells an expansion reaches is the iteration order of its
+// std::unordered_map<NodeCoords, path_to_neighbor_t> (TPS_Astar.cpp:565-566, 806-814), which assigns the node ids. On
+// the device-expansion path the cells arrive distinct and in first-insertion order, so all the host needs from that
+// container is the resulting ORDER. CellOrder replays libstdc++'s hashtable for exactly that — a singly linked list
+// threaded through the buckets, a new node going to the front of its bucket or, if the bucket is empty, to the front of
+// the whole list; a rehash re-threads the nodes in list order (_M_insert_bucket_begin / _M_rehash_aux, unique keys) —
+// on index arrays, without allocation, look-up or node construction. The bucket counts come from a real
+// std::unordered_map of this very library, grown once at start-up. selftest_cell_order() compares it with the real
+// container on random key sets (tests/test_host_cpu.py).
+class CellOrder
+{
+   public:
+    static constexpr uint16_t kNil = 0xffff;
+    void reset()
+    {
+        n_       = 0;
+        head_    = kNil;
+        level_   = 0;
+        buckets_ = growth().counts[0];
+        std::fill(bucketBefore_.begin(), bucketBefore_.begin() + static_cast<std::ptrdiff_t>(std::min(bucketBefore_.size(), buckets_)), kEmpty);
+    }
+    /** the n-th key (n = number of keys so far) with hash code `code`; keys must be distinct */
+    void insert(size_t code)
+    {
+        const Growth& G = growth();
+        if (level_ + 1 < G.counts.size() && n_ + 1 > G.maxSize[level_]) rehash(G.counts[++level_]);
+        if (n_ >= next_.size())
+        {
+            next_.resize(std::max<size_t>(64, 2 * next_.size()));
+            code_.resize(next_.size());
+        }
+        const uint16_t me = static_cast<uint16_t>(n_++);
+        code_[me]         = code;
+        link(me, code % buckets_);
+    }
+    uint16_t first() const { return head_; }
+    uint16_t next(uint16_t i) const { return next_[i]; }
+
+   private:
+    // bucketBefore_[b]: the list node BEFORE the first node of bucket b; kHead = the list head itself; kEmpty = no node
+    static constexpr uint16_t kEmpty = 0xfffe, kHead = 0xfffd;
+    struct Growth
+    {
+        std::vector<size_t> counts;   // bucket counts the container steps through, from its first allocation
+        std::vector<size_t> maxSize;  // elements it holds at most with counts[i] buckets before it rehashes
+    };
+    static const Growth& growth()
+    {
+        static const Growth g = [] {
+            Growth                       r;
+            std::unordered_map<int, int> m;
+            for (int i = 0; i < 20000; i++)
+            {
+                m[i];
+                if (r.counts.empty() || m.bucket_count() != r.counts.back())
+                {
+                    if (!r.counts.empty()) r.maxSize.push_back(static_cast<size_t>(i));
+                    r.counts.push_back(m.bucket_count());
+                }
+            }
+            r.maxSize.push_back(static_cast<size_t>(-1));
+            return r;
+        }();
+        return g;
+    }
+    void link(uint16_t me, size_t b)
+    {
+        if (b >= bucketBefore_.size()) bucketBefore_.resize(b + 1, kEmpty);
+        const uint16_t before = bucketBefore_[b];
+        if (before != kEmpty)
+        {
+            // bucket not empty: the new node goes right after the node before the bucket's first one
+            uint16_t& link = before == kHead ? head_ : next_[before];
+            next_[me]      = link;
+            link           = me;
+        }
+        else
+        {
+            // empty bucket: front of the whole list; the former first node's bucket now starts after the new node
+            next_[me] = head_;
+            head_     = me;
+            if (next_[me] != kNil) bucketBefore_[code_[next_[me]] % buckets_] = me;
+            bucketBefore_[b] = kHead;
+        }
+    }
+    void rehash(size_t newCount)
+    {
+        buckets_ = newCount;
+        if (bucketBefore_.size() < newCount) bucketBefore_.resize(newCount);
+        std::fill(bucketBefore_.begin(), bucketBefore_.begin() + static_cast<std::ptrdiff_t>(newCount), kEmpty);
+        uint16_t p = head_;
+        head_      = kNil;
+        size_t bbeginBkt = 0;
+        while (p != kNil)
+        {
+            const uint16_t nxt = next_[p];
+            const size_t   b   = code_[p] % newCount;
+            if (bucketBefore_[b] == kEmpty)
+            {
+                next_[p]         = head_;
+                head_            = p;
+                bucketBefore_[b] = kHead;
+                if (next_[p] != kNil) bucketBefore_[bbeginBkt] = p;
+                bbeginBkt = b;
+            }
+            else
+            {
+                const uint16_t before = bucketBefore_[b];
+                uint16_t&      link   = before == kHead ? head_ : next_[before];
+                next_[p]              = link;
+                link                  = p;
+            }
+            p = nxt;
+        }
+    }
+    std::vector<uint16_t> next_, bucketBefore_;
+    std::vector<size_t>   code_;
+    size_t                n_ = 0, buckets_ = 1, level_ = 0;
+    uint16_t              head_ = kNil;
+};
+
 struct PathToNeighbor
 {
     std::optional<size_t>    ptgIndex;
@@ -402,6 +594,57 @@ int selftest_lattice_index(uint64_t seed, size_t ops, int range)
     return bad;
 }
 
+// Host self-test of CellOrder (no GPU): `trials` random sets of up to max_keys distinct lattice cells; returns the number
+// of sets whose CellOrder iteration differs from the iteration order of the reference's
+// std::unordered_map<NodeCoords, ..., NodeCoordsHash> fed the same keys in the same sequence (0 = identical).
+int selftest_cell_order(uint64_t seed, size_t trials, int max_keys)
+{
+    uint64_t x   = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto     rnd = [&x]() {
+        x ^= x << 13;
+        x ^= x >> 7;
+        x ^= x << 17;
+        return x;
+    };
+    CellOrder      order;
+    NodeCoordsHash hash;
+    int            bad = 0;
+    for (size_t t = 0; t < trials; t++)
+    {
+        const size_t                                              n = 1 + rnd() % static_cast<uint64_t>(std::max(1, max_keys));
+        std::unordered_map<NodeCoords, uint32_t, NodeCoordsHash>  ref;
+        std::vector<NodeCoords>                                   keys;
+        // cells as an expansion reaches them: a small neighbourhood around some centre, occasionally far apart
+        const int32_t cx = static_cast<int32_t>(rnd() % 2000) - 1000, cy = static_cast<int32_t>(rnd() % 2000) - 1000;
+        const int32_t span = (rnd() % 4 == 0) ? 100000 : 24;
+        order.reset();
+        while (keys.size() < n)
+        {
+            const NodeCoords c(cx + static_cast<int32_t>(rnd() % static_cast<uint64_t>(span)) - span / 2,
+                               cy + static_cast<int32_t>(rnd() % static_cast<uint64_t>(span)) - span / 2,
+                               static_cast<int32_t>(rnd() % 15) - 7);
+            if (ref.count(c)) continue;
+            ref[c] = static_cast<uint32_t>(keys.size());
+            keys.push_back(c);
+            order.insert(hash(c));
+        }
+        uint16_t i  = order.first();
+        bool     ok = true;
+        for (const auto& kv : ref)
+        {
+            if (i == CellOrder::kNil || i != kv.second)
+            {
+                ok = false;
+                break;
+            }
+            i = order.next(i);
+        }
+        if (i != CellOrder::kNil) ok = false;
+        bad += ok ? 0 : 1;
+    }
+    return bad;
+}
+
 // Host self-test of the open set (no GPU): `ops` random insertions (keys drawn from `distinct_keys` values, so that
 // equal keys are frequent) interleaved with pops; returns the number of pops that differ from a std::multimap
 // driven the same way (0 = same order).
@@ -532,9 +775,6 @@ struct TPS_Astar::Impl
     // evaluator lives in a GPU slot; then phases A (second half), C, D and E leave the host altogether
     bool                     useExpand = false;
     uint32_t                 expandStride = 0;  // neighbour records per node in hNeighbors
-    Pinned<mppb_expand_node> hExpandIn;
-    Pinned<mppb_neighbor>    hNeighbors;
-    Pinned<uint32_t>         hExpandCounts;
     void                     setupExpand();
 
     Pinned<double>         hPoses, hHoloOut, hFrom, hRel, hCost;
@@ -547,7 +787,7 @@ struct TPS_Astar::Impl
     void                       uploadPtgs(const TrajectoriesAndRobotShape& trs);
     void                       uploadCloud(const std::vector<ObstacleSource::Ptr>& srcs, const float* box);
     void                       uploadEvaluators();
-    std::vector<PlannerOutput> run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads);
+    std::vector<PlannerOutput> run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads, bool materializeTrees);
 };
 
 // ---- one planning query: all the A* state of the reference's plan() ----------------------------------
@@ -617,34 +857,21 @@ struct TPS_Astar::Impl::Query
         treeOps.clear();
     }
 
-    // ---- device-side expansion path: what the host still does per expansion, and the compact log of the search ----
-    // The motion tree does not influence the search, so the expansion path does not touch it while searching: every
-    // accepted relaxation is appended to a log (80 bytes, no allocation), and the tree — one map node, one list node
-    // with a 600-byte edge and its interpolated samples per TREE NODE — is built once, when the query ends, from each
-    // node's last entry. That is the reference's tree: a node is expanded at most once (visited nodes are never
-    // relaxed again), so a parent's cost is final when its children are logged, a node's tree cost equals its gScore,
-    // and a parent's edge list is its surviving children in log order.
+    // ---- device-side expansion path ----
+    // The motion tree does not influence the search, so this path does not touch it while searching: what the tree
+    // needs is kept in the lattice nodes themselves (see Node), and the tree — a map node plus a list node with a
+    // 600-byte edge and its interpolated samples per tree node — is built once from them: when the query ends, or, for
+    // a batch planned with materializeTrees == false, when somebody asks for it.
     bool             useExpand = false;
-    mppb_expand_node expIn{};  // this round's record for mppb_expand_nodes
-    struct ExpansionRec
-    {
-        TNodeID      parent;
-        SE2_KinState stateFrom;
-        TPose2D      goalRel;  // the goal as seen from the parent (MoveEdgeSE2_TPS::ptgFinalRelativeGoal)
-    };
-    struct EdgeRec
-    {
-        uint32_t     expansion;  // index into expansions
-        uint32_t     step;
-        TNodeID      child;
-        SE2_KinState stateTo;
-        double       cost;
-        float        ptgDist;
-        uint16_t     k;
-        uint8_t      ptg;
-    };
-    std::vector<ExpansionRec>               expansions;
-    std::vector<EdgeRec>                    edgeLog;
+    bool             lazyTree  = false;   // leave po.motionTree empty; the caller builds it on demand
+    CellOrder        cellOrder;           // see CellOrder
+    mppb_expand_node expIn{};             // this round's record for mppb_expand_nodes
+    uint32_t         relaxSeq     = 0;    // accepted relaxations so far
+    size_t           treeNodes    = 1;    // nodes the tree would hold now (the root + every node relaxed at least once)
+    size_t           treeParents  = 0;    // nodes that own an edge list
+    const Node*      bestNode     = nullptr;
+    TNodeID          rootId       = 0;
+    size_t           nSeg         = 0;    // pathInterpolatedSegments (the planner's parameters may be gone later)
     std::optional<std::pair<TNodeID, TPose2D>> goalSnap;  // node whose pose popNext() moved onto the exact goal
 
     // phase scratch
@@ -704,7 +931,9 @@ struct TPS_Astar::Impl::Query
             Node& n   = getOrCreateNodeByPose(in->stateStart);
             n.state   = in->stateStart;
             tree.root = n.id.value();
-            tree.insert_root_node(tree.root, n.state);
+            rootId    = tree.root;
+            nSeg      = P->pathInterpolatedSegments;
+            if (!useExpand) tree.insert_root_node(tree.root, n.state);
             n.gScore           = 0;
             n.fScore           = planner->heuristic(n.state, in->stateGoal);
             n.pendingInOpenSet = true;
@@ -732,25 +961,30 @@ struct TPS_Astar::Impl::Query
         {
             flushTreeOps();
             // snap the node onto the exact goal; refine_trajectory() fixes the last edge later
+            TPose2D snapped = cur.state.pose;
             if (in->stateGoal.state.isPoint())
             {
                 const TPoint2D g        = in->stateGoal.state.point();
-                cur.state.pose.x        = g.x;
-                cur.state.pose.y        = g.y;
+                snapped.x               = g.x;
+                snapped.y               = g.y;
                 nodeGoal                = &cur;
                 po.goalNodeId           = cur.id.value();
                 po.bestNodeId           = po.goalNodeId;
+                bestNode                = &cur;
                 po.bestNodeIdCostToGoal = 0;
             }
             else
             {
-                cur.state.pose          = in->stateGoal.state.pose();
+                snapped                 = in->stateGoal.state.pose();
                 po.bestNodeIdCostToGoal = 0;
             }
             if (useExpand)
-                goalSnap = std::make_pair(*cur.id, cur.state.pose);  // applied when the tree is built
+                goalSnap = std::make_pair(*cur.id, snapped);  // the tree node moves; the edge keeps its stateTo (= cur.state)
             else
+            {
+                cur.state.pose                         = snapped;
                 po.motionTree.node_state(*cur.id).pose = cur.state.pose;
+            }
             finish();
             return false;
         }
@@ -765,11 +999,27 @@ struct TPS_Astar::Impl::Query
     void finish()
     {
         flushTreeOps();
-        if (useExpand) buildTreeFromLog(po.motionTree);
         done       = true;
         current    = nullptr;
         po.success = po.goalNodeId == po.bestNodeId;
-        if (po.bestNodeId) po.pathCost = po.motionTree.nodes().at(*po.bestNodeId).cost_;
+        if (useExpand)
+        {
+            if (bestNode) po.pathCost = bestNode->gScore;  // a node's tree cost is its gScore (see Node)
+            po.treeNodes   = treeNodes;
+            po.treeParents = treeParents;
+            po.pathLength  = 0;
+            for (const Node* n = bestNode; n; n = n->cameFrom) po.pathLength++;
+            if (!lazyTree) buildTree(po.motionTree, *in);
+        }
+        else
+        {
+            if (po.bestNodeId) po.pathCost = po.motionTree.nodes().at(*po.bestNodeId).cost_;
+            po.treeNodes   = po.motionTree.nodes().size();
+            po.treeParents = po.motionTree.edges_to_children.size();
+            po.pathLength  = 0;
+            if (po.bestNodeId)
+                for (std::optional<TNodeID> id = po.bestNodeId; id; id = po.motionTree.nodes().at(*id).parentID_) po.pathLength++;
+        }
         po.computationTime = seconds_since(t0);
     }
 
@@ -1148,7 +1398,6 @@ struct TPS_Astar::Impl::Query
     {
         const Node&   from    = *current;
         const TPose2D relGoal = in->stateGoal.asSE2KinState().pose - from.state.pose;
-        expansions.push_back(ExpansionRec{from.id.value(), from.state, relGoal});
         for (int i = 0; i < 3; i++)
         {
             const double* lo = &in->worldBboxMin.x;  // (x, y, phi are consecutive doubles of TPose2D)
@@ -1192,19 +1441,36 @@ struct TPS_Astar::Impl::Query
     {
         po.tpsPointsEvaluated += tpsPoints;
         arena.release();
-        std::pmr::unordered_map<NodeCoords, uint32_t, NodeCoordsHash> bestPaths(&arena);
-        for (uint32_t i = 0; i < n; i++)
+        // The neighbours' lattice nodes are scattered over a search state far larger than the caches: three passes, so
+        // that the misses overlap instead of queueing up behind each other — (1) the reference's map of reached cells
+        // (its iteration order is the order in which cells become nodes) while the index slots are prefetched,
+        // (2) the existing nodes are found and their first cache line is prefetched, (3) the ordered pass.
+        cellOrder.reset();
         {
-            const mppb_neighbor& r = recs[i];
-            bestPaths[NodeCoords(r.cell[0], r.cell[1], r.cell[2])] = i;
-            grid.prefetch(r.cell[0], r.cell[1], r.cell[2]);
+            MPPB_PROF(2);
+            for (uint32_t i = 0; i < n; i++)
+            {
+                const mppb_neighbor& r = recs[i];
+                cellOrder.insert(NodeCoordsHash()(NodeCoords(r.cell[0], r.cell[1], r.cell[2])));
+                grid.prefetch(r.cell[0], r.cell[1], r.cell[2]);
+            }
         }
-        const uint32_t expIdx = static_cast<uint32_t>(expansions.size() - 1);
-        for (const auto& kv : bestPaths)  // unordered_map order, as in the reference
+        Node** known = static_cast<Node**>(arena.allocate(sizeof(Node*) * std::max<uint32_t>(n, 1), alignof(Node*)));
         {
-            const mppb_neighbor& r = recs[kv.second];
+            MPPB_PROF(3);
+            for (uint32_t i = 0; i < n; i++)
+            {
+                const mppb_neighbor& r = recs[i];
+                known[i]               = grid.find(r.cell[0], r.cell[1], r.cell[2]);
+                if (known[i]) __builtin_prefetch(known[i]);
+            }
+        }
+        MPPB_PROF(4);
+        for (uint16_t ri = cellOrder.first(); ri != CellOrder::kNil; ri = cellOrder.next(ri))  // the reference's map order
+        {
+            const mppb_neighbor& r = recs[ri];
             if (!r.in_bbox) continue;
-            Node& nbNode = grid[kv.first];
+            Node& nbNode = known[ri] ? *known[ri] : grid[NodeCoords(r.cell[0], r.cell[1], r.cell[2])];
             if (!nbNode.id.has_value())
             {
                 nbNode.id         = nextFreeId++;
@@ -1217,23 +1483,46 @@ struct TPS_Astar::Impl::Query
             MPP_ASSERT(edgeCost > .0);
             const cost_t tentative_gScore = current->gScore + edgeCost;
             if (tentative_gScore >= nbNode.gScore) continue;
-            nbNode.cameFrom = current;
-            nbNode.gScore   = tentative_gScore;
+            const bool firstTime = nbNode.cameFrom == nullptr;
+            nbNode.cameFrom      = current;
+            nbNode.gScore        = tentative_gScore;
             // NOTE: the heuristic is taken at the node's previous state, before it is overwritten
-            const cost_t costToGoal = planner->heuristic(nbNode.state, in->stateGoal);
-            nbNode.fScore           = tentative_gScore + costToGoal;
+            cost_t costToGoal;
+            {
+                MPPB_PROF(5);
+                costToGoal = planner->heuristic(nbNode.state, in->stateGoal);
+            }
+            nbNode.fScore = tentative_gScore + costToGoal;
             if (!nbNode.pendingInOpenSet)
             {
+                MPPB_PROF(6);
                 nbNode.pendingInOpenSet = true;
                 openSet.insert(nbNode.fScore, &nbNode);
             }
             nbNode.state.pose = TPose2D(r.pose[0], r.pose[1], r.pose[2]);
             nbNode.state.vel  = TTwist2D(r.vel[0], r.vel[1], r.vel[2]);
-            edgeLog.push_back(EdgeRec{expIdx, r.step, nbNode.id.value(), nbNode.state, edgeCost, r.ptg_dist, r.k, r.ptg_index});
+            // the node's place in the tree (insert_node_and_edge / rewire_node_parent of the reference, :380-398)
+            nbNode.edgePtg  = r.ptg_index;
+            nbNode.edgeK    = r.k;
+            nbNode.edgeStep = r.step;
+            nbNode.edgeDist = r.ptg_dist;
+            nbNode.edgeCost = edgeCost;
+            nbNode.edgeSeq  = relaxSeq++;
+            if (firstTime)
+            {
+                nbNode.firstState = nbNode.state;
+                treeNodes++;
+            }
+            if (!current->everParent)
+            {
+                current->everParent = true;
+                treeParents++;
+            }
             if (costToGoal < po.bestNodeIdCostToGoal)
             {
                 po.bestNodeIdCostToGoal = costToGoal;
                 po.bestNodeId           = nbNode.id.value();
+                bestNode                = &nbNode;
             }
         }
         const double tNow = seconds_since(t0);
@@ -1246,7 +1535,7 @@ struct TPS_Astar::Impl::Query
         {
             tLastCallback = tNow;
             MotionPrimitivesTreeSE2 tree;  // the tree as it stands now
-            buildTreeFromLog(tree);
+            buildTree(tree, *in);
             auto [foundPath, pathEdges] = tree.backtrack_path(*po.bestNodeId);
             ProgressCallbackData pcd;
             pcd.bestCostFromStart = tree.nodes().at(*po.bestNodeId).cost_;
@@ -1260,55 +1549,52 @@ struct TPS_Astar::Impl::Query
         }
     }
 
-    // The motion tree of the reference from the log: see the comment at `edgeLog`.
-    void buildTreeFromLog(MotionPrimitivesTreeSE2& tree) const
+    // The motion tree of the reference from the lattice nodes (see Node): every relaxed node with its last accepted edge,
+    // in the order of the accepting relaxations.
+    void buildTree(MotionPrimitivesTreeSE2& tree, const PlannerInput& input) const
     {
-        if (tree.nodes().empty())
-        {
-            tree.root = po.motionTree.root;
-            tree.insert_root_node(tree.root, in->stateStart);
-        }
-        // last entry of every node = its edge, parent and cost; FIRST entry = its state in the tree (the reference's
-        // rewire_node_parent updates parent and cost only, MotionPrimitivesTree.h:173-215)
-        std::vector<uint32_t> lastOf(static_cast<size_t>(nextFreeId), 0xffffffffu), firstOf(static_cast<size_t>(nextFreeId), 0xffffffffu);
-        for (size_t i = 0; i < edgeLog.size(); i++)
-        {
-            const size_t c = static_cast<size_t>(edgeLog[i].child);
-            lastOf[c]      = static_cast<uint32_t>(i);
-            if (firstOf[c] == 0xffffffffu) firstOf[c] = static_cast<uint32_t>(i);
-        }
+        tree      = MotionPrimitivesTreeSE2();
+        tree.root = rootId;
+        tree.insert_root_node(rootId, input.stateStart);
+        std::vector<const Node*> order;
+        order.reserve(treeNodes);
+        grid.forEachNode([&](const Node& n) {
+            if (n.cameFrom) order.push_back(&n);
+            // (a parent whose children were all re-parented later still owns an — empty — edge list, as after the
+            // reference's rewire_node_parent)
+            if (n.everParent) tree.edges_to_children[n.id.value()];
+        });
+        std::sort(order.begin(), order.end(), [](const Node* a, const Node* b) { return a->edgeSeq < b->edgeSeq; });
+        const TPose2D                          goalPose    = input.stateGoal.asSE2KinState().pose;
+        const Node*                            curParent   = nullptr;
         MotionPrimitivesTreeSE2::TListEdges*   parentEdges = nullptr;
         const MotionPrimitivesTreeSE2::node_t* parentNode  = nullptr;
-        uint32_t                               curExp      = 0xffffffffu;
-        for (size_t i = 0; i < edgeLog.size(); i++)
+        TPose2D                                goalRel;
+        for (const Node* n : order)
         {
-            const EdgeRec& r = edgeLog[i];
-            if (r.expansion != curExp)
+            const Node&   par      = *n->cameFrom;
+            const TNodeID parentId = par.id.value();
+            if (&par != curParent)
             {
-                // (a parent whose children were all re-parented later still owns an — empty — edge list, as after
-                // the reference's rewire_node_parent)
-                const ExpansionRec& x = expansions[r.expansion];
-                parentEdges           = &tree.edges_to_children[x.parent];
-                parentNode            = &tree.nodes().at(x.parent);
-                curExp                = r.expansion;
+                parentEdges = &tree.edges_to_children[parentId];
+                parentNode  = &tree.nodes().at(parentId);
+                goalRel     = goalPose - par.state.pose;  // the goal as seen from the parent when it was expanded
+                curParent   = &par;
             }
-            if (lastOf[static_cast<size_t>(r.child)] != i) continue;  // superseded by a later, cheaper edge
-            const ExpansionRec& x = expansions[r.expansion];
-            MoveEdgeSE2_TPS     e;
-            e.parentId             = x.parent;
-            e.ptgDist              = r.ptgDist;
-            e.ptgIndex             = static_cast<int8_t>(r.ptg);
-            e.ptgPathIndex         = static_cast<int16_t>(r.k);
+            MoveEdgeSE2_TPS e;
+            e.parentId             = parentId;
+            e.ptgDist              = n->edgeDist;
+            e.ptgIndex             = static_cast<int8_t>(n->edgePtg);
+            e.ptgPathIndex         = static_cast<int16_t>(n->edgeK);
             e.ptgTrimmableSpeed    = 1.0;  // never assigned by the reference's neighbour search: stays 1.0
             e.ptgFinalGoalRelSpeed = 0;
-            e.ptgFinalRelativeGoal = x.goalRel;
-            e.stateFrom            = x.stateFrom;
-            e.stateTo              = r.stateTo;
-            e.ptgStep              = r.step;
-            e.cost                 = r.cost;
-            edge_interpolated_path(e, trs, trs.ptgs[r.ptg]->getPathPose(r.k, r.step), r.step, P->pathInterpolatedSegments);
-            tree.insert_child_of(*parentEdges, *parentNode, x.parent, r.child,
-                                 edgeLog[firstOf[static_cast<size_t>(r.child)]].stateTo, std::move(e));
+            e.ptgFinalRelativeGoal = goalRel;
+            e.stateFrom            = par.state;  // frozen since the parent was popped
+            e.stateTo              = n->state;
+            e.ptgStep              = n->edgeStep;
+            e.cost                 = n->edgeCost;
+            edge_interpolated_path(e, trs, trs.ptgs[n->edgePtg]->getPathPose(n->edgeK, n->edgeStep), n->edgeStep, nSeg);
+            tree.insert_child_of(*parentEdges, *parentNode, parentId, n->id.value(), n->firstState, std::move(e));
         }
         if (goalSnap) tree.node_state(goalSnap->first).pose = goalSnap->second;
     }
@@ -1518,7 +1804,8 @@ void TPS_Astar::Impl::setupExpand()
     useExpand    = expandStride > 0;
 }
 
-std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads)
+std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerInput*>& ins, bool sharedCloud, int nThreads,
+                                                bool materializeTrees)
 {
     ensureContext();
     self->lastGpuStats = GpuStats();
@@ -1540,10 +1827,10 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     uploadEvaluators();
     setupExpand();
 
-    std::vector<std::unique_ptr<Query>> qs(Q);
+    std::vector<std::shared_ptr<Query>> qs(Q);
     for (size_t i = 0; i < Q; i++)
     {
-        qs[i]               = std::make_unique<Query>();
+        qs[i]               = std::make_shared<Query>();
         Query& q            = *qs[i];
         q.planner           = self;
         q.P                 = &self->params_;
@@ -1554,6 +1841,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
             for (auto& p : q.trs.ptgs) p = std::shared_ptr<ptg_t>(p->cloneForQuery());
         q.deferTreeOps = Q == 1 && std::getenv("MPPB_NO_OVERLAP") == nullptr;
         q.useExpand    = useExpand;
+        q.lazyTree     = useExpand && !materializeTrees;
         q.start();
     }
     // obstacles: one query -> clipped to its world box at upload (ObstacleSource::apply_clipping_box);
@@ -1577,48 +1865,107 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     };
     lap(tSetup, 0);
     // ---- device-side expansion: per round ONE parallel host section (relaxation of the previous round's neighbours,
-    // pop, goal direction per PTG) and ONE GPU call (collision rows + expansion of every current node) ----
-    for (; useExpand;)
+    // pop, goal direction per PTG) and ONE GPU call (collision rows + expansion of every current node). A batch is
+    // cut into two waves that alternate: while the GPU expands the nodes of one wave, the workers relax the other
+    // wave's neighbours, so the GPU time (a quarter of a round on a 16-core host) costs no wall time. ----
+    if (useExpand)
     {
-        auto tl = Clock::now();
-        const mppb_neighbor* nbrs   = hNeighbors.p;
-        const uint32_t*      counts = hExpandCounts.p;
-        pool.run(Q, [&](size_t i) {
-            Query& q = *qs[i];
-            q.active = false;
-            if (q.done) return;
-            if (q.needF)
-            {
-                q.consumeNeighbors(nbrs + q.slot * expandStride, counts[2 * q.slot], counts[2 * q.slot + 1]);
-                q.needF = false;
-            }
-            q.active = q.popNext();
-            if (q.active) q.phaseAExpand();
-        });
-        active.clear();
-        for (size_t i = 0; i < Q; i++)
-            if (qs[i]->active) active.push_back(i);
-        if (active.empty()) break;
-        const size_t      A  = active.size();
-        mppb_expand_node* in = hExpandIn.reserve(A);
-        mppb_neighbor*    nb = hNeighbors.reserve(A * expandStride);
-        uint32_t*         ct = hExpandCounts.reserve(2 * A);
-        for (size_t a = 0; a < A; a++)
+        struct Wave
         {
-            Query& q = *qs[active[a]];
-            q.slot   = a;
-            q.needF  = true;
-            in[a]    = q.expIn;
+            std::vector<size_t>      members, active;
+            Pinned<mppb_expand_node> in;
+            Pinned<mppb_neighbor>    nbrs;
+            Pinned<uint32_t>         counts;
+            bool                     inFlight = false;
+        };
+        static const bool   noWaves = std::getenv("MPPB_NO_WAVES") != nullptr;  // A/B measurements only
+        static const size_t minQ    = std::getenv("MPPB_WAVES_MIN_QUERIES") ? std::strtoul(std::getenv("MPPB_WAVES_MIN_QUERIES"), nullptr, 10)
+                                                                             : 64;  // (tests lower it)
+        const size_t        nW      = (Q >= std::max<size_t>(2, minQ) && !noWaves) ? 2 : 1;
+        Wave              W[2];
+        for (size_t i = 0; i < Q; i++) W[i % nW].members.push_back(i);
+        const double clip = qs[0]->MAX_XY_DIST;
+        // relaxation of the wave's previous neighbours, pop, phase A; then the wave's input records
+        auto hostSection = [&](Wave& w) {
+            auto                 tl     = Clock::now();
+            const mppb_neighbor* nbrs   = w.nbrs.p;
+            const uint32_t*      counts = w.counts.p;
+            pool.run(w.members.size(), [&](size_t j) {
+                Query& q = *qs[w.members[j]];
+                q.active = false;
+                if (q.done) return;
+                if (q.needF)
+                {
+                    q.consumeNeighbors(nbrs + q.slot * expandStride, counts[2 * q.slot], counts[2 * q.slot + 1]);
+                    q.needF = false;
+                }
+                {
+                    MPPB_PROF(0);
+                    q.active = q.popNext();
+                }
+                if (q.active)
+                {
+                    MPPB_PROF(1);
+                    q.phaseAExpand();
+                }
+            });
+            w.active.clear();
+            for (size_t i : w.members)
+                if (qs[i]->active) w.active.push_back(i);
+            const size_t A = w.active.size();
+            if (A)
+            {
+                mppb_expand_node* in = w.in.reserve(A);
+                w.nbrs.reserve(A * expandStride);
+                w.counts.reserve(2 * A);
+                for (size_t a = 0; a < A; a++)
+                {
+                    Query& q = *qs[w.active[a]];
+                    q.slot   = a;
+                    in[a]    = q.expIn;
+                }
+            }
+            lap(tl, 1);
+        };
+        auto launch = [&](Wave& w) {
+            const size_t A = w.active.size();
+            if (!A) return;
+            ck(ctx, mppb_expand_nodes_begin(ctx, A, w.in.p, sharedCloud ? 1 : 0, clip, w.nbrs.p, w.counts.p));
+            w.inFlight = true;
+            st.collisionBatches++;
+            st.nodesEvaluated += A;
+        };
+        auto wait = [&](Wave& w) {
+            if (!w.inFlight) return;
+            auto tl = Clock::now();
+            ck(ctx, mppb_sync(ctx));
+            w.inFlight = false;
+            for (size_t a = 0; a < w.active.size(); a++)
+            {
+                qs[w.active[a]]->needF = true;
+                st.edgesCosted += w.counts.p[2 * a];
+            }
+            st.gpuSeconds += seconds_since(tl);  // the part of the GPU call the host could not hide
+            lap(tl, 2);
+        };
+        hostSection(W[0]);
+        launch(W[0]);
+        if (nW == 2) hostSection(W[1]);
+        for (size_t turn = 0;;)
+        {
+            // here: W[turn] is on the GPU (or has nothing left); with two waves, the other one is ready to launch
+            wait(W[turn]);
+            if (nW == 2) launch(W[1 - turn]);
+            hostSection(W[turn]);
+            if (nW == 1)
+            {
+                if (W[0].active.empty()) break;
+                launch(W[0]);
+                continue;
+            }
+            if (W[0].active.empty() && W[1].active.empty() && !W[0].inFlight && !W[1].inFlight) break;
+            turn = 1 - turn;
         }
-        lap(tl, 1);
-        const auto tB = Clock::now();
-        ck(ctx, mppb_expand_nodes_begin(ctx, A, in, sharedCloud ? 1 : 0, qs[active[0]]->MAX_XY_DIST, nb, ct));
-        ck(ctx, mppb_sync(ctx));
-        st.gpuSeconds += seconds_since(tB);
-        st.collisionBatches++;
-        st.nodesEvaluated += A;
-        for (size_t a = 0; a < A; a++) st.edgesCosted += ct[2 * a];
-        lap(tl, 2);
     }
     double* costs = nullptr;  // evaluator values of the previous round's tentative edges (pinned buffer)
     for (; !useExpand;)
@@ -1768,6 +2115,16 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     auto tEnd = Clock::now();
     pool.run(Q, [&](size_t i) {
         outs[i] = std::move(qs[i]->po);
+        if (qs[i]->lazyTree)
+        {
+            // the query's search state stays alive behind the output until the tree has been built from it (or the
+            // output dies); what the builder reads no longer refers to the planner or to the caller's input
+            std::shared_ptr<Query> q = std::move(qs[i]);
+            q->planner               = nullptr;
+            q->P                     = nullptr;
+            q->in                    = nullptr;
+            outs[i].treeBuilder      = [q](PlannerOutput& o) { q->buildTree(o.motionTree, o.originalInput); };
+        }
         qs[i].reset();
     });
     lap(tEnd, 6);
@@ -1777,14 +2134,14 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
 PlannerOutput TPS_Astar::plan(const PlannerInput& in)
 {
     std::vector<const PlannerInput*> v{&in};
-    return std::move(impl_->run(v, false, 1)[0]);
+    return std::move(impl_->run(v, false, 1, true)[0]);
 }
 
-std::vector<PlannerOutput> TPS_Astar::plan_batch(const std::vector<PlannerInput>& ins, int nThreads)
+std::vector<PlannerOutput> TPS_Astar::plan_batch(const std::vector<PlannerInput>& ins, int nThreads, bool materializeTrees)
 {
     std::vector<const PlannerInput*> v;
     for (const auto& i : ins) v.push_back(&i);
-    return impl_->run(v, true, nThreads);
+    return impl_->run(v, true, nThreads, materializeTrees);
 }
 
 // ---- heuristics (TPS_Astar.cpp:477-537) --------------------------------------------------------------

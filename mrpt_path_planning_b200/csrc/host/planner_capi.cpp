@@ -18,6 +18,7 @@ struct mppb_planner
     std::vector<mpp::PlannerOutput>              outputs;
     std::vector<mpp::MotionPrimitivesTreeSE2::path_t>          paths;
     std::vector<mpp::MotionPrimitivesTreeSE2::edge_sequence_t> pathEdges;
+    std::vector<char>                            havePath;  // paths[i] / pathEdges[i] are built (on first use)
     std::string                                  lastError, text;
 };
 
@@ -45,6 +46,16 @@ void require(bool cond, const char* msg)
 {
     if (!cond) throw std::runtime_error(msg);
 }
+// motion tree and backtracked path of one query, built on first use
+void ensure_path(mppb_planner* p, size_t query)
+{
+    require(query < p->outputs.size() && query < p->paths.size() && query < p->havePath.size(), "query index out of range");
+    if (p->havePath[query]) return;
+    mpp::PlannerOutput& o = p->outputs[query];
+    o.materializeTree();
+    if (o.bestNodeId) std::tie(p->paths[query], p->pathEdges[query]) = o.motionTree.backtrack_path(*o.bestNodeId);
+    p->havePath[query] = 1;
+}
 }  // namespace
 
 namespace mpp
@@ -52,6 +63,7 @@ namespace mpp
 int selftest_worker_pool(int n_threads, size_t count, int rounds);  // planner.cpp
 int selftest_open_set(uint64_t seed, size_t ops, int distinct_keys);  // planner.cpp
 int selftest_lattice_index(uint64_t seed, size_t ops, int range);     // planner.cpp
+int selftest_cell_order(uint64_t seed, size_t trials, int max_keys);  // planner.cpp
 }
 
 extern "C" {
@@ -85,6 +97,18 @@ int mppb_selftest_lattice_index(uint64_t seed, size_t ops, int range)
     try
     {
         return mpp::selftest_lattice_index(seed, ops, range);
+    }
+    catch (const std::exception&)
+    {
+        return -2;
+    }
+}
+
+int mppb_selftest_cell_order(uint64_t seed, size_t trials, int max_keys)
+{
+    try
+    {
+        return mpp::selftest_cell_order(seed, trials, max_keys);
     }
     catch (const std::exception&)
     {
@@ -241,6 +265,7 @@ int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* 
         // a plan that throws must not leave them dangling behind a non-empty `outputs`
         p->paths.clear();
         p->pathEdges.clear();
+        p->havePath.clear();
         if (p->outputs.size() > 16)
         {
             // the previous batch's motion trees are hundreds of thousands of small nodes: drop them on several
@@ -256,19 +281,19 @@ int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* 
         p->outputs.clear();
         if (n_queries == 1)
             p->outputs.push_back(p->planner->plan(p->inputs[0]));
-        else
-            p->outputs = p->planner->plan_batch(p->inputs, n_threads);
+        else  // a batch: motion trees and paths are built per query when somebody asks (ensure_path below)
+            p->outputs = p->planner->plan_batch(p->inputs, n_threads, false);
         p->paths.assign(n_queries, {});
         p->pathEdges.assign(n_queries, {});
+        p->havePath.assign(n_queries, 0);
         for (size_t i = 0; i < n_queries; i++)
         {
             const mpp::PlannerOutput& o = p->outputs[i];
-            if (o.bestNodeId) std::tie(p->paths[i], p->pathEdges[i]) = o.motionTree.backtrack_path(*o.bestNodeId);
             mppb_plan_result& r = res[i];
             r.success           = o.success ? 1 : 0;
             r.path_cost         = o.pathCost;
-            r.tree_nodes        = o.motionTree.nodes().size();
-            r.tree_parents      = o.motionTree.edges_to_children.size();
+            r.tree_nodes        = o.treeNodes;
+            r.tree_parents      = o.treeParents;
             r.nodes_expanded    = o.nodesExpanded;
             r.tps_points        = o.tpsPointsEvaluated;
             r.edges_costed      = o.edgesCosted;
@@ -276,7 +301,7 @@ int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* 
             r.goal_node         = o.goalNodeId ? static_cast<int64_t>(*o.goalNodeId) : -1;
             r.computation_time  = o.computationTime;
             r.best_cost_to_goal = o.bestNodeIdCostToGoal;
-            r.path_len          = static_cast<uint32_t>(p->paths[i].size());
+            r.path_len          = static_cast<uint32_t>(o.pathLength);
         }
     });
 }
@@ -285,7 +310,7 @@ int mppb_planner_refine(mppb_planner* p, size_t query)
 {
     if (!p) return MPPB_ERR_INVALID_ARG;
     return guarded(p, [&]() {
-        require(query < p->outputs.size() && query < p->paths.size(), "query index out of range");
+        ensure_path(p, query);
         mpp::refine_trajectory(p->paths[query], p->pathEdges[query], p->inputs[query].ptgs);
     });
 }
@@ -294,7 +319,7 @@ int mppb_planner_path(mppb_planner* p, size_t query, double* nodes, double* edge
 {
     if (!p) return MPPB_ERR_INVALID_ARG;
     return guarded(p, [&]() {
-        require(query < p->outputs.size() && query < p->paths.size(), "query index out of range");
+        ensure_path(p, query);
         size_t i = 0;
         if (nodes)
             for (const auto& n : p->paths[query])
@@ -331,6 +356,7 @@ int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t ca
     if (!p || query >= p->outputs.size()) return -1;
     int64_t n  = 0;
     const int rc = guarded(p, [&]() {
+        ensure_path(p, query);
         const auto& tree = p->outputs[query].motionTree;
         for (const auto& kv : tree.nodes())
         {
@@ -355,6 +381,7 @@ int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample
 {
     if (!p || query >= p->outputs.size() || query >= p->pathEdges.size()) return -1;
     const int rc = guarded(p, [&]() {
+        ensure_path(p, query);
         auto traj = mpp::plan_to_trajectory(p->pathEdges[query], p->inputs[query].ptgs, sample_period);
         // the trajectory is relative to the start pose; path-planner-cli re-bases it (path-planner-cli.cpp:396-399)
         const mpp::TPose2D start = p->outputs[query].originalInput.stateStart.pose;

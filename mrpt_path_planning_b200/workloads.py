@@ -72,3 +72,53 @@ def planning_queries(n, extent=200.0, dmin=10.0, dmax=40.0, margin=4.0, seed=C4_
         out.append(([s[0], s[1], hs, 0.0, 0.0, 0.0], [g[0], g[1], hg, 0.0, 0.0, 0.0],
                     [lo[0], lo[1], -np.pi], [hi[0], hi[1], np.pi], False))
     return out
+
+
+C4_MAP_SEED = 20240606
+
+
+def pillars_map(n, extent=200.0, r_min=0.5, r_max=1.5, spacing=0.005, seed=C4_MAP_SEED):
+    """Config C4's "synthetic 200x200 m map": n float32 points on the outlines of round pillars (radius U[r_min, r_max],
+    points every `spacing` m along the outline), centres U[0, extent)^2, drawn until the n points are used up — about
+    800 pillars for n = 2**20, one per ~48 m^2, i.e. a map a car-like robot can cross in any direction (the uniform C3
+    cloud, 26 points per m^2, leaves no free space at all). Returns (xs, ys, pillars[m][3] = cx, cy, r)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xs = np.empty(n, dtype=np.float64)
+    ys = np.empty(n, dtype=np.float64)
+    pillars = []
+    i = 0
+    while i < n:
+        cx, cy = rng.uniform(0.0, extent, 2)
+        r = rng.uniform(r_min, r_max)
+        m = min(n - i, max(8, int(2.0 * np.pi * r / spacing)))
+        a = np.arange(m) * (2.0 * np.pi / m)
+        xs[i:i + m] = cx + r * np.cos(a)
+        ys[i:i + m] = cy + r * np.sin(a)
+        pillars.append((cx, cy, r))
+        i += m
+    return xs.astype(np.float32), ys.astype(np.float32), np.array(pillars)
+
+
+def planning_queries_free(n, pillars, extent=200.0, dmin=10.0, dmax=40.0, margin=4.0, clearance=1.0,
+                          seed=C4_QUERIES_SEED):
+    """planning_queries() on a pillars_map(): start and goal keep `clearance` m from every pillar outline (a start pose
+    in collision cannot be planned from)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pc, pr = pillars[:, :2], pillars[:, 2]
+
+    def free(p):
+        return bool(np.all(np.hypot(pc[:, 0] - p[0], pc[:, 1] - p[1]) > pr + clearance))
+
+    out = []
+    while len(out) < n:
+        s = rng.uniform(10.0, extent - 10.0, 2)
+        g = rng.uniform(10.0, extent - 10.0, 2)
+        d = float(np.hypot(*(g - s)))
+        hs, hg = rng.uniform(-np.pi, np.pi, 2)
+        if not (dmin <= d <= dmax) or not free(s) or not free(g):
+            continue
+        lo = np.minimum(s, g) - margin
+        hi = np.maximum(s, g) + margin
+        out.append(([s[0], s[1], hs, 0.0, 0.0, 0.0], [g[0], g[1], hg, 0.0, 0.0, 0.0],
+                    [lo[0], lo[1], -np.pi], [hi[0], hi[1], np.pi], False))
+    return out

@@ -113,6 +113,8 @@ def random_queries(rng, n, extent, dmin, dmax, margin=4.0):
 
 def main():
     out = {}
+    # batches of two or more queries alternate between two waves (normally from 64 queries on)
+    os.environ["MPPB_WAVES_MIN_QUERIES"] = "2"
     # must fail loudly without the stand-in's context: the real library has no CPU path
     try:
         capi.Context(0)

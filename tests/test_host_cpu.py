@@ -133,3 +133,12 @@ def test_lattice_index_is_a_stable_map(capi):
     indexing: one node per coordinate, stable addresses through table growth"""
     for seed, ops, rng_ in ((1, 100, 2), (2, 50000, 40), (3, 200000, 400), (4, 3000, 100000)):
         assert capi.lib().mppb_selftest_lattice_index(seed, ops, rng_) == 0, (seed, ops, rng_)
+
+
+def test_cell_order_equals_unordered_map_iteration_order(capi):
+    """on the device-expansion path the host replays the ORDER in which the reference's unordered_map of reached cells
+    is iterated (it assigns the node ids) instead of filling a real container: same order for any key set, through
+    every rehash (14th, 30th, 60th, 128th ... key)"""
+    for seed, trials, max_keys in ((1, 2000, 13), (2, 2000, 14), (3, 3000, 31), (4, 3000, 61), (5, 3000, 90),
+                                   (6, 1000, 300), (7, 200, 2000)):
+        assert capi.lib().mppb_selftest_cell_order(seed, trials, max_keys) == 0, (seed, trials, max_keys)
