@@ -53,7 +53,7 @@ __device__ __forceinline__ int phi2idx_f(float yaw, double resYaw)
 }
 
 __global__ void __launch_bounds__(kMaxCand)
-    expand_kernel(const ExpandParamsDev* __restrict__ Pp, const EvaluatorDev* __restrict__ evals, int nEvals,
+    expand_kernel(const __grid_constant__ ExpandParamsDev P, const EvaluatorDev* __restrict__ evalsGlobal, int nEvals,
                   const mppb_expand_node* __restrict__ nodes, const double* __restrict__ nodes4 /* [n][4] x,y,cos,sin */,
                   const float* __restrict__ rows /* [n][totalPaths] */, int totalPaths, mppb_neighbor* __restrict__ out,
                   uint32_t* __restrict__ counts)
@@ -70,9 +70,19 @@ __global__ void __launch_bounds__(kMaxCand)
     __shared__ mppb_expand_node sN;  // the node's record (it may live in pinned host memory: fetched once)
     __shared__ double           sCS[2];
 
-    const ExpandParamsDev& P    = *Pp;
-    const int              node = blockIdx.x;
-    const int              c    = threadIdx.x;
+    // evaluator descriptors and (short) waypoint lists in shared memory: the waypoint evaluator walks its list once
+    // per match and sample
+    constexpr int           kMaxWpsShared = 64;
+    __shared__ EvaluatorDev sEvals[MPPB_MAX_EVALUATORS];
+    __shared__ float2       sWps[MPPB_MAX_EVALUATORS][kMaxWpsShared];
+    const int node = blockIdx.x;
+    const int c    = threadIdx.x;
+    {
+        constexpr int kEvalWords = sizeof(EvaluatorDev) / 8;
+        static_assert(sizeof(EvaluatorDev) % 8 == 0, "descriptor is copied in 8-byte words");
+        for (int i = c; i < nEvals * kEvalWords; i += blockDim.x)
+            reinterpret_cast<uint64_t*>(sEvals)[i] = reinterpret_cast<const uint64_t*>(evalsGlobal)[i];
+    }
     {
         static_assert(sizeof(mppb_expand_node) % 8 == 0, "record is copied in 8-byte words");
         constexpr int   kWords = sizeof(mppb_expand_node) / 8;
@@ -86,7 +96,18 @@ __global__ void __launch_bounds__(kMaxCand)
         }
     }
     __syncthreads();
-    const mppb_expand_node& N = sN;
+    for (int e = 0; e < nEvals; e++)
+        if (sEvals[e].kind == 2 && sEvals[e].nWps <= kMaxWpsShared)
+        {
+            const float2* src = sEvals[e].wps;
+            for (int i = c; i < sEvals[e].nWps; i += blockDim.x) sWps[e][i] = src[i];
+        }
+    __syncthreads();
+    if (c == 0)
+        for (int e = 0; e < nEvals; e++)
+            if (sEvals[e].kind == 2 && sEvals[e].nWps <= kMaxWpsShared) sEvals[e].wps = sWps[e];
+    const EvaluatorDev* const evals = sEvals;
+    const mppb_expand_node&   N     = sN;
     const double x0 = N.pose[0], y0 = N.pose[1], phi0 = N.pose[2];
     const double cs0 = sCS[0], sn0 = sCS[1];
 
@@ -140,6 +161,7 @@ __global__ void __launch_bounds__(kMaxCand)
     uint8_t state = 0;
     double  ax = 0, ay = 0, aphi = 0, rx = 0, ry = 0;
     float   distF = 0;
+    bool    inBox = false;
     if (k >= 0)
     {
         const PathTableDev& T = P.paths[p];
@@ -154,19 +176,24 @@ __global__ void __launch_bounds__(kMaxCand)
         aphi = wrap_to_pi_d(phi0 + rphi);
         const bool outLo = ax < N.bbox_min[0] || ay < N.bbox_min[1] || aphi < N.bbox_min[2];
         const bool outHi = ax > N.bbox_max[0] - P.halfCell || ay > N.bbox_max[1] - P.halfCell || aphi > N.bbox_max[2];
-        if (!outLo && !outHi)
-        {
-            state = 1;
-            sCell[0][c] = x2idx_f(static_cast<float>(ax), P.resXY);
-            sCell[1][c] = x2idx_f(static_cast<float>(ay), P.resXY);
-            sCell[2][c] = phi2idx_f(static_cast<float>(aphi), P.resYaw);
-            sDist[c]    = __float_as_uint(distF);
-            // blocked iff relTrgDist >= freeDistance = min(initTPObstacleSingle(k), row[k]) (:744-757)
-            const double raw      = rows[static_cast<size_t>(node) * totalPaths + T.colOffset + k];
-            const double init     = T.initDist[k];
-            const double freeDist = raw < init ? raw : init;
-            if (!(static_cast<double>(distF) >= freeDist)) state |= 2;
-        }
+        inBox            = !outLo && !outHi;
+    }
+    // Programmatic dependent launch: this kernel may start while tpobs_grid_kernel is still running; everything above
+    // reads tables and the node record only. The collision rows must wait for that kernel's completion.
+    cudaGridDependencySynchronize();
+    if (inBox)
+    {
+        const PathTableDev& T = P.paths[p];
+        state       = 1;
+        sCell[0][c] = x2idx_f(static_cast<float>(ax), P.resXY);
+        sCell[1][c] = x2idx_f(static_cast<float>(ay), P.resXY);
+        sCell[2][c] = phi2idx_f(static_cast<float>(aphi), P.resYaw);
+        sDist[c]    = __float_as_uint(distF);
+        // blocked iff relTrgDist >= freeDistance = min(initTPObstacleSingle(k), row[k]) (:744-757)
+        const double raw      = rows[static_cast<size_t>(node) * totalPaths + T.colOffset + k];
+        const double init     = T.initDist[k];
+        const double freeDist = raw < init ? raw : init;
+        if (!(static_cast<double>(distF) >= freeDist)) state |= 2;
     }
     sState[c] = state;
     if (state & 1) atomicAdd(&sTps, P.copies[p]);
@@ -395,12 +422,7 @@ int expand_prepare(mppb_ctx* ctx)
     }
     if (E.candBase[nP] > kMaxCand) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many candidate TPS points per node for the device expansion");
     E.maxCand = E.candBase[nP];
-    MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
-    MPPB_CUDA(ctx, ctx->expandDev.reserve(sizeof(ExpandParamsDev)));
-    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // no kernel may still be reading the old block
-    MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->expandDev.p, &E, sizeof(E), cudaMemcpyHostToDevice, ctx->stream));
-    MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->expandReady = true;
+    ctx->expandReady = true;  // (the block travels as a kernel parameter)
     return MPPB_OK;
 }
 }  // namespace
@@ -415,11 +437,21 @@ int launch_expand(mppb_ctx* ctx, size_t nNodes, const mppb_expand_node* dIn, con
     const size_t smem    = static_cast<size_t>(ctx->expandHost.maxCand) * sizeof(mppb_neighbor);
     if (smem > 16 * 1024)  // (static shared memory of the kernel: ~30 KB)
         MPPB_CUDA(ctx, cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    expand_kernel<<<static_cast<unsigned>(nNodes), threads, smem, ctx->stream>>>(
-        ctx->expandDev.as<ExpandParamsDev>(), ctx->evalDescs.as<EvaluatorDev>(), ctx->numEvals, dIn, dNodes4, dRows,
-        ctx->totalPaths, dOut, dCounts);
+    // launched with programmatic stream serialization: it may begin (parameters, tables, node records) while the
+    // collision kernel before it on the stream is still draining, and waits for its rows inside the kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(static_cast<unsigned>(nNodes));
+    cfg.blockDim           = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = 1;
+    MPPB_CUDA(ctx, cudaLaunchKernelEx(&cfg, expand_kernel, ctx->expandHost, static_cast<const EvaluatorDev*>(ctx->evalDescs.as<EvaluatorDev>()),
+                                      ctx->numEvals, dIn, dNodes4, dRows, ctx->totalPaths, dOut, dCounts));
     ctx->launches++;
-    MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;
 }
 }  // namespace mppb

@@ -243,6 +243,9 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
     __shared__ uint32_t longCell[kMaxLong];
     __shared__ unsigned nLong;
 
+    // A kernel launched behind this one with programmatic stream serialization (expand_kernel) may start its prologue
+    // now; it waits for this grid's completion (and memory flush) before it reads the rows written below.
+    cudaTriggerProgrammaticLaunchCompletion();
     const int    node = SPLIT > 1 ? blockIdx.x / SPLIT : blockIdx.x;
     const int    part = SPLIT > 1 ? blockIdx.x % SPLIT : 0;  // this CTA's share of the output columns
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
