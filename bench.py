@@ -187,6 +187,7 @@ def run_reference(args, rank, world):
 
 
 C4_COSTMAP = (0.10, 0.5, 4.0)  # resolution, preferredClearanceDistance, maxCost
+C4_CPU_SAMPLE_CAP = 100
 WAYPOINTS01 = ([3.0, 5.0, 9.0, 20.0, 26.0], [2.0, 5.0, 8.0, 7.0, 3.0])  # share/mvsim-demo-waypoints01.yaml targets
 
 
@@ -274,10 +275,10 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
     runs = {}
     # (a) every host thread this rank may use; (b) the share of the host a rank has when all GPUs of the box are busy
     # (cpu_count / GPUs on the box, the same number at every N): the figure to compare across N
-    # (the fixed-thread run takes every fourth query of this rank's share: with an eighth of the host it would
+    # (the fixed-thread run takes every eighth query of this rank's share: with an eighth of the host it would
     # otherwise take minutes)
     for label, n_threads, qsel in (("all_threads", max(1, cpus // world), mine),
-                                   ("fixed_threads", max(1, cpus // max(8, gpus_on_box)), mine[::4])):
+                                   ("fixed_threads", max(1, cpus // max(8, gpus_on_box)), mine[::8])):
         pl.plan_many(mine[:16], n_threads=n_threads)  # warm-up
         t0 = time.perf_counter()
         res = pl.plan_many(qsel, n_threads=n_threads)
@@ -296,30 +297,48 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
               "tree_nodes": int(sum(r["tree_nodes"] for r in res)),
               "max_rss_gb": __import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0})
     if with_cpu:
-        # bounded CPU sample: a few of the same queries through the reference planner, one per host thread
+        # bounded CPU sample: the first few queries through the reference planner, one per host thread, at a small
+        # expansion cap (the reference scans the whole 2^20-point cloud for every expanded node: ~6 ms per expansion)
+        # and with the costmap limited to 40 m around the first start (the reference's builder takes a kd-tree query
+        # per cell); the product plans the same queries with the same settings, and the trees must be identical
         from concurrent.futures import ThreadPoolExecutor
 
+        n_cpu = min(4, cpus)
+        sparams = list(params)
+        sparams[8] = C4_CPU_SAMPLE_CAP
+        # (costmap of the CPU sample: 12 m around the first start, from the points within reach of its cells — the
+        # checker's nearest-point search is a plain scan, so the full map is out of its reach; cells and costs are
+        # those the full cloud would give inside that window)
+        s0 = mine[0][0]
+        near = (np.abs(mx - s0[0]) < 12.0 + 1.5) & (np.abs(my - s0[1]) < 12.0 + 1.5)
+        cmx, cmy = np.ascontiguousarray(mx[near]), np.ascontiguousarray(my[near])
+        if len(cmx) == 0:
+            cmx, cmy = mx[:1].copy(), my[:1].copy()
+        cm_args = (C4_COSTMAP[0], C4_COSTMAP[1], C4_COSTMAP[2], False, 12.0, s0[:3])
         t0 = time.perf_counter()
-        ocm = orc.CostMap(mx, my, C4_COSTMAP[0], C4_COSTMAP[1], C4_COSTMAP[2], False, 0.0, None)
+        ocm = orc.CostMap(cmx, cmy, *cm_args)
         d["cpu_costmap_build_s"] = time.perf_counter() - t0
-        optgs_pool = [orc.ackermann_ptgs() for _ in range(min(4, cpus))]
+        optgs_pool = [orc.ackermann_ptgs() for _ in range(n_cpu)]
 
         def one(i):
-            opl = orc.Planner(optgs_pool[i % len(optgs_pool)], params, wl.DEMO_ASTAR_TIMESTAMPS)
+            opl = orc.Planner(optgs_pool[i], sparams, wl.DEMO_ASTAR_TIMESTAMPS)
             opl.add_obstacles(mx, my)
             opl.add_costmap(ocm)
             return opl.plan(*mine[i][:4]), opl.tree()
 
-        n_cpu = len(optgs_pool)
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=n_cpu) as ex:
             cpu_res = list(ex.map(one, range(n_cpu)))
         t_cpu = time.perf_counter() - t0
-        d["cpu_sample_queries"] = n_cpu
-        d["cpu_sample_threads"] = n_cpu
-        d["cpu_plans_per_s"] = n_cpu / t_cpu
-        d["cpu_expansions_per_s"] = sum(r["expanded"] for r, _ in cpu_res) / t_cpu
-        d["identical_trees_on_sample"] = bool(all(np.array_equal(pl.tree(i), t) for i, (_, t) in enumerate(cpu_res)))
+        pl2 = capi.Planner(ctx, ptgs, sparams, wl.DEMO_ASTAR_TIMESTAMPS)
+        pl2.add_obstacles(mx, my)
+        pl2.add_costmap(cmx, cmy, *cm_args)
+        pl2.plan_many(mine[:n_cpu], n_threads=n_cpu)
+        d["cpu_sample"] = {"queries": n_cpu, "threads": n_cpu, "max_expansions": C4_CPU_SAMPLE_CAP,
+                           "costmap": "as above, limited to 12 m around the first start",
+                           "expansions_per_s": sum(r["expanded"] for r, _ in cpu_res) / t_cpu, "seconds": t_cpu}
+        d["identical_trees_on_sample"] = bool(all(np.array_equal(pl2.tree(i), t) for i, (_, t) in enumerate(cpu_res)))
+        pl2.close()
     pl.close()
     ctx.close()
     out["c4_batch"] = d

@@ -317,6 +317,7 @@ typedef struct mppb_expand_node
     double   bbox_min[3], bbox_max[3];   /* world box of the node's query: x y phi */
     int32_t  goal_k[MPPB_MAX_PTGS];      /* per PTG: path straight to the goal if inverseMap_WS2TP is exact, else -1 */
     uint32_t goal_step[MPPB_MAX_PTGS];   /* its step if getPathStepForDist found one, else 0xffffffff */
+    double   cos_phi, sin_phi;           /* cos / sin of pose[2] from the caller's C library, or both 0: the call takes them */
 } mppb_expand_node;
 
 typedef struct mppb_neighbor

@@ -97,11 +97,12 @@ class PathsDesc(C.Structure):
 
 
 EXPAND_NODE_DTYPE = np.dtype([("pose", np.float64, 3), ("bbox_min", np.float64, 3), ("bbox_max", np.float64, 3),
-                              ("goal_k", np.int32, MAX_PTGS), ("goal_step", np.uint32, MAX_PTGS)])
+                              ("goal_k", np.int32, MAX_PTGS), ("goal_step", np.uint32, MAX_PTGS),
+                              ("cos_phi", np.float64), ("sin_phi", np.float64)])
 NEIGHBOR_DTYPE = np.dtype([("cell", np.int32, 3), ("ptg_index", np.uint8), ("in_bbox", np.uint8), ("k", np.uint16),
                            ("step", np.uint32), ("ptg_dist", np.float32), ("pose", np.float64, 3),
                            ("vel", np.float64, 3), ("cost", np.float64)])
-assert EXPAND_NODE_DTYPE.itemsize == 136 and NEIGHBOR_DTYPE.itemsize == 80
+assert EXPAND_NODE_DTYPE.itemsize == 152 and NEIGHBOR_DTYPE.itemsize == 80
 
 
 class PlanQuery(C.Structure):

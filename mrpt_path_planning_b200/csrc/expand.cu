@@ -492,8 +492,16 @@ int expand_nodes_impl(mppb_ctx* ctx, size_t n, const mppb_expand_node* nodes, in
         const mppb_expand_node& N = nodes[i];
         hN[4 * i + 0]             = N.pose[0];
         hN[4 * i + 1]             = N.pose[1];
-        hN[4 * i + 2]             = std::cos(N.pose[2]);
-        hN[4 * i + 3]             = std::sin(N.pose[2]);
+        if (N.cos_phi == 0.0 && N.sin_phi == 0.0)
+        {
+            hN[4 * i + 2] = std::cos(N.pose[2]);
+            hN[4 * i + 3] = std::sin(N.pose[2]);
+        }
+        else  // taken by the caller (the planner's workers have them at hand: one thread would otherwise take them all)
+        {
+            hN[4 * i + 2] = N.cos_phi;
+            hN[4 * i + 3] = N.sin_phi;
+        }
         if (useBoxes)
         {
             // world box as apply_clipping_box sees it: double -> float (ObstacleSource.cpp:29-30)

@@ -81,6 +81,12 @@ struct TPose2D
         const double dx = x - b.x, dy = y - b.y;
         return {dx * c + dy * s, -dx * s + dy * c, wrap_to_pi(phi - b.phi)};
     }
+    /** operator-(b) with cos(b.phi), sin(b.phi) taken by the caller */
+    TPose2D minusCS(const TPose2D& b, double c, double s) const
+    {
+        const double dx = x - b.x, dy = y - b.y;
+        return {dx * c + dy * s, -dx * s + dy * c, wrap_to_pi(phi - b.phi)};
+    }
     double   norm() const { return std::sqrt(x * x + y * y); }
     TPoint2D translation() const { return {x, y}; }
     bool     operator==(const TPose2D& o) const { return x == o.x && y == o.y && phi == o.phi; }

@@ -1396,8 +1396,13 @@ struct TPS_Astar::Impl::Query
     // :650-677; inverseMap_WS2TP takes atan2 from the host C library) ----
     void phaseAExpand()
     {
-        const Node&   from    = *current;
-        const TPose2D relGoal = in->stateGoal.asSE2KinState().pose - from.state.pose;
+        const Node& from = *current;
+        // cos/sin of the node's heading, once: for the goal as seen from the node, for the local velocity, and for the
+        // expansion call (which would otherwise take them for every node of the batch on one thread)
+        const double  fromC = std::cos(from.state.pose.phi), fromS = std::sin(from.state.pose.phi);
+        const TPose2D relGoal = in->stateGoal.asSE2KinState().pose.minusCS(from.state.pose, fromC, fromS);
+        expIn.cos_phi = fromC;
+        expIn.sin_phi = fromS;
         for (int i = 0; i < 3; i++)
         {
             const double* lo = &in->worldBboxMin.x;  // (x, y, phi are consecutive doubles of TPose2D)
@@ -1414,7 +1419,7 @@ struct TPS_Astar::Impl::Query
             ptg_t& ptg = *trs.ptgs[ptgIdx];
             {
                 TNavDynamicState ds;
-                (ds.curVelLocal = from.state.vel).rotate(-from.state.pose.phi);
+                (ds.curVelLocal = from.state.vel).rotateCS(fromC, -fromS);  // rotate(-phi): cos is even, sin is odd
                 ds.relTarget      = relGoal;
                 ds.targetRelSpeed = itSpeed != nodesWithDesiredSpeed.end() ? itSpeed->second : 0;
                 ptg.updateNavDynamicState(ds);
