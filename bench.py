@@ -186,6 +186,7 @@ def run_reference(args, rank, world):
     }))
 
 
+TRAFFIC_FILE = "r1p_traffic.json"  # ncu counters of tpobs_grid_kernel (dram bytes, warp instructions) per launch
 C4_COSTMAP = (0.10, 0.5, 4.0)  # resolution, preferredClearanceDistance, maxCost
 C4_CPU_SAMPLE_CAP = 100
 WAYPOINTS01 = ([3.0, 5.0, 9.0, 20.0, 26.0], [2.0, 5.0, 8.0, 7.0, 3.0])  # share/mvsim-demo-waypoints01.yaml targets
@@ -559,25 +560,42 @@ def run_ours(args, rank, local_rank, world):
     peaks, peak_src = measured_peaks()
     kernel_s = dev_ms * 1e-3  # the step is exactly one launch of tpobs_grid_kernel
     achieved_tf = work["flop_ref"] / kernel_s / 1e12
+    # Roofline of the dominant kernel (the step is exactly one launch of tpobs_grid_kernel). Nothing on this path is a
+    # dense contraction and the cloud is L2-resident, so neither of the contract's two bounds ("hbm", "tensor") is the
+    # limiter; the headline fraction is the PHYSICAL one against the CUDA-core FP32 peak: the FLOPs the binned kernel
+    # has to execute (B * N_in * (6 + 8 + 6 P)) over the measured launch time. Next to it: the HBM figure, the
+    # issue-slot figure (warp instructions of the ncu capture against the SMs' issue rate: what actually bounds the
+    # kernel) and, under its own key, SURVEY 8(d)'s reference-equivalent convention, which exceeds 1 because the
+    # kernel skips the 99 % of the reference's per-point tests that the bin index makes unnecessary.
+    binned_tf = work["flop_binned"] / kernel_s / 1e12
     roofline = {
-        "bound": "fp32", "kernel": "tpobs_grid_kernel", "achieved": achieved_tf, "peak": fp32_peak,
-        "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
+        "bound": "fp32 (CUDA cores; the contract's 'hbm' and 'tensor' figures do not bind this kernel: see 'hbm')",
+        "kernel": "tpobs_grid_kernel", "achieved": binned_tf, "peak": fp32_peak,
+        "unit": "TFLOP/s", "frac": binned_tf / fp32_peak if fp32_peak else None,
         "peak_source": "FMA microbenchmark on this GPU (MEASURED_PEAKS.json has no CUDA-core figure)",
-        "convention": "SURVEY 8(d) reference-equivalent FLOPs: every node tests every point (26.2 kFLOP/edge); "
-                      "the kernel bins the cloud and skips out-of-window points, so frac can exceed 1",
-        "flop_per_launch": work["flop_ref"],
-        "binned": {"flop_per_launch": work["flop_binned"], "achieved": work["flop_binned"] / kernel_s / 1e12,
-                   "frac": work["flop_binned"] / kernel_s / 1e12 / fp32_peak if fp32_peak else None},
+        "convention": "physical: FLOPs of the binned kernel, B * N_in * (6 + 8 + 6 P) per launch",
+        "flop_per_launch": work["flop_binned"],
         "hbm": {"algorithmic_bytes": work["hbm_bytes"], "achieved": work["hbm_bytes"] / kernel_s / 1e9,
                 "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peak_src,
                 "frac": work["hbm_bytes"] / kernel_s / 1e9 / peaks.get("hbm_gbs", 1)},
+        "survey_convention": {
+            "what": "SURVEY 8(d) reference-equivalent FLOPs: every node tests every point (26.2 kFLOP/edge)",
+            "flop_per_launch": work["flop_ref"], "achieved": achieved_tf,
+            "frac": achieved_tf / fp32_peak if fp32_peak else None},
         "fp64_peak_tflops": fp64_peak, "traffic": None,
     }
-    tpath = os.path.join(ROOT, "profiles", "r1p_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
     if os.path.exists(tpath) and B == 4096 and args.points == (1 << 20):
         t = json.load(open(tpath))["tpobs_grid_kernel"]
         roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]  # bytes per launch, from the ncu capture
-        roofline["traffic_source"] = "profiles/r1p_grid_ncu_full.txt"
+        roofline["traffic_source"] = "profiles/" + TRAFFIC_FILE
+        # issue slots: one warp instruction per scheduler and cycle, 4 schedulers per SM
+        sm_hz = 1e6 * (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        issue_peak = 148 * 4 * sm_hz
+        roofline["issue_slots"] = {"warp_instructions_per_launch": t["warp_instructions"],
+                                   "achieved_per_s": t["warp_instructions"] / kernel_s, "peak_per_s": issue_peak,
+                                   "frac": t["warp_instructions"] / kernel_s / issue_peak,
+                                   "ncu_issue_active_pct": t["issue_active_pct"], "ncu_warps_active_pct": t["warps_active_pct"]}
         roofline["limiter"] = ("instruction issue and per-CTA latency: %.0f %% issue-slot utilisation at %.0f %% occupancy "
                                "(9 CTAs per SM, register-bound), %.1f M warp instructions per launch (ncu); neither HBM "
                                "nor FMA throughput bounds this kernel" % (

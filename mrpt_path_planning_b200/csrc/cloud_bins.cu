@@ -7,6 +7,7 @@
 // passes over the cloud (8 B/point read, 8 B/point written).
 #include <cfloat>
 #include <cmath>
+#include <limits>
 
 #include "mppb_internal.cuh"
 #include "scan.cuh"
@@ -160,7 +161,9 @@ int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize)
     // 3) histogram, scan, scatter
     MPPB_CUDA(ctx, cs.binStart.reserve((static_cast<size_t>(nb) + 1) * sizeof(uint32_t)));
     MPPB_CUDA(ctx, cs.binCursor.reserve(static_cast<size_t>(nb) * sizeof(uint32_t)));
-    MPPB_CUDA(ctx, cs.sortedPts.reserve(n * sizeof(float2)));
+    // (+2 points: the staged form of tpobs_grid_kernel copies 16-byte-aligned pieces, which may take one point past a
+    // run's end; past the last point it finds a sentinel that no clipping square contains)
+    MPPB_CUDA(ctx, cs.sortedPts.reserve((n + 2) * sizeof(float2)));
     MPPB_CUDA(ctx, cudaMemsetAsync(cs.binCursor.p, 0, static_cast<size_t>(nb) * sizeof(uint32_t), st));
     bin_count_kernel<<<blocks, threads, 0, st>>>(xs, ys, n, keep, b.minx, b.miny, b.invBin, b.nbx, b.nby,
                                                 cs.binCursor.as<uint32_t>());
@@ -178,6 +181,11 @@ int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize)
     MPPB_CUDA(ctx, cudaMemcpyAsync(&total, cs.binStart.as<uint32_t>() + nb, sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, st));
     MPPB_CUDA(ctx, cudaStreamSynchronize(st));
+    {
+        const float  inf       = std::numeric_limits<float>::infinity();
+        const float2 sentinel[2] = {make_float2(inf, inf), make_float2(inf, inf)};
+        MPPB_CUDA(ctx, cudaMemcpyAsync(cs.sortedPts.as<float2>() + total, sentinel, sizeof(sentinel), cudaMemcpyHostToDevice, st));
+    }
     MPPB_CUDA(ctx, cudaGetLastError());
     b.n        = total;
     b.pts      = cs.sortedPts.as<float2>();

@@ -222,16 +222,74 @@ __device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned
 // at eight consecutive chunks at a time. A lone CTA is bound by the latency of its dependent loads (a free path is
 // ~35 chunk loads in a row, a sparse window a chain of by-cell lists: 13-27 us measured on the reference's demo
 // map); split, the whole scan is a handful of load round trips and there is no communication between the CTAs.
-template <bool HAS_BOX, int SPLIT>
+// STAGED: phase 1 reads the node's points from shared memory, where a producer warp puts them with bulk asynchronous
+// copies (cp.async.bulk + mbarrier transaction counts, the 1-D form of TMA): the bin-row runs of the node's window are
+// cut into 16-byte-aligned pieces and packed, piece after piece, into a ring of kStages buffers of kStagePts points; the
+// other warps consume stage s while the copies of stages s+1.. are in flight. The point loop is then a dense loop over
+// shared memory — no chunk table, no per-iteration look-up of the next run, no global-load latency inside it.
+constexpr int kStages   = 3;
+constexpr int kStagePts = 512;  // 4 KB per stage
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool HAS_BOX, int SPLIT, bool STAGED = false>
 __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
                       float* __restrict__ out)
 {
-    extern __shared__ unsigned smem[];
+    extern __shared__ __align__(16) unsigned smem[];
     unsigned*           smin   = smem;               // [totalPaths] float bits
     unsigned*           bitmap = smem + totalPaths;  // [bitmapWords] one bit per grid cell, in 8 x 4 tiles per word
+    // STAGED: the ring of point buffers follows (16-byte aligned), kStages x kStagePts float2
+    float2* const stageBuf = reinterpret_cast<float2*>(smem + ((totalPaths + bitmapWords + 3) & ~3));
+    __shared__ __align__(8) uint64_t fullBar[kStages], emptyBar[kStages];  // data landed / every warp done with the slot
+    uint32_t stageCount = 0;  // stages consumed so far by this CTA (slot = count % kStages, parity = (count / kStages) & 1)
+    if constexpr (STAGED)
+    {
+        if (threadIdx.x == 0)
+        {
+            for (int i = 0; i < kStages; i++)
+            {
+                mbar_init(&fullBar[i], 1);
+                mbar_init(&emptyBar[i], kWarps);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     __shared__ uint32_t rowBeg[kRowsPerPass];
     __shared__ uint32_t rowPrefix[kRowsPerPass + 1];
     __shared__ uint32_t rowLen[kRowsPerPass];
@@ -320,7 +378,148 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
         const int words = grid_tiles_x(gnx) * grid_tiles_y(gny);
         for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
 
+        // one point of the node's window: FP32 filtered path, exact FP64 chain for the undecided ones
+        auto processPoint = [&](const float2 g) {
+            if (HAS_BOX && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) return;
+            if (fastOk)
+            {
+                // ---- FP32 filtered path ----
+                const float dx = (g.x - x0h) - x0l, dy = (g.y - y0h) - y0l;
+                const float am = fmaxf(fabsf(dx), fabsf(dy));
+                if (am > clipHi) return;  // certainly outside the clipping square
+                // cell coordinates q = (R^T d - gmin) / res, folded into two FMAs per axis
+                const float qx = fmaf(dx, cq, fmaf(dy, sq, offx));
+                const float qy = fmaf(dy, cq, fmaf(-dx, sq, offy));
+                const float rx = qx - floorf(qx), ry = qy - floorf(qy);
+                const float edge = fmaxf(fabsf(rx - 0.5f), fabsf(ry - 0.5f));  // > 0.5-mq: near a cell edge
+                const bool  unsure = am >= clipLo || edge > halfMinusMq || fmaf(dx, dx, dy * dy) <= guardHi;
+                if (!unsure)
+                {
+                    // x2idx truncates toward zero: q in (-1,0) still maps to cell 0
+                    const unsigned cx = static_cast<unsigned>(__float2int_rz(qx));
+                    const unsigned cy = static_cast<unsigned>(__float2int_rz(qy));
+                    if (cx >= static_cast<unsigned>(gnx) || cy >= static_cast<unsigned>(gny)) return;
+                    atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
+                    return;
+                }
+            }
+            // ---- exact FP64 chain (reference operation order, no FMA) ----
+            const double gx = g.x, gy = g.y;
+            if (clipped_out(gx, x0, clip) || clipped_out(gy, y0, clip)) return;
+            // composePoint with the inverse pose
+            const double ox = __dadd_rn(__dadd_rn(ix, __dmul_rn(gx, c)), __dmul_rn(gy, s));
+            const double oy = __dadd_rn(__dsub_rn(iy, __dmul_rn(gx, s)), __dmul_rn(gy, c));
+            const float  fx = __double2float_rn(ox), fy = __double2float_rn(oy);  // CPointsMap stores float
+            const double lx = fx, ly = fy;
+            const int    cx = grid_index(lx, gxmin, gres, ginv);
+            const int    cy = grid_index(ly, gymin, gres, ginv);
+            if (cx < 0 || cx >= gnx || cy < 0 || cy >= gny) return;
+            const uint32_t cell = cx + cy * gnx;
+            // isPointInsideRobotShape: only points within the bounding radius can be inside
+            if (__builtin_expect(fx * fx + fy * fy <= guardR2, 0))
+            {
+                if (polygon_contains(G, lx, ly))
+                {
+                    // obstacle inside the robot shape: no bit; its cell is queued for phase 1b
+                    const unsigned slot = atomicAdd(&nInside, 1u);
+                    if (slot < kMaxInside)
+                        insideCell[slot] = cell;
+                    else
+                        apply_inside_cell(G, cell, smin, 0, 1);  // queue overflow: do it right here
+                    return;
+                }
+            }
+            atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
+        };
+
         // ---- phase 1: points -> occupancy bitmap ----
+        if constexpr (STAGED)
+        {
+            for (int rowBase = by0; rowBase <= by1; rowBase += kRowsPerPass)
+            {
+                const int nRows = min(kRowsPerPass, by1 - rowBase + 1);
+                __syncthreads();  // bitmap cleared / previous pass done with the row tables and the stage buffers
+                if (threadIdx.x < nRows)
+                {
+                    const size_t   r = static_cast<size_t>(rowBase + threadIdx.x) * bins.nbx;
+                    const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
+                    // 16-byte-aligned piece around the run: at most one foreign point at either end, which the clip
+                    // test rejects like any other point outside the window (past the cloud's end: a sentinel)
+                    const uint32_t ba = b & ~1u, ea = (e + 1u) & ~1u;
+                    rowBeg[threadIdx.x]        = ba;
+                    rowPrefix[threadIdx.x + 1] = e != b ? ea - ba : 0u;  // points staged for this row
+                    if (e != b) atomicAdd(&ptsTotal, e - b);
+                }
+                __syncthreads();
+                if (warp == 0)
+                {
+                    // inclusive scan of up to 64 piece lengths, two per lane
+                    uint32_t a0 = (2 * lane < nRows) ? rowPrefix[2 * lane + 1] : 0u;
+                    uint32_t a1 = (2 * lane + 1 < nRows) ? rowPrefix[2 * lane + 2] : 0u;
+                    uint32_t v  = a0 + a1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const uint32_t t = __shfl_up_sync(kFull, v, o);
+                        if (lane >= o) v += t;
+                    }
+                    if (lane == 0) rowPrefix[0] = 0;
+                    if (2 * lane < nRows) rowPrefix[2 * lane + 1] = v - a1;
+                    if (2 * lane + 1 < nRows) rowPrefix[2 * lane + 2] = v;
+                }
+                __syncthreads();
+                const uint32_t total   = rowPrefix[nRows];
+                const uint32_t nStages = (total + kStagePts - 1) / kStagePts;
+                // producer (warp 0): the pieces of stage st, one row per lane and round, into slot (stageCount+st) % kStages
+                auto issue = [&](uint32_t st) {
+                    const uint32_t slot = (stageCount + st) % kStages;
+                    const uint32_t lo = st * kStagePts, hi = min(total, lo + kStagePts);
+                    uint32_t       myBytes = 0;
+                    for (int r = lane; r < nRows; r += 32)
+                    {
+                        const uint32_t plo = max(rowPrefix[r], lo), phi = min(rowPrefix[r + 1], hi);
+                        if (plo < phi) myBytes += (phi - plo) * static_cast<uint32_t>(sizeof(float2));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) myBytes += __shfl_xor_sync(kFull, myBytes, o);
+                    if (lane == 0)
+                    {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot was read through the generic proxy
+                        mbar_arrive_expect_tx(&fullBar[slot], myBytes);
+                    }
+                    __syncwarp();
+                    for (int r = lane; r < nRows; r += 32)
+                    {
+                        const uint32_t plo = max(rowPrefix[r], lo), phi = min(rowPrefix[r + 1], hi);
+                        if (plo < phi)
+                            bulk_copy_g2s(stageBuf + static_cast<size_t>(slot) * kStagePts + (plo - lo),
+                                          bins.pts + rowBeg[r] + (plo - rowPrefix[r]),
+                                          (phi - plo) * static_cast<uint32_t>(sizeof(float2)), &fullBar[slot]);
+                    }
+                };
+                if (warp == 0)
+                    for (uint32_t st = 0; st < min(nStages, static_cast<uint32_t>(kStages)); st++) issue(st);
+                for (uint32_t st = 0; st < nStages; st++)
+                {
+                    const uint32_t seq = stageCount + st, slot = seq % kStages;
+                    mbar_wait(&fullBar[slot], (seq / kStages) & 1u);
+                    const uint32_t cnt = min(total - st * kStagePts, static_cast<uint32_t>(kStagePts));
+                    const float2*  sp  = stageBuf + static_cast<size_t>(slot) * kStagePts;
+                    for (uint32_t i = threadIdx.x; i < cnt; i += kThreads) processPoint(sp[i]);
+                    // slot released warp by warp; only the producer warp waits for the others before it refills the
+                    // slot, the consumers run on into the next stage (already in flight or landed)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&emptyBar[slot]);
+                    if (warp == 0 && st + kStages < nStages)
+                    {
+                        mbar_wait(&emptyBar[slot], (seq / kStages) & 1u);
+                        issue(st + kStages);
+                    }
+                }
+                stageCount += nStages;
+            }
+        }
+        else
 #ifdef MPPB_DBG_SKIP_PHASE1  // timing attribution experiments only
         for (int rowBase = by0; rowBase <= by1 && clip < 0; rowBase += kRowsPerPass)
 #else
@@ -399,56 +598,7 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
                         validNext = true;
                     }
                     if (!valid) continue;
-                    if (HAS_BOX && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) continue;
-                    if (fastOk)
-                    {
-                        // ---- FP32 filtered path ----
-                        const float dx = (g.x - x0h) - x0l, dy = (g.y - y0h) - y0l;
-                        const float am = fmaxf(fabsf(dx), fabsf(dy));
-                        if (am > clipHi) continue;  // certainly outside the clipping square
-                        // cell coordinates q = (R^T d - gmin) / res, folded into two FMAs per axis
-                        const float qx = fmaf(dx, cq, fmaf(dy, sq, offx));
-                        const float qy = fmaf(dy, cq, fmaf(-dx, sq, offy));
-                        const float rx = qx - floorf(qx), ry = qy - floorf(qy);
-                        const float edge = fmaxf(fabsf(rx - 0.5f), fabsf(ry - 0.5f));  // > 0.5-mq: near a cell edge
-                        const bool  unsure = am >= clipLo || edge > halfMinusMq || fmaf(dx, dx, dy * dy) <= guardHi;
-                        if (!unsure)
-                        {
-                            // x2idx truncates toward zero: q in (-1,0) still maps to cell 0
-                            const unsigned cx = static_cast<unsigned>(__float2int_rz(qx));
-                            const unsigned cy = static_cast<unsigned>(__float2int_rz(qy));
-                            if (cx >= static_cast<unsigned>(gnx) || cy >= static_cast<unsigned>(gny)) continue;
-                            atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
-                            continue;
-                        }
-                    }
-                    // ---- exact FP64 chain (reference operation order, no FMA) ----
-                    const double gx = g.x, gy = g.y;
-                    if (clipped_out(gx, x0, clip) || clipped_out(gy, y0, clip)) continue;
-                    // composePoint with the inverse pose
-                    const double ox = __dadd_rn(__dadd_rn(ix, __dmul_rn(gx, c)), __dmul_rn(gy, s));
-                    const double oy = __dadd_rn(__dsub_rn(iy, __dmul_rn(gx, s)), __dmul_rn(gy, c));
-                    const float  fx = __double2float_rn(ox), fy = __double2float_rn(oy);  // CPointsMap stores float
-                    const double lx = fx, ly = fy;
-                    const int    cx = grid_index(lx, gxmin, gres, ginv);
-                    const int    cy = grid_index(ly, gymin, gres, ginv);
-                    if (cx < 0 || cx >= gnx || cy < 0 || cy >= gny) continue;
-                    const uint32_t cell = cx + cy * gnx;
-                    // isPointInsideRobotShape: only points within the bounding radius can be inside
-                    if (__builtin_expect(fx * fx + fy * fy <= guardR2, 0))
-                    {
-                        if (polygon_contains(G, lx, ly))
-                        {
-                            // obstacle inside the robot shape: no bit; its cell is queued for phase 1b
-                            const unsigned slot = atomicAdd(&nInside, 1u);
-                            if (slot < kMaxInside)
-                                insideCell[slot] = cell;
-                            else
-                                apply_inside_cell(G, cell, smin, 0, 1);  // queue overflow: do it right here
-                            continue;
-                        }
-                    }
-                    atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
+                    processPoint(g);
                 }
             }
         }
@@ -620,11 +770,15 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     size_t words = 1;
     for (const auto& g : ctx->groups)
         words = std::max(words, static_cast<size_t>(grid_tiles_x(g.dev.nx)) * grid_tiles_y(g.dev.ny));
-    const size_t smem = (static_cast<size_t>(ctx->totalPaths) + words) * sizeof(unsigned);
-    if (smem > 200 * 1024)
-        return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
     // small batches: kSplit CTAs per node (see the kernel), else one
     const bool split = nNodes <= static_cast<size_t>(kSplitMaxNodes) && !g_noSplit;
+    // the staged form (points through cp.async.bulk into a shared-memory ring) of the one-CTA-per-node kernel
+    static const bool staged = std::getenv("MPPB_GRID_STAGED") != nullptr && std::atoi(std::getenv("MPPB_GRID_STAGED")) != 0;
+    const bool        useStaged = staged && !split;
+    size_t            smem = ((static_cast<size_t>(ctx->totalPaths) + words + 3) & ~static_cast<size_t>(3)) * sizeof(unsigned);
+    if (useStaged) smem += static_cast<size_t>(kStages) * kStagePts * sizeof(float2);
+    if (smem > 200 * 1024)
+        return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
     auto       launch = [&](auto kernel, unsigned ctasPerNode) -> int {
         if (smem > 48 * 1024)
             MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -636,6 +790,8 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     int rc;
     if (split)
         rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit>, kSplit) : launch(tpobs_grid_kernel<false, kSplit>, kSplit);
+    else if (useStaged)
+        rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, true>, 1) : launch(tpobs_grid_kernel<false, 1, true>, 1);
     else
         rc = dBoxes ? launch(tpobs_grid_kernel<true, 1>, 1) : launch(tpobs_grid_kernel<false, 1>, 1);
     if (rc != MPPB_OK) return rc;

@@ -1,5 +1,7 @@
 """GPU parity of stage (a)+(b) for collision-grid PTGs: libmpp_b200 (through the C ABI) vs the
 CPU oracle on the same seeded inputs. Bar: bit-exact (the values are table floats, 0 or +inf)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -269,3 +271,18 @@ def test_many_nodes_in_one_batch(gpu_ctx):
     out = gpu_ctx.eval_nodes(big, 5.0)
     assert out.shape[0] > 65535
     assert np.array_equal(out, np.tile(rows, (reps, 1)))
+
+
+def test_staged_form_of_the_kernel_is_bit_identical():
+    """tpobs_grid_kernel's STAGED form (points through cp.async.bulk + mbarrier into a shared-memory ring; selected
+    with MPPB_GRID_STAGED=1, read once per process) gives the same rows as the default form: the parity tests of this
+    file and the golden vectors, in a child process with the variable set."""
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, MPPB_GRID_STAGED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_tpobs_grid_gpu.py"),
+                        os.path.join(here, "test_golden_gpu.py"), "-x", "-q", "-k", "not staged_form"], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
