@@ -247,6 +247,10 @@ void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, doubl
 /* Diagnostic switch: on == 0 runs the HolonomicBlend kernel without its geometric pre-filter (every in-window point
  * goes through the exact FP64 chain). Results are identical either way; the tests compare the two. Default: on. */
 int mppb_set_holo_filter(mppb_ctx* ctx, int on);
+/* Diagnostic switch: on != 0 runs host batches of mppb_eval_holo_candidates* whose candidates are grouped by node on
+ * the one-CTA-per-node form of the kernel (the node's window is walked once for all its candidates). Results are
+ * identical either way; the tests compare the two. Measured no faster on B200, so the default is off. */
+int mppb_set_holo_by_node(mppb_ctx* ctx, int on);
 
 /* HolonomicBlend: out[c] = min over the in-window points of node cands[c].node of the
  * TP-space collision distance of candidate c (+INF if unconstrained), in double.
@@ -532,11 +536,12 @@ int mppb_planner_path(mppb_planner* p, size_t query, double* nodes, double* edge
 int64_t mppb_planner_tree(mppb_planner* p, size_t query, double* out, int64_t cap);
 /* plan_to_trajectory + save_to_txt text (src/algos/trajectories.cpp:15-106); returns the text length */
 int64_t mppb_planner_trajectory_txt(mppb_planner* p, size_t query, double sample_period, char* buf, int64_t cap);
-/* Work of the last plan, out13 = collision batches, cost batches, nodes, holo candidates, edges, seconds in GPU
+/* Work of the last plan, out14 = collision batches, cost batches, nodes, holo candidates, edges, seconds in GPU
  * calls, then wall seconds per phase: set-up, F relax + pop + A enumerate, B collision (GPU; for a single query it
  * includes the second half of A, which the host runs while the kernels do), C+D select/build, E assemble,
- * E cost (GPU), teardown */
-int mppb_planner_gpu_stats(const mppb_planner* p, double* out13);
+ * E cost (GPU), teardown; [13] = HolonomicBlend free/blocked decisions taken within 1e-9 relative of a tie (the guard
+ * on the device's acos/cos in the quartic's trigonometric branch; expected 0) */
+int mppb_planner_gpu_stats(const mppb_planner* p, double* out14);
 /* Host self-test (no GPU) of the worker pool behind plan_batch: `rounds` times every index of [0,count) must run
  * exactly once on n_threads workers, and an exception thrown by a work item must reach the caller. Returns the number
  * of indices that did not (0 = correct), negative on a lost exception. */

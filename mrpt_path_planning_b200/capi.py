@@ -178,6 +178,7 @@ _SIGS = {
     "mppb_set_waypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
                                      C.c_double, C.c_int]),
     "mppb_set_holo_filter": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppb_set_holo_by_node": (C.c_int, [C.c_void_p, C.c_int]),
     "mppb_evaluators_epoch": (C.c_uint64, [C.c_void_p]),
     "mppb_num_evaluators": (C.c_int, [C.c_void_p]),
     "mppb_eval_edge_costs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -436,6 +437,10 @@ class Context:
     def set_holo_filter(self, on):
         """Diagnostic: run tpobs_holo_kernel with (default) or without its geometric pre-filter."""
         self._ck(lib().mppb_set_holo_filter(self.h, int(on)))
+
+    def set_holo_by_node(self, on):
+        """Diagnostic: grouped host batches on the one-CTA-per-node form of the HolonomicBlend kernel."""
+        self._ck(lib().mppb_set_holo_by_node(self.h, int(on)))
 
     def colgrid_build_stats(self):
         """Timings of the last mppb_build_collision_grid on this context."""
@@ -822,9 +827,9 @@ class Planner:
         return buf.value.decode()
 
     def gpu_stats(self):
-        v = np.zeros(13)
+        v = np.zeros(14)
         self._ck(lib().mppb_planner_gpu_stats(self.h, v.ctypes.data_as(c_double_p)))
         names = ["setup_uploads", "F_relax+pop+A_enumerate", "B_collision_gpu", "CD_select_build", "E_assemble",
                  "E_cost_gpu", "teardown"]
         return dict(collision_batches=int(v[0]), cost_batches=int(v[1]), nodes=int(v[2]), holo_candidates=int(v[3]),
-                    edges=int(v[4]), gpu_seconds=v[5], phase_seconds={n: float(x) for n, x in zip(names, v[6:]) if not n.startswith("_")})
+                    edges=int(v[4]), gpu_seconds=v[5], holo_near_ties=int(v[13]), phase_seconds={n: float(x) for n, x in zip(names, v[6:13]) if not n.startswith("_")})

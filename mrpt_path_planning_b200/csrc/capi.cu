@@ -131,6 +131,7 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     ctx->hNodesHolo.release();
     ctx->dNodesHolo.release();
     ctx->dBoxesHolo.release();
+    ctx->dCandBegin.release();
     ctx->dNodes.release();
     ctx->dOut.release();
     ctx->dStage.release();
@@ -163,6 +164,12 @@ int mppb_set_holo_filter(mppb_ctx* ctx, int on)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     ctx->holoFilter = on != 0;
+    return MPPB_OK;
+}
+int mppb_set_holo_by_node(mppb_ctx* ctx, int on)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    ctx->holoByNode = on != 0;
     return MPPB_OK;
 }
 void*    mppb_stream(mppb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
@@ -772,7 +779,28 @@ static int eval_holo_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* pos
         MPPB_CUDA(ctx, ctx->dStage2.reserve(outBytes));
         dOut = ctx->dStage2.as<double>();
     }
-    const int rc = launch_tpobs_holo(ctx, n_cands, dCands, dNodes, dBoxes, clip_dist, dOut, n_nodes);
+    // Diagnostic alternative (mppb_set_holo_by_node; measured no faster, see tpobs_holo.cu): candidates grouped by node
+    // -> one CTA per node, which walks the node's window once for all its candidates.
+    bool grouped = ctx->holoByNode && n_nodes >= 2;
+    for (size_t i = 1; grouped && i < n_cands; i++) grouped = cands[i].node >= cands[i - 1].node;
+    int rc;
+    if (grouped)
+    {
+        std::vector<uint32_t> begin(n_nodes + 1, 0);
+        for (size_t i = 0; i < n_cands; i++) begin[static_cast<size_t>(cands[i].node) + 1]++;
+        uint32_t maxPerNode = 0;
+        for (size_t b = 0; b < n_nodes; b++)
+        {
+            maxPerNode = std::max(maxPerNode, begin[b + 1]);
+            begin[b + 1] += begin[b];
+        }
+        MPPB_CUDA(ctx, ctx->dCandBegin.reserve((n_nodes + 1) * sizeof(uint32_t)));
+        MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->dCandBegin.p, begin.data(), (n_nodes + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                       ctx->stream));  // (pageable source: staged by the driver before the call returns)
+        rc = launch_tpobs_holo_by_node(ctx, n_nodes, ctx->dCandBegin.as<uint32_t>(), maxPerNode, dCands, dNodes, dBoxes, clip_dist, dOut);
+    }
+    else
+        rc = launch_tpobs_holo(ctx, n_cands, dCands, dNodes, dBoxes, clip_dist, dOut, n_nodes);
     if (rc != MPPB_OK) return rc;
     if (!outInPlace) MPPB_CUDA(ctx, cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (wait) MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // _begin: the caller's mppb_sync() completes the call

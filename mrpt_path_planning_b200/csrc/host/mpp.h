@@ -512,6 +512,10 @@ class TPS_Astar : public Planner
     struct GpuStats
     {
         size_t collisionBatches = 0, costBatches = 0, nodesEvaluated = 0, holoCandidates = 0, edgesCosted = 0;
+        /** HolonomicBlend TPS points whose free/blocked decision (relTrgDist >= freeDistance, TPS_Astar.cpp:749) was
+         *  taken with the two distances within 1e-9 relative of each other — the only place where the device's
+         *  acos/cos (CUDA libm, not glibc) could tip a decision. Expected: 0. */
+        size_t holoNearTies = 0;
         double gpuSeconds = 0;
         /** wall seconds per phase: [0] set-up and uploads, [1] F relax + pop + A enumerate (fused per query), [2] B collision (GPU),
          *  [3] C+D select/build, [4] E assemble, [5] E cost (GPU), [6] result hand-over and teardown */

@@ -862,6 +862,7 @@ struct TPS_Astar::Impl::Query
     // needs is kept in the lattice nodes themselves (see Node), and the tree — a map node plus a list node with a
     // 600-byte edge and its interpolated samples per tree node — is built once from them: when the query ends, or, for
     // a batch planned with materializeTrees == false, when somebody asks for it.
+    size_t           nearTies  = 0;       // see GpuStats::holoNearTies
     bool             useExpand = false;
     bool             lazyTree  = false;   // leave po.motionTree empty; the caller builds it on demand
     CellOrder        cellOrder;           // see CellOrder
@@ -1238,6 +1239,9 @@ struct TPS_Astar::Impl::Query
             MPP_ASSERT(!c.onGrid || c.evalIndex < gridCols);
             const double     raw          = c.onGrid ? static_cast<double>(gridRow[c.evalIndex]) : holoOut[c.evalIndex];
             const distance_t freeDistance = std::min(c.initDist, raw);
+            // decision guard (HolonomicBlend distances come out of a quartic whose trigonometric branch uses the
+            // device's acos/cos): count the decisions taken within 1e-9 relative of a tie
+            if (!c.onGrid && raw < c.initDist && std::fabs(c.relTrgDist - freeDistance) < 1e-9 * freeDistance) nearTies++;
             if (c.relTrgDist >= freeDistance) continue;  // blocked
             if (c.isTarget)
                 goalNodeCoords.insert(c.nc);
@@ -2118,6 +2122,7 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
     }
     // hand the results over and tear the per-query search state down in parallel (millions of small nodes)
     auto tEnd = Clock::now();
+    for (size_t i = 0; i < Q; i++) st.holoNearTies += qs[i]->nearTies;
     pool.run(Q, [&](size_t i) {
         outs[i] = std::move(qs[i]->po);
         if (qs[i]->lazyTree)

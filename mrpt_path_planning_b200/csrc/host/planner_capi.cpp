@@ -409,6 +409,7 @@ int mppb_planner_gpu_stats(const mppb_planner* p, double* out6)
     out6[3]       = static_cast<double>(s.holoCandidates);
     out6[4]       = static_cast<double>(s.edgesCosted);
     out6[5]       = s.gpuSeconds;
+    out6[13]      = static_cast<double>(s.holoNearTies);
     return MPPB_OK;
 }
 

@@ -276,6 +276,7 @@ struct mppb_ctx
     std::string  lastError;
     uint64_t     launches = 0;
     bool         holoFilter = true;  // geometric pre-filter of tpobs_holo_kernel (mppb_set_holo_filter)
+    bool         holoByNode = false; // host batches grouped by node run tpobs_holo_node_kernel (mppb_set_holo_by_node)
     cudaEvent_t  evBegin = nullptr, evEnd = nullptr;
     // second stream + fork/join events: the host entry points pipeline sub-batches over two streams
     cudaStream_t auxStream = nullptr;
@@ -324,7 +325,7 @@ struct mppb_ctx
 
     // staging for the host entry points
     mppb::PinnedBuf hNodes, hOut, hStage, hNodesHolo;
-    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes, dNodesHolo, dBoxesHolo;
+    mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes, dNodesHolo, dBoxesHolo, dCandBegin;
 };
 
 namespace mppb
@@ -346,6 +347,9 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
 // nNodes = rows of dNodes if the caller knows it (1 lets the kernel fetch the row early), 0 otherwise
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
                       const float* dBoxes, double clip, double* dOut, size_t nNodes = 0);
+// one CTA per node: candidates grouped by node, dCandBegin[nNodes+1] offsets into dCands
+int launch_tpobs_holo_by_node(mppb_ctx* ctx, size_t nNodes, const uint32_t* dCandBegin, size_t maxCandsPerNode,
+                              const mppb_holo_cand* dCands, const double* dNodes, const float* dBoxes, double clip, double* dOut);
 // nSamples = dOffsets[nEdges] if the caller knows it (selects the small-batch kernel), 0 otherwise
 int launch_edge_costs(mppb_ctx* ctx, size_t nEdges, const double* dFrom, const uint32_t* dOffsets, const double* dRel,
                       double* dOut, size_t nSamples = 0);

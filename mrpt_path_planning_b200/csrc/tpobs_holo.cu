@@ -29,6 +29,7 @@
 // per-candidate minimum is an order-independent min, reduced with warp shuffles.
 // This file is compiled with -fmad=false (see build.py): all arithmetic rounds as on the
 // reference's x86-64 build; acos/cos in the cubic's trigonometric branch are CUDA libm.
+#include <algorithm>
 #include <cfloat>
 
 #include <math_constants.h>
@@ -120,6 +121,31 @@ struct CandConsts
     double T, vxi, vyi, vxf, vyf, vf;
     double k2, k4, qa, qb, TR_2, T099, T101, R, Vmax, distAtT;
 };
+
+// the per-candidate constants of HolonomicBlend::updateTPObstacleSingle (HolonomicBlend.cpp:722-749), by a whole warp
+// whose lanes hold the same candidate (the 20-panel distance integral is shared out among the lanes)
+__device__ __forceinline__ CandConsts make_consts(const mppb_holo_cand& cd, const HoloPtgDev& P, int lane)
+{
+    CandConsts q;
+    q.T               = cd.T_ramp;
+    q.vxi             = cd.vxi;
+    q.vyi             = cd.vyi;
+    q.vxf             = cd.vxf;
+    q.vyf             = cd.vyf;
+    q.vf              = cd.vf;
+    q.R               = P.robotRadius;
+    q.Vmax            = P.vMax;
+    const double TR2_ = 1.0 / (2 * q.T);
+    q.TR_2            = q.T * 0.5;
+    q.T099            = q.T * 0.99;
+    q.T101            = q.T * 1.01;
+    q.k2              = (q.vxf - q.vxi) * TR2_;
+    q.k4              = (q.vyf - q.vyi) * TR2_;
+    q.qa              = (q.k2 * q.k2 + q.k4 * q.k4);
+    q.qb              = (q.k2 * q.vxi * 2.0 + q.k4 * q.vyi * 2.0);
+    q.distAtT         = ramp_distance_warp(q.k2, q.k4, q.vxi, q.vyi, q.T, lane);
+    return q;
+}
 
 // HolonomicBlend.cpp:719-840 for one local obstacle point; returns the candidate's updated minimum
 __device__ __forceinline__ double update_tp_obstacle(const CandConsts& q, double ox, double oy, double cur)
@@ -278,24 +304,7 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     const mppb_holo_cand cd = cands[ci];
     const HoloPtgDev     P  = ptgs[cd.ptg_index];
 
-    CandConsts q;
-    q.T               = cd.T_ramp;
-    q.vxi             = cd.vxi;
-    q.vyi             = cd.vyi;
-    q.vxf             = cd.vxf;
-    q.vyf             = cd.vyf;
-    q.vf              = cd.vf;
-    q.R               = P.robotRadius;
-    q.Vmax            = P.vMax;
-    const double TR2_ = 1.0 / (2 * q.T);
-    q.TR_2            = q.T * 0.5;
-    q.T099            = q.T * 0.99;
-    q.T101            = q.T * 1.01;
-    q.k2              = (q.vxf - q.vxi) * TR2_;
-    q.k4              = (q.vyf - q.vyi) * TR2_;
-    q.qa              = (q.k2 * q.k2 + q.k4 * q.k4);
-    q.qb              = (q.k2 * q.vxi * 2.0 + q.k4 * q.vyi * 2.0);
-    q.distAtT         = ramp_distance_warp(q.k2, q.k4, q.vxi, q.vyi, q.T, lane);
+    const CandConsts q = make_consts(cd, P, lane);
 
     const double x0 = nNodes == 1 ? row0[0] : nodes[4 * cd.node + 0], y0 = nNodes == 1 ? row0[1] : nodes[4 * cd.node + 1];
     const double c = nNodes == 1 ? row0[2] : nodes[4 * cd.node + 2], s = nNodes == 1 ? row0[3] : nodes[4 * cd.node + 3];
@@ -428,7 +437,207 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(kFull, best, o));
     if (lane == 0) out[ci] = best;
 }
+// ---- one CTA per node (diagnostic alternative, mppb_set_holo_by_node) ------------------------------------------------
+// The warp-per-candidate kernel above makes every candidate of a node walk the node's window on its own: the bin-row
+// runs are located, loaded, box- and clip-tested once per candidate — 129 times per node for the reference's demo
+// parameters. Here a CTA owns a node: (1) all threads walk the window ONCE and keep the points that may lie inside the
+// clipping square (conservative FP32 test; the exact FP64 test still decides) in shared memory, (2) each warp then
+// takes the node's candidates in turn over that dense array: FP32 transform, hull filter, queue, exact chain — the
+// same per-point arithmetic as above on the same set of points, so the results are the same minima (tested bit for
+// bit). Measured on B200 (21 504 candidates of 512 nodes, 2 621 in-window points each): 0.90 ms against 0.85 ms of the
+// kernel above — the time goes into the per-(candidate, point) filter and the exact chain, not into the window walk,
+// which the candidates of one node, sitting in consecutive warps, share through L1 anyway. Kept as an opt-in.
+// candBegin[b] .. candBegin[b+1]: the candidates of node b (the caller's array is grouped by node).
+constexpr int kNodeThreads = 256;
+constexpr int kNodeWarps   = kNodeThreads / 32;
+constexpr int kNodeMaxPts  = 6144;  // window points held per pass (48 KB)
+constexpr int kNodeRows    = 64;    // bin rows located together
+__global__ void __launch_bounds__(kNodeThreads, 3)
+    tpobs_holo_node_kernel(CloudBins bins, const HoloPtgDev* __restrict__ ptgs, const mppb_holo_cand* __restrict__ cands,
+                           const uint32_t* __restrict__ candBegin, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
+                           const float4* __restrict__ boxes, double clip, int useFilter, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char dynSmem[];
+    float2* const sPts  = reinterpret_cast<float2*>(dynSmem);                                   // [kNodeMaxPts]
+    double* const sBest = reinterpret_cast<double*>(dynSmem + sizeof(float2) * kNodeMaxPts);  // [candidates of the node]
+    __shared__ float2   queue[kNodeWarps][64];
+    __shared__ uint32_t rowBeg[kNodeRows], rowPrefix[kNodeRows + 1];
+    __shared__ unsigned sCount;
+
+    const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int      node = blockIdx.x;
+    const uint32_t cBeg = candBegin[node], cEnd = candBegin[node + 1];
+    if (cBeg == cEnd) return;
+    const double x0 = nodes[4 * node + 0], y0 = nodes[4 * node + 1], c = nodes[4 * node + 2], s = nodes[4 * node + 3];
+    const double ix = -x0 * c - y0 * s;  // CPose2D unary minus
+    const double iy = x0 * s - y0 * c;
+    const bool   hasBox = boxes != nullptr;
+    const float4 box    = hasBox ? boxes[node] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float  clipF  = static_cast<float>(clip);
+    const float  x0h = static_cast<float>(x0), x0l = static_cast<float>(x0 - static_cast<double>(x0h));
+    const float  y0h = static_cast<float>(y0), y0l = static_cast<float>(y0 - static_cast<double>(y0h));
+    const float  cf = static_cast<float>(c), sf = static_cast<float>(s);
+    const float  clipHi     = clipF + 1e-4f * fmaxf(clipF, 1.f);
+    const bool   clipFinite = isfinite(clipF) && clipF < 1e3f;
+
+    for (uint32_t i = threadIdx.x; i < cEnd - cBeg; i += kNodeThreads) sBest[i] = CUDART_INF;
+
+    if (bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0)
+    {
+        const float lox = nextafterf(__double2float_rd(x0 - clip), -FLT_MAX);
+        const float hix = nextafterf(__double2float_ru(x0 + clip), FLT_MAX);
+        const float loy = nextafterf(__double2float_rd(y0 - clip), -FLT_MAX);
+        const float hiy = nextafterf(__double2float_ru(y0 + clip), FLT_MAX);
+        const int   bx0 = bin_coord(lox, bins.minx, bins.invBin, bins.nbx);
+        const int   bx1 = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
+        const int   by0 = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
+        const int   by1 = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
+        for (int rowBase = by0; rowBase <= by1; rowBase += kNodeRows)
+        {
+            const int nRows = min(kNodeRows, by1 - rowBase + 1);
+            __syncthreads();  // previous pass done with the row tables
+            if (threadIdx.x < nRows)
+            {
+                const size_t   r = static_cast<size_t>(rowBase + threadIdx.x) * bins.nbx;
+                const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
+                rowBeg[threadIdx.x]        = b;
+                rowPrefix[threadIdx.x + 1] = e - b;
+            }
+            __syncthreads();
+            if (warp == 0)
+            {
+                // inclusive scan of up to 64 run lengths, two per lane
+                uint32_t a0 = (2 * lane < nRows) ? rowPrefix[2 * lane + 1] : 0u;
+                uint32_t a1 = (2 * lane + 1 < nRows) ? rowPrefix[2 * lane + 2] : 0u;
+                uint32_t v  = a0 + a1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t t = __shfl_up_sync(kFull, v, o);
+                    if (lane >= o) v += t;
+                }
+                if (lane == 0) rowPrefix[0] = 0;
+                if (2 * lane < nRows) rowPrefix[2 * lane + 1] = v - a1;
+                if (2 * lane + 1 < nRows) rowPrefix[2 * lane + 2] = v;
+            }
+            __syncthreads();
+            const uint32_t total = rowPrefix[nRows];
+            for (uint32_t f0 = 0; f0 < total; f0 += kNodeMaxPts)
+            {
+                // ---- (1) the window's points [f0, f1) of this row group -> shared memory, once for all candidates ----
+                const uint32_t f1 = min(total, f0 + static_cast<uint32_t>(kNodeMaxPts));
+                __syncthreads();  // the candidates of the previous pass are done with sPts
+                if (threadIdx.x == 0) sCount = 0;
+                __syncthreads();
+                for (uint32_t fb = f0; fb < f1; fb += kNodeThreads)
+                {
+                    const uint32_t f    = fb + threadIdx.x;
+                    bool           keep = false;
+                    float2         g    = make_float2(0.f, 0.f);
+                    if (f < f1)
+                    {
+                        int lo = 0, hi = nRows;  // the row whose flat range holds f
+                        while (hi - lo > 1)
+                        {
+                            const int mid = (lo + hi) >> 1;
+                            if (rowPrefix[mid] <= f)
+                                lo = mid;
+                            else
+                                hi = mid;
+                        }
+                        g    = bins.pts[rowBeg[lo] + (f - rowPrefix[lo])];
+                        keep = !(hasBox && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w));
+                        if (clipFinite)
+                        {
+                            const float dx = (g.x - x0h) - x0l, dy = (g.y - y0h) - y0l;
+                            keep           = keep && fmaxf(fabsf(dx), fabsf(dy)) <= clipHi;  // conservative; exact() decides
+                        }
+                    }
+                    const unsigned m    = __ballot_sync(kFull, keep);
+                    unsigned       base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&sCount, __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (keep) sPts[base + __popc(m & ((1u << lane) - 1u))] = g;
+                }
+                __syncthreads();
+                const uint32_t nPts = sCount;
+                // ---- (2) every candidate of the node over the dense array, one warp per candidate at a time ----
+                for (uint32_t ci = cBeg + warp; ci < cEnd; ci += kNodeWarps)
+                {
+                    const mppb_holo_cand cd = cands[ci];
+                    const HoloPtgDev     P  = ptgs[cd.ptg_index];
+                    const CandConsts     q  = make_consts(cd, P, lane);
+                    const PathHull       hull   = make_hull(q);
+                    const bool           filter = useFilter && hull.enabled && clipFinite;
+                    auto exact = [&](float2 g, double cur) -> double {
+                        const double gx = g.x, gy = g.y;
+                        // transform_pc_square_clipping.cpp:30-31
+                        if (fabs(gx - x0) > clip || fabs(gy - y0) > clip) return cur;
+                        const double ox = (ix + gx * c) + gy * s;
+                        const double oy = (iy - gx * s) + gy * c;
+                        const float  fx = static_cast<float>(ox), fy = static_cast<float>(oy);  // CPointsMap stores float
+                        return update_tp_obstacle(q, static_cast<double>(fx), static_cast<double>(fy), cur);
+                    };
+                    double best = CUDART_INF;
+                    int    qn   = 0;
+                    for (uint32_t pb = 0; pb < nPts || qn > 0; pb += 32)
+                    {
+                        const bool haveChunk = pb < nPts;
+                        if (haveChunk)
+                        {
+                            const uint32_t i    = pb + lane;
+                            bool           pass = i < nPts;
+                            float2         g    = make_float2(0.f, 0.f);
+                            if (pass)
+                            {
+                                g = sPts[i];
+                                if (filter)
+                                {
+                                    const float dx = (g.x - x0h) - x0l, dy = (g.y - y0h) - y0l;
+                                    pass           = hull_may_hit(hull, dx * cf + dy * sf, dy * cf - dx * sf);
+                                }
+                            }
+                            const unsigned m = __ballot_sync(kFull, pass);
+                            if (pass) queue[warp][qn + __popc(m & ((1u << lane) - 1u))] = g;
+                            qn += __popc(m);
+                        }
+                        if (qn >= 32 || (!haveChunk && qn > 0))
+                        {
+                            __syncwarp();
+                            const int take = min(qn, 32);
+                            if (lane < take) best = exact(queue[warp][qn - take + lane], best);
+                            qn -= take;
+                            __syncwarp();
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(kFull, best, o));
+                    if (lane == 0) sBest[ci - cBeg] = fmin(sBest[ci - cBeg], best);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cEnd - cBeg; i += kNodeThreads) out[cBeg + i] = sBest[i];
+}
 }  // namespace
+
+// One CTA per node (candidates grouped by node, offsets in dCandBegin[nNodes+1])
+int launch_tpobs_holo_by_node(mppb_ctx* ctx, size_t nNodes, const uint32_t* dCandBegin, size_t maxCandsPerNode,
+                              const mppb_holo_cand* dCands, const double* dNodes, const float* dBoxes, double clip, double* dOut)
+{
+    if (nNodes == 0) return MPPB_OK;
+    if (ctx->holos.empty()) return fail(ctx, MPPB_ERR_STATE, "no HolonomicBlend PTG set (mppb_set_ptg_holo)");
+    const size_t smem = sizeof(float2) * kNodeMaxPts + sizeof(double) * std::max<size_t>(maxCandsPerNode, 1);
+    if (smem > 200 * 1024) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many candidates per node");
+    MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_holo_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    tpobs_holo_node_kernel<<<static_cast<unsigned>(nNodes), kNodeThreads, smem, ctx->stream>>>(
+        ctx->bins, ctx->holoDescs.as<HoloPtgDev>(), dCands, dCandBegin, dNodes, reinterpret_cast<const float4*>(dBoxes), clip,
+        ctx->holoFilter ? 1 : 0, dOut);
+    ctx->launches++;
+    MPPB_CUDA(ctx, cudaGetLastError());
+    return MPPB_OK;
+}
 
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
                       const float* dBoxes, double clip, double* dOut, size_t nNodes)

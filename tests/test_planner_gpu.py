@@ -62,6 +62,9 @@ def test_c1_holonomic_demo_identical_tree_and_path(ctx, capi, orc):
     assert prod.trajectory_txt() == ora.trajectory_txt()
     st = prod.gpu_stats()
     assert st["collision_batches"] == r_p["expanded"] and st["holo_candidates"] > 0 and st["edges"] == r_p["edges_costed"]
+    # decision guard: no free/blocked decision of the search was taken within 1e-9 relative of a tie, so the device's
+    # acos/cos (the one non-IEEE ingredient of the HolonomicBlend distances) cannot have tipped one
+    assert st["holo_near_ties"] == 0
     # planning again on the same planner object (resident cloud and tables) gives the same answer
     r_p2 = prod.plan(start, goal, lo, hi)
     assert r_p2["path_cost"] == r_p["path_cost"] and r_p2["tree_nodes"] == r_p["tree_nodes"]

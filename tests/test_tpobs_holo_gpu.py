@@ -245,3 +245,58 @@ def test_split_calls_equal_blocking_calls(capi, product_ackermann, n_nodes, boxe
         assert np.array_equal(rows, want_rows)
         assert np.array_equal(hout, want_holo)
     ctx.close()
+
+
+@pytest.mark.parametrize("density,boxed,filt", [(3.0, False, True), (26.0, True, True), (90.0, False, True), (8.0, True, False)])
+def test_cta_per_node_kernel_equals_warp_per_candidate_kernel(holo_ctx, capi, orc, density, boxed, filt):
+    """mppb_set_holo_by_node: batches whose candidates are grouped by node run tpobs_holo_node_kernel (one CTA per node:
+    the window is walked once for all the node's candidates) instead of the warp-per-candidate kernel. Same points, same
+    per-point arithmetic: the same bits. 90 points/m^2 puts > 6144 points into a window (several passes)."""
+    ctx, ptg = holo_ctx
+    extent = 26.0
+    xs, ys = wl.uniform_cloud(int(density * extent * extent), extent, seed=int(density) + 3)
+    rng = np.random.default_rng(int(density) + 9)
+    n = 72
+    nodes, rel = random_nodes(rng, n, extent)
+    ks = [sorted(rng.choice(191, size=int(rng.integers(1, 20)), replace=False).tolist()) for _ in range(n)]
+    ks[5] = []  # a node without candidates
+    cands, cn, ck, cs = make_candidates(ptg, nodes, rel, ks, (1 / 3, 1.0))
+    boxes = None
+    if boxed:
+        boxes = np.stack([nodes[:, 0] - rng.uniform(1, 6, n), nodes[:, 1] - rng.uniform(1, 6, n),
+                          nodes[:, 0] + rng.uniform(1, 6, n), nodes[:, 1] + rng.uniform(1, 6, n)], 1).astype(np.float32)
+    ctx.set_obstacles(xs, ys)
+    L = capi.lib()
+
+    def run(node_sel):
+        sel = np.isin(cands["node"], node_sel)
+        sub = cands[sel].copy()
+        remap = {int(b): i for i, b in enumerate(node_sel)}
+        sub["node"] = [remap[int(b)] for b in sub["node"]]
+        poses = np.ascontiguousarray(nodes[node_sel, :3])
+        bx = np.ascontiguousarray(boxes[node_sel]) if boxes is not None else None
+        out = np.empty(len(sub), dtype=np.float64)
+        rc = L.mppb_eval_holo_candidates_boxed(ctx.h, len(poses), poses.ctypes.data, bx.ctypes.data if bx is not None else None,
+                                               len(sub), sub.ctypes.data, 5.0, out.ctypes.data)
+        assert rc == 0
+        return sel, out
+
+    try:
+        ctx.set_holo_filter(filt)
+        ctx.set_holo_by_node(True)
+        _, whole = run(list(range(n)))                       # CTA per node
+        ctx.set_holo_by_node(False)
+        parts = np.empty_like(whole)
+        for lo in range(0, n, 24):                            # warp per candidate, 24 nodes at a time
+            sel, o = run(list(range(lo, lo + 24)))
+            parts[sel] = o
+    finally:
+        ctx.set_holo_filter(True)
+        ctx.set_holo_by_node(False)
+    assert np.array_equal(whole.view(np.uint64), parts.view(np.uint64))
+    assert np.isfinite(whole).any()
+    if not boxed:
+        ref, _, _ = orc.eval_candidates(orc.holonomic_ptgs()[0], xs, ys, nodes, rel, cn, ck, cs, 5.0, want_free=False)
+        assert np.array_equal(np.isinf(whole), np.isinf(ref)) and np.array_equal(whole == 0.0, ref == 0.0)
+        fin = np.isfinite(ref)
+        assert (np.abs(whole[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-12)).max() <= RTOL
