@@ -356,8 +356,11 @@ def config_dict(args, **extra):
 
 
 def cloud_sharded_bench(ctx, dev, stream, rank, world, args, d_nodes, d_out, flush):
-    """Config C5 in weak-scaling form: a cloud of world x 2^23 points, sharded by point index; every rank evaluates
-    the SAME 4096-node batch against its shard and the per-edge minima are merged with NCCL all_reduce(MIN)."""
+    """Config C5 in weak-scaling form: a cloud of world x 2^23 points, sharded by point index; every rank evaluates the
+    SAME 4096-node batch against its shard and the per-edge minima are merged inside the library
+    (mppb_eval_nodes_sharded_device): by the fused peer-memory epilogue of tpobs_grid_kernel, and, for comparison, by
+    ncclAllReduce(min). Rank 0 checks the merged rows against an evaluation of the whole cloud on one GPU (all nodes,
+    bit for bit) and against the reference's own CPU code on the whole cloud (a node sample)."""
     import torch
     import torch.distributed as dist
 
@@ -365,39 +368,71 @@ def cloud_sharded_bench(ctx, dev, stream, rank, world, args, d_nodes, d_out, flu
 
     n_total = args.c5_points_per_gpu * world
     xs, ys = wl.uniform_cloud(n_total, EXTENT, seed=wl.C5_CLOUD_SEED)
-    sx, sy = sharding.cloud_shard(xs, ys, rank, world)
-    ctx.set_obstacles(sx, sy)
+    ctx.set_obstacles_shard(xs, ys, rank, world)
     poses = wl.node_poses(args.nodes, EXTENT, seed=wl.C3_NODES_SEED)  # same nodes on every rank
     with torch.cuda.stream(stream):
         d_nodes.copy_(torch.from_numpy(capi.nodes_xycs_from_poses(poses)).to(dev))
 
-    def steps(n):
+    def steps(n, fn):
         evs = []
         with torch.cuda.stream(stream):
             for _ in range(n):
                 flush.zero_()
-                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a, b = (torch.cuda.Event(enable_timing=True) for _ in range(2))
                 a.record(stream)
-                ctx.eval_nodes_device(args.nodes, d_nodes, CLIP, d_out)
+                fn()
                 b.record(stream)
-                sharding.allreduce_min_(d_out)
-                c.record(stream)
-                evs.append((a, b, c))
+                evs.append((a, b))
         torch.cuda.synchronize(dev)
-        return [(a.elapsed_time(b), b.elapsed_time(c)) for a, b, c in evs]
+        return [a.elapsed_time(b) for a, b in evs]
 
-    steps(3)
-    dist.barrier()
-    ts = steps(max(5, args.steps // 2))
-    k_ms = sum(t[0] for t in ts) / len(ts)
-    ar_ms = sum(t[1] for t in ts) / len(ts)
-    t = torch.tensor([k_ms + ar_ms, k_ms, ar_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot, k_ms, ar_ms = t.tolist()
+    def timed(fn):
+        steps(3, fn)
+        dist.barrier()
+        ts = steps(max(5, args.steps // 2), fn)
+        t = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    res = {"points_total": n_total, "points_per_gpu": int(ctx.num_obstacles), "nodes": args.nodes,
+           "merge_bytes": int(d_out.numel() * 4), "scaling": "weak in cloud size (edges fixed)"}
+    # (1) the shard evaluation alone, (2) + ncclAllReduce(min) by the library, (3) the fused peer-memory merge
+    res["kernel_only_ms"] = timed(lambda: ctx.eval_nodes_device(args.nodes, d_nodes, CLIP, d_out))
+    sharding.attach_ranks(ctx, rank, world, max_nodes=0)
+    assert ctx.sharded_mode == "nccl"
+    res["nccl_ms_per_step"] = timed(lambda: ctx.eval_nodes_sharded_device(args.nodes, d_nodes, CLIP, d_out))
+    torch.cuda.synchronize(dev)
+    merged_nccl = d_out.cpu().numpy().copy() if rank == 0 else None
+    sharding.attach_ranks(ctx, rank, world, max_nodes=args.nodes)
+    assert ctx.sharded_mode == "fused"
+    res["fused_ms_per_step"] = timed(lambda: ctx.eval_nodes_sharded_device(args.nodes, d_nodes, CLIP, d_out))
+    ctx.sync()
+    res["ms_per_step"] = min(res["fused_ms_per_step"], res["nccl_ms_per_step"])
+    res["merge_share_nccl"] = 1.0 - res["kernel_only_ms"] / res["nccl_ms_per_step"]
+    res["merge_share_fused"] = 1.0 - res["kernel_only_ms"] / res["fused_ms_per_step"]
     edges = args.nodes * N_PTGS * K_PATHS
-    return {"points_total": n_total, "points_per_gpu": len(sx), "nodes": args.nodes, "ms_per_step": tot,
-            "kernel_ms": k_ms, "allreduce_min_ms": ar_ms, "allreduce_bytes": int(d_out.numel() * 4),
-            "edges_per_s": edges / (tot * 1e-3), "scaling": "weak in cloud size (edges fixed)"}
+    res["edges_per_s"] = edges / (res["ms_per_step"] * 1e-3)
+    if rank == 0:
+        merged = d_out.cpu().numpy()
+        res["fused_equals_nccl"] = bool(np.array_equal(merged, merged_nccl))
+        # the whole cloud on ONE GPU (a second context on this rank's device): must give the merged rows bit for bit
+        one = capi.Context(dev.index)
+        for p in capi.ackermann_ptgs(ctx=one):
+            one.add_ptg(p)
+        one.set_obstacles(xs, ys)
+        h_one = one.eval_nodes(poses, CLIP)
+        res["parity_vs_single_gpu_whole_cloud"] = bool(np.array_equal(h_one, merged))
+        one.close()
+        # the reference's own CPU evaluation of the whole cloud on a node sample
+        orc, kind = cpu_checker()
+        optgs = orc.ackermann_ptgs()
+        n_ref = min(16, args.nodes)
+        ref, t_ref = orc.eval_nodes(optgs, xs, ys, poses[:n_ref], CLIP, mode=0, nthreads=0)
+        init = np.concatenate([np.array([p.init_dist(k) for k in range(p.num_paths)]) for p in capi.ackermann_ptgs()])
+        res["parity_vs_cpu_checker"] = {"kind": kind, "nodes": n_ref, "seconds": t_ref,
+                                        "identical": bool(np.array_equal(np.minimum(init[None, :], merged[:n_ref].astype(np.float64)), ref))}
+    dist.barrier()
+    return res
 
 
 def run_ours(args, rank, local_rank, world):

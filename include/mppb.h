@@ -30,6 +30,9 @@
  *                               FromStaticPointObstacles (CostEvaluatorCostMap.cpp:91-97)
  *   mppb_set_obstacles_clipped <- ObstacleSource::apply_clipping_box (src/interfaces/
  *                               ObstacleSource.cpp:19-42)
+ *   mppb_comm_* / mppb_set_obstacles_shard / mppb_eval_nodes_sharded_device
+ *                            <- (no reference counterpart: the reference is single-threaded) cloud sharding over
+ *                               several GPUs with a min-merge of the partial TP-obstacle rows
  *   mppb_set_ptg_paths / mppb_expand_nodes
  *                            <- the candidate set, end poses, blocked test, per-cell selection and edge costs of
  *                               TPS_Astar::find_feasible_paths_to_neighbors (src/algos/TPS_Astar.cpp:538-826) and
@@ -270,6 +273,45 @@ int mppb_eval_holo_candidates_boxed_device(mppb_ctx* ctx, size_t n_cands, const 
 int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* poses_xyphi,
                                           const float* node_boxes, size_t n_cands, const mppb_holo_cand* cands,
                                           double clip_dist, double* out);
+
+/* ---- several GPUs: cloud sharding and the min-merge of partial rows -------------------
+ * A cloud too large for one GPU (or simply large) is split by point index over the ranks; every rank evaluates ALL
+ * nodes against its shard, and because a path's free distance is an order-independent minimum over points, the
+ * element-wise minimum of the partial rows is the single-GPU result bit for bit. One process per GPU; the caller
+ * carries a few bytes between the ranks once (MPI, torch.distributed, files: its choice), after that everything
+ * runs on the contexts' streams.
+ *   merge by NCCL:  mppb_comm_unique_id (rank 0) -> mppb_comm_init (every rank) -> mppb_eval_nodes_sharded_device
+ *   fused merge:    additionally mppb_peer_rows_create (every rank) -> mppb_peer_rows_attach (every rank, with all
+ *                   ranks' handles): tpobs_grid_kernel then stores each finished row straight into every peer's
+ *                   memory over NVLink while the other nodes are still being evaluated (a slot per source rank, no
+ *                   atomics), a flag per rank closes the step, and a short kernel takes the minimum over the slots.
+ * libnccl.so.2 is opened at run time (dlopen); nothing here is needed for single-GPU use. */
+#define MPPB_COMM_ID_BYTES 128
+#define MPPB_IPC_HANDLE_BYTES 64
+#define MPPB_MAX_RANKS 16
+/* ncclGetUniqueId: called on ONE rank; the bytes go to every rank's mppb_comm_init */
+int mppb_comm_unique_id(uint8_t* out_id /* [MPPB_COMM_ID_BYTES] */);
+/* ncclCommInitRank on the context's device (collective: every rank must call it) */
+int mppb_comm_init(mppb_ctx* ctx, int world, int rank, const uint8_t* id /* [MPPB_COMM_ID_BYTES] */);
+int mppb_comm_world(const mppb_ctx* ctx); /* 1 without a communicator */
+int mppb_comm_rank(const mppb_ctx* ctx);
+/* this rank's shard of the cloud: the points i with i % n_shards == shard (strided, so that every shard covers the
+ * whole map and the ranks stay balanced wherever the nodes are); xs, ys: the WHOLE cloud, host pointers */
+int mppb_set_obstacles_shard(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, double bin_size, int shard,
+                             int n_shards);
+/* in-place element-wise minimum over the ranks of a device array of floats (ncclAllReduce, ncclMin) on the context's
+ * stream; asynchronous */
+int mppb_allreduce_min_device(mppb_ctx* ctx, float* d_rows, size_t count);
+/* fused merge, set-up: allocates this rank's receive slots for batches of up to max_nodes nodes and returns the IPC
+ * handle the other ranks open; then every rank attaches to all of them (handles in rank order, its own included) */
+int mppb_peer_rows_create(mppb_ctx* ctx, size_t max_nodes, uint8_t* out_handle /* [MPPB_IPC_HANDLE_BYTES] */);
+int mppb_peer_rows_attach(mppb_ctx* ctx, int world, int rank, const uint8_t* handles /* [world][MPPB_IPC_HANDLE_BYTES] */);
+/* mppb_eval_nodes_device against this rank's shard + the merge: d_out [n_nodes][total_paths] holds the merged rows
+ * on every rank when the stream reaches the end of the call. Uses the fused path if peers are attached, NCCL if only
+ * a communicator is, and is a plain mppb_eval_nodes_device without either. */
+int mppb_eval_nodes_sharded_device(mppb_ctx* ctx, size_t n_nodes, const double* d_nodes_xycs, double clip_dist, float* d_out);
+/* 0 = plain, 1 = NCCL merge, 2 = fused peer-memory merge: what mppb_eval_nodes_sharded_device will do */
+int mppb_sharded_mode(const mppb_ctx* ctx);
 
 /* ---- one A* expansion per node on the device (collision-grid PTGs) ------------------------
  * Everything TPS_Astar::find_feasible_paths_to_neighbors (src/algos/TPS_Astar.cpp:538-826) and the per-neighbour

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-ccbin", "/usr/bin/g++",
 ]
 LINK_FLAGS = ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
-              "-gencode", "arch=compute_100a,code=sm_100a"]
+              "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
 # Kernels whose arithmetic must round exactly like the reference's x86-64 build (no FMA contraction).
 PER_FILE_FLAGS = {
     "tpobs_holo.cu": ["-fmad=false"],

@@ -88,6 +88,17 @@ class AstarParams(C.Structure):
 
 
 MAX_PTGS = 8
+COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (call on one rank, hand the bytes to the others)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    if lib().mppb_comm_unique_id(buf) != 0:
+        raise MppbError(lib().mppb_last_global_error().decode())
+    return bytes(buf)
+
 
 
 class PathsDesc(C.Structure):
@@ -224,6 +235,16 @@ _SIGS = {
     "mppb_planner_tree": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64]),
     "mppb_planner_trajectory_txt": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int64]),
     "mppb_planner_gpu_stats": (C.c_int, [C.c_void_p, c_double_p]),
+    "mppb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mppb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mppb_comm_world": (C.c_int, [C.c_void_p]),
+    "mppb_comm_rank": (C.c_int, [C.c_void_p]),
+    "mppb_set_obstacles_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_int]),
+    "mppb_allreduce_min_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mppb_peer_rows_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mppb_peer_rows_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mppb_eval_nodes_sharded_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p]),
+    "mppb_sharded_mode": (C.c_int, [C.c_void_p]),
     "mppb_set_ptg_paths": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PathsDesc)]),
     "mppb_ptg_paths_export": (C.c_int, [C.c_void_p, C.POINTER(PathsDesc)]),
     "mppb_set_expand_params": (C.c_int, [C.c_void_p, C.POINTER(AstarParams)]),
@@ -540,6 +561,37 @@ class Context:
     def eval_holo_candidates_device(self, n_cands, d_cands, d_nodes_xycs, clip_dist, d_out):
         self._ck(lib().mppb_eval_holo_candidates_device(self.h, n_cands, _ptr(d_cands), _ptr(d_nodes_xycs),
                                                         clip_dist, _ptr(d_out)))
+
+    # -- several GPUs: cloud sharding + min-merge --
+    def set_obstacles_shard(self, xs, ys, shard, n_shards, bin_size=0.0):
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        self._ck(lib().mppb_set_obstacles_shard(self.h, _ptr(xs), _ptr(ys), xs.size, bin_size, shard, n_shards))
+
+    def comm_init(self, world, rank, unique_id):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(lib().mppb_comm_init(self.h, world, rank, buf))
+
+    def peer_rows_create(self, max_nodes):
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        self._ck(lib().mppb_peer_rows_create(self.h, max_nodes, buf))
+        return bytes(buf)
+
+    def peer_rows_attach(self, world, rank, handles):
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == world * IPC_HANDLE_BYTES
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._ck(lib().mppb_peer_rows_attach(self.h, world, rank, buf))
+
+    def allreduce_min_device(self, d_rows, count):
+        self._ck(lib().mppb_allreduce_min_device(self.h, _ptr(d_rows), count))
+
+    def eval_nodes_sharded_device(self, n_nodes, d_nodes_xycs, clip_dist, d_out):
+        self._ck(lib().mppb_eval_nodes_sharded_device(self.h, n_nodes, _ptr(d_nodes_xycs), clip_dist, _ptr(d_out)))
+
+    @property
+    def sharded_mode(self):
+        return {0: "plain", 1: "nccl", 2: "fused"}[lib().mppb_sharded_mode(self.h)]
 
     # -- one A* expansion per node on the device --
     def set_expand_params(self, params, timestamps):

@@ -119,6 +119,7 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     }
     ctx->evalDescs.release();
     ctx->colgrid.release();
+    multigpu_release(ctx);
     for (auto& t : ctx->pathTables) t.release();
     ctx->expandDev.release();
     for (mppb::DevBuf* b : {&ctx->dExpandIn, &ctx->dExpandRows, &ctx->dExpandOut, &ctx->dExpandCounts, &ctx->dExpandNodes, &ctx->dExpandBoxes})
@@ -158,6 +159,15 @@ int mppb_sync(mppb_ctx* ctx)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
     MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->peer.world > 1)
+    {
+        // fused multi-GPU merge: a peer that never raised its flag ends the wait kernel with an error word, not a hang
+        const size_t areaFloats = 2 * static_cast<size_t>(ctx->peer.world) * ctx->peerMaxNodes * ctx->peerCols;
+        int          status     = 0;
+        MPPB_CUDA(ctx, cudaMemcpy(&status, reinterpret_cast<const uint32_t*>(ctx->peerLocal.as<float>() + areaFloats) + MPPB_MAX_RANKS,
+                                  sizeof(int), cudaMemcpyDeviceToHost));
+        if (status != 0) return fail(ctx, MPPB_ERR_STATE, "multi-GPU merge timed out waiting for a peer's rows");
+    }
     return MPPB_OK;
 }
 int mppb_set_holo_filter(mppb_ctx* ctx, int on)

@@ -124,6 +124,18 @@ struct ExpandParamsDev
     PathTableDev paths[MPPB_MAX_PTGS];
 };
 
+// Fused merge of cloud-sharded rows (multigpu.cu): where tpobs_grid_kernel sends a finished row. Every rank owns
+// `world` receive slots per epoch parity, slot r filled by rank r; flags[r] = last epoch rank r completed.
+struct PeerRowsDev
+{
+    float*    rows[MPPB_MAX_RANKS];   // base of rank p's receive area: [2][world][maxNodes][cols]
+    uint32_t* flags[MPPB_MAX_RANKS];  // rank p's flag array [world]
+    int       world, rank;
+    uint32_t  epoch;                  // this step (1, 2, ...); parity selects the half of the receive area
+    size_t    slotStride;             // floats per slot = maxNodes * cols
+    unsigned* done;                   // local counter of finished CTAs (reset by the last one)
+};
+
 // ---------------------------------------------------------------------------------------
 // Host-side context
 // ---------------------------------------------------------------------------------------
@@ -311,6 +323,16 @@ struct mppb_ctx
 
     mppb::ColgridBuildBufs colgrid;
 
+    // several GPUs (multigpu.cu): NCCL communicator (opened at run time) and the peer-memory receive slots
+    void*        ncclComm  = nullptr;
+    int          commWorld = 1, commRank = 0;
+    mppb::DevBuf peerLocal;                 // this rank's receive area + flags (cudaMalloc, exported through IPC)
+    size_t       peerMaxNodes = 0, peerCols = 0;
+    void*        peerOpened[MPPB_MAX_RANKS] = {};  // cudaIpcOpenMemHandle mappings of the other ranks' areas
+    mppb::PeerRowsDev peer{};               // device pointers as the kernel takes them (world == 0: not attached)
+    uint32_t     peerEpoch = 0;
+    mppb::DevBuf peerDone;
+
     // device-side expansion (expand.cu): sampled paths per PTG index, the planner parameters, staging
     mppb::PathTableHost  pathTables[MPPB_MAX_PTGS];
     bool                 expandParamsSet = false;
@@ -344,6 +366,9 @@ void set_global_error(const std::string& msg);
 int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize);
 int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
                       float* dOut);
+// same, each finished row also stored into slot `rank` of every attached peer (fused merge of cloud-sharded rows)
+int launch_tpobs_grid_peers(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, const PeerRowsDev& peers);
+void multigpu_release(mppb_ctx* ctx);
 // nNodes = rows of dNodes if the caller knows it (1 lets the kernel fetch the row early), 0 otherwise
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
                       const float* dBoxes, double clip, double* dOut, size_t nNodes = 0);

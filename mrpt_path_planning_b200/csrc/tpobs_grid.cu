@@ -263,12 +263,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
                  : "memory");
 }
 
-template <bool HAS_BOX, int SPLIT, bool STAGED = false>
+// PEERS: the cloud is sharded over several GPUs (multigpu.cu). Each finished row is stored not into `out` but into slot
+// `rank` of EVERY rank's receive area — this GPU's own and, over NVLink, its peers' — while the other CTAs are still
+// evaluating their nodes, so the exchange overlaps the computation node by node; the last CTA to finish raises this
+// rank's flag on every peer. A short kernel on each rank then waits for all flags and takes the minimum over the slots.
+template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false>
 __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
-                      float* __restrict__ out)
+                      float* __restrict__ out, const PeerRowsDev peers)
 {
     extern __shared__ __align__(16) unsigned smem[];
     unsigned*           smin   = smem;               // [totalPaths] float bits
@@ -740,6 +744,32 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
     }
     if (sparseWords) sparse_phase2(groups[numGroups - 1], bitmap, sparseWords, smin, longCell, &nLong);
     __syncthreads();
+    if constexpr (PEERS)
+    {
+        // slot `rank` of every rank's receive area (parity half of this epoch), coalesced stores; then, once every CTA
+        // of this grid has done so, the flag
+        const size_t slot = (static_cast<size_t>(peers.epoch & 1u) * peers.world + peers.rank) * peers.slotStride +
+                            static_cast<size_t>(node) * totalPaths;
+        for (int p = 0; p < peers.world; p++)
+        {
+            float* dst = peers.rows[p] + slot;
+            for (int i = threadIdx.x; i < totalPaths; i += kThreads) dst[i] = __uint_as_float(smin[i]);
+        }
+        __threadfence_system();  // this thread's row stores are visible system-wide before the arrival below
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned arrived = atomicAdd(peers.done, 1u);
+            if (arrived == gridDim.x - 1)
+            {
+                *peers.done = 0;  // for the next launch (stream order)
+                __threadfence_system();
+                for (int p = 0; p < peers.world; p++)
+                    *reinterpret_cast<volatile uint32_t*>(peers.flags[p] + peers.rank) = peers.epoch;
+            }
+        }
+        return;
+    }
     float* o = out + static_cast<size_t>(node) * totalPaths;
     if constexpr (SPLIT > 1)
     {
@@ -784,7 +814,7 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
             MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kernel<<<static_cast<unsigned>(nNodes) * ctasPerNode, kThreads, smem, ctx->stream>>>(
             ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
-            static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut);
+            static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut, PeerRowsDev{});
         return MPPB_OK;
     };
     int rc;
@@ -795,6 +825,28 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     else
         rc = dBoxes ? launch(tpobs_grid_kernel<true, 1>, 1) : launch(tpobs_grid_kernel<false, 1>, 1);
     if (rc != MPPB_OK) return rc;
+    ctx->launches++;
+    MPPB_CUDA(ctx, cudaGetLastError());
+    return MPPB_OK;
+}
+
+// the one-CTA-per-node kernel with the peer-memory epilogue (see PEERS)
+int launch_tpobs_grid_peers(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, const PeerRowsDev& peers)
+{
+    if (nNodes == 0) return MPPB_OK;
+    if (ctx->grids.empty()) return fail(ctx, MPPB_ERR_STATE, "no PTG tables set (mppb_set_ptg_grid)");
+    size_t words = 1;
+    for (const auto& g : ctx->groups)
+        words = std::max(words, static_cast<size_t>(grid_tiles_x(g.dev.nx)) * grid_tiles_y(g.dev.ny));
+    const size_t smem = ((static_cast<size_t>(ctx->totalPaths) + words + 3) & ~static_cast<size_t>(3)) * sizeof(unsigned);
+    if (smem > 200 * 1024)
+        return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
+    auto kernel = tpobs_grid_kernel<false, 1, false, true>;
+    if (smem > 48 * 1024)
+        MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
+        ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
+        static_cast<int>(words), dNodes, nullptr, clip, nullptr, peers);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;

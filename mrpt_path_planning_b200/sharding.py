@@ -40,11 +40,33 @@ def allreduce_min_(t, group=None):
     return t
 
 
+def attach_ranks(ctx, rank, world, max_nodes=0, group=None):
+    """The hand-shake of the library's multi-GPU layer (include/mppb.h, "several GPUs") over torch.distributed: rank 0
+    draws the NCCL unique id, every rank builds its communicator on the context's device; with max_nodes > 0 every
+    rank also creates its receive slots for the fused merge and attaches to all the others' (CUDA IPC handles).
+    After this, ctx.eval_nodes_sharded_device() evaluates against the rank's shard and merges on the context's stream;
+    torch.distributed is not involved in the data path."""
+    import torch.distributed as dist
+
+    from . import capi
+
+    box = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(world, rank, box[0])
+    if max_nodes > 0 and world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_rows_create(max_nodes), group=group)
+        ctx.peer_rows_attach(world, rank, handles)
+        dist.barrier(group=group)  # nobody evaluates before everybody is attached
+    return ctx.sharded_mode
+
+
 def eval_nodes_cloud_sharded(ctx, n_nodes, d_nodes_xycs, clip, d_out, group=None):
-    """Stage (a)+(b) against this rank's cloud shard (already uploaded into ctx), then the min-merge.
-    d_nodes_xycs / d_out are torch CUDA tensors on the context's stream; d_out is [n_nodes][total_paths] float32."""
-    ctx.eval_nodes_device(n_nodes, d_nodes_xycs, clip, d_out)
-    return allreduce_min_(d_out, group)
+    """Stage (a)+(b) against this rank's cloud shard (already uploaded into ctx), then the min-merge, all inside the
+    library (mppb_eval_nodes_sharded_device: fused peer-memory merge or NCCL, see attach_ranks).
+    d_nodes_xycs / d_out are device arrays on the context's stream; d_out is [n_nodes][total_paths] float32."""
+    ctx.eval_nodes_sharded_device(n_nodes, d_nodes_xycs, clip, d_out)
+    return d_out
 
 
 def gather_rows(local_rows, n_total, rank, world, group=None):
