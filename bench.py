@@ -99,15 +99,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def bind_to_gpu_numa_node(index):
+def bind_to_gpu_numa_node(index, local_world=1):
     """One process per GPU: pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned
-    host buffers the kernels write into over PCIe are allocated on the GPU's own NUMA node."""
+    host buffers the kernels write into over PCIe are allocated on the GPU's own NUMA node; when several ranks share
+    those CPUs, each takes a disjoint slice of them (its host threads — the per-call cos/sin of the e2e path, the
+    planner's workers — then never compete with another rank's for a core)."""
     try:
         import pynvml
 
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         pynvml.nvmlDeviceSetCpuAffinity(h)
+    except Exception:
+        pass
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if local_world > 1 and len(cpus) >= local_world:
+            k = len(cpus) // local_world
+            mine = cpus[(index % local_world) * k:(index % local_world + 1) * k]
+            os.sched_setaffinity(0, mine)
         return len(os.sched_getaffinity(0))
     except Exception:
         return None
@@ -266,7 +276,8 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
     t0 = time.perf_counter()
     pl.add_costmap(mx, my, C4_COSTMAP[0], C4_COSTMAP[1], C4_COSTMAP[2], False, 0.0, None)
     t_cm = time.perf_counter() - t0
-    cpus = os.cpu_count() or 1
+    cpus_total = os.cpu_count() or 1
+    cpus = cpus_total
     try:
         import torch
 
@@ -278,8 +289,9 @@ def planner_bench(ctx_factory, rank, world, args, with_cpu):
     # (cpu_count / GPUs on the box, the same number at every N): the figure to compare across N
     # (the fixed-thread run takes every eighth query of this rank's share: with an eighth of the host it would
     # otherwise take minutes)
-    for label, n_threads, qsel in (("all_threads", max(1, cpus // world), mine),
-                                   ("fixed_threads", max(1, cpus // max(8, gpus_on_box)), mine[::8])):
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else max(1, cpus // world)
+    for label, n_threads, qsel in (("all_threads", max(1, min(avail, cpus // world)), mine),
+                                   ("fixed_threads", max(1, min(avail, cpus // max(8, gpus_on_box))), mine[::8])):
         pl.plan_many(mine[:16], n_threads=n_threads)  # warm-up
         t0 = time.perf_counter()
         res = pl.plan_many(qsel, n_threads=n_threads)
@@ -444,7 +456,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device — libmpp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    affinity = bind_to_gpu_numa_node(local_rank, world) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 

@@ -569,6 +569,13 @@ int mppb_planner_add_waypoints(mppb_planner* p, const double* xs, const double* 
  * each result equals what plan() returns for that query alone. */
 int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* queries, int n_threads,
                       mppb_plan_result* results);
+/* Independent queries over several GPUs of ONE process: planners[i] was created on a context of its own (normally one
+ * per device) and set up like the others (same PTGs, obstacles, evaluators, parameters). Query q is planned by planner
+ * q % n_planners as its local query q / n_planners; the planners run at once, each on a thread of its own with
+ * n_threads_per_planner host threads (0 = all). results[q] is what mppb_planner_plan returns for that query; paths and
+ * trees are read from the owning planner with the local query index. */
+int mppb_planner_plan_multi(mppb_planner** planners, int n_planners, size_t n_queries, const mppb_plan_query* queries,
+                            int n_threads_per_planner, mppb_plan_result* results);
 /* refine_trajectory on the backtracked path of a query (src/algos/refine_trajectory.cpp:14-89) */
 int mppb_planner_refine(mppb_planner* p, size_t query);
 /* nodes [path_len][8] = id x y phi vx vy omega cost; edges [path_len-1][8] = ptgIndex k step ptgDist cost

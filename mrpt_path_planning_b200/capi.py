@@ -235,6 +235,7 @@ _SIGS = {
     "mppb_planner_tree": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64]),
     "mppb_planner_trajectory_txt": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int64]),
     "mppb_planner_gpu_stats": (C.c_int, [C.c_void_p, c_double_p]),
+    "mppb_planner_plan_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
     "mppb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mppb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mppb_comm_world": (C.c_int, [C.c_void_p]),
@@ -851,6 +852,31 @@ class Planner:
 
     def plan(self, start, goal, bbox_min, bbox_max, goal_is_point=False):
         return self.plan_many([(start, goal, bbox_min, bbox_max, goal_is_point)])[0]
+
+    @staticmethod
+    def plan_multi(planners, queries, n_threads_per_planner=0):
+        """mppb_planner_plan_multi: queries dealt round-robin to planners on several devices of this process; results
+        in query order (query q is local query q // len(planners) of planners[q % len(planners)])."""
+        n = len(queries)
+        qs = (PlanQuery * n)()
+        for i, (start, goal, lo, hi, is_pt) in enumerate(queries):
+            qs[i].start[:] = list(start)
+            qs[i].goal[:] = list(goal)
+            qs[i].goal_is_point = int(is_pt)
+            qs[i].bbox_min[:] = list(lo)
+            qs[i].bbox_max[:] = list(hi)
+        rs = (PlanResult * n)()
+        hs = (C.c_void_p * len(planners))(*[p.h for p in planners])
+        rc = lib().mppb_planner_plan_multi(hs, len(planners), n, qs, n_threads_per_planner, rs)
+        if rc != 0:
+            raise MppbError("; ".join(lib().mppb_planner_last_error(p.h).decode() for p in planners))
+        out = [dict(success=float(r.success), path_cost=r.path_cost, tree_nodes=float(r.tree_nodes),
+                    tree_parents=float(r.tree_parents), expanded=float(r.nodes_expanded), tps_points=float(r.tps_points),
+                    edges_costed=float(r.edges_costed), best_node=float(r.best_node), goal_node=float(r.goal_node),
+                    time_s=r.computation_time, best_cost_to_goal=r.best_cost_to_goal, path_len=int(r.path_len)) for r in rs]
+        for i, p in enumerate(planners):
+            p._path_len = [d["path_len"] for d in out[i::len(planners)]]
+        return out
 
     def refine(self, query=0):
         self._ck(lib().mppb_planner_refine(self.h, query))

@@ -306,6 +306,35 @@ int mppb_planner_plan(mppb_planner* p, size_t n_queries, const mppb_plan_query* 
     });
 }
 
+int mppb_planner_plan_multi(mppb_planner** planners, int n_planners, size_t n_queries, const mppb_plan_query* qs,
+                            int n_threads_per_planner, mppb_plan_result* res)
+{
+    if (!planners || n_planners < 1 || !qs || !res || n_queries == 0) return MPPB_ERR_INVALID_ARG;
+    for (int i = 0; i < n_planners; i++)
+        if (!planners[i]) return MPPB_ERR_INVALID_ARG;
+    // query q goes to planner q % n_planners as its local query q / n_planners; every planner plans its share on a
+    // thread of its own (its context's device, its own worker pool), all at once
+    const size_t                               P = static_cast<size_t>(n_planners);
+    std::vector<std::vector<mppb_plan_query>>  share(P);
+    std::vector<std::vector<mppb_plan_result>> out(P);
+    for (size_t q = 0; q < n_queries; q++) share[q % P].push_back(qs[q]);
+    std::vector<int>         rc(P, MPPB_OK);
+    std::vector<std::thread> ts;
+    for (size_t i = 0; i < P; i++)
+    {
+        out[i].resize(share[i].size());
+        if (share[i].empty()) continue;
+        ts.emplace_back([&, i]() {
+            rc[i] = mppb_planner_plan(planners[i], share[i].size(), share[i].data(), n_threads_per_planner, out[i].data());
+        });
+    }
+    for (auto& t : ts) t.join();
+    for (size_t i = 0; i < P; i++)
+        if (rc[i] != MPPB_OK) return rc[i];  // (the failing planner holds the message: mppb_planner_last_error)
+    for (size_t q = 0; q < n_queries; q++) res[q] = out[q % P][q / P];
+    return MPPB_OK;
+}
+
 int mppb_planner_refine(mppb_planner* p, size_t query)
 {
     if (!p) return MPPB_ERR_INVALID_ARG;

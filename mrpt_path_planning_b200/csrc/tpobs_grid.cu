@@ -755,10 +755,10 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
             float* dst = peers.rows[p] + slot;
             for (int i = threadIdx.x; i < totalPaths; i += kThreads) dst[i] = __uint_as_float(smin[i]);
         }
-        __threadfence_system();  // this thread's row stores are visible system-wide before the arrival below
-        __syncthreads();
+        __syncthreads();  // the row stores of all threads are observed by thread 0 ...
         if (threadIdx.x == 0)
         {
+            __threadfence_system();  // ... whose fence orders them, system-wide, before its arrival (fence cumulativity)
             const unsigned arrived = atomicAdd(peers.done, 1u);
             if (arrived == gridDim.x - 1)
             {

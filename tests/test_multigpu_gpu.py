@@ -91,3 +91,46 @@ def test_cloud_sharded_over_two_gpus_equals_one_gpu(tmp_path, capi, orc, oracle_
     ref, _ = orc.eval_nodes(oracle_ackermann, xs, ys, poses[:32], 5.0, mode=1, nthreads=0)
     init = np.concatenate([[p.init_dist(k) for k in range(p.num_paths)] for p in capi.ackermann_ptgs()])
     assert np.array_equal(np.minimum(init[None, :], whole[:32].astype(np.float64)), ref)
+
+
+def test_queries_over_two_devices_in_one_process(capi, orc, oracle_ackermann):
+    """mppb_planner_plan_multi: independent queries dealt to planners on two devices of this process, run at once;
+    every result equals the single-planner batch and the oracle planner's tree."""
+    import torch
+
+    from mrpt_path_planning_b200 import workloads as wl
+    from test_oracle_known_answers import C1_PARAMS, C1_TIMESTAMPS
+    from test_planner_gpu import _random_queries
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    extent = 40.0
+    xs, ys = wl.walls_cloud(6000, extent, wall_fraction=0.8, seed=33)
+    qs = _random_queries(np.random.default_rng(35), 9, extent, 3.0, 8.0)
+    params = list(C1_PARAMS)
+    params[8] = 40
+    ptgs = capi.ackermann_ptgs()
+    ctxs = [capi.Context(d) for d in range(2)]
+    planners = []
+    for c in ctxs:
+        pl = capi.Planner(c, ptgs, params, C1_TIMESTAMPS)
+        pl.add_obstacles(xs, ys)
+        pl.add_waypoints([20.0, 10.0], [20.0, 30.0], 3.0, 0.5, True)
+        planners.append(pl)
+    multi = capi.Planner.plan_multi(planners, qs, n_threads_per_planner=2)
+    single = planners[0].plan_many(qs, n_threads=2)
+    trees_single = [planners[0].tree(i) for i in range(len(qs))]
+    multi = capi.Planner.plan_multi(planners, qs, n_threads_per_planner=2)  # (again: planners[0] now holds its share)
+    for i, q in enumerate(qs):
+        for key in ("success", "tree_nodes", "tree_parents", "expanded", "path_cost", "best_node", "path_len"):
+            assert multi[i][key] == single[i][key], (i, key)
+        assert np.array_equal(planners[i % 2].tree(i // 2), trees_single[i])
+    ora = orc.Planner(oracle_ackermann, params, C1_TIMESTAMPS)
+    ora.add_obstacles(xs, ys)
+    ora.add_waypoints(orc.Waypoints([20.0, 10.0], [20.0, 30.0], 3.0, 0.5, True))
+    ora.plan(*qs[3][:4])
+    assert np.array_equal(planners[1].tree(1), ora.tree())
+    for pl in planners:
+        pl.close()
+    for c in ctxs:
+        c.close()
