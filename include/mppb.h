@@ -274,6 +274,17 @@ int mppb_eval_holo_candidates_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const d
                                           const float* node_boxes, size_t n_cands, const mppb_holo_cand* cands,
                                           double clip_dist, double* out);
 
+/* ---- free-function seams -------------------------------------------------------------------------------------
+ * mpp::transform_pc_square_clipping (include/mpp/algos/transform_pc_square_clipping.h:16-19; src/algos/
+ * transform_pc_square_clipping.cpp:9-43) for ONE pose, as a single call: the points of (xs, ys) inside the +-max_dist
+ * square around the pose (global axes, FP64 compare), composed with the inverse pose in FP64 and stored as float, in
+ * input order. Host pointers; out_x / out_y hold up to n points; *out_n = points written. (The batched kernels fuse
+ * this step and never materialise the local cloud; this entry point exists for callers of the reference's function.)
+ * The single-call form of mpp::tp_obstacles_single_path (.h:17-19) is mpp::tp_obstacles_single_path() of the C++
+ * mirror (csrc/host/mpp.h), built on mppb_set_obstacles + mppb_eval_nodes / mppb_eval_holo_candidates. */
+int mppb_transform_pc_square_clipping(mppb_ctx* ctx, const float* xs, const float* ys, size_t n, const double* pose_xyphi,
+                                      double max_dist, float* out_x, float* out_y, size_t* out_n);
+
 /* ---- several GPUs: cloud sharding and the min-merge of partial rows -------------------
  * A cloud too large for one GPU (or simply large) is split by point index over the ranks; every rank evaluates ALL
  * nodes against its shard, and because a path's free distance is an order-independent minimum over points, the

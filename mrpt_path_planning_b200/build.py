@@ -27,6 +27,7 @@ PER_FILE_FLAGS = {
     "tpobs_holo.cu": ["-fmad=false"],
     "edge_cost.cu": ["-fmad=false"],
     "expand.cu": ["-fmad=false"],
+    "seams.cu": ["-fmad=false"],
 }
 OBJ_DIR = os.path.join(HERE, "lib", "obj")
 BIN_DIR = os.path.join(HERE, "bin")
@@ -94,7 +95,7 @@ def build_library(force=False, verbose=False):
     # the headless path-planner-cli front end, linked against the library next to it
     os.makedirs(BIN_DIR, exist_ok=True)
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-o", CLI_PATH, CLI_SRC,
-                        "-L" + LIB_DIR, "-lmpp_b200", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"],
+                        "-L" + LIB_DIR, "-lmpp_b200", "-Wl,-rpath,$ORIGIN/../lib", "-pthread", "-ldl"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

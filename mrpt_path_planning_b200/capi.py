@@ -236,6 +236,8 @@ _SIGS = {
     "mppb_planner_trajectory_txt": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int64]),
     "mppb_planner_gpu_stats": (C.c_int, [C.c_void_p, c_double_p]),
     "mppb_planner_plan_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
+    "mppb_transform_pc_square_clipping": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double,
+                                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "mppb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mppb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mppb_comm_world": (C.c_int, [C.c_void_p]),
@@ -562,6 +564,18 @@ class Context:
     def eval_holo_candidates_device(self, n_cands, d_cands, d_nodes_xycs, clip_dist, d_out):
         self._ck(lib().mppb_eval_holo_candidates_device(self.h, n_cands, _ptr(d_cands), _ptr(d_nodes_xycs),
                                                         clip_dist, _ptr(d_out)))
+
+    # -- free-function seams --
+    def transform_pc_square_clipping(self, xs, ys, pose, max_dist):
+        """mpp::transform_pc_square_clipping for one pose -> (local_x, local_y) float32, input order"""
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        ox, oy = np.empty_like(xs), np.empty_like(ys)
+        n = C.c_size_t(0)
+        self._ck(lib().mppb_transform_pc_square_clipping(self.h, _ptr(xs), _ptr(ys), xs.size, _ptr(pose), max_dist, _ptr(ox),
+                                                         _ptr(oy), C.byref(n)))
+        return ox[:n.value].copy(), oy[:n.value].copy()
 
     # -- several GPUs: cloud sharding + min-merge --
     def set_obstacles_shard(self, xs, ys, shard, n_shards, bin_size=0.0):

@@ -154,9 +154,6 @@ void do_plan_path(const Args& a)
               << pi.worldBboxMax.y << ")\n";
 
     const std::string plannerName = a.get("--planner", "mpp::TPS_Astar");
-    if (plannerName != "mpp::TPS_Astar" && plannerName != "mpp::TPS_Astar_B200")
-        throw std::runtime_error("Given classname '" + plannerName +
-                                 "' does not seem to be a known C++ class implementing `Planner");
 
     mppb_ctx* ctx = nullptr;
     if (mppb_ctx_create(std::stoi(a.get("--device", "0")), nullptr, &ctx) != MPPB_OK)
@@ -166,8 +163,12 @@ void do_plan_path(const Args& a)
         mppb_ctx* c;
         ~CtxGuard() { mppb_ctx_destroy(c); }
     };
-    auto planner = std::make_shared<mpp::TPS_Astar>(ctx);
     CtxGuard guard{ctx};  // destroyed after the planner's last use below (planner does not own ctx)
+    // the planner class by name, from the class registry (the library's own classes and those of --plugins)
+    std::shared_ptr<mpp::Planner> planner = mpp::ClassRegistry::instance().createPlanner(plannerName, ctx);
+    if (!planner)
+        throw std::runtime_error("Given classname '" + plannerName +
+                                 "' does not seem to be a known C++ class implementing `Planner");
 
     if (a.isSet("--costmap-obstacles"))
     {
@@ -205,10 +206,14 @@ void do_plan_path(const Args& a)
     std::cout << "Success: " << (plan.success ? "YES" : "NO") << "\n";
     std::cout << "Plan has " << plan.motionTree.edges_to_children.size() << " overall edges, "
               << plan.motionTree.nodes().size() << " nodes\n";
-    const auto& gs = planner->lastGpuStats;
     std::cout << "Plan time: " << plan.computationTime * 1e3 << " ms (" << plan.nodesExpanded << " nodes expanded, "
-              << plan.tpsPointsEvaluated << " TPS points, " << plan.edgesCosted << " edges costed; GPU: "
-              << gs.collisionBatches << "+" << gs.costBatches << " batches, " << gs.gpuSeconds * 1e3 << " ms)\n";
+              << plan.tpsPointsEvaluated << " TPS points, " << plan.edgesCosted << " edges costed";
+    if (auto* astar = dynamic_cast<mpp::TPS_Astar*>(planner.get()))
+    {
+        const auto& gs = astar->lastGpuStats;
+        std::cout << "; GPU: " << gs.collisionBatches << "+" << gs.costBatches << " batches, " << gs.gpuSeconds * 1e3 << " ms";
+    }
+    std::cout << ")\n";
     if (plan.success) std::cout << "Path cost: " << plan.pathCost << "\n";
 
     if (!plan.bestNodeId.has_value())
@@ -269,7 +274,12 @@ int main(int argc, char** argv)
                 usage();
                 return 1;
             }
-        if (a.isSet("--plugins")) throw std::runtime_error("Could not load plugins, error: plug-in PTG classes need MRPT's RTTI");
+        if (a.isSet("--plugins"))
+        {
+            // shared objects whose initialisers register Planner / PTG classes (path-planner-cli.cpp:452-461)
+            std::string err;
+            if (!mpp::loadPluginModules(a.get("--plugins"), &err)) throw std::runtime_error("Could not load plugins, error: " + err);
+        }
         do_plan_path(a);
         return 0;
     }

@@ -2,6 +2,8 @@
 // Reference files followed: src/data/SE2_KinState.cpp, src/data/MoveEdgeSE2_TPS.cpp,
 // include/mpp/data/MotionPrimitivesTree.h, src/data/TrajectoriesAndRobotShape.cpp,
 // src/algos/edge_interpolated_path.cpp, src/algos/refine_trajectory.cpp, src/algos/trajectories.cpp.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <fstream>
@@ -250,38 +252,9 @@ void TrajectoriesAndRobotShape::initFromConfigFile(const ConfigFile& c, const st
     {
         const std::string pre  = "PTG" + std::to_string(n) + "_";
         const std::string type = c.read_string(s, pre + "Type", "", true);
-        // CPTG_DiffDrive_C names MRPT's upstream class; it is served by the in-repo fork's semantics
-        if (type == "CPTG_DiffDrive_C" || type == "mpp::ptg::DiffDrive_C" || type == "mpp::DiffDrive_C")
-        {
-            DiffDriveCParams p;
-            p.num_paths   = static_cast<unsigned>(c.read_int(s, pre + "num_paths", 0, true));
-            p.refDistance = c.read_double(s, pre + "refDistance", 0, true);
-            p.resolution  = c.read_double(s, pre + "resolution", 0.05, true);
-            p.v_max_mps   = c.read_double(s, pre + "v_max_mps", 0, true);
-            p.w_max_rps   = c.read_double(s, pre + "w_max_dps", 0, true) * M_PI / 180.0;
-            p.K           = c.read_double(s, pre + "K", 1.0, true);
-            p.turningRadiusReference = c.read_double(s, pre + "turningRadiusReference", 0.10);
-            if (shape_xs.size() < 3) throw std::runtime_error("PTG " + type + " needs a polygonal robot shape");
-            p.shape_x = shape_xs;
-            p.shape_y = shape_ys;
-            ptgs.push_back(std::make_shared<DiffDrive_C>(p, buildCtx));
-        }
-        else if (type == "mpp::ptg::HolonomicBlend" || type == "HolonomicBlend")
-        {
-            HolonomicBlendParams p;
-            p.num_paths   = static_cast<unsigned>(c.read_int(s, pre + "num_paths", 0, true));
-            p.refDistance = c.read_double(s, pre + "refDistance", 0, true);
-            p.T_ramp_max  = c.read_double(s, pre + "T_ramp_max", 0, true);
-            p.v_max_mps   = c.read_double(s, pre + "v_max_mps", 0, true);
-            p.w_max_rps   = c.read_double(s, pre + "w_max_dps", 0, true) * M_PI / 180.0;
-            p.expr_V      = c.read_string(s, pre + "expr_V", "V_MAX");
-            p.expr_W      = c.read_string(s, pre + "expr_W", "W_MAX");
-            if (!shape_radius) throw std::runtime_error("PTG " + type + " needs RobotModel_circular_shape_radius");
-            p.robot_radius = *shape_radius;
-            ptgs.push_back(std::make_shared<HolonomicBlend>(p));
-        }
-        else
-            throw std::runtime_error("Unknown PTG class name: " + type);
+        auto              ptg  = ClassRegistry::instance().createPtg(type, c, s, pre, *this, buildCtx);
+        if (!ptg) throw std::runtime_error("Unknown PTG class name: " + type);
+        ptgs.push_back(std::move(ptg));
     }
     initialized_ = true;
 }
@@ -314,6 +287,65 @@ void edge_interpolated_path(MoveEdgeSE2_TPS& edge, const TrajectoriesAndRobotSha
     }
     ip[ptg_step * dt]      = *reconstrRelPoseOpt;
     edge.estimatedExecTime = ptg_step * dt;
+}
+
+// ---- single-call seams of the reference's free functions ---------------------------------------------------------
+void transform_pc_square_clipping(mppb_ctx* ctx, const PointCloud& inMap, const TPose2D& asSeenFrom, double maxDistXY, PointCloud& outMap,
+                                  bool appendToOutMap)
+{
+    if (!ctx) throw std::runtime_error("transform_pc_square_clipping needs a libmpp_b200 context (no CPU fallback)");
+    if (!appendToOutMap)
+    {
+        outMap.xs.clear();
+        outMap.ys.clear();
+    }
+    const size_t       n = inMap.size();
+    std::vector<float> ox(n), oy(n);
+    const double       pose[3] = {asSeenFrom.x, asSeenFrom.y, asSeenFrom.phi};
+    size_t             m       = 0;
+    if (mppb_transform_pc_square_clipping(ctx, inMap.xs.data(), inMap.ys.data(), n, pose, maxDistXY, ox.data(), oy.data(), &m) != MPPB_OK)
+        throw std::runtime_error(std::string("libmpp_b200: ") + mppb_last_error(ctx));
+    outMap.xs.insert(outMap.xs.end(), ox.begin(), ox.begin() + static_cast<std::ptrdiff_t>(m));
+    outMap.ys.insert(outMap.ys.end(), oy.begin(), oy.begin() + static_cast<std::ptrdiff_t>(m));
+}
+
+distance_t tp_obstacles_single_path(mppb_ctx* ctx, trajectory_index_t k, const PointCloud& localObstacles, const ptg_t& ptg)
+{
+    if (!ctx) throw std::runtime_error("tp_obstacles_single_path needs a libmpp_b200 context (no CPU fallback)");
+    auto ck = [ctx](int rc) {
+        if (rc != MPPB_OK) throw std::runtime_error(std::string("libmpp_b200: ") + mppb_last_error(ctx));
+    };
+    MPP_ASSERT(k >= 0 && k < static_cast<int>(ptg.getPathCount()));
+    // the context's PTG set becomes this PTG alone (its tables travel once per call: single-call interface)
+    ck(mppb_clear_ptgs(ctx));
+    static const float none = 0;
+    const size_t       n    = localObstacles.size();
+    ck(mppb_set_obstacles(ctx, n ? localObstacles.xs.data() : &none, n ? localObstacles.ys.data() : &none, n, 0.0, 0));
+    // the points are local already: the node is the origin, and the clipping square is wide open
+    const double     origin[3] = {0, 0, 0};
+    const double     wide      = 1e30;
+    const distance_t init      = ptg.initTPObstacleSingle(static_cast<uint16_t>(k));
+    if (auto* dd = dynamic_cast<const DiffDrive_C*>(&ptg))
+    {
+        const mppb_ptg_grid_desc d = dd->gridDesc();
+        ck(mppb_set_ptg_grid(ctx, 0, &d));
+        std::vector<float> row(static_cast<size_t>(d.num_paths));
+        ck(mppb_eval_nodes(ctx, 1, origin, wide, row.data()));
+        return std::min(init, static_cast<double>(row[static_cast<size_t>(k)]));
+    }
+    if (auto* hb = dynamic_cast<const HolonomicBlend*>(&ptg))
+    {
+        const mppb_ptg_holo_desc d = hb->holoDesc();
+        ck(mppb_set_ptg_holo(ctx, 0, &d));
+        mppb_holo_cand c;
+        hb->holoParams(static_cast<uint16_t>(k), c);
+        c.node      = 0;
+        c.ptg_index = 0;
+        double out  = 0;
+        ck(mppb_eval_holo_candidates(ctx, 1, origin, 1, &c, wide, &out));
+        return std::min(init, out);
+    }
+    throw std::runtime_error("tp_obstacles_single_path: PTG of a kind the GPU library does not know");
 }
 
 // ---- refine_trajectory --------------------------------------------------------------------------------------
@@ -414,6 +446,95 @@ bool save_to_txt(const trajectory_t& traj, const std::string& fileName)
     std::ofstream f(fileName);
     if (!f.is_open()) return false;
     f << trajectory_as_text(traj);
+    return true;
+}
+
+// ---- class registry ---------------------------------------------------------------------------------------------
+ClassRegistry& ClassRegistry::instance()
+{
+    static ClassRegistry r;
+    return r;
+}
+// the classes of this library (src/registerClasses.cpp:16-37 of the reference)
+ClassRegistry::ClassRegistry()
+{
+    const PlannerFactory astar = [](mppb_ctx* ctx) { return std::static_pointer_cast<Planner>(std::make_shared<TPS_Astar>(ctx)); };
+    planners_["mpp::TPS_Astar"]      = astar;
+    planners_["mpp::TPS_Astar_B200"] = astar;
+    // CPTG_DiffDrive_C names MRPT's upstream class; it is served by the in-repo fork's semantics
+    const PtgFactory diffDrive = [](const ConfigFile& c, const std::string& s, const std::string& pre, const TrajectoriesAndRobotShape& shape,
+                                    mppb_ctx* buildCtx) -> std::shared_ptr<ptg_t> {
+        DiffDriveCParams p;
+        p.num_paths   = static_cast<unsigned>(c.read_int(s, pre + "num_paths", 0, true));
+        p.refDistance = c.read_double(s, pre + "refDistance", 0, true);
+        p.resolution  = c.read_double(s, pre + "resolution", 0.05, true);
+        p.v_max_mps   = c.read_double(s, pre + "v_max_mps", 0, true);
+        p.w_max_rps   = c.read_double(s, pre + "w_max_dps", 0, true) * M_PI / 180.0;
+        p.K           = c.read_double(s, pre + "K", 1.0, true);
+        p.turningRadiusReference = c.read_double(s, pre + "turningRadiusReference", 0.10);
+        if (shape.shape_xs.size() < 3) throw std::runtime_error("PTG DiffDrive_C needs a polygonal robot shape");
+        p.shape_x = shape.shape_xs;
+        p.shape_y = shape.shape_ys;
+        return std::make_shared<DiffDrive_C>(p, buildCtx);
+    };
+    for (const char* n : {"CPTG_DiffDrive_C", "mpp::ptg::DiffDrive_C", "mpp::DiffDrive_C"}) ptgs_[n] = diffDrive;
+    const PtgFactory holo = [](const ConfigFile& c, const std::string& s, const std::string& pre, const TrajectoriesAndRobotShape& shape,
+                               mppb_ctx*) -> std::shared_ptr<ptg_t> {
+        HolonomicBlendParams p;
+        p.num_paths   = static_cast<unsigned>(c.read_int(s, pre + "num_paths", 0, true));
+        p.refDistance = c.read_double(s, pre + "refDistance", 0, true);
+        p.T_ramp_max  = c.read_double(s, pre + "T_ramp_max", 0, true);
+        p.v_max_mps   = c.read_double(s, pre + "v_max_mps", 0, true);
+        p.w_max_rps   = c.read_double(s, pre + "w_max_dps", 0, true) * M_PI / 180.0;
+        p.expr_V      = c.read_string(s, pre + "expr_V", "V_MAX");
+        p.expr_W      = c.read_string(s, pre + "expr_W", "W_MAX");
+        if (!shape.shape_radius) throw std::runtime_error("PTG HolonomicBlend needs RobotModel_circular_shape_radius");
+        p.robot_radius = *shape.shape_radius;
+        return std::make_shared<HolonomicBlend>(p);
+    };
+    for (const char* n : {"mpp::ptg::HolonomicBlend", "HolonomicBlend"}) ptgs_[n] = holo;
+}
+void ClassRegistry::registerPlanner(const std::string& name, PlannerFactory f) { planners_[name] = std::move(f); }
+void ClassRegistry::registerPtg(const std::string& name, PtgFactory f) { ptgs_[name] = std::move(f); }
+std::shared_ptr<Planner> ClassRegistry::createPlanner(const std::string& name, mppb_ctx* ctx) const
+{
+    const auto it = planners_.find(name);
+    return it == planners_.end() ? nullptr : it->second(ctx);
+}
+std::shared_ptr<ptg_t> ClassRegistry::createPtg(const std::string& name, const ConfigFile& cfg, const std::string& section,
+                                                const std::string& keyPrefix, const TrajectoriesAndRobotShape& shape,
+                                                mppb_ctx* buildCtx) const
+{
+    const auto it = ptgs_.find(name);
+    return it == ptgs_.end() ? nullptr : it->second(cfg, section, keyPrefix, shape, buildCtx);
+}
+std::vector<std::string> ClassRegistry::plannerNames() const
+{
+    std::vector<std::string> v;
+    for (const auto& kv : planners_) v.push_back(kv.first);
+    return v;
+}
+std::vector<std::string> ClassRegistry::ptgNames() const
+{
+    std::vector<std::string> v;
+    for (const auto& kv : ptgs_) v.push_back(kv.first);
+    return v;
+}
+bool loadPluginModules(const std::string& list, std::string* error)
+{
+    std::stringstream ss(list);
+    std::string       lib;
+    while (std::getline(ss, lib, ','))
+    {
+        while (!lib.empty() && (lib.front() == ' ' || lib.front() == '\t')) lib.erase(lib.begin());
+        while (!lib.empty() && (lib.back() == ' ' || lib.back() == '\t')) lib.pop_back();
+        if (lib.empty()) continue;
+        if (!dlopen(lib.c_str(), RTLD_NOW | RTLD_GLOBAL))
+        {
+            if (error) *error = std::string("cannot load plug-in module '") + lib + "': " + (dlerror() ? dlerror() : "?");
+            return false;
+        }
+    }
     return true;
 }
 

@@ -527,11 +527,61 @@ class TPS_Astar : public Planner
     std::unique_ptr<Impl> impl_;
 };
 
+// ---- class registry and plug-ins ---------------------------------------------------------------------
+/** What MRPT's RTTI class factory does for the reference: classes register under their names when a library is
+ *  loaded (src/registerClasses.cpp:16-37), `--planner <name>` instantiates by name (path-planner-cli.cpp:256-265),
+ *  `--plugins a.so,b.so` loads further libraries whose initialisers register more classes (:452-461), and the
+ *  `PTGn_Type` keys of a PTG configuration name PTG classes (TrajectoriesAndRobotShape.cpp:58-64). */
+class ClassRegistry
+{
+   public:
+    using PlannerFactory = std::function<std::shared_ptr<Planner>(mppb_ctx*)>;
+    /** builds PTG #index of section `section`; shape: the robot shape read from the same section; buildCtx: see
+     *  TrajectoriesAndRobotShape::initFromConfigFile */
+    using PtgFactory = std::function<std::shared_ptr<ptg_t>(const ConfigFile& cfg, const std::string& section, const std::string& keyPrefix,
+                                                            const TrajectoriesAndRobotShape& shape, mppb_ctx* buildCtx)>;
+    static ClassRegistry& instance();
+    void                  registerPlanner(const std::string& name, PlannerFactory f);
+    void                  registerPtg(const std::string& name, PtgFactory f);
+    /** nullptr if no class of that name is registered */
+    std::shared_ptr<Planner> createPlanner(const std::string& name, mppb_ctx* ctx) const;
+    std::shared_ptr<ptg_t>   createPtg(const std::string& name, const ConfigFile& cfg, const std::string& section,
+                                       const std::string& keyPrefix, const TrajectoriesAndRobotShape& shape, mppb_ctx* buildCtx) const;
+    std::vector<std::string> plannerNames() const;
+    std::vector<std::string> ptgNames() const;
+
+   private:
+    ClassRegistry();
+    std::map<std::string, PlannerFactory> planners_;
+    std::map<std::string, PtgFactory>     ptgs_;
+};
+/** Loads the shared objects of a comma-separated list (RTLD_NOW | RTLD_GLOBAL); their static initialisers call
+ *  ClassRegistry::instance().register...(). Returns false and fills `error` if one cannot be loaded. */
+bool loadPluginModules(const std::string& commaSeparatedList, std::string* error = nullptr);
+/** in a plug-in: MPP_REGISTER_PLANNER("my::Planner", MyPlanner)  (MyPlanner constructible from mppb_ctx*) */
+#define MPP_REGISTER_PLANNER(NAME, CLASS)                                                                              \
+    namespace                                                                                                          \
+    {                                                                                                                  \
+    const bool mpp_registered_##CLASS = (::mpp::ClassRegistry::instance().registerPlanner(                            \
+                                             NAME, [](mppb_ctx* c) { return std::static_pointer_cast<::mpp::Planner>(std::make_shared<CLASS>(c)); }), \
+                                         true);                                                                        \
+    }
+
 // ---- free functions ----------------------------------------------------------------------------------
 void edge_interpolated_path(MoveEdgeSE2_TPS& edge, const TrajectoriesAndRobotShape& trs,
                             const std::optional<TPose2D>& reconstrRelPoseOpt = std::nullopt,
                             const std::optional<size_t>& ptg_stepOpt = std::nullopt,
                             const std::optional<size_t>& numSegments = std::nullopt);
+
+/** mpp::transform_pc_square_clipping (transform_pc_square_clipping.h:16-19) on the GPU of `ctx`: the points of
+ *  inMap inside the +-maxDistXY square around the pose, in its local frame, appended to (or replacing) outMap. */
+void transform_pc_square_clipping(mppb_ctx* ctx, const PointCloud& inMap, const TPose2D& asSeenFrom, double maxDistXY, PointCloud& outMap,
+                                  bool appendToOutMap = true);
+/** mpp::tp_obstacles_single_path (tp_obstacles_single_path.h:17-19) on the GPU of `ctx`: free TP-distance of path k
+ *  against obstacle points given in the robot frame, initTPObstacleSingle's value included. One call uploads the
+ *  points and, if they are not the context's current PTG set, the PTG's tables: this is the reference's single-call
+ *  interface; a planner should use the batched entry points. */
+distance_t tp_obstacles_single_path(mppb_ctx* ctx, trajectory_index_t tp_space_k_direction, const PointCloud& localObstacles, const ptg_t& ptg);
 
 void refine_trajectory(const MotionPrimitivesTreeSE2::path_t& inPath, MotionPrimitivesTreeSE2::edge_sequence_t& edgesToRefine,
                        const TrajectoriesAndRobotShape& ptgInfo, const double ptg_tolerance_dist = 0.10);
