@@ -531,11 +531,27 @@ bool loadPluginModules(const std::string& list, std::string* error)
         if (lib.empty()) continue;
         if (!dlopen(lib.c_str(), RTLD_NOW | RTLD_GLOBAL))
         {
-            if (error) *error = std::string("cannot load plug-in module '") + lib + "': " + (dlerror() ? dlerror() : "?");
+            const char* why = dlerror();  // (cleared by the call: read once)
+            if (error) *error = std::string("cannot load plug-in module '") + lib + "': " + (why ? why : "?");
             return false;
         }
     }
     return true;
+}
+
+std::string TimeLogger::getStatsAsText() const
+{
+    std::string out;
+    char        buf[256];
+    snprintf(buf, sizeof(buf), "%-45s %12s %14s %14s\n", "section", "calls", "total [s]", "mean [s]");
+    out += buf;
+    for (const auto& kv : sections_)
+    {
+        snprintf(buf, sizeof(buf), "%-45s %12zu %14.6f %14.3e\n", kv.first.c_str(), kv.second.calls, kv.second.seconds,
+                 kv.second.calls ? kv.second.seconds / static_cast<double>(kv.second.calls) : 0.0);
+        out += buf;
+    }
+    return out;
 }
 
 bool within_bbox(const TPose2D& p, const TPose2D& max, const TPose2D& min)

@@ -443,6 +443,35 @@ struct ProgressCallbackData
 };
 using planner_progress_callback_t = std::function<void(const ProgressCallbackData&)>;
 
+/** Named timing sections ([MRPT] mrpt::system::CTimeLogger as Planner::profiler_() of the reference exposes it,
+ *  Planner.h:44-46): number of calls and accumulated seconds per section name. */
+class TimeLogger
+{
+   public:
+    struct Section
+    {
+        size_t calls   = 0;
+        double seconds = 0;
+    };
+    void   clear() { sections_.clear(); }
+    void   registerUserMeasure(const std::string& name, double seconds, size_t calls = 1)
+    {
+        Section& s = sections_[name];
+        s.calls += calls;
+        s.seconds += seconds;
+    }
+    const std::map<std::string, Section>& sections() const { return sections_; }
+    double      getMeanTime(const std::string& name) const
+    {
+        const auto it = sections_.find(name);
+        return it == sections_.end() || !it->second.calls ? 0.0 : it->second.seconds / static_cast<double>(it->second.calls);
+    }
+    std::string getStatsAsText() const;
+
+   private:
+    std::map<std::string, Section> sections_;
+};
+
 class Planner
 {
    public:
@@ -458,6 +487,13 @@ class Planner
 
     /** estimatedExecTime + sum of the evaluators (Planner.cpp:15-29); known evaluator types run on the GPU */
     cost_t cost_path_segment(const MoveEdgeSE2_TPS& edge) const;
+
+    /** timing sections of the last plan(s) under the reference's section names (TPS_Astar.cpp:89,195,548,574,605,
+     *  701,740,803,833): see TPS_Astar::plan */
+    TimeLogger& profiler_() { return profiler__; }
+
+   protected:
+    TimeLogger profiler__;
 };
 
 struct TPS_Astar_Parameters

@@ -2138,6 +2138,34 @@ std::vector<PlannerOutput> TPS_Astar::Impl::run(const std::vector<const PlannerI
         qs[i].reset();
     });
     lap(tEnd, 6);
+    // The reference's profiler sections (TPS_Astar.cpp:89 plan, :195 plan.iter, :548 find_feasible, :574
+    // find_feasible.ptgUpdateDyn, :605 find_feasible.loop1, :701 find_feasible.loop2, :740
+    // find_feasible.tp_obstacles_single, :803 find_feasible.finalFill, :833 cached_local_obstacles), fed from the
+    // phase timers of this restructured loop. One expansion = one plan.iter = one find_feasible. The clip/transform
+    // of cached_local_obstacles is fused into the collision kernels: it is counted, its time is part of
+    // find_feasible.tp_obstacles_single. loop1 + ptgUpdateDyn (candidate enumeration) share phase A's timer with the
+    // relaxation of the previous round; loop2 is the blocked test + selection (phases C, D; on the device-expansion
+    // path inside the GPU call); finalFill is part of the same.
+    {
+        const double* ph = st.phaseSeconds;
+        size_t        expansions = 0, tps = 0;
+        for (const auto& o : outs)
+        {
+            expansions += o.nodesExpanded;
+            tps += o.tpsPointsEvaluated;
+        }
+        TimeLogger&  prof = self->profiler_();
+        const double loop = ph[1] + ph[2] + ph[3] + ph[4] + ph[5];
+        prof.registerUserMeasure("plan", ph[0] + loop + ph[6], Q);
+        prof.registerUserMeasure("plan.iter", loop, expansions);
+        prof.registerUserMeasure("find_feasible", ph[1] + ph[2] + ph[3], expansions);
+        prof.registerUserMeasure("find_feasible.loop1", ph[1], expansions);
+        prof.registerUserMeasure("find_feasible.ptgUpdateDyn", 0.0, expansions * ins[0]->ptgs.ptgs.size());
+        prof.registerUserMeasure("find_feasible.loop2", ph[3], expansions);
+        prof.registerUserMeasure("find_feasible.tp_obstacles_single", ph[2], tps);
+        prof.registerUserMeasure("find_feasible.finalFill", 0.0, expansions);
+        prof.registerUserMeasure("cached_local_obstacles", 0.0, st.nodesEvaluated);
+    }
     return outs;
 }
 

@@ -56,7 +56,8 @@ NcclApi& nccl()
         }
         if (!a.lib)
         {
-            a.error = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+            const char* why = dlerror();  // (cleared by the call: read once)
+            a.error         = std::string("libnccl.so.2 not found: ") + (why ? why : "");
             return a;
         }
         a.GetUniqueId    = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));

@@ -67,6 +67,18 @@ int main(int argc, char** argv)
     const mpp::PlannerOutput plain = planner.plan(pi);
     CHECK(plain.success && plain.nodesExpanded > 3);
 
+    // the reference's profiler sections exist under their names (TPS_Astar.cpp:89-833)
+    {
+        const auto& sec = planner.profiler_().sections();
+        for (const char* name : {"plan", "plan.iter", "find_feasible", "find_feasible.loop1", "find_feasible.ptgUpdateDyn",
+                                 "find_feasible.loop2", "find_feasible.tp_obstacles_single", "find_feasible.finalFill",
+                                 "cached_local_obstacles"})
+            CHECK(sec.count(name) == 1);
+        CHECK(sec.at("plan").calls == 1 && sec.at("plan.iter").calls == plain.nodesExpanded && sec.at("plan").seconds > 0);
+        CHECK(sec.at("find_feasible.tp_obstacles_single").calls == plain.tpsPointsEvaluated);
+        CHECK(!planner.profiler_().getStatsAsText().empty());
+    }
+
     // --- (2) a user evaluator: called on the host for every tentative edge, its value enters every edge cost ---
     auto user = std::make_shared<ConstantCost>();
     planner.costEvaluators_.push_back(user);

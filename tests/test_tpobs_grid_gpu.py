@@ -273,6 +273,56 @@ def test_many_nodes_in_one_batch(gpu_ctx):
     assert np.array_equal(out, np.tile(rows, (reps, 1)))
 
 
+def test_more_than_128_points_inside_the_robot_shape(gpu_ctx, orc, oracle_ackermann):
+    """The kernel queues obstacle points that fall inside the robot polygon (COLL_BEH_BACK_AWAY) in a 128-entry list per
+    node; beyond that it applies them on the spot. 600 points inside the shape of each node, plus a uniform background
+    (dense window form) and alone (sparse window form, <= 256 points is exceeded on purpose by the 600)."""
+    rng = np.random.default_rng(31)
+    extent = 30.0
+    poses = wl.node_poses(12, extent, margin=3.0, seed=32)
+    px, py = [], []
+    for x, y, phi in poses:
+        # a disc of radius 0.09 around the local point (0.05, 0) lies inside the polygon (x in [-0.1, 0.3], |y| <= 0.1)
+        r, a = 0.09 * np.sqrt(rng.uniform(size=600)), rng.uniform(-np.pi, np.pi, 600)
+        lx, ly = 0.05 + r * np.cos(a), r * np.sin(a)
+        px.append(x + lx * np.cos(phi) - ly * np.sin(phi))
+        py.append(y + lx * np.sin(phi) + ly * np.cos(phi))
+    inx, iny = np.concatenate(px).astype(np.float32), np.concatenate(py).astype(np.float32)
+    inside_frac = np.mean([oracle_ackermann[0].inside_shape(0.05 + 0.08 * np.cos(t), 0.08 * np.sin(t)) for t in np.linspace(0, 6.2, 40)])
+    assert inside_frac == 1.0
+    bx, by = wl.uniform_cloud(int(2.0 * extent * extent), extent, seed=33)
+    for xs, ys in ((inx, iny), (np.concatenate([inx, bx]), np.concatenate([iny, by]))):
+        got = _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+        # points inside the shape block paths at distance 0 unless the path's cell distance is below the robot radius
+        assert (got == 0.0).any()
+
+
+def test_more_than_128_long_cell_lists_in_a_sparse_window(gpu_ctx, capi, orc, oracle_ackermann, product_ackermann):
+    """Sparse windows (<= 256 points) scatter the by-cell lists of the occupied cells; lists longer than 32 entries
+    (cells near the robot carry an entry for most paths) are queued, 128 per node, and folded by the whole block;
+    beyond 128 the thread folds them itself. ~230 points in distinct cells with long lists around each node."""
+    g0, g1 = product_ackermann[0].grid(), product_ackermann[1].grid()
+    lens = (np.diff(g0["offsets"]) + np.diff(g1["offsets"])).reshape(g0["ny"], g0["nx"])  # merged list length per cell
+    cy, cx = np.nonzero(lens > 32)
+    # cell centres outside the robot's bounding circle (so that the points are plain obstacles, not inside-shape ones)
+    ccx = g0["xmin"] + (cx + 0.5) * g0["res"]
+    ccy = g0["ymin"] + (cy + 0.5) * g0["res"]
+    keep = np.hypot(ccx, ccy) > g0["max_radius"] + 0.08
+    ccx, ccy = ccx[keep], ccy[keep]
+    assert len(ccx) > 400
+    rng = np.random.default_rng(41)
+    poses = wl.node_poses(6, 300.0, margin=20.0, seed=42)  # far apart: each window holds its own points only
+    px, py = [], []
+    for x, y, phi in poses:
+        pick = rng.choice(len(ccx), size=230, replace=False)
+        lx, ly = ccx[pick], ccy[pick]
+        px.append(x + lx * np.cos(phi) - ly * np.sin(phi))
+        py.append(y + lx * np.sin(phi) + ly * np.cos(phi))
+    xs, ys = np.concatenate(px).astype(np.float32), np.concatenate(py).astype(np.float32)
+    got = _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
+    assert (got < 5.0).mean() > 0.5
+
+
 def test_staged_form_of_the_kernel_is_bit_identical():
     """tpobs_grid_kernel's STAGED form (points through cp.async.bulk + mbarrier into a shared-memory ring; selected
     with MPPB_GRID_STAGED=1, read once per process) gives the same rows as the default form: the parity tests of this
