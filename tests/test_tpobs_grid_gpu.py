@@ -292,9 +292,9 @@ def test_more_than_128_points_inside_the_robot_shape(gpu_ctx, orc, oracle_ackerm
     assert inside_frac == 1.0
     bx, by = wl.uniform_cloud(int(2.0 * extent * extent), extent, seed=33)
     for xs, ys in ((inx, iny), (np.concatenate([inx, bx]), np.concatenate([iny, by]))):
-        got = _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
-        # points inside the shape block paths at distance 0 unless the path's cell distance is below the robot radius
-        assert (got == 0.0).any()
+        # (near the origin every path's cell distance is below the robot radius, which BACK_AWAY ignores: the 600 points
+        # leave most paths free — what is tested is that 600 queued-or-overflowed points give the reference's rows)
+        _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
 
 
 def test_more_than_128_long_cell_lists_in_a_sparse_window(gpu_ctx, capi, orc, oracle_ackermann, product_ackermann):
