@@ -267,7 +267,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 // `rank` of EVERY rank's receive area — this GPU's own and, over NVLink, its peers' — while the other CTAs are still
 // evaluating their nodes, so the exchange overlaps the computation node by node; the last CTA to finish raises this
 // rank's flag on every peer. A short kernel on each rank then waits for all flags and takes the minimum over the slots.
-template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false>
+// BITMAP = false: collision grids whose occupancy bitmap does not fit shared memory (beyond ~1260 x 1260 cells, e.g.
+// a 40 m reference distance at 0.05 m cells). No bitmap and no column scan: every point that passes phase 1 folds the
+// (column, d) list of its cell straight into the per-path minima (atomicMin), the plain form of
+// updateTPObstacleSingle (DiffDriveCollisionGridBased.cpp:826-838). Slower per point, correct for any grid size.
+template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false, bool BITMAP = true>
 __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS)
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
@@ -380,8 +384,24 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
             nLong    = 0;
         }
         const int words = grid_tiles_x(gnx) * grid_tiles_y(gny);
-        for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
+        if constexpr (BITMAP)
+            for (int i = threadIdx.x; i < words; i += kThreads) bitmap[i] = 0u;
 
+        // an obstacle point in cell (cx, cy) outside the robot shape: its bit, or (no bitmap) its cell's list at once
+        auto markCell = [&](unsigned cx, unsigned cy) {
+            if constexpr (BITMAP)
+                atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
+            else
+            {
+                const uint32_t cell = cx + cy * static_cast<unsigned>(gnx);
+                const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
+                for (uint32_t e = eb; e < ee; e++)
+                {
+                    const uint2 kd = G.entries[e];
+                    atomicMin(&smin[kd.x], kd.y);
+                }
+            }
+        };
         // one point of the node's window: FP32 filtered path, exact FP64 chain for the undecided ones
         auto processPoint = [&](const float2 g) {
             if (HAS_BOX && (g.x < box.x || g.x > box.z || g.y < box.y || g.y > box.w)) return;
@@ -403,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
                     const unsigned cx = static_cast<unsigned>(__float2int_rz(qx));
                     const unsigned cy = static_cast<unsigned>(__float2int_rz(qy));
                     if (cx >= static_cast<unsigned>(gnx) || cy >= static_cast<unsigned>(gny)) return;
-                    atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
+                    markCell(cx, cy);
                     return;
                 }
             }
@@ -433,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
                     return;
                 }
             }
-            atomicOr(&bitmap[grid_tile_word(cx, cy, tilesX)], 1u << grid_tile_bit(cx, cy));
+            markCell(static_cast<unsigned>(cx), static_cast<unsigned>(cy));
         };
 
         // ---- phase 1: points -> occupancy bitmap ----
@@ -605,6 +625,14 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
                     processPoint(g);
                 }
             }
+        }
+        if constexpr (!BITMAP)
+        {
+            // no bitmap, no column scan: the points' lists are folded already; only the queued inside-shape points remain
+            __syncthreads();
+            const unsigned nIn = min(nInside, static_cast<unsigned>(kMaxInside));
+            for (unsigned q = 0; q < nIn; q++) apply_inside_cell(G, insideCell[q], smin, threadIdx.x, kThreads);
+            continue;
         }
         if constexpr (SPLIT > 1)
         {
@@ -807,8 +835,10 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     const bool        useStaged = staged && !split;
     size_t            smem = ((static_cast<size_t>(ctx->totalPaths) + words + 3) & ~static_cast<size_t>(3)) * sizeof(unsigned);
     if (useStaged) smem += static_cast<size_t>(kStages) * kStagePts * sizeof(float2);
-    if (smem > 200 * 1024)
-        return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
+    // a grid whose occupancy bitmap does not fit shared memory takes the form without one (see BITMAP)
+    const bool noBitmap = smem > 200 * 1024;
+    if (noBitmap) smem = ((static_cast<size_t>(ctx->totalPaths) + 3) & ~static_cast<size_t>(3)) * sizeof(unsigned);
+    if (smem > 200 * 1024) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many PTG paths for the shared-memory minima");
     auto       launch = [&](auto kernel, unsigned ctasPerNode) -> int {
         if (smem > 48 * 1024)
             MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -818,7 +848,9 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
         return MPPB_OK;
     };
     int rc;
-    if (split)
+    if (noBitmap)
+        rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, false>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, false>, 1);
+    else if (split)
         rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit>, kSplit) : launch(tpobs_grid_kernel<false, kSplit>, kSplit);
     else if (useStaged)
         rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, true>, 1) : launch(tpobs_grid_kernel<false, 1, true>, 1);

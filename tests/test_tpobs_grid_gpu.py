@@ -323,6 +323,35 @@ def test_more_than_128_long_cell_lists_in_a_sparse_window(gpu_ctx, capi, orc, or
     assert (got < 5.0).mean() > 0.5
 
 
+def test_collision_grid_larger_than_the_shared_memory_bitmap(capi, orc):
+    """A 35 m reference distance at 0.05 m cells is a 1400 x 1400 grid: its occupancy bitmap (245 KB) does not fit
+    shared memory, so the kernel takes its form without a bitmap (every point folds its cell's list at once). Same rows
+    as the checker, whose tables are built independently."""
+    p_ptgs = capi.ackermann_ptgs(num_paths=11, ref_distance=35.0)
+    o_ptgs = orc.ackermann_ptgs(num_paths=11, ref_distance=35.0)
+    for p, o in zip(p_ptgs, o_ptgs):
+        gp, go = p.grid(), o.grid()
+        assert gp["nx"] == 1400 and np.array_equal(gp["offsets"], go["offsets"]) and np.array_equal(gp["ds"], go["ds"])
+    ctx = capi.Context(0)
+    for p in p_ptgs:
+        ctx.add_ptg(p)
+    extent = 160.0
+    xs, ys = wl.uniform_cloud(int(0.4 * extent * extent), extent, seed=51)
+    poses = wl.node_poses(24, extent, margin=5.0, seed=52)
+    got = _check(ctx, orc, o_ptgs, xs, ys, poses, clip=35.0)
+    assert (got < 35.0).any()
+    # per-node world boxes on the same form
+    boxes = np.stack([poses[:, 0] - 20, poses[:, 1] - 20, poses[:, 0] + 20, poses[:, 1] + 20], 1).astype(np.float32)
+    out = np.empty((len(poses), ctx.total_paths), dtype=np.float32)
+    assert capi.lib().mppb_eval_nodes_boxed(ctx.h, len(poses), np.ascontiguousarray(poses).ctypes.data, boxes.ctypes.data, 35.0,
+                                             out.ctypes.data) == 0
+    for i in range(0, len(poses), 6):
+        m = (xs >= boxes[i, 0]) & (xs <= boxes[i, 2]) & (ys >= boxes[i, 1]) & (ys <= boxes[i, 3])
+        ref, _ = orc.eval_nodes(o_ptgs, xs[m], ys[m], poses[i:i + 1], 35.0, mode=1, nthreads=0)
+        assert np.array_equal(free_dist(out[i:i + 1], o_ptgs), ref)
+    ctx.close()
+
+
 def test_staged_form_of_the_kernel_is_bit_identical():
     """tpobs_grid_kernel's STAGED form (points through cp.async.bulk + mbarrier into a shared-memory ring; selected
     with MPPB_GRID_STAGED=1, read once per process) gives the same rows as the default form: the parity tests of this
