@@ -58,15 +58,21 @@ __global__ void __launch_bounds__(kMaxCand)
                   const float* __restrict__ rows /* [n][totalPaths] */, int totalPaths, mppb_neighbor* __restrict__ out,
                   uint32_t* __restrict__ counts)
 {
-    __shared__ int      sCell[3][kMaxCand];
-    __shared__ unsigned sDist[kMaxCand];     // relTrgDist as float bits (a non-negative table float: unsigned order)
-    __shared__ uint8_t  sState[kMaxCand];    // bit0 passed phase A, bit1 unblocked, bit2 valid after the goal-cell rule
-    __shared__ uint8_t  sLeader[kMaxCand];   // first candidate (in enumeration order) of its cell among the valid ones
-    __shared__ uint32_t sWinStep[kMaxCand];  // per output position: the winning candidate's step, path and PTG
-    __shared__ uint16_t sWinK[kMaxCand];
-    __shared__ uint8_t  sWinPtg[kMaxCand];
-    __shared__ double   sVal[kMaxCand * MPPB_MAX_EVALUATORS];
-    __shared__ int      sTps, sOut;
+    // per-candidate arrays in dynamic shared memory, sized by the candidate slots of THIS parameter set (86 for the
+    // reference's demo parameters, not the 512 the kernel admits): ~140 bytes per slot, so that a dozen and more CTAs
+    // share an SM — the kernel is a chain of dependent look-ups and barriers, and only resident CTAs hide that
+    extern __shared__ uint4 sRecRaw[];  // [mc] neighbour records (80 bytes each) come first: see below
+    const int        mc       = (P.maxCand + 31) & ~31;  // = the CTA's thread count: every thread owns a slot
+    double* const    sVal     = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sRecRaw) + static_cast<size_t>(mc) * sizeof(mppb_neighbor));
+    int* const       sCellAll = reinterpret_cast<int*>(sVal + static_cast<size_t>(mc) * MPPB_MAX_EVALUATORS);
+    int* const       sCell[3] = {sCellAll, sCellAll + mc, sCellAll + 2 * mc};
+    unsigned* const  sDist    = reinterpret_cast<unsigned*>(sCellAll + 3 * mc);  // relTrgDist as float bits (non-negative table float: unsigned order)
+    uint32_t* const  sWinStep = sDist + mc;  // per output position: the winning candidate's step, path and PTG
+    uint16_t* const  sWinK    = reinterpret_cast<uint16_t*>(sWinStep + mc);
+    uint8_t* const   sState   = reinterpret_cast<uint8_t*>(sWinK + mc);  // bit0 passed phase A, bit1 unblocked, bit2 valid after the goal-cell rule
+    uint8_t* const   sLeader  = sState + mc;   // first candidate (in enumeration order) of its cell among the valid ones
+    uint8_t* const   sWinPtg  = sLeader + mc;
+    __shared__ int   sTps, sOut;
     __shared__ mppb_expand_node sN;  // the node's record (it may live in pinned host memory: fetched once)
     __shared__ double           sCS[2];
 
@@ -241,8 +247,7 @@ __global__ void __launch_bounds__(kMaxCand)
     // ---- the winners write their cell's record at the position of the cell's first appearance ----
     // (records are assembled in shared memory and leave with 16-byte stores of consecutive threads: the destination
     // may be pinned host memory, where field-by-field stores of single threads would each be a PCIe transaction)
-    extern __shared__ uint4 sRecRaw[];
-    mppb_neighbor* const    o = reinterpret_cast<mppb_neighbor*>(sRecRaw);
+    mppb_neighbor* const o = reinterpret_cast<mppb_neighbor*>(sRecRaw);
     if (winner)
     {
         int pos = 0;
@@ -434,8 +439,10 @@ int launch_expand(mppb_ctx* ctx, size_t nNodes, const mppb_expand_node* dIn, con
 {
     if (nNodes == 0) return MPPB_OK;
     const int    threads = std::min(kMaxCand, (ctx->expandHost.maxCand + 31) / 32 * 32);
-    const size_t smem    = static_cast<size_t>(ctx->expandHost.maxCand) * sizeof(mppb_neighbor);
-    if (smem > 16 * 1024)  // (static shared memory of the kernel: ~30 KB)
+    // per candidate slot: record 80 + evaluator values 32 + cell 12 + dist 4 + step 4 + k 2 + three flags (see the kernel)
+    const size_t mc   = (static_cast<size_t>(ctx->expandHost.maxCand) + 31) & ~static_cast<size_t>(31);
+    const size_t smem = mc * (sizeof(mppb_neighbor) + MPPB_MAX_EVALUATORS * sizeof(double) + 3 * 4 + 4 + 4 + 2 + 3);
+    if (smem > 40 * 1024)
         MPPB_CUDA(ctx, cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     // launched with programmatic stream serialization: it may begin (parameters, tables, node records) while the
     // collision kernel before it on the stream is still draining, and waits for its rows inside the kernel

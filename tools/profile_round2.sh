@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-2 profile capture on the GPU box (one GPU). Each ncu pass follows a plain run of the same command that exited 0.
+# Outputs land in gpurun_out/ (scratch); summaries are written to profiles/ by tools/ncu_summary.py afterwards.
+#   usage: bash tools/profile_round2.sh <tag>
+TAG=${1:-r2}
+BENCH="python bench.py --no-planner --no-cpu-baseline --steps 3 --warmup 3"
+set -x
+$BENCH > gpurun_out/${TAG}_plain_bench.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    $BENCH > gpurun_out/${TAG}_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tpobs_grid_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_grid \
+    $BENCH > gpurun_out/${TAG}_ncu_grid.log 2>&1
+MPPB_GRID_STAGED=1 $BENCH > gpurun_out/${TAG}_plain_bench_staged.log 2>&1 && \
+MPPB_GRID_STAGED=1 ncu --set full --clock-control none --import-source on -k regex:tpobs_grid_kernel -s 4 -c 1 -f -o gpurun_out/${TAG}_grid_staged \
+    $BENCH > gpurun_out/${TAG}_ncu_grid_staged.log 2>&1
+python tools/profile_targets.py expand > gpurun_out/${TAG}_plain_expand.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:expand_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_expand \
+    python tools/profile_targets.py expand > gpurun_out/${TAG}_ncu_expand.log 2>&1
+python tools/profile_targets.py holo > gpurun_out/${TAG}_plain_holo.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tpobs_holo_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_holo \
+    python tools/profile_targets.py holo > gpurun_out/${TAG}_ncu_holo.log 2>&1
+for k in grid grid_staged expand holo; do python tools/ncu_summary.py gpurun_out/${TAG}_$k.ncu-rep > gpurun_out/${TAG}_${k}_ncu_full.txt 2>&1; done
+tail -2 gpurun_out/${TAG}_plain_expand.log
+ls -la gpurun_out/${TAG}_* | head -30

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver that launches each product kernel a few times on bench-shaped inputs (for ncu captures).
 
-  python tools/profile_targets.py [grid|holo|cost|all]
+  python tools/profile_targets.py [grid|holo|cost|expand|all]
 """
 import os
 import sys
@@ -77,4 +77,53 @@ if what in ("cost", "all"):
         ctx.eval_edge_costs(frm, off, rel)
         dt = time.perf_counter() - t
         print("cost: %d edges x 2 evaluators %.3f ms -> %.3g edges/s" % (n, 1e3 * dt, n / dt))
+    ctx.close()
+
+if what in ("expand", "all"):
+    # one C4-shaped round: 4096 nodes on the pillars map, both Ackermann PTGs, obstacle costmap, demo parameters
+    import bench
+
+    mx, my, pillars = wl.pillars_map(1 << 20, 200.0)
+    ctx = capi.Context(0)
+    ptgs = capi.ackermann_ptgs()
+    for p in ptgs:
+        ctx.add_ptg(p)
+    ctx.set_obstacles(mx, my)
+    pl = capi.Planner(ctx, ptgs, wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
+    pl.add_obstacles(mx, my)
+    pl.add_costmap(mx, my, bench.C4_COSTMAP[0], bench.C4_COSTMAP[1], bench.C4_COSTMAP[2], False, 0.0, None)
+    info, cells = pl.costmap_cells(0)
+    ctx.set_costmap(0, cells, info["xmin"], info["ymin"], info["res"], False)
+    ctx.set_expand_params(wl.DEMO_ASTAR_PARAMS, wl.DEMO_ASTAR_TIMESTAMPS)
+    qs = wl.planning_queries_free(4096, pillars, 200.0)
+    nodes = capi.pinned_empty((len(qs),), capi.EXPAND_NODE_DTYPE)
+    for i, (s0, g0, lo, hi, _) in enumerate(qs):
+        nodes["pose"][i] = s0[:3]
+        nodes["bbox_min"][i] = lo
+        nodes["bbox_max"][i] = hi
+        c, sn = np.cos(s0[2]), np.sin(s0[2])
+        rx, ry = (g0[0] - s0[0]) * c + (g0[1] - s0[1]) * sn, -(g0[0] - s0[0]) * sn + (g0[1] - s0[1]) * c
+        nodes["goal_k"][i][:] = -1
+        nodes["goal_step"][i][:] = 0xFFFFFFFF
+        for p, ptg in enumerate(ptgs):
+            exact, k, dn = ptg.inverse_map(rx, ry, 0.4)
+            if exact:
+                nodes["goal_k"][i][p] = k
+                found, step = ptg.step_for_dist(k, dn)
+                if found:
+                    nodes["goal_step"][i][p] = step
+    stride = ctx.expand_max_neighbors
+    out = capi.pinned_empty((len(qs), stride), capi.NEIGHBOR_DTYPE)
+    counts = capi.pinned_empty((len(qs), 2), np.uint32)
+    L = capi.lib()
+    for _ in range(4):
+        ctx.timer_begin()
+        t = time.perf_counter()
+        rc = L.mppb_expand_nodes(ctx.h, len(qs), nodes.ctypes.data, 1, 5.0, out.ctypes.data, counts.ctypes.data)
+        dt = time.perf_counter() - t
+        dev_ms = ctx.timer_end()
+        assert rc == 0
+        print("expand: %d nodes wall %.3f ms, device (copies + 2 kernels, CUDA events) %.3f ms, %.1f neighbours per node, %d TPS points" % (
+            len(qs), 1e3 * dt, dev_ms, counts[:, 0].mean(), int(counts[:, 1].sum())))
+    pl.close()
     ctx.close()
