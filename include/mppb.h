@@ -248,7 +248,9 @@ int mppb_eval_nodes_boxed_begin(mppb_ctx* ctx, size_t n_nodes, const double* pos
 void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, double* out_xycs);
 
 /* Diagnostic switch: on == 0 runs the HolonomicBlend kernel without its geometric pre-filter (every in-window point
- * goes through the exact FP64 chain). Results are identical either way; the tests compare the two. Default: on. */
+ * goes through the exact FP64 chain); on == 2 keeps the per-point pre-filter but walks the whole clipping window
+ * instead of only the cloud bins the candidate's path can reach. Results are identical in all three modes; the tests
+ * compare them. Default: 1 (pre-filter and bin culling). */
 int mppb_set_holo_filter(mppb_ctx* ctx, int on);
 /* Diagnostic switch: on != 0 runs host batches of mppb_eval_holo_candidates* whose candidates are grouped by node on
  * the one-CTA-per-node form of the kernel (the node's window is walked once for all its candidates). Results are

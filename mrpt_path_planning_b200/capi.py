@@ -459,7 +459,8 @@ class Context:
         return lib().mppb_launch_count(self.h)
 
     def set_holo_filter(self, on):
-        """Diagnostic: run tpobs_holo_kernel with (default) or without its geometric pre-filter."""
+        """Diagnostic: tpobs_holo_kernel without its geometric pre-filter (0/False), with pre-filter and bin culling
+        (1/True, the default), or with the pre-filter over the whole window (2)."""
         self._ck(lib().mppb_set_holo_filter(self.h, int(on)))
 
     def set_holo_by_node(self, on):

@@ -173,7 +173,7 @@ int mppb_sync(mppb_ctx* ctx)
 int mppb_set_holo_filter(mppb_ctx* ctx, int on)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
-    ctx->holoFilter = on != 0;
+    ctx->holoFilter = on == 0 ? 0 : (on == 2 ? 2 : 1);
     return MPPB_OK;
 }
 int mppb_set_holo_by_node(mppb_ctx* ctx, int on)

@@ -287,7 +287,7 @@ struct mppb_ctx
     int          numSMs    = 0;
     std::string  lastError;
     uint64_t     launches = 0;
-    bool         holoFilter = true;  // geometric pre-filter of tpobs_holo_kernel (mppb_set_holo_filter)
+    int          holoFilter = 1;  // tpobs_holo_kernel: 0 no pre-filter, 1 pre-filter + bin culling, 2 pre-filter only (mppb_set_holo_filter)
     bool         holoByNode = false; // host batches grouped by node run tpobs_holo_node_kernel (mppb_set_holo_by_node)
     cudaEvent_t  evBegin = nullptr, evEnd = nullptr;
     // second stream + fork/join events: the host entry points pipeline sub-batches over two streams

@@ -283,6 +283,61 @@ __device__ __forceinline__ bool hull_may_hit(const PathHull& h, float lx, float 
     return d2 <= h.thr2;
 }
 
+// ---- bin culling ------------------------------------------------------------------------------------------------
+// The hull above is thin (a triangle and a ray, inflated by the robot radius), the node's clipping square is not:
+// of the ~440 cloud bins of a 10 m window a candidate's hull touches a few dozen. Per bin row the warp therefore
+// narrows the row's run [bx0, bx1] to the bins the inflated hull can reach inside that row's strip of y, in FP64 and
+// with a margin (thr = R + 1 cm, against FP32 rounding of ~1e-6 m in the exact chain's inputs), so only a tenth of
+// the window's points are loaded and filtered at all. The hull is taken in the node's "d frame" (global axes, origin
+// at the node), where a bin row is a horizontal strip. Conservative by construction: a point that can collide lies
+// within R of the path, the path lies in (triangle U ray), and bin_coord() is monotone.
+// widens [xl, xh] by the x extent of segment A-B inside the strip ya <= y <= yb
+__device__ __forceinline__ void strip_extent(double ax, double ay, double bx, double by, double ya, double yb, double& xl,
+                                             double& xh)
+{
+    if (fmax(ay, by) < ya || fmin(ay, by) > yb) return;
+    const double dy = by - ay;
+    double       t0 = 0.0, t1 = 1.0;
+    if (fabs(dy) > 1e-9)
+    {
+        const double ta = (ya - ay) / dy, tb = (yb - ay) / dy;
+        t0              = fmax(0.0, fmin(ta, tb));
+        t1              = fmin(1.0, fmax(ta, tb));
+    }
+    const double xa = ax + t0 * (bx - ax), xb = ax + t1 * (bx - ax);
+    xl = fmin(xl, fmin(xa, xb));
+    xh = fmax(xh, fmax(xa, xb));
+}
+// x extent, in the d frame, of the candidate's hull (control triangle of the ramp + cruise ray cut where it leaves
+// `reach`) inside the strip yLo <= y <= yHi; empty: .x > .y. Out of line and fed by value: it runs once per bin row and
+// must not cost the point loop registers. (c, s): the node's heading.
+__device__ __noinline__ double2 hull_strip_extent(double T, double vxi, double vyi, double vxf, double vyf, double c, double s,
+                                                  double reach, double yLo, double yHi)
+{
+    const double tau = T * 1.01, TR2_ = 1.0 / (2 * T);
+    const double k2 = (vxf - vxi) * TR2_, k4 = (vyf - vyi) * TR2_;
+    double       lx[5] = {0.0, vxi * tau * 0.5, vxi * tau + k2 * tau * tau, T * 0.5 * (vxi + vxf) - 0.01 * T * vxf, 0.0};
+    double       ly[5] = {0.0, vyi * tau * 0.5, vyi * tau + k4 * tau * tau, T * 0.5 * (vyi + vyf) - 0.01 * T * vyf, 0.0};
+    const double vn  = sqrt(vxf * vxf + vyf * vyf);
+    // a ray point at parameter t is at least t - |Q| from the node; window points are within `reach` of it
+    const double len = hypot(lx[3], ly[3]) + reach;
+    lx[4]            = lx[3] + (vxf / vn) * len;
+    ly[4]            = ly[3] + (vyf / vn) * len;
+    double vx[5], vy[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+    {
+        vx[i] = lx[i] * c - ly[i] * s;  // robot frame -> d frame
+        vy[i] = lx[i] * s + ly[i] * c;
+    }
+    double xl = CUDART_INF, xh = -CUDART_INF;
+    strip_extent(vx[0], vy[0], vx[1], vy[1], yLo, yHi, xl, xh);
+    strip_extent(vx[1], vy[1], vx[2], vy[2], yLo, yHi, xl, xh);
+    strip_extent(vx[2], vy[2], vx[0], vy[0], yLo, yHi, xl, xh);
+    strip_extent(vx[3], vy[3], vx[4], vy[4], yLo, yHi, xl, xh);
+    return make_double2(xl, xh);
+}
+
 #ifndef MPPB_HOLO_MIN_BLOCKS
 #define MPPB_HOLO_MIN_BLOCKS 6  // 80 registers: the FP32 filter loop dominates, the rare exact path may spill
 #endif
@@ -346,6 +401,13 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
         const int   bx1 = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         const int   by0 = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
         const int   by1 = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
+        // bin culling (see HullD): margin = robot radius + 1 cm + what the float row boundaries can be off by
+        const bool   cull       = filter && useFilter == 1;
+        const double binSize    = 1.0 / static_cast<double>(bins.invBin);
+        const double cullMargin = q.R + 0.01 + 1e-3 +
+                                  1e-6 * (fabs(static_cast<double>(bins.miny)) + fabs(y0) + fabs(x0) +
+                                          fabs(static_cast<double>(bins.minx)) + clip + binSize * (bins.nby + bins.nbx));
+        const double cullReach = 1.5 * clip + cullMargin + 1.0;  // > sqrt(2) clip: no window point is farther from the node
         // The window's points, 32 at a time across bin rows: the runs of up to 32 rows are fetched together (one
         // row per lane, so their binStart reads are ONE round trip instead of one per row — on a sparse map the
         // rows hold a dozen points each and a row-by-row loop is a chain of dependent loads), a warp scan of the
@@ -367,9 +429,30 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
                     runBeg           = 0;
                     if (lane < nRows)
                     {
-                        const size_t r = static_cast<size_t>(rowBase + lane) * bins.nbx;
-                        runBeg         = bins.binStart[r + bx0];
-                        runLen         = bins.binStart[r + bx1 + 1] - runBeg;
+                        int cx0 = bx0, cx1 = bx1;
+                        if (cull)
+                        {
+                            // this row's strip of y in the d frame (first/last rows also hold what lies beyond the grid)
+                            const int    row = rowBase + lane;
+                            const double yLo = row == 0 ? -CUDART_INF : (bins.miny + row * binSize - y0) - cullMargin;
+                            const double yHi =
+                                row == bins.nby - 1 ? CUDART_INF : (bins.miny + (row + 1) * binSize - y0) + cullMargin;
+                            const double2 ext = hull_strip_extent(q.T, q.vxi, q.vyi, q.vxf, q.vyf, c, s, cullReach, yLo, yHi);
+                            const double  xl = ext.x, xh = ext.y;
+                            if (xl <= xh)
+                            {
+                                cx0 = max(bx0, bin_coord(__double2float_rd(x0 + xl - cullMargin), bins.minx, bins.invBin, bins.nbx));
+                                cx1 = min(bx1, bin_coord(__double2float_ru(x0 + xh + cullMargin), bins.minx, bins.invBin, bins.nbx));
+                            }
+                            else
+                                cx1 = cx0 - 1;
+                        }
+                        if (cx0 <= cx1)
+                        {
+                            const size_t r = static_cast<size_t>(rowBase + lane) * bins.nbx;
+                            runBeg         = bins.binStart[r + cx0];
+                            runLen         = bins.binStart[r + cx1 + 1] - runBeg;
+                        }
                     }
                     uint32_t incl = runLen;
 #pragma unroll
@@ -633,7 +716,7 @@ int launch_tpobs_holo_by_node(mppb_ctx* ctx, size_t nNodes, const uint32_t* dCan
     MPPB_CUDA(ctx, cudaFuncSetAttribute(tpobs_holo_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     tpobs_holo_node_kernel<<<static_cast<unsigned>(nNodes), kNodeThreads, smem, ctx->stream>>>(
         ctx->bins, ctx->holoDescs.as<HoloPtgDev>(), dCands, dCandBegin, dNodes, reinterpret_cast<const float4*>(dBoxes), clip,
-        ctx->holoFilter ? 1 : 0, dOut);
+        ctx->holoFilter, dOut);
     ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;
@@ -642,7 +725,7 @@ int launch_tpobs_holo_by_node(mppb_ctx* ctx, size_t nNodes, const uint32_t* dCan
 int launch_tpobs_holo(mppb_ctx* ctx, size_t nCands, const mppb_holo_cand* dCands, const double* dNodes,
                       const float* dBoxes, double clip, double* dOut, size_t nNodes)
 {
-    const int useFilter = ctx->holoFilter ? 1 : 0;  // off: the unfiltered kernel, for A/B tests (mppb_set_holo_filter)
+    const int useFilter = ctx->holoFilter;  // 0: the unfiltered kernel, 2: filter without bin culling (mppb_set_holo_filter)
     if (nCands == 0) return MPPB_OK;
     if (ctx->holos.empty()) return fail(ctx, MPPB_ERR_STATE, "no HolonomicBlend PTG set (mppb_set_ptg_holo)");
     if (nCands > 0x3fffffffull) return fail(ctx, MPPB_ERR_INVALID_ARG, "too many candidates in one batch");

@@ -179,6 +179,37 @@ def test_filter_is_conservative(holo_ctx, density, seed):
     assert np.isfinite(plain).any()
 
 
+@pytest.mark.parametrize("offset,extent,clip", [(0.0, 24.0, 5.0), (-3000.0, 30.0, 7.5), (1.0e5, 40.0, 5.0), (0.0, 6.0, 12.0)])
+def test_bin_culling_is_conservative(holo_ctx, offset, extent, clip):
+    """Bin culling (the warp walks only the cloud bins its candidate's inflated hull can reach) returns the same bits
+    as the pre-filter over the whole window (mode 2) and as no filter at all (mode 0): nodes inside, at the border of
+    and outside the cloud's bin grid (first/last bin rows and columns catch everything beyond), clouds far from the
+    origin (float coordinates with a coarse ulp), windows larger than the cloud."""
+    ctx, ptg = holo_ctx
+    xs, ys = wl.uniform_cloud(int(12.0 * extent * extent), extent, seed=int(extent))
+    xs = (xs + np.float32(offset)).astype(np.float32)
+    ys = (ys - np.float32(offset)).astype(np.float32)
+    rng = np.random.default_rng(int(extent) + 1)
+    nodes, rel = random_nodes(rng, 16, extent)
+    nodes[:4, 0] = [-1.0, extent + 1.0, 0.01, extent - 0.01]  # outside and on the border of the bin grid
+    nodes[4:8, 1] = [-2.0, extent + 0.5, 0.0, extent]
+    nodes[::5, 3:] = 0.0
+    nodes[:, 0] += offset
+    nodes[:, 1] -= offset
+    cands, *_ = make_candidates(ptg, nodes, rel, [list(range(0, 191, 3))] * len(nodes), (1 / 3, 1.0))
+    ctx.set_obstacles(xs, ys)
+    res = {}
+    try:
+        for mode in (0, 2, 1):
+            ctx.set_holo_filter(mode)
+            res[mode] = ctx.eval_holo_candidates(nodes[:, :3], cands, clip)
+    finally:
+        ctx.set_holo_filter(1)
+    assert np.array_equal(res[0].view(np.uint64), res[2].view(np.uint64))
+    assert np.array_equal(res[0].view(np.uint64), res[1].view(np.uint64))
+    assert np.isfinite(res[0]).any() and np.isinf(res[0]).any()
+
+
 HOLO_VARIANTS = [
     # num_paths, ref_distance, T_ramp_max, v_max, w_max, radius, expr_V, expr_W
     (61, 4.0, 0.5, 0.8, np.deg2rad(90.0), 0.30, "", ""),

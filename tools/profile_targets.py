@@ -51,6 +51,7 @@ if what in ("holo", "all"):
     hp[:] = poses[:nb]
     out = capi.pinned_empty((len(rows),), np.float64)
     L = capi.lib()
+    ctx.set_holo_filter(int(os.environ.get("HOLO_FILTER", "1")))
     for _ in range(5):
         ctx.timer_begin()
         t = time.perf_counter()
