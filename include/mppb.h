@@ -252,6 +252,16 @@ void mppb_nodes_xycs_from_poses(size_t n_nodes, const double* poses_xyphi, doubl
  * instead of only the cloud bins the candidate's path can reach. Results are identical in all three modes; the tests
  * compare them. Default: 1 (pre-filter and bin culling). */
 int mppb_set_holo_filter(mppb_ctx* ctx, int on);
+/* Near-first evaluation of node batches against collision-grid PTGs (more than 256 nodes per call). Every entry (k, d)
+ * of a collision-grid cell has d >= distance(robot origin, cell) - (largest robot radius), which is measured on the
+ * tables when they are set; so once every path of a node is blocked within `bound` by obstacle points of the cloud
+ * bins around the node, no farther point can change the row, and the rest of the clipping window is not looked at.
+ * Nodes that are not decided that way are evaluated on the whole window by a second launch behind the first. Results
+ * are identical in all modes (tested). mode 0: off; 1 (default): on, and switched off for the next 256 calls whenever
+ * more than 2 % of a batch needed the second launch (maps with free space around the nodes); 2: always on.
+ * mppb_grid_near_stats: out3 = {calls that took the two-launch form, their nodes, nodes that needed the second launch}. */
+int mppb_set_grid_near(mppb_ctx* ctx, int mode);
+int mppb_grid_near_stats(const mppb_ctx* ctx, uint64_t* out3);
 /* Diagnostic switch: on != 0 runs host batches of mppb_eval_holo_candidates* whose candidates are grouped by node on
  * the one-CTA-per-node form of the kernel (the node's window is walked once for all its candidates). Results are
  * identical either way; the tests compare the two. Measured no faster on B200, so the default is off. */

@@ -189,6 +189,8 @@ _SIGS = {
     "mppb_set_waypoints": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
                                      C.c_double, C.c_int]),
     "mppb_set_holo_filter": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppb_set_grid_near": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppb_grid_near_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "mppb_set_holo_by_node": (C.c_int, [C.c_void_p, C.c_int]),
     "mppb_evaluators_epoch": (C.c_uint64, [C.c_void_p]),
     "mppb_num_evaluators": (C.c_int, [C.c_void_p]),
@@ -462,6 +464,16 @@ class Context:
         """Diagnostic: tpobs_holo_kernel without its geometric pre-filter (0/False), with pre-filter and bin culling
         (1/True, the default), or with the pre-filter over the whole window (2)."""
         self._ck(lib().mppb_set_holo_filter(self.h, int(on)))
+
+    def set_grid_near(self, mode):
+        """Near-first evaluation of node batches (mppb_set_grid_near): 0 off, 1 adaptive (default), 2 always."""
+        self._ck(lib().mppb_set_grid_near(self.h, int(mode)))
+
+    def grid_near_stats(self):
+        """(calls in the two-launch form, their nodes, nodes that needed the second launch)"""
+        out = (C.c_uint64 * 3)()
+        self._ck(lib().mppb_grid_near_stats(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def set_holo_by_node(self, on):
         """Diagnostic: grouped host batches on the one-CTA-per-node form of the HolonomicBlend kernel."""

@@ -111,6 +111,9 @@ void mppb_ctx_destroy(mppb_ctx* ctx)
     ctx->bboxScratch.release();
     for (auto& g : ctx->groups) g.release();
     ctx->groupDescs.release();
+    for (auto& b : ctx->nearList) b.release();
+    ctx->nearCounters.release();
+    if (ctx->nearLastCount) cudaFreeHost(ctx->nearLastCount);
     ctx->holoDescs.release();
     for (int i = 0; i < MPPB_MAX_EVALUATORS; i++)
     {
@@ -176,6 +179,44 @@ int mppb_set_holo_filter(mppb_ctx* ctx, int on)
     ctx->holoFilter = on == 0 ? 0 : (on == 2 ? 2 : 1);
     return MPPB_OK;
 }
+// the adaptive switch of the near-first evaluation starts afresh (new cloud, new tables, new mode): what earlier calls
+// reported goes into the statistics
+static void near_reset_adaptive(mppb_ctx* ctx)
+{
+    ctx->nearSkip = 0;
+    for (int i = 0; i < mppb_ctx::kNearSlots; i++)
+        if (ctx->nearNodesOfSlot[i])
+        {
+            ctx->nearPendingSeen += ctx->nearLastCount[i];
+            ctx->nearNodesSeen += ctx->nearNodesOfSlot[i];
+            ctx->nearNodesOfSlot[i] = 0;
+            ctx->nearLastCount[i]   = 0;
+        }
+}
+int mppb_set_grid_near(mppb_ctx* ctx, int mode)
+{
+    if (!ctx) return MPPB_ERR_INVALID_ARG;
+    ctx->gridNear = mode == 0 ? 0 : (mode == 2 ? 2 : 1);
+    near_reset_adaptive(ctx);
+    return MPPB_OK;
+}
+int mppb_grid_near_stats(const mppb_ctx* ctx, uint64_t* out3)
+{
+    if (!ctx || !out3) return MPPB_ERR_INVALID_ARG;
+    // the counts of launches still in flight are not in yet; the caller synchronises first if it wants them exact
+    uint64_t pend = ctx->nearPendingSeen, nodes = ctx->nearNodesSeen;
+    if (ctx->nearLastCount)
+        for (int i = 0; i < mppb_ctx::kNearSlots; i++)
+            if (ctx->nearNodesOfSlot[i])
+            {
+                pend += ctx->nearLastCount[i];
+                nodes += ctx->nearNodesOfSlot[i];
+            }
+    out3[0] = ctx->nearLaunches;
+    out3[1] = nodes;
+    out3[2] = pend;
+    return MPPB_OK;
+}
 int mppb_set_holo_by_node(mppb_ctx* ctx, int on)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;
@@ -222,7 +263,11 @@ static int set_cloud(mppb_ctx* ctx, CloudStore& cs, const float* xs, const float
 {
     if (n > 0 && (!xs || !ys)) return fail(ctx, MPPB_ERR_INVALID_ARG, "null cloud pointers");
     MPPB_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (&cs == &ctx->cloud) ctx->cloudEpoch++;  // whatever happens below, the resident cloud is no longer the old one
+    if (&cs == &ctx->cloud)
+    {
+        ctx->cloudEpoch++;  // whatever happens below, the resident cloud is no longer the old one
+        near_reset_adaptive(ctx);
+    }
     const size_t keep  = append ? cs.rawN : 0;
     const size_t total = keep + n;
     if (!append)
@@ -325,6 +370,9 @@ static int rebuild_groups(mppb_ctx* ctx)
         if (!placed) members.push_back({i});
     }
     std::vector<GridGroupDev> descs;
+    near_reset_adaptive(ctx);
+    ctx->nearSlackDiag = 0;
+    bool nearApplies   = !members.empty();
     for (const auto& m : members)
     {
         const PtgGridHost& g0     = ctx->grids[m[0]];
@@ -351,6 +399,24 @@ static int rebuild_groups(mppb_ctx* ctx)
                 }
             }
         }
+        // near-first evaluation (NearPassDev): slack = max over the entries of dist(origin, cell) - d, measured here
+        {
+            double slack = 0;
+            for (size_t c = 0; c < ncells; c++)
+            {
+                if (off[c + 1] == off[c]) continue;
+                const double xa = g0.xmin + static_cast<double>(c % g0.nx) * g0.res, ya = g0.ymin + static_cast<double>(c / g0.nx) * g0.res;
+                const double nx = std::min(std::max(0.0, xa), xa + g0.res), ny = std::min(std::max(0.0, ya), ya + g0.res);
+                const double dc = std::hypot(nx, ny);
+                for (size_t i : m)
+                {
+                    const PtgGridHost& g = ctx->grids[i];
+                    for (uint32_t e = g.offsets[c]; e < g.offsets[c + 1]; e++)
+                        slack = std::max(slack, dc - static_cast<double>(g.entryD[e]));
+                }
+            }
+            ctx->nearSlackDiag = std::max(ctx->nearSlackDiag, slack + g0.res * 1.4142136);
+        }
         GridGroupHost G;
         MPPB_CUDA(ctx, G.offsets.reserve((ncells + 1) * sizeof(uint32_t)));
         MPPB_CUDA(ctx, G.entries.reserve(std::max<size_t>(ent.size(), 1) * sizeof(uint2)));
@@ -375,6 +441,7 @@ static int rebuild_groups(mppb_ctx* ctx)
                     perK[g.entryK[e]].emplace_back(g.entryD[e], static_cast<uint32_t>(c));
             for (int k = 0; k < g.K; k++)
             {
+                if (perK[k].empty()) nearApplies = false;  // a path without cells can never be decided by near points
                 std::sort(perK[k].begin(), perK[k].end());
                 uint32_t w[4] = {0, 0, 0, 0}, mk[4] = {0, 0, 0, 0};
                 float    dOf[4][32];
@@ -472,6 +539,7 @@ static int rebuild_groups(mppb_ctx* ctx)
         ctx->groups.push_back(G);
         descs.push_back(v);
     }
+    if (!nearApplies) ctx->nearSlackDiag = 0;
     MPPB_CUDA(ctx, ctx->groupDescs.reserve(std::max<size_t>(descs.size(), 1) * sizeof(GridGroupDev)));
     MPPB_CUDA(ctx, cudaMemcpyAsync(ctx->groupDescs.p, descs.data(), descs.size() * sizeof(GridGroupDev),
                                    cudaMemcpyHostToDevice, ctx->stream));
@@ -648,7 +716,8 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
     // <= 5 sub-batches of >= 820 nodes (API calls cost ~5 us each), round-robin over 4 streams: a sub-batch on a
     // stream of its own can start while the tails of the two before it are still draining (measured: 2 streams
     // 0.175 ms, 4 streams 0.165-0.170 ms per 4096-node call)
-    constexpr int kSubBatches = 5, kSubStreams = 4;
+    constexpr int    kSubStreams = 4;
+    static const int kSubBatches = std::getenv("MPPB_E2E_SUBS") ? std::max(1, std::atoi(std::getenv("MPPB_E2E_SUBS"))) : 5;  // experiments
     const size_t  sub = n_nodes <= 1024 ? n_nodes : std::max<size_t>(820, (n_nodes + kSubBatches - 1) / kSubBatches);
     cudaStream_t  streams[kSubStreams] = {ctx->stream, ctx->auxStream, ctx->auxMore[0], ctx->auxMore[1]};
     const bool    single   = n_nodes <= sub;  // one sub-batch: no second stream, no fork/join events
@@ -680,7 +749,9 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
             break;
         }
         ctx->stream = st;  // launch on the sub-batch's stream
-        rc          = launch_tpobs_grid(ctx, n, dN, dBoxes ? dBoxes + 4 * lo : nullptr, clip_dist, dO);
+        // (plain form: this path is bound by the host's cos/sin and the rows' way over PCIe, measured; the second
+        // launch of the near-first form would only add API calls)
+        rc          = launch_tpobs_grid(ctx, n, dN, dBoxes ? dBoxes + 4 * lo : nullptr, clip_dist, dO, /*allowNear=*/false);
         ctx->stream = saved;
         if (rc != MPPB_OK) break;
         if (outDev) continue;  // rows already land in the caller's pinned buffer

@@ -553,7 +553,8 @@ int expand_nodes_impl(mppb_ctx* ctx, size_t n, const mppb_expand_node* nodes, in
         dOut    = ctx->dExpandOut.as<mppb_neighbor>();
         dCounts = ctx->dExpandCounts.as<uint32_t>();
     }
-    int rc = launch_tpobs_grid(ctx, n, dN, dB, clip, ctx->dExpandRows.as<float>());
+    // (plain form: the expansion kernel is launched behind it with programmatic stream serialization)
+    int rc = launch_tpobs_grid(ctx, n, dN, dB, clip, ctx->dExpandRows.as<float>(), /*allowNear=*/false);
     if (rc != MPPB_OK) return rc;
     rc = launch_expand(ctx, n, dIn, dN, ctx->dExpandRows.as<float>(), dOut, dCounts);
     if (rc != MPPB_OK) return rc;

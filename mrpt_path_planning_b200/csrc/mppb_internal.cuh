@@ -136,6 +136,25 @@ struct PeerRowsDev
     unsigned* done;                   // local counter of finished CTAs (reset by the last one)
 };
 
+// Near-first evaluation of large node batches (tpobs_grid_kernel, MODE 1 and 2). Every entry (k, d) of a collision-grid
+// cell satisfies d >= dist(robot origin, cell) - slack, slack = max over the table of that difference (the robot's largest
+// radius, measured on the tables when they are uploaded): an obstacle point farther than r from the node can only block
+// a path at a distance >= r - cell diagonal - slack. A first pass therefore looks only at the cloud bins around the node
+// (half-size r); if every path already has a minimum <= bound = r - cell diagonal - slack, no farther point can lower any
+// of them and the row is final. Nodes that cannot be decided that way (free space ahead, or too few points nearby to
+// be worth trying) are appended to a list and a second launch evaluates them on the whole clipping window.
+struct NearPassDev
+{
+    double    r          = 0;        // MODE 1: half-size of the near window, global axes
+    unsigned  boundBits  = 0;        // MODE 1: float bits of `bound`
+    unsigned  minPoints  = 0;        // MODE 1: fewer points in the near bins -> straight to the list
+    uint32_t* count      = nullptr;  // nodes in the list (MODE 1 appends, MODE 2 consumes)
+    uint32_t* countOther = nullptr;  // the counter of this slot's next use; MODE 2 zeroes it (nobody reads it meanwhile)
+    uint32_t* list       = nullptr;
+    uint32_t* lastCount  = nullptr;  // host-visible copy of `count` of the last MODE 2 launch (adaptive switch)
+    uint32_t  totalNodes = 0;        // rows the two launches produce together (peer epilogue)
+};
+
 // ---------------------------------------------------------------------------------------
 // Host-side context
 // ---------------------------------------------------------------------------------------
@@ -309,6 +328,17 @@ struct mppb_ctx
     std::vector<mppb::GridGroupHost> groups;  // merged tables, rebuilt when a PTG is added
     mppb::DevBuf                     groupDescs;  // GridGroupDev[numGroups] on the device
     int                              totalPaths = 0;
+    // near-first evaluation (NearPassDev): table statistics from rebuild_groups, per-launch slots, adaptive switch
+    double       nearSlackDiag = 0;     // max over groups of (slack + cell diagonal); 0: not applicable (e.g. a path without cells)
+    int          gridNear      = 1;     // mppb_set_grid_near: 0 off, 1 adaptive (default), 2 always
+    static constexpr int kNearSlots = 8;
+    mppb::DevBuf nearList[kNearSlots];  // pending-node lists
+    mppb::DevBuf nearCounters;          // [kNearSlots][2] count, arrived
+    uint32_t*    nearLastCount = nullptr;   // pinned, [kNearSlots]
+    uint32_t     nearNodesOfSlot[kNearSlots] = {};
+    unsigned     nearSlot = 0, nearSkip = 0;
+    uint8_t      nearParity[kNearSlots] = {};  // which of a slot's two counters its next use appends to
+    uint64_t     nearLaunches = 0, nearPendingSeen = 0, nearNodesSeen = 0;  // statistics (mppb_grid_near_stats)
     std::vector<mppb::HoloPtgDev>    holos;      // indexed by PTG index (zero for other kinds)
     mppb::DevBuf                     holoDescs;  // HoloPtgDev[MPPB_MAX_PTGS]
 
@@ -365,7 +395,7 @@ void set_global_error(const std::string& msg);
 // kernels / launchers implemented in the .cu files
 int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize);
 int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
-                      float* dOut);
+                      float* dOut, bool allowNear = true);
 // same, each finished row also stored into slot `rank` of every attached peer (fused merge of cloud-sharded rows)
 int launch_tpobs_grid_peers(mppb_ctx* ctx, size_t nNodes, const double* dNodes, double clip, const PeerRowsDev& peers);
 void multigpu_release(mppb_ctx* ctx);

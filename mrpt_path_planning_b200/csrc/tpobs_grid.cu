@@ -41,6 +41,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 
 #include "mppb_internal.cuh"
 
@@ -171,7 +172,7 @@ __device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned
         }
     };
     const uint32_t gnx = static_cast<uint32_t>(G.nx), tilesX = static_cast<uint32_t>(grid_tiles_x(G.nx));
-    for (int i = threadIdx.x; i < words; i += kThreads)
+    for (int i = threadIdx.x; i < words; i += blockDim.x)
     {
         unsigned bits = bitmap[i];
         if (!bits) continue;
@@ -203,7 +204,7 @@ __device__ __noinline__ void sparse_phase2(const GridGroupDev& G, const unsigned
     {
         const uint32_t cell = longCell[q];
         const uint32_t eb = G.offsets[cell], ee = G.offsets[cell + 1];
-        for (uint32_t e = eb + threadIdx.x; e < ee; e += kThreads)
+        for (uint32_t e = eb + threadIdx.x; e < ee; e += blockDim.x)
         {
             const uint2 kd = G.entries[e];
             atomicMin(&smin[kd.x], kd.y);
@@ -271,13 +272,21 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 // a 40 m reference distance at 0.05 m cells). No bitmap and no column scan: every point that passes phase 1 folds the
 // (column, d) list of its cell straight into the per-path minima (atomicMin), the plain form of
 // updateTPObstacleSingle (DiffDriveCollisionGridBased.cpp:826-838). Slower per point, correct for any grid size.
-template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false, bool BITMAP = true>
-__global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS)
-    tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
-                      int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
-                      const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
-                      float* __restrict__ out, const PeerRowsDev peers)
+// MODE 1 / MODE 2: near-first evaluation of a large batch in two launches (NearPassDev, mppb_internal.cuh). MODE 1 looks
+// only at the cloud bins within near.r of the node; a node whose paths are all blocked within near.boundBits is final
+// and its row is written, any other node is appended to near.list. MODE 2 is the plain kernel over the nodes of that
+// list (CTAs beyond its length leave at once).
+// THREADS: CTA size. The near pass takes one warp per node (THREADS = 32): a near window holds a few hundred points, and
+// four warps would each repeat the per-node set-up for a quarter of them.
+template <bool HAS_BOX, int SPLIT, bool STAGED, bool PEERS, bool BITMAP, int MODE, int THREADS>
+__device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const GridGroupDev* __restrict__ groups, int numGroups,
+                                                int totalPaths, int bitmapWords, const double* __restrict__ nodes,
+                                                const float4* __restrict__ boxes, double clip, float* __restrict__ out,
+                                                const PeerRowsDev& peers, const NearPassDev& near, const int node, const int part)
 {
+    static_assert(MODE != 1 || (SPLIT == 1 && !STAGED && BITMAP), "near pass: one CTA per node, bitmap form");
+    static_assert(!STAGED || THREADS >= 64, "staged form: row tables are filled by the first 64 threads");
+    constexpr int kThreads = THREADS, kWarps = THREADS / 32;  // (shadow the namespace-level defaults)
     extern __shared__ __align__(16) unsigned smem[];
     unsigned*           smin   = smem;               // [totalPaths] float bits
     unsigned*           bitmap = smem + totalPaths;  // [bitmapWords] one bit per grid cell, in 8 x 4 tiles per word
@@ -309,11 +318,6 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
     __shared__ uint32_t longCell[kMaxLong];
     __shared__ unsigned nLong;
 
-    // A kernel launched behind this one with programmatic stream serialization (expand_kernel) may start its prologue
-    // now; it waits for this grid's completion (and memory flush) before it reads the rows written below.
-    cudaTriggerProgrammaticLaunchCompletion();
-    const int    node = SPLIT > 1 ? blockIdx.x / SPLIT : blockIdx.x;
-    const int    part = SPLIT > 1 ? blockIdx.x % SPLIT : 0;  // this CTA's share of the output columns
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double x0 = nodes[4 * node + 0], y0 = nodes[4 * node + 1];
     const double c = nodes[4 * node + 2], s = nodes[4 * node + 3];
@@ -340,17 +344,20 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
     const bool any = bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0;
     if (any)
     {
-        const float lox = nextafterf(__double2float_rd(x0 - clip), -FLT_MAX);
-        const float hix = nextafterf(__double2float_ru(x0 + clip), FLT_MAX);
-        const float loy = nextafterf(__double2float_rd(y0 - clip), -FLT_MAX);
-        const float hiy = nextafterf(__double2float_ru(y0 + clip), FLT_MAX);
+        // MODE 1: the bins that hold every point within near.r of the node (the clip test per point stays the reference's)
+        const double win = MODE == 1 ? fmin(near.r, clip) : clip;
+        const float  lox = nextafterf(__double2float_rd(x0 - win), -FLT_MAX);
+        const float  hix = nextafterf(__double2float_ru(x0 + win), FLT_MAX);
+        const float  loy = nextafterf(__double2float_rd(y0 - win), -FLT_MAX);
+        const float  hiy = nextafterf(__double2float_ru(y0 + win), FLT_MAX);
         bx0             = bin_coord(lox, bins.minx, bins.invBin, bins.nbx);
         bx1             = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         by0             = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
         by1             = bin_coord(hiy, bins.miny, bins.invBin, bins.nby);
     }
 
-    int sparseWords = 0;  // > 0: phase 2 of the last group is done in its sparse form after the loop
+    int  sparseWords   = 0;      // > 0: phase 2 of the last group is done in its sparse form after the loop
+    bool nearUndecided = false;  // MODE 1: this node goes to the list (same value in all threads)
     for (int gi = 0; any && gi < numGroups; gi++)
     {
         const GridGroupDev& G = groups[gi];
@@ -552,16 +559,25 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
         {
             const int nRows = min(kRowsPerPass, by1 - rowBase + 1);
             __syncthreads();  // bitmap cleared / previous pass done with the row tables
-            if (threadIdx.x < nRows)
+            for (int t = threadIdx.x; t < nRows; t += kThreads)
             {
-                const size_t   r = static_cast<size_t>(rowBase + threadIdx.x) * bins.nbx;
+                const size_t   r = static_cast<size_t>(rowBase + t) * bins.nbx;
                 const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
-                rowBeg[threadIdx.x]        = b;
-                rowLen[threadIdx.x]        = e - b;
-                rowPrefix[threadIdx.x + 1] = (e - b + 31) >> 5;  // 32-point chunks of this row's run
-                if (e != b) atomicAdd(&ptsTotal, e - b);         // points in the bin window: decides the form of phase 2
+                rowBeg[t]        = b;
+                rowLen[t]        = e - b;
+                rowPrefix[t + 1] = (e - b + 31) >> 5;     // 32-point chunks of this row's run
+                if (e != b) atomicAdd(&ptsTotal, e - b);  // points in the bin window: decides the form of phase 2
             }
             __syncthreads();
+            if constexpr (MODE == 1)
+            {
+                // too few points nearby to decide all paths: not worth a near pass (block-uniform decision)
+                if (gi == 0 && rowBase == by0 && nRows == by1 - by0 + 1 && ptsTotal < near.minPoints)
+                {
+                    nearUndecided = true;
+                    break;
+                }
+            }
             if (warp == 0)
             {
                 // inclusive scan of up to 64 chunk counts, two per lane
@@ -626,6 +642,7 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
                 }
             }
         }
+        if (MODE == 1 && nearUndecided) break;
         if constexpr (!BITMAP)
         {
             // no bitmap, no column scan: the points' lists are folded already; only the queued inside-shape points remain
@@ -727,7 +744,8 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
         // ---- phase 2, sparse clouds (few points in the bin window): scatter form ----
         // (only for the last group, after the loop: a call in here would keep the whole kernel state alive across it;
         // earlier groups of a multi-geometry PTG set take the column scan, which is correct for any density)
-        if (gi == numGroups - 1 && ptsTotal <= static_cast<unsigned>(kScatterMax))
+        // (not in MODE 1: its points lie around the robot, where the by-cell lists are at their longest)
+        if (MODE != 1 && gi == numGroups - 1 && ptsTotal <= static_cast<unsigned>(kScatterMax))
         {
             sparseWords = words;
             break;
@@ -770,27 +788,58 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
             openColumn(base + threadIdx.x + kThreads, B);
         }
     }
-    if (sparseWords) sparse_phase2(groups[numGroups - 1], bitmap, sparseWords, smin, longCell, &nLong);
+    if constexpr (MODE != 1)
+        if (sparseWords) sparse_phase2(groups[numGroups - 1], bitmap, sparseWords, smin, longCell, &nLong);
     __syncthreads();
+    if constexpr (MODE == 1)
+    {
+        // final iff every path is blocked within the bound (a point outside the near window cannot lower such a minimum)
+        bool open = nearUndecided;
+        if (!open)
+            for (int i = threadIdx.x; i < totalPaths; i += kThreads) open |= smin[i] > near.boundBits;
+        if (__syncthreads_or(open))
+        {
+            if (threadIdx.x == 0) near.list[atomicAdd(near.count, 1u)] = static_cast<uint32_t>(node);
+            return;
+        }
+    }
+    // this CTA's columns of the row: all of it, or (SPLIT) its contiguous share of every group's columns
+    auto forMyColumns = [&](auto&& f) {
+        if constexpr (SPLIT > 1)
+        {
+            for (int gi = 0; gi < numGroups; gi++)
+            {
+                const GridGroupDev& G       = groups[gi];
+                const int           perPart = (G.nCols + SPLIT - 1) / SPLIT;
+                const int           colEnd  = min(G.nCols, (part + 1) * perPart);
+                for (int col = part * perPart + static_cast<int>(threadIdx.x); col < colEnd; col += kThreads) f(G.colOut[col]);
+            }
+        }
+        else
+            for (int i = threadIdx.x; i < totalPaths; i += kThreads) f(i);
+    };
     if constexpr (PEERS)
     {
         // slot `rank` of every rank's receive area (parity half of this epoch), coalesced stores; then, once every CTA
-        // of this grid has done so, the flag
+        // of this step has done so, the flag. A step evaluated near-first is two launches: a row the near pass decides
+        // counts for all kSplit parts in which the second launch would have delivered it.
         const size_t slot = (static_cast<size_t>(peers.epoch & 1u) * peers.world + peers.rank) * peers.slotStride +
                             static_cast<size_t>(node) * totalPaths;
         for (int p = 0; p < peers.world; p++)
         {
             float* dst = peers.rows[p] + slot;
-            for (int i = threadIdx.x; i < totalPaths; i += kThreads) dst[i] = __uint_as_float(smin[i]);
+            forMyColumns([&](int i) { dst[i] = __uint_as_float(smin[i]); });
         }
         __syncthreads();  // the row stores of all threads are observed by thread 0 ...
         if (threadIdx.x == 0)
         {
+            const unsigned weight   = MODE == 1 ? static_cast<unsigned>(kSplit) : 1u;
+            const unsigned expected = MODE == 0 ? gridDim.x : near.totalNodes * static_cast<unsigned>(kSplit);
             __threadfence_system();  // ... whose fence orders them, system-wide, before its arrival (fence cumulativity)
-            const unsigned arrived = atomicAdd(peers.done, 1u);
-            if (arrived == gridDim.x - 1)
+            const unsigned arrived = atomicAdd(peers.done, weight);
+            if (arrived + weight == expected)
             {
-                *peers.done = 0;  // for the next launch (stream order)
+                *peers.done = 0;  // for the next step (stream order)
                 __threadfence_system();
                 for (int p = 0; p < peers.world; p++)
                     *reinterpret_cast<volatile uint32_t*>(peers.flags[p] + peers.rank) = peers.epoch;
@@ -799,28 +848,123 @@ __global__ void __launch_bounds__(kThreads, SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS
         return;
     }
     float* o = out + static_cast<size_t>(node) * totalPaths;
-    if constexpr (SPLIT > 1)
+    forMyColumns([&](int i) { o[i] = __uint_as_float(smin[i]); });
+}
+
+#ifndef MPPB_GRID_NEAR_MIN_BLOCKS
+#define MPPB_GRID_NEAR_MIN_BLOCKS 20
+#endif
+template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false, bool BITMAP = true, int MODE = 0,
+          int THREADS = MPPB_GRID_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS < 128 ? MPPB_GRID_NEAR_MIN_BLOCKS : (SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS))
+    tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
+                      int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
+                      const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
+                      float* __restrict__ out, const PeerRowsDev peers, const NearPassDev near)
+{
+    // A kernel launched behind this one with programmatic stream serialization (expand_kernel) may start its prologue
+    // now; it waits for this grid's completion (and memory flush) before it reads the rows written below.
+    cudaTriggerProgrammaticLaunchCompletion();
+    if constexpr (MODE == 2)
     {
-        // this CTA's columns of the row (the other CTAs of the node write theirs)
-        for (int gi = 0; gi < numGroups; gi++)
+        // the nodes the near pass left in its list, SPLIT CTAs per node, this grid striding over them
+        const uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(near.count);
+        if (blockIdx.x == 0 && threadIdx.x == 0)
         {
-            const GridGroupDev& G       = groups[gi];
-            const int           perPart = (G.nCols + SPLIT - 1) / SPLIT;
-            const int           colEnd  = min(G.nCols, (part + 1) * perPart);
-            for (int col = part * perPart + static_cast<int>(threadIdx.x); col < colEnd; col += kThreads)
-            {
-                const int oc = G.colOut[col];
-                o[oc]        = __uint_as_float(smin[oc]);
-            }
+            *near.lastCount  = cnt;  // what the adaptive switch looks at (pinned host memory)
+            *near.countOther = 0;    // the counter the NEXT near pass on this slot appends to
+        }
+        for (uint32_t item = blockIdx.x; item < cnt * static_cast<uint32_t>(SPLIT); item += gridDim.x)
+        {
+            tpobs_grid_node<HAS_BOX, SPLIT, STAGED, PEERS, BITMAP, MODE, THREADS>(
+                bins, groups, numGroups, totalPaths, bitmapWords, nodes, boxes, clip, out, peers, near,
+                static_cast<int>(near.list[item / SPLIT]), static_cast<int>(item % SPLIT));
+            __syncthreads();  // the next node reuses the shared arrays
         }
     }
     else
-        for (int i = threadIdx.x; i < totalPaths; i += kThreads) o[i] = __uint_as_float(smin[i]);
+        tpobs_grid_node<HAS_BOX, SPLIT, STAGED, PEERS, BITMAP, MODE, THREADS>(
+            bins, groups, numGroups, totalPaths, bitmapWords, nodes, boxes, clip, out, peers, near,
+            SPLIT > 1 ? blockIdx.x / SPLIT : blockIdx.x, SPLIT > 1 ? blockIdx.x % SPLIT : 0);
 }
 }  // namespace
 
+// Near-first evaluation (NearPassDev): decides whether this launch takes the two-launch form and, if so, fills `np` and
+// claims a slot of pending-list buffers. The adaptive switch (mode 1) looks at how many nodes of earlier batches needed
+// the second launch — the count a finished second launch leaves in pinned memory — and keeps to the plain form for the
+// next 256 calls whenever that was more than 2 % of the batch.
+constexpr size_t kNearMinNodes  = 256;
+constexpr size_t kNearRestNodes = 64;   // listed nodes the second launch takes at a time (kSplit CTAs each)
+static int near_pass_setup(mppb_ctx* ctx, size_t nNodes, double clip, bool eligible, NearPassDev& np, bool& use)
+{
+    use = false;
+    static const bool envOff = std::getenv("MPPB_NO_GRID_NEAR") != nullptr;  // A/B measurements only
+    if (!eligible || envOff || ctx->gridNear == 0 || nNodes <= kNearMinNodes || !(ctx->nearSlackDiag > 0) || ctx->bins.n == 0 ||
+        !(ctx->bins.invBin > 0))
+        return MPPB_OK;
+    double maxRadius = 0;
+    for (const auto& g : ctx->groups) maxRadius = std::max(maxRadius, g.dev.maxRadius);
+    const double sd = ctx->nearSlackDiag, binSize = 1.0 / static_cast<double>(ctx->bins.invBin);
+    static const double rFactor = std::getenv("MPPB_GRID_NEAR_R") ? std::atof(std::getenv("MPPB_GRID_NEAR_R")) : 4.0;  // experiments
+    const double r     = std::max({rFactor * sd, 2.0 * binSize, 2.0 * maxRadius + 0.1});
+    const float  bound = static_cast<float>(r - sd - 1e-3);  // (1 mm: float rounding of the local coordinates)
+    if (!(r <= 0.4 * clip) || !(bound > 0.f)) return MPPB_OK;
+    if (!ctx->nearLastCount)
+    {
+        MPPB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->nearLastCount), mppb_ctx::kNearSlots * sizeof(uint32_t),
+                                     cudaHostAllocMapped));
+        std::memset(ctx->nearLastCount, 0, mppb_ctx::kNearSlots * sizeof(uint32_t));
+        MPPB_CUDA(ctx, ctx->nearCounters.reserve(mppb_ctx::kNearSlots * 2 * sizeof(uint32_t)));
+        MPPB_CUDA(ctx, cudaMemset(ctx->nearCounters.p, 0, mppb_ctx::kNearSlots * 2 * sizeof(uint32_t)));
+    }
+    // what earlier two-launch calls reported
+    for (int i = 0; i < mppb_ctx::kNearSlots; i++)
+    {
+        const uint32_t nodes = ctx->nearNodesOfSlot[i], pend = ctx->nearLastCount[i];
+        // a listed node costs the second launch kSplit CTAs that each walk the whole window: beyond a few per cent of
+        // the batch the two launches together are slower than the plain form
+        if (nodes && pend * 50ull > nodes && ctx->gridNear == 1) ctx->nearSkip = 256;
+    }
+    if (ctx->nearSkip > 0 && ctx->gridNear == 1)
+    {
+        ctx->nearSkip--;
+        for (int i = 0; i < mppb_ctx::kNearSlots; i++)
+            if (ctx->nearNodesOfSlot[i])
+            {
+                ctx->nearPendingSeen += ctx->nearLastCount[i];
+                ctx->nearNodesSeen += ctx->nearNodesOfSlot[i];
+                ctx->nearNodesOfSlot[i] = 0;
+                ctx->nearLastCount[i]   = 0;
+            }
+        return MPPB_OK;
+    }
+    const unsigned slot = ctx->nearSlot++ % mppb_ctx::kNearSlots;
+    if (ctx->nearNodesOfSlot[slot])
+    {
+        ctx->nearPendingSeen += ctx->nearLastCount[slot];
+        ctx->nearNodesSeen += ctx->nearNodesOfSlot[slot];
+    }
+    MPPB_CUDA(ctx, ctx->nearList[slot].reserve(nNodes * sizeof(uint32_t)));
+    ctx->nearLastCount[slot]   = 0;
+    ctx->nearNodesOfSlot[slot] = static_cast<uint32_t>(nNodes);
+    ctx->nearLaunches++;
+    np.r          = r;
+    np.boundBits  = 0;
+    std::memcpy(&np.boundBits, &bound, sizeof(float));
+    np.minPoints  = 48;
+    const unsigned parity = ctx->nearParity[slot];
+    ctx->nearParity[slot] ^= 1;
+    np.count      = ctx->nearCounters.as<uint32_t>() + 2 * slot + parity;
+    np.countOther = ctx->nearCounters.as<uint32_t>() + 2 * slot + (parity ^ 1u);
+    np.list       = ctx->nearList[slot].as<uint32_t>();
+    np.lastCount  = ctx->nearLastCount + slot;  // (mapped pinned memory: the same address on the device under UVA)
+    np.totalNodes = static_cast<uint32_t>(nNodes);
+    use           = true;
+    return MPPB_OK;
+}
+
 int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
-                      float* dOut)
+                      float* dOut, bool allowNear)
 {
     if (nNodes == 0) return MPPB_OK;
     if (ctx->grids.empty()) return fail(ctx, MPPB_ERR_STATE, "no PTG tables set (mppb_set_ptg_grid)");
@@ -839,16 +983,37 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     const bool noBitmap = smem > 200 * 1024;
     if (noBitmap) smem = ((static_cast<size_t>(ctx->totalPaths) + 3) & ~static_cast<size_t>(3)) * sizeof(unsigned);
     if (smem > 200 * 1024) return fail(ctx, MPPB_ERR_UNSUPPORTED, "too many PTG paths for the shared-memory minima");
-    auto       launch = [&](auto kernel, unsigned ctasPerNode) -> int {
+    NearPassDev np;
+    bool        useNear = false;
+    {
+        const int rcn = near_pass_setup(ctx, nNodes, clip, allowNear && !split && !useStaged && !noBitmap, np, useNear);
+        if (rcn != MPPB_OK) return rcn;
+    }
+    auto       launch = [&](auto kernel, unsigned ctasPerNode, size_t gridNodes = 0, unsigned threads = kThreads) -> int {
         if (smem > 48 * 1024)
             MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<static_cast<unsigned>(nNodes) * ctasPerNode, kThreads, smem, ctx->stream>>>(
+        kernel<<<static_cast<unsigned>(gridNodes ? gridNodes : nNodes) * ctasPerNode, threads, smem, ctx->stream>>>(
             ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
-            static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut, PeerRowsDev{});
+            static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut, PeerRowsDev{}, np);
+        ctx->launches++;
         return MPPB_OK;
     };
     int rc;
-    if (noBitmap)
+    if (useNear)
+    {
+        // near pass: a warp per node; rest pass: kSplit CTAs per listed node, a grid for kNearRestNodes of them at a time
+        const size_t restNodes = std::min(nNodes, kNearRestNodes);
+        static const bool warpNear = std::getenv("MPPB_GRID_NEAR_WARP") != nullptr;  // A/B measurements only
+        if (warpNear)
+            rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1, 32>, 1, 0, 32)
+                        : launch(tpobs_grid_kernel<false, 1, false, false, true, 1, 32>, 1, 0, 32);
+        else
+            rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, true, 1>, 1);
+        if (rc == MPPB_OK)
+            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2>, kSplit, restNodes)
+                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2>, kSplit, restNodes);
+    }
+    else if (noBitmap)
         rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, false>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, false>, 1);
     else if (split)
         rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit>, kSplit) : launch(tpobs_grid_kernel<false, kSplit>, kSplit);
@@ -857,7 +1022,6 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     else
         rc = dBoxes ? launch(tpobs_grid_kernel<true, 1>, 1) : launch(tpobs_grid_kernel<false, 1>, 1);
     if (rc != MPPB_OK) return rc;
-    ctx->launches++;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;
 }
@@ -873,13 +1037,31 @@ int launch_tpobs_grid_peers(mppb_ctx* ctx, size_t nNodes, const double* dNodes, 
     const size_t smem = ((static_cast<size_t>(ctx->totalPaths) + words + 3) & ~static_cast<size_t>(3)) * sizeof(unsigned);
     if (smem > 200 * 1024)
         return fail(ctx, MPPB_ERR_UNSUPPORTED, "collision grid too large for the shared-memory occupancy bitmap");
-    auto kernel = tpobs_grid_kernel<false, 1, false, true>;
-    if (smem > 48 * 1024)
-        MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel<<<static_cast<unsigned>(nNodes), kThreads, smem, ctx->stream>>>(
-        ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
-        static_cast<int>(words), dNodes, nullptr, clip, nullptr, peers);
-    ctx->launches++;
+    NearPassDev np;
+    bool        useNear = false;
+    {
+        const int rcn = near_pass_setup(ctx, nNodes, clip, true, np, useNear);
+        if (rcn != MPPB_OK) return rcn;
+    }
+    auto launch = [&](auto kernel, size_t grid, unsigned threads) -> int {
+        if (smem > 48 * 1024)
+            MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<static_cast<unsigned>(grid), threads, smem, ctx->stream>>>(
+            ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
+            static_cast<int>(words), dNodes, nullptr, clip, nullptr, peers, np);
+        ctx->launches++;
+        return MPPB_OK;
+    };
+    int rc;
+    if (useNear)
+    {
+        rc = launch(tpobs_grid_kernel<false, 1, false, true, true, 1, 32>, nNodes, 32);
+        if (rc == MPPB_OK)
+            rc = launch(tpobs_grid_kernel<false, kSplit, false, true, true, 2>, std::min(nNodes, kNearRestNodes) * kSplit, kThreads);
+    }
+    else
+        rc = launch(tpobs_grid_kernel<false, 1, false, true>, nNodes, kThreads);
+    if (rc != MPPB_OK) return rc;
     MPPB_CUDA(ctx, cudaGetLastError());
     return MPPB_OK;
 }

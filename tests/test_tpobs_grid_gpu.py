@@ -259,6 +259,103 @@ def test_large_world_coordinates(gpu_ctx, orc, oracle_ackermann, offset):
     _check(gpu_ctx, orc, oracle_ackermann, xs, ys, poses)
 
 
+NEAR_CLOUDS = {
+    "dense": lambda: wl.uniform_cloud(int(26.0 * 60 * 60), 60.0, seed=41),      # every path blocked nearby: one launch decides
+    "medium": lambda: wl.uniform_cloud(int(6.0 * 60 * 60), 60.0, seed=42),      # some nodes decided, some not
+    "sparse": lambda: wl.uniform_cloud(int(0.3 * 60 * 60), 60.0, seed=43),      # too few points nearby: straight to the list
+    "walls": lambda: wl.walls_cloud(120000, 60.0, seed=44),
+    "half_empty": lambda: tuple(a[: int(26.0 * 30 * 60)] * np.float32(s) for a, s in zip(wl.uniform_cloud(int(26.0 * 30 * 60), 60.0, seed=45), (0.5, 1.0))),
+}
+
+
+def _eval_resident(capi, ctx, poses, boxes, clip=5.0):
+    """mppb_eval_nodes_boxed_device: inputs and rows resident in device memory (the entry point that takes the near-first form)."""
+    import torch
+
+    xycs = torch.from_numpy(capi.nodes_xycs_from_poses(np.ascontiguousarray(poses))).cuda()
+    d_boxes = torch.from_numpy(boxes).cuda() if boxes is not None else None
+    out = torch.full((len(poses), ctx.total_paths), -1.0, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    rc = capi.lib().mppb_eval_nodes_boxed_device(ctx.h, len(poses), xycs.data_ptr(), d_boxes.data_ptr() if boxes is not None else None,
+                                                  clip, out.data_ptr())
+    assert rc == 0
+    ctx.sync()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("cloud", sorted(NEAR_CLOUDS))
+@pytest.mark.parametrize("boxed", [False, True])
+def test_near_first_evaluation_is_bit_identical(gpu_ctx, capi, orc, oracle_ackermann, cloud, boxed):
+    """Batches of more than 256 nodes are evaluated near-first (two launches: the cloud bins around the node decide the
+    rows whose paths are all blocked within the bound, a second launch takes the other nodes on the whole window):
+    forced on (mode 2), adaptive (mode 1) and off (mode 0) return the same rows, equal to the checker's, on clouds
+    where the first launch decides everything, something, and nothing."""
+    xs, ys = NEAR_CLOUDS[cloud]()
+    n = 700
+    poses = wl.node_poses(n, 60.0, margin=-3.0, seed=46)  # some nodes outside the cloud's bounding box
+    poses[3, 2] = np.nan
+    rng = np.random.default_rng(47)
+    boxes = None
+    if boxed:
+        boxes = np.stack([poses[:, 0] - rng.uniform(0.2, 6, n), poses[:, 1] - rng.uniform(0.2, 6, n),
+                          poses[:, 0] + rng.uniform(0.2, 6, n), poses[:, 1] + rng.uniform(0.2, 6, n)], 1).astype(np.float32)
+        boxes[3] = 0.0
+    gpu_ctx.set_obstacles(xs, ys)
+    rows = {}
+    try:
+        for mode in (0, 2, 1):
+            gpu_ctx.set_grid_near(mode)
+            before = gpu_ctx.grid_near_stats()
+            rows[mode] = _eval_resident(capi, gpu_ctx, poses, boxes)
+            after = gpu_ctx.grid_near_stats()
+            if mode == 0:
+                assert after[0] == before[0]
+            elif mode == 2 and not os.environ.get("MPPB_GRID_STAGED"):  # (the staged form keeps to one launch)
+                assert after[0] == before[0] + 1 and after[1] == before[1] + n
+                pending = after[2] - before[2]
+                assert 0 <= pending <= n
+                if cloud == "dense" and not boxed:
+                    assert pending < n // 3, pending  # (nodes at the cloud border see free space)
+                if cloud == "sparse":
+                    assert pending > n // 2, pending
+    finally:
+        gpu_ctx.set_grid_near(1)
+    assert np.array_equal(rows[0].view(np.uint32), rows[2].view(np.uint32))
+    assert np.array_equal(rows[0].view(np.uint32), rows[1].view(np.uint32))
+    host = gpu_ctx.eval_nodes_boxed(poses, boxes, 5.0) if boxed else gpu_ctx.eval_nodes(poses, 5.0)  # host buffers: plain form
+    assert np.array_equal(rows[0].view(np.uint32), host.view(np.uint32))
+    if not boxed:
+        sel = np.r_[0:48, n - 48:n]
+        want, _ = orc.eval_nodes(oracle_ackermann, xs, ys, poses[sel], 5.0, mode=1, nthreads=0)
+        assert np.array_equal(free_dist(rows[2][sel], oracle_ackermann), want)
+
+
+def test_near_first_adaptive_switch(gpu_ctx, capi):
+    """Mode 1 stops trying after a batch of which more than 2 % needed the second launch (a map with free space), starts
+    afresh on a new cloud, and the rows do not depend on it."""
+    xs, ys = wl.walls_cloud(20000, 60.0, seed=51)
+    poses = wl.node_poses(600, 60.0, margin=1.0, seed=52)
+    gpu_ctx.set_obstacles(xs, ys)
+    gpu_ctx.set_grid_near(0)
+    want = _eval_resident(capi, gpu_ctx, poses, None)
+    gpu_ctx.set_grid_near(1)
+    s0 = gpu_ctx.grid_near_stats()
+    for _ in range(6):
+        assert np.array_equal(_eval_resident(capi, gpu_ctx, poses, None).view(np.uint32), want.view(np.uint32))
+    s1 = gpu_ctx.grid_near_stats()
+    if os.environ.get("MPPB_GRID_STAGED"):
+        return
+    assert 1 <= s1[0] - s0[0] <= 2  # the first call (and at most the one issued before its count was in) took two launches
+    # a dense cloud afterwards: the switch starts afresh and stays on
+    xs, ys = wl.uniform_cloud(int(26.0 * 60 * 60), 60.0, seed=53)
+    poses = wl.node_poses(600, 60.0, margin=6.0, seed=54)
+    gpu_ctx.set_obstacles(xs, ys)
+    for _ in range(4):
+        _eval_resident(capi, gpu_ctx, poses, None)
+    s2 = gpu_ctx.grid_near_stats()
+    assert s2[0] - s1[0] == 4 and s2[2] - s1[2] <= 4 * 12
+
+
 def test_many_nodes_in_one_batch(gpu_ctx):
     """A batch far above the sub-batch size and above 65 535 nodes: every row equals the row of its pose evaluated
     alone in a small batch."""
