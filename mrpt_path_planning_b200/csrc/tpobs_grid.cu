@@ -550,6 +550,19 @@ __device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const Gri
                 stageCount += nStages;
             }
         }
+        else if constexpr (MODE == 1)
+        {
+            // near pass: a handful of short bin rows — no row tables, no chunk table, no barriers: warps take rows,
+            // lanes stride over a row's run
+            __syncthreads();  // bitmap cleared
+            for (int row = by0 + warp; row <= by1; row += kWarps)
+            {
+                const size_t   r = static_cast<size_t>(row) * bins.nbx;
+                const uint32_t b = bins.binStart[r + bx0], e = bins.binStart[r + bx1 + 1];
+                if (lane == 0 && e != b) atomicAdd(&ptsTotal, e - b);
+                for (uint32_t i = b + lane; i < e; i += 32) processPoint(bins.pts[i]);
+            }
+        }
         else
 #ifdef MPPB_DBG_SKIP_PHASE1  // timing attribution experiments only
         for (int rowBase = by0; rowBase <= by1 && clip < 0; rowBase += kRowsPerPass)
@@ -642,7 +655,13 @@ __device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const Gri
                 }
             }
         }
-        if (MODE == 1 && nearUndecided) break;
+        if constexpr (MODE == 1)
+        {
+            // too few points nearby to decide all paths (block-uniform): the node goes to the list
+            __syncthreads();
+            if (gi == 0 && ptsTotal < near.minPoints) nearUndecided = true;
+            if (nearUndecided) break;
+        }
         if constexpr (!BITMAP)
         {
             // no bitmap, no column scan: the points' lists are folded already; only the queued inside-shape points remain
@@ -854,9 +873,13 @@ __device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const Gri
 #ifndef MPPB_GRID_NEAR_MIN_BLOCKS
 #define MPPB_GRID_NEAR_MIN_BLOCKS 20
 #endif
+#ifndef MPPB_GRID_NEAR128_MIN_BLOCKS
+#define MPPB_GRID_NEAR128_MIN_BLOCKS 10  // the near pass keeps less state: 48 registers, 10 CTAs per SM (measured: 9 -> 10: -4 %, 12: spills)
+#endif
 template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false, bool BITMAP = true, int MODE = 0,
           int THREADS = MPPB_GRID_THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS < 128 ? MPPB_GRID_NEAR_MIN_BLOCKS : (SPLIT > 1 ? 4 : MPPB_GRID_MIN_BLOCKS))
+__global__ void __launch_bounds__(THREADS, THREADS < 128 ? MPPB_GRID_NEAR_MIN_BLOCKS
+                                                         : (SPLIT > 1 ? 4 : (MODE == 1 ? MPPB_GRID_NEAR128_MIN_BLOCKS : MPPB_GRID_MIN_BLOCKS)))
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
@@ -1055,7 +1078,7 @@ int launch_tpobs_grid_peers(mppb_ctx* ctx, size_t nNodes, const double* dNodes, 
     int rc;
     if (useNear)
     {
-        rc = launch(tpobs_grid_kernel<false, 1, false, true, true, 1, 32>, nNodes, 32);
+        rc = launch(tpobs_grid_kernel<false, 1, false, true, true, 1>, nNodes, kThreads);
         if (rc == MPPB_OK)
             rc = launch(tpobs_grid_kernel<false, kSplit, false, true, true, 2>, std::min(nNodes, kNearRestNodes) * kSplit, kThreads);
     }

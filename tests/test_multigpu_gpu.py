@@ -57,6 +57,7 @@ def _worker(rank, world, port, tmp):
     out["nccl"] = d_out.cpu().numpy().copy()
     assert sharding.attach_ranks(ctx, rank, world, max_nodes=n) == "fused"
     for step in range(5):  # several epochs: both parity halves of the receive area, flags, counters
+        ctx.set_grid_near((1, 2, 0, 2, 2)[step])  # near-first form of the step (two launches share the epilogue's count) and plain
         d_out.zero_()
         torch.cuda.synchronize()
         ctx.eval_nodes_sharded_device(n - 7 * step, d_nodes, 5.0, d_out)
