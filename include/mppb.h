@@ -262,6 +262,9 @@ int mppb_set_holo_filter(mppb_ctx* ctx, int on);
  * mppb_grid_near_stats: out3 = {calls that took the two-launch form, their nodes, nodes that needed the second launch}. */
 int mppb_set_grid_near(mppb_ctx* ctx, int mode);
 int mppb_grid_near_stats(const mppb_ctx* ctx, uint64_t* out3);
+/* The near window's half-size and the bound (both in metres) a batch with this clipping distance would use with the
+ * tables and cloud now resident; both 0 when the near-first form does not apply. */
+int mppb_grid_near_window(const mppb_ctx* ctx, double clip_dist, double* half_size, double* bound);
 /* Diagnostic switch: on != 0 runs host batches of mppb_eval_holo_candidates* whose candidates are grouped by node on
  * the one-CTA-per-node form of the kernel (the node's window is walked once for all its candidates). Results are
  * identical either way; the tests compare the two. Measured no faster on B200, so the default is off. */

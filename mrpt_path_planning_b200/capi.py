@@ -191,6 +191,7 @@ _SIGS = {
     "mppb_set_holo_filter": (C.c_int, [C.c_void_p, C.c_int]),
     "mppb_set_grid_near": (C.c_int, [C.c_void_p, C.c_int]),
     "mppb_grid_near_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "mppb_grid_near_window": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mppb_set_holo_by_node": (C.c_int, [C.c_void_p, C.c_int]),
     "mppb_evaluators_epoch": (C.c_uint64, [C.c_void_p]),
     "mppb_num_evaluators": (C.c_int, [C.c_void_p]),
@@ -474,6 +475,12 @@ class Context:
         out = (C.c_uint64 * 3)()
         self._ck(lib().mppb_grid_near_stats(self.h, out))
         return int(out[0]), int(out[1]), int(out[2])
+
+    def grid_near_window(self, clip_dist):
+        """(half-size of the near window, bound) in metres for this clipping distance; (0, 0): not applicable"""
+        r, b = C.c_double(0), C.c_double(0)
+        self._ck(lib().mppb_grid_near_window(self.h, float(clip_dist), C.byref(r), C.byref(b)))
+        return r.value, b.value
 
     def set_holo_by_node(self, on):
         """Diagnostic: grouped host batches on the one-CTA-per-node form of the HolonomicBlend kernel."""

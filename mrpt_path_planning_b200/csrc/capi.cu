@@ -217,6 +217,16 @@ int mppb_grid_near_stats(const mppb_ctx* ctx, uint64_t* out3)
     out3[2] = pend;
     return MPPB_OK;
 }
+int mppb_grid_near_window(const mppb_ctx* ctx, double clip_dist, double* half_size, double* bound)
+{
+    if (!ctx || !half_size || !bound) return MPPB_ERR_INVALID_ARG;
+    double r = 0;
+    float  b = 0;
+    const bool ok = near_window(ctx, clip_dist, r, b);
+    *half_size    = ok ? r : 0.0;
+    *bound        = ok ? static_cast<double>(b) : 0.0;
+    return MPPB_OK;
+}
 int mppb_set_holo_by_node(mppb_ctx* ctx, int on)
 {
     if (!ctx) return MPPB_ERR_INVALID_ARG;

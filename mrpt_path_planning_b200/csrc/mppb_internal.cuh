@@ -394,6 +394,7 @@ void set_global_error(const std::string& msg);
 
 // kernels / launchers implemented in the .cu files
 int build_cloud_bins(mppb_ctx* ctx, CloudStore& cs, double binSize);
+bool near_window(const mppb_ctx* ctx, double clip, double& r, float& bound);  // near-first evaluation: window and bound
 int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const float* dBoxes, double clip,
                       float* dOut, bool allowNear = true);
 // same, each finished row also stored into slot `rank` of every attached peer (fused merge of cloud-sharded rows)

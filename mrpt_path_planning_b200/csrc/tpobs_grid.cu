@@ -916,22 +916,29 @@ __global__ void __launch_bounds__(THREADS, THREADS < 128 ? MPPB_GRID_NEAR_MIN_BL
 // claims a slot of pending-list buffers. The adaptive switch (mode 1) looks at how many nodes of earlier batches needed
 // the second launch — the count a finished second launch leaves in pinned memory — and keeps to the plain form for the
 // next 256 calls whenever that was more than 2 % of the batch.
+// half-size of the near window and the bound a launch with this clipping distance would use; false: not applicable
+bool near_window(const mppb_ctx* ctx, double clip, double& r, float& bound)
+{
+    if (!(ctx->nearSlackDiag > 0) || ctx->bins.n == 0 || !(ctx->bins.invBin > 0)) return false;
+    double maxRadius = 0;
+    for (const auto& g : ctx->groups) maxRadius = std::max(maxRadius, g.dev.maxRadius);
+    const double sd = ctx->nearSlackDiag, binSize = 1.0 / static_cast<double>(ctx->bins.invBin);
+    static const double rFactor = std::getenv("MPPB_GRID_NEAR_R") ? std::atof(std::getenv("MPPB_GRID_NEAR_R")) : 4.0;  // experiments
+    // 4 x (slack + cell diagonal): on a dense cloud (C3) 3 x leaves 11 of 4096 nodes to the second launch, whose
+    // latency then shows; 4 x leaves none, 5 x makes the first launch slower
+    r     = std::max({rFactor * sd, 2.0 * binSize, 2.0 * maxRadius + 0.1});
+    bound = static_cast<float>(r - sd - 1e-3);  // (1 mm: float rounding of the local coordinates)
+    return r <= 0.4 * clip && bound > 0.f;
+}
 constexpr size_t kNearMinNodes  = 256;
 constexpr size_t kNearRestNodes = 64;   // listed nodes the second launch takes at a time (kSplit CTAs each)
 static int near_pass_setup(mppb_ctx* ctx, size_t nNodes, double clip, bool eligible, NearPassDev& np, bool& use)
 {
     use = false;
     static const bool envOff = std::getenv("MPPB_NO_GRID_NEAR") != nullptr;  // A/B measurements only
-    if (!eligible || envOff || ctx->gridNear == 0 || nNodes <= kNearMinNodes || !(ctx->nearSlackDiag > 0) || ctx->bins.n == 0 ||
-        !(ctx->bins.invBin > 0))
-        return MPPB_OK;
-    double maxRadius = 0;
-    for (const auto& g : ctx->groups) maxRadius = std::max(maxRadius, g.dev.maxRadius);
-    const double sd = ctx->nearSlackDiag, binSize = 1.0 / static_cast<double>(ctx->bins.invBin);
-    static const double rFactor = std::getenv("MPPB_GRID_NEAR_R") ? std::atof(std::getenv("MPPB_GRID_NEAR_R")) : 4.0;  // experiments
-    const double r     = std::max({rFactor * sd, 2.0 * binSize, 2.0 * maxRadius + 0.1});
-    const float  bound = static_cast<float>(r - sd - 1e-3);  // (1 mm: float rounding of the local coordinates)
-    if (!(r <= 0.4 * clip) || !(bound > 0.f)) return MPPB_OK;
+    double r     = 0;
+    float  bound = 0;
+    if (!eligible || envOff || ctx->gridNear == 0 || nNodes <= kNearMinNodes || !near_window(ctx, clip, r, bound)) return MPPB_OK;
     if (!ctx->nearLastCount)
     {
         MPPB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->nearLastCount), mppb_ctx::kNearSlots * sizeof(uint32_t),
