@@ -879,7 +879,8 @@ __device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const Gri
 template <bool HAS_BOX, int SPLIT, bool STAGED = false, bool PEERS = false, bool BITMAP = true, int MODE = 0,
           int THREADS = MPPB_GRID_THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS < 128 ? MPPB_GRID_NEAR_MIN_BLOCKS
-                                                         : (SPLIT > 1 ? 4 : (MODE == 1 ? MPPB_GRID_NEAR128_MIN_BLOCKS : MPPB_GRID_MIN_BLOCKS)))
+                                           : THREADS > 128 ? 512 / THREADS
+                                                           : (SPLIT > 1 ? 4 : (MODE == 1 ? MPPB_GRID_NEAR128_MIN_BLOCKS : MPPB_GRID_MIN_BLOCKS)))
     tpobs_grid_kernel(CloudBins bins, const GridGroupDev* __restrict__ groups, int numGroups, int totalPaths,
                       int bitmapWords, const double* __restrict__ nodes /* [n][4] x,y,cos,sin */,
                       const float4* __restrict__ boxes /* [n] minx,miny,maxx,maxy */, double clip,
@@ -931,7 +932,7 @@ bool near_window(const mppb_ctx* ctx, double clip, double& r, float& bound)
     return r <= 0.4 * clip && bound > 0.f;
 }
 constexpr size_t kNearMinNodes  = 256;
-constexpr size_t kNearRestNodes = 64;   // listed nodes the second launch takes at a time (kSplit CTAs each)
+constexpr size_t kNearRestNodes = 16;   // listed nodes the second launch takes at a time (kSplit CTAs each)
 static int near_pass_setup(mppb_ctx* ctx, size_t nNodes, double clip, bool eligible, NearPassDev& np, bool& use)
 {
     use = false;
@@ -1031,7 +1032,9 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
     int rc;
     if (useNear)
     {
-        // near pass: a warp per node; rest pass: kSplit CTAs per listed node, a grid for kNearRestNodes of them at a time
+        // rest pass: kSplit CTAs per listed node, a grid for kNearRestNodes of them at a time; 512 threads per CTA, since
+        // every one of a node's CTAs walks the whole window (one listed node in a C3 batch: +16 us with 128 threads, +8 us
+        // with 512)
         const size_t restNodes = std::min(nNodes, kNearRestNodes);
         static const bool warpNear = std::getenv("MPPB_GRID_NEAR_WARP") != nullptr;  // A/B measurements only
         if (warpNear)
@@ -1039,7 +1042,14 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
                         : launch(tpobs_grid_kernel<false, 1, false, false, true, 1, 32>, 1, 0, 32);
         else
             rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, true, 1>, 1);
-        if (rc == MPPB_OK)
+        static const int restThreads = std::getenv("MPPB_GRID_REST_THREADS") ? std::atoi(std::getenv("MPPB_GRID_REST_THREADS")) : 512;  // (128, 256: A/B measurements)
+        if (rc == MPPB_OK && restThreads == 512)
+            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512)
+                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512);
+        else if (rc == MPPB_OK && restThreads == 256)
+            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 256>, kSplit, restNodes, 256)
+                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 256>, kSplit, restNodes, 256);
+        else if (rc == MPPB_OK)
             rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2>, kSplit, restNodes)
                         : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2>, kSplit, restNodes);
     }
@@ -1087,7 +1097,7 @@ int launch_tpobs_grid_peers(mppb_ctx* ctx, size_t nNodes, const double* dNodes, 
     {
         rc = launch(tpobs_grid_kernel<false, 1, false, true, true, 1>, nNodes, kThreads);
         if (rc == MPPB_OK)
-            rc = launch(tpobs_grid_kernel<false, kSplit, false, true, true, 2>, std::min(nNodes, kNearRestNodes) * kSplit, kThreads);
+            rc = launch(tpobs_grid_kernel<false, kSplit, false, true, true, 2, 512>, std::min(nNodes, kNearRestNodes) * kSplit, 512);
     }
     else
         rc = launch(tpobs_grid_kernel<false, 1, false, true>, nNodes, kThreads);

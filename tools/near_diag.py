@@ -15,7 +15,7 @@ from mrpt_path_planning_b200 import capi, workloads as wl  # noqa: E402
 
 walls = len(sys.argv) > 1 and sys.argv[1] == "walls"
 xs, ys = (wl.walls_cloud(1 << 20, 200.0) if walls else wl.uniform_cloud(1 << 20, 200.0))
-poses = wl.node_poses(4096, 200.0)
+poses = wl.node_poses(4096, 200.0, seed=wl.C3_NODES_SEED + int(os.environ.get("NODE_SEED_OFFSET", "0")))
 ctx = capi.Context(0)
 for p in capi.ackermann_ptgs():
     ctx.add_ptg(p)
