@@ -891,7 +891,9 @@ __global__ void __launch_bounds__(THREADS, THREADS < 128 ? MPPB_GRID_NEAR_MIN_BL
     cudaTriggerProgrammaticLaunchCompletion();
     if constexpr (MODE == 2)
     {
-        // the nodes the near pass left in its list, SPLIT CTAs per node, this grid striding over them
+        // the nodes the near pass left in its list, SPLIT CTAs per node, this grid striding over them. Launched with
+        // programmatic stream serialization: resident while the near pass drains, released when its list is complete.
+        cudaGridDependencySynchronize();
         const uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(near.count);
         if (blockIdx.x == 0 && threadIdx.x == 0)
         {
@@ -1020,12 +1022,22 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
         const int rcn = near_pass_setup(ctx, nNodes, clip, allowNear && !split && !useStaged && !noBitmap, np, useNear);
         if (rcn != MPPB_OK) return rcn;
     }
-    auto       launch = [&](auto kernel, unsigned ctasPerNode, size_t gridNodes = 0, unsigned threads = kThreads) -> int {
+    auto       launch = [&](auto kernel, unsigned ctasPerNode, size_t gridNodes = 0, unsigned threads = kThreads, bool pdl = false) -> int {
         if (smem > 48 * 1024)
             MPPB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<static_cast<unsigned>(gridNodes ? gridNodes : nNodes) * ctasPerNode, threads, smem, ctx->stream>>>(
-            ctx->bins, ctx->groupDescs.as<GridGroupDev>(), static_cast<int>(ctx->groups.size()), ctx->totalPaths,
-            static_cast<int>(words), dNodes, reinterpret_cast<const float4*>(dBoxes), clip, dOut, PeerRowsDev{}, np);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim            = dim3(static_cast<unsigned>(gridNodes ? gridNodes : nNodes) * ctasPerNode);
+        cfg.blockDim           = dim3(threads);
+        cfg.dynamicSmemBytes   = smem;
+        cfg.stream             = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs                                          = attr;
+        cfg.numAttrs                                       = pdl ? 1 : 0;
+        MPPB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, ctx->bins, static_cast<const GridGroupDev*>(ctx->groupDescs.as<GridGroupDev>()),
+                                          static_cast<int>(ctx->groups.size()), ctx->totalPaths, static_cast<int>(words), dNodes,
+                                          reinterpret_cast<const float4*>(dBoxes), clip, dOut, PeerRowsDev{}, static_cast<const NearPassDev&>(np)));
         ctx->launches++;
         return MPPB_OK;
     };
@@ -1043,9 +1055,10 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
         else
             rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, true, 1>, 1);
         static const int restThreads = std::getenv("MPPB_GRID_REST_THREADS") ? std::atoi(std::getenv("MPPB_GRID_REST_THREADS")) : 512;  // (128, 256: A/B measurements)
+        static const bool restPdl = std::getenv("MPPB_GRID_REST_NO_PDL") == nullptr;  // (A/B measurements)
         if (rc == MPPB_OK && restThreads == 512)
-            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512)
-                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512);
+            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512, restPdl)
+                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512, restPdl);
         else if (rc == MPPB_OK && restThreads == 256)
             rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 256>, kSplit, restNodes, 256)
                         : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 256>, kSplit, restNodes, 256);
