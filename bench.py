@@ -644,7 +644,8 @@ def run_ours(args, rank, local_rank, world):
     binned_tf = work["flop_binned"] / kernel_s / 1e12
     roofline = {
         "bound": "fp32 (CUDA cores; the contract's 'hbm' and 'tensor' figures do not bind this kernel: see 'hbm')",
-        "kernel": "tpobs_grid_kernel", "achieved": binned_tf, "peak": fp32_peak,
+        "kernel": "tpobs_grid_kernel (near pass + rest pass of the near-first form)" if near_first else "tpobs_grid_kernel",
+        "achieved": binned_tf, "peak": fp32_peak,
         "unit": "TFLOP/s", "frac": binned_tf / fp32_peak if fp32_peak else None,
         "peak_source": "FMA microbenchmark on this GPU (MEASURED_PEAKS.json has no CUDA-core figure)",
         "convention": "FLOPs of the binned algorithm over the whole clipping window, B * N_in * (6 + 8 + 6 P) per step "
