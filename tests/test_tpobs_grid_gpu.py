@@ -330,6 +330,40 @@ def test_near_first_evaluation_is_bit_identical(gpu_ctx, capi, orc, oracle_acker
         assert np.array_equal(free_dist(rows[2][sel], oracle_ackermann), want)
 
 
+def test_near_first_with_mixed_geometry_groups(capi, orc):
+    """The near-first form with several kernel groups (grids of other extents and resolutions, other path counts): one
+    near window and one bound — from the largest slack + cell diagonal over the groups — serve all of them."""
+    from oracle.orc import ACKERMANN_SHAPE_X as X, ACKERMANN_SHAPE_Y as Y
+
+    w = 60.0 * np.pi / 180.0
+    specs = [(121, 5.0, 0.05, 1.0, w, +1.0), (31, 3.0, 0.1, 0.8, 1.3 * w, -1.0), (25, 2.35, 0.1, 0.6, 1.1 * w, +1.0)]
+    optgs = [orc.diffdrive_c(n, rd, res, v, ww, K, X, Y) for (n, rd, res, v, ww, K) in specs]
+    pptgs = [capi.PTG.diffdrive_c(n, rd, res, v, ww, K, X, Y) for (n, rd, res, v, ww, K) in specs]
+    ctx = capi.Context(0)
+    for p in pptgs:
+        ctx.add_ptg(p)
+    r, bound = None, None
+    for density, seed in ((26.0, 91), (5.0, 92)):
+        xs, ys = wl.uniform_cloud(int(density * 50 * 50), 50.0, seed=seed)
+        poses = wl.node_poses(400, 50.0, margin=0.0, seed=seed + 10)
+        ctx.set_obstacles(xs, ys)
+        r, bound = ctx.grid_near_window(5.0)
+        assert 0.0 < bound < r <= 2.0
+        rows = {}
+        for mode in (0, 2):
+            ctx.set_grid_near(mode)
+            s0 = ctx.grid_near_stats()
+            rows[mode] = _eval_resident(capi, ctx, poses, None)
+            s1 = ctx.grid_near_stats()
+            assert s1[0] - s0[0] == (1 if mode else 0)
+        assert np.array_equal(rows[0].view(np.uint32), rows[2].view(np.uint32))
+        sel = np.r_[0:40, 360:400]
+        want, _ = orc.eval_nodes(optgs, xs, ys, poses[sel], 5.0, mode=1, nthreads=0)
+        assert np.array_equal(free_dist(rows[2][sel], optgs), want)
+    assert ctx.grid_near_window(3.0) == (0.0, 0.0)  # a clipping distance too small for a near window
+    ctx.close()
+
+
 def test_near_first_adaptive_switch(gpu_ctx, capi):
     """Mode 1 stops trying after a batch of which more than 2 % needed the second launch (a map with free space), starts
     afresh on a new cloud, and the rows do not depend on it."""
