@@ -376,6 +376,8 @@ struct mppb_ctx
     size_t               expandRowsNodes = 0;  // rows held by dExpandRows (mppb_expand_last_rows)
 
     // staging for the host entry points
+    void*           sincosHelper = nullptr;  // capi.cu: helper thread that takes part of a large batch's heading cos/sin
+    unsigned        helperSlowStreak = 0, helperPause = 0;  // calls in a row that waited for it / calls it sits out
     mppb::PinnedBuf hNodes, hOut, hStage, hNodesHolo;
     mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes, dNodesHolo, dBoxesHolo, dCandBegin;
 };
