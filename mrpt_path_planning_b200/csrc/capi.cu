@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <sched.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -831,9 +833,22 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
     // stream of its own can start while the tails of the two before it are still draining (measured: 2 streams
     // 0.175 ms, 4 streams 0.165-0.170 ms per 4096-node call)
     constexpr int    kSubStreams = 4;
-    // (if the helper keeps this thread waiting — it shares a core with it, or the machine is busy — it sits out the
-    // next 1000 calls: the call is then what it was without a helper)
-    const bool wantHelper = !noHelper && n_nodes >= 2048 && (ctx->helperPause == 0 || --ctx->helperPause == 0);
+    if (ctx->helperAllowed < 0)
+    {
+        // a spinning helper needs a core of its own: with fewer than 8 CPUs in the process's affinity mask (e.g. one of
+        // eight ranks on a 32-CPU box) it would take it from this thread or from a neighbour's (measured: slower)
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        ctx->helperAllowed = (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) >= 8) ? 1 : 0;
+    }
+    // Whether the helper pays depends on where the scheduler puts it (next to this thread on one core it costs more than
+    // it saves): the 4th, the 7th and every 16th large call run without it, and when the calls with it are not at least 3 % faster in two
+    // such comparisons in a row it sits out the next 1000 calls.
+    const bool helperOk   = wait && !noHelper && ctx->helperAllowed == 1 && n_nodes >= 2048 && (ctx->helperPause == 0 || --ctx->helperPause == 0);
+    const bool helperIsNew = ctx->sincosHelper == nullptr;  // (its first call starts the thread: not a measurement)
+    const bool probePlain  = helperOk && (++ctx->helperCalls % 16u == 0 || ctx->helperCalls == 4 || ctx->helperCalls == 7);
+    const bool wantHelper = helperOk && !probePlain;
+    const auto tCall0     = std::chrono::steady_clock::now();
     // (5 sub-batches without the helper thread, 3 with it: measured 157-165 us and 141-144 us per 4096-node call)
     static const int envSubs     = std::getenv("MPPB_E2E_SUBS") ? std::max(1, std::atoi(std::getenv("MPPB_E2E_SUBS"))) : 0;
     const int        kSubBatches = envSubs ? envSubs : (wantHelper ? 3 : 5);
@@ -851,7 +866,6 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
     size_t       j     = 0;
     // cos/sin of the headings: this thread takes the first sub-batch, the helper thread everything behind it
     SincosHelper* helper    = (wantHelper && !single) ? sincos_helper(ctx) : nullptr;
-    double        waitedUs  = 0;
     if (helper) helper->post(poses_xyphi, ctx->hNodes.as<double>(), sub, n_nodes);
     for (size_t lo = 0; lo < n_nodes && rc == MPPB_OK; lo += sub, j++)
     {
@@ -861,11 +875,7 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
         double*       dN = ctx->dNodes.as<double>() + 4 * lo;
         float*        dO = outDev ? outDev + lo * cols : ctx->dOut.as<float>() + lo * cols;
         if (helper && lo > 0)
-        {
-            const auto tw = std::chrono::steady_clock::now();
             helper->wait_for(lo + n);
-            waitedUs += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tw).count();
-        }
         else
             mppb_nodes_xycs_from_poses(n, poses_xyphi + 3 * lo, hN);
         cudaError_t e = cudaSuccess;
@@ -888,16 +898,7 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
         e = cudaMemcpyAsync(out + lo * cols, dO, n * cols * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "D2H result");
     }
-    if (helper)
-    {
-        helper->wait_for(n_nodes);  // (also on the error paths: it reads the caller's poses until it is through)
-        ctx->helperSlowStreak = waitedUs > 15.0 ? ctx->helperSlowStreak + 1 : 0;
-        if (ctx->helperSlowStreak >= 3)
-        {
-            ctx->helperSlowStreak = 0;
-            ctx->helperPause      = 1000;
-        }
-    }
+    if (helper) helper->wait_for(n_nodes);  // (also on the error paths: it reads the caller's poses until it is through)
     if (!single)
     {
         cudaEvent_t evs[3] = {ctx->evJoin, ctx->evJoinMore[0], ctx->evJoinMore[1]};
@@ -908,6 +909,22 @@ static int eval_nodes_boxed_impl(mppb_ctx* ctx, size_t n_nodes, const double* po
         }
     }
     if (wait) MPPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // _begin: the caller's mppb_sync() completes the call
+    if (helperOk && rc == MPPB_OK && !(helperIsNew && !probePlain))
+    {
+        const double us  = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tCall0).count();
+        double&      ema = probePlain ? ctx->helperEmaWithout : ctx->helperEmaWith;
+        ema              = ema > 0 ? 0.75 * ema + 0.25 * us : us;
+        if (probePlain && ctx->helperEmaWith > 0)
+        {
+            ctx->helperLoses = ctx->helperEmaWith > 0.97 * ctx->helperEmaWithout ? ctx->helperLoses + 1 : 0;
+            if (ctx->helperLoses >= 2)
+            {
+                ctx->helperPause = 1000;
+                ctx->helperLoses = 0;
+                ctx->helperEmaWith = ctx->helperEmaWithout = 0;
+            }
+        }
+    }
     return rc;
 }
 

@@ -377,7 +377,9 @@ struct mppb_ctx
 
     // staging for the host entry points
     void*           sincosHelper = nullptr;  // capi.cu: helper thread that takes part of a large batch's heading cos/sin
-    unsigned        helperSlowStreak = 0, helperPause = 0;  // calls in a row that waited for it / calls it sits out
+    unsigned        helperPause = 0, helperCalls = 0, helperLoses = 0;  // calls it sits out / large calls so far / probes it lost
+    double          helperEmaWith = 0, helperEmaWithout = 0;            // running call times (us) with and without it
+    int             helperAllowed = -1;  // -1: not decided yet; 0: the process has too few CPUs to spare one
     mppb::PinnedBuf hNodes, hOut, hStage, hNodesHolo;
     mppb::DevBuf    dNodes, dOut, dStage, dStage2, dStage3, dBoxes, dNodesHolo, dBoxesHolo, dCandBegin;
 };
