@@ -638,6 +638,12 @@ int mppb_selftest_lattice_index(uint64_t seed, size_t ops, int range);
  * Returns the number of sets iterated in a different order (0 = identical). */
 int mppb_selftest_cell_order(uint64_t seed, size_t trials, int max_keys);
 
+/* Host self-test (no GPU) of the helper thread behind mppb_eval_nodes' heading cos/sin (large host batches): `rounds`
+ * batches of n random poses are split between the calling thread and the helper as the entry point splits them, with
+ * pauses of 0 to 5 ms between them (spinning and sleeping helper); every (x, y, cos, sin) row must equal the
+ * single-threaded mppb_nodes_xycs_from_poses bit for bit. Returns the number of rows that differ (0 = correct). */
+int mppb_selftest_sincos_helper(uint64_t seed, size_t n, int rounds);
+
 #ifdef __cplusplus
 }
 #endif

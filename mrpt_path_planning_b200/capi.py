@@ -220,6 +220,7 @@ _SIGS = {
     "mppb_selftest_open_set": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int]),
     "mppb_selftest_lattice_index": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int]),
     "mppb_selftest_cell_order": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int]),
+    "mppb_selftest_sincos_helper": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int]),
     "mppb_planner_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mppb_planner_destroy": (None, [C.c_void_p]),
     "mppb_planner_last_error": (C.c_char_p, [C.c_void_p]),

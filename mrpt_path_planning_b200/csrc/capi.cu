@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <vector>
 
 #include "mppb_internal.cuh"
 
@@ -736,6 +737,41 @@ SincosHelper* sincos_helper(mppb_ctx* ctx)
     return static_cast<SincosHelper*>(ctx->sincosHelper);
 }
 }  // namespace
+int mppb_selftest_sincos_helper(uint64_t seed, size_t n, int rounds)
+{
+    if (n < 8) return -1;
+    SincosHelper h;
+    h.th = std::thread([&h] { h.run(); });
+    std::vector<double> poses(3 * n), got(4 * n), want(4 * n);
+    uint64_t            x = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto                rnd = [&]() {
+        x ^= x << 13;
+        x ^= x >> 7;
+        x ^= x << 17;
+        return static_cast<double>(x >> 11) / 9007199254740992.0;
+    };
+    int bad = 0;
+    for (int r = 0; r < rounds; r++)
+    {
+        for (size_t i = 0; i < n; i++)
+        {
+            poses[3 * i + 0] = 200.0 * rnd();
+            poses[3 * i + 1] = 200.0 * rnd();
+            poses[3 * i + 2] = (rnd() - 0.5) * (r % 3 == 2 ? 1e6 : 6.283185307179586);
+        }
+        std::fill(got.begin(), got.end(), -7.0);
+        const size_t split = 1 + static_cast<size_t>(rnd() * static_cast<double>(n - 2));
+        h.post(poses.data(), got.data(), split, n);
+        mppb_nodes_xycs_from_poses(split, poses.data(), got.data());
+        // (the entry point asks for sub-batch after sub-batch)
+        for (size_t upTo = split; upTo < n; upTo = std::min(n, upTo + n / 4 + 1)) h.wait_for(upTo);
+        h.wait_for(n);
+        mppb_nodes_xycs_from_poses(n, poses.data(), want.data());
+        for (size_t i = 0; i < n; i++) bad += std::memcmp(&got[4 * i], &want[4 * i], 4 * sizeof(double)) != 0;
+        if (r % 4 == 1) std::this_thread::sleep_for(std::chrono::microseconds(static_cast<int>(5000 * rnd())));
+    }
+    return bad;
+}
 static void sincos_helper_destroy(mppb_ctx* ctx)
 {
     delete static_cast<SincosHelper*>(ctx->sincosHelper);

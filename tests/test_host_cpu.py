@@ -142,3 +142,11 @@ def test_cell_order_equals_unordered_map_iteration_order(capi):
     for seed, trials, max_keys in ((1, 2000, 13), (2, 2000, 14), (3, 3000, 31), (4, 3000, 61), (5, 3000, 90),
                                    (6, 1000, 300), (7, 200, 2000)):
         assert capi.lib().mppb_selftest_cell_order(seed, trials, max_keys) == 0, (seed, trials, max_keys)
+
+
+def test_sincos_helper_thread_is_transparent(capi):
+    """large host batches share the heading cos/sin between the calling thread and a helper thread (spinning for 2 ms
+    after a request, asleep afterwards): every row equals the single-threaded one bit for bit, at any split point,
+    with small and huge angles, with pauses that let the helper fall asleep"""
+    for seed, n, rounds in ((1, 4096, 40), (2, 8, 200), (3, 2049, 60), (4, 100000, 6)):
+        assert capi.lib().mppb_selftest_sincos_helper(seed, n, rounds) == 0, (seed, n, rounds)
