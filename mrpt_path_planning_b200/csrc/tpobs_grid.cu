@@ -346,10 +346,10 @@ __device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const Gri
     {
         // MODE 1: the bins that hold every point within near.r of the node (the clip test per point stays the reference's)
         const double win = MODE == 1 ? fmin(near.r, clip) : clip;
-        const float  lox = nextafterf(__double2float_rd(x0 - win), -FLT_MAX);
-        const float  hix = nextafterf(__double2float_ru(x0 + win), FLT_MAX);
-        const float  loy = nextafterf(__double2float_rd(y0 - win), -FLT_MAX);
-        const float  hiy = nextafterf(__double2float_ru(y0 + win), FLT_MAX);
+        const float  lox = float_below(x0 - win);
+        const float  hix = float_above(x0 + win);
+        const float  loy = float_below(y0 - win);
+        const float  hiy = float_above(y0 + win);
         bx0             = bin_coord(lox, bins.minx, bins.invBin, bins.nbx);
         bx1             = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         by0             = bin_coord(loy, bins.miny, bins.invBin, bins.nby);

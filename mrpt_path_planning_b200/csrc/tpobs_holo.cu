@@ -393,10 +393,10 @@ __global__ void __launch_bounds__(kThreads, MPPB_HOLO_MIN_BLOCKS)
     if (bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0)
     {
         // conservative float window -> bin range (the exact test is per point, in double)
-        const float lox = nextafterf(__double2float_rd(x0 - clip), -FLT_MAX);
-        const float hix = nextafterf(__double2float_ru(x0 + clip), FLT_MAX);
-        const float loy = nextafterf(__double2float_rd(y0 - clip), -FLT_MAX);
-        const float hiy = nextafterf(__double2float_ru(y0 + clip), FLT_MAX);
+        const float lox = float_below(x0 - clip);
+        const float hix = float_above(x0 + clip);
+        const float loy = float_below(y0 - clip);
+        const float hiy = float_above(y0 + clip);
         const int   bx0 = bin_coord(lox, bins.minx, bins.invBin, bins.nbx);
         const int   bx1 = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         const int   by0 = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
@@ -567,10 +567,10 @@ __global__ void __launch_bounds__(kNodeThreads, 3)
 
     if (bins.n > 0 && isfinite(x0) && isfinite(y0) && clip >= 0)
     {
-        const float lox = nextafterf(__double2float_rd(x0 - clip), -FLT_MAX);
-        const float hix = nextafterf(__double2float_ru(x0 + clip), FLT_MAX);
-        const float loy = nextafterf(__double2float_rd(y0 - clip), -FLT_MAX);
-        const float hiy = nextafterf(__double2float_ru(y0 + clip), FLT_MAX);
+        const float lox = float_below(x0 - clip);
+        const float hix = float_above(x0 + clip);
+        const float loy = float_below(y0 - clip);
+        const float hiy = float_above(y0 + clip);
         const int   bx0 = bin_coord(lox, bins.minx, bins.invBin, bins.nbx);
         const int   bx1 = bin_coord(hix, bins.minx, bins.invBin, bins.nbx);
         const int   by0 = bin_coord(loy, bins.miny, bins.invBin, bins.nby);
