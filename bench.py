@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
     }))
 
 
-TRAFFIC_FILE = "r2t_traffic.json"  # ncu counters of the step's launches of tpobs_grid_kernel (dram bytes, warp instructions)
+TRAFFIC_FILE = "r2z_traffic.json"  # ncu counters of the step's launches of tpobs_grid_kernel (dram bytes, warp instructions)
 C4_COSTMAP = (0.10, 0.5, 4.0)  # resolution, preferredClearanceDistance, maxCost
 C4_CPU_SAMPLE_CAP = 100
 WAYPOINTS01 = ([3.0, 5.0, 9.0, 20.0, 26.0], [2.0, 5.0, 8.0, 7.0, 3.0])  # share/mvsim-demo-waypoints01.yaml targets
