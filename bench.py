@@ -684,7 +684,7 @@ def run_ours(args, rank, local_rank, world):
         "config": config_dict(args), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_poses.nbytes),
                 "d2h_bytes_per_step": int(h_out.nbytes),
-                "note": "mppb_eval_nodes with pinned host buffers: host cos/sin + H2D of the poses + kernel, whose result rows are stored straight into the host buffer over PCIe (counted as D2H bytes) + sync; cloud resident"},
+                "note": "mppb_eval_nodes with pinned host buffers: host cos/sin (shared with the library's helper thread when the process may run on >= 8 CPUs) + H2D of the poses + kernel, whose result rows are stored straight into the host buffer over PCIe (counted as D2H bytes) + sync; cloud resident"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_affinity_cpus": affinity, "per_rank": per_rank,
         "setup": {"ptg_tables_s": t_tables, "ptg_tables_builder": "gpu (mppb_build_collision_grid)",
                   "last_collision_grid": t_grid, "cloud_upload_and_binning_s": t_cloud,
