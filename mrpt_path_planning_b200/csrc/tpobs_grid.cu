@@ -276,8 +276,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 // only at the cloud bins within near.r of the node; a node whose paths are all blocked within near.boundBits is final
 // and its row is written, any other node is appended to near.list. MODE 2 is the plain kernel over the nodes of that
 // list (CTAs beyond its length leave at once).
-// THREADS: CTA size. The near pass takes one warp per node (THREADS = 32): a near window holds a few hundred points, and
-// four warps would each repeat the per-node set-up for a quarter of them.
+// THREADS: CTA size (128; 512 for the second launch of the near-first form, whose CTAs each walk a whole window).
 template <bool HAS_BOX, int SPLIT, bool STAGED, bool PEERS, bool BITMAP, int MODE, int THREADS>
 __device__ __forceinline__ void tpobs_grid_node(const CloudBins& bins, const GridGroupDev* __restrict__ groups, int numGroups,
                                                 int totalPaths, int bitmapWords, const double* __restrict__ nodes,
@@ -1048,23 +1047,11 @@ int launch_tpobs_grid(mppb_ctx* ctx, size_t nNodes, const double* dNodes, const 
         // every one of a node's CTAs walks the whole window (one listed node in a C3 batch: +16 us with 128 threads, +8 us
         // with 512)
         const size_t restNodes = std::min(nNodes, kNearRestNodes);
-        static const bool warpNear = std::getenv("MPPB_GRID_NEAR_WARP") != nullptr;  // A/B measurements only
-        if (warpNear)
-            rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1, 32>, 1, 0, 32)
-                        : launch(tpobs_grid_kernel<false, 1, false, false, true, 1, 32>, 1, 0, 32);
-        else
-            rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, true, 1>, 1);
-        static const int restThreads = std::getenv("MPPB_GRID_REST_THREADS") ? std::atoi(std::getenv("MPPB_GRID_REST_THREADS")) : 512;  // (128, 256: A/B measurements)
+        rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, true, 1>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, true, 1>, 1);
         static const bool restPdl = std::getenv("MPPB_GRID_REST_NO_PDL") == nullptr;  // (A/B measurements)
-        if (rc == MPPB_OK && restThreads == 512)
+        if (rc == MPPB_OK)
             rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512, restPdl)
                         : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 512>, kSplit, restNodes, 512, restPdl);
-        else if (rc == MPPB_OK && restThreads == 256)
-            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2, 256>, kSplit, restNodes, 256)
-                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2, 256>, kSplit, restNodes, 256);
-        else if (rc == MPPB_OK)
-            rc = dBoxes ? launch(tpobs_grid_kernel<true, kSplit, false, false, true, 2>, kSplit, restNodes)
-                        : launch(tpobs_grid_kernel<false, kSplit, false, false, true, 2>, kSplit, restNodes);
     }
     else if (noBitmap)
         rc = dBoxes ? launch(tpobs_grid_kernel<true, 1, false, false, false>, 1) : launch(tpobs_grid_kernel<false, 1, false, false, false>, 1);
