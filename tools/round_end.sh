@@ -8,7 +8,7 @@ python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; tail -2
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.log
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_ref.err; echo "reference arm rc=$?"
-bash tools/profile_round.sh ${TAG} > gpurun_out/${TAG}_profile.log 2>&1; echo "profile rc=$?"
+bash tools/profile_round2b.sh ${TAG} > gpurun_out/${TAG}_profile.log 2>&1; echo "profile rc=$?"
 python - <<PY
 import json
 d = json.load(open("gpurun_out/${TAG}_bench.json")); p = d.get("planner") or {}
